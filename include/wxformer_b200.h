@@ -1,0 +1,138 @@
+/*
+ * wxformer_b200.h — C ABI of the B200-native WXFormer/CrossFormer forecast forward step.
+ *
+ * The reference (NCAR/miles-credit) has no native code: its boundary for this path is the Python
+ * nn.Module `credit.models.crossformer.CrossFormer` called as `y = model(x)`
+ * (credit/trainers/rollout_utils.py:281).  The entry points below are what a binding for that path
+ * binds: one per fused block of `CrossFormer.forward` (credit/models/crossformer.py:593-644).
+ *
+ * Conventions
+ *  - plain C: raw device pointers, ints, a cudaStream_t passed as void*; no torch types.
+ *  - every function only enqueues work on `stream` (no sync, no allocation, graph-capturable),
+ *    returns 0 on success, a positive cudaError_t, or a negative WXF_E* code for bad arguments.
+ *  - activations are fp32 "pixel-major" (NHWC): element (b, y, x, c) of a [B,H,W,C] field lives at
+ *    ((b*H + y)*W + x)*ld + c, where ld >= C is the pixel stride in elements (so a producer can
+ *    write straight into a channel slice of a concatenated tensor).
+ *  - the caller owns every buffer.
+ */
+#ifndef WXFORMER_B200_H
+#define WXFORMER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WXF_ABI_VERSION 1
+
+#define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
+#define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
+#define WXF_EUNSUPPORTED (-3)
+
+#define WXF_PAD_EARTH 0
+#define WXF_PAD_MIRROR 1
+
+#define WXF_ACT_NONE 0
+#define WXF_ACT_GELU_ERF 1
+
+#define WXF_ATTN_SHORT 0
+#define WXF_ATTN_LONG 1
+
+/* ABI version of the loaded library (WXF_ABI_VERSION). */
+int wxf_abi_version(void);
+
+/* Last error text of the calling thread (static storage; never NULL). */
+const char* wxf_last_error(void);
+
+/*
+ * Boundary padding fused with the NCHW -> pixel-major transpose.
+ * Replaces TensorPadding.pad (credit/boundary_padding.py:20-33: _earth_padding :50-72,
+ * _mirror_padding :98-117) and the frame flatten (credit/models/crossformer.py:604-609).
+ *   x  : [B, C, T, H, W] fp32 contiguous
+ *   xp : [B, H+pt+pb, W+pl+pr, ld] fp32, channel index c*T + t; channels [C*T, ld) are zero-filled.
+ */
+int wxf_pad_to_pixel_major(const float* x, float* xp, int B, int C, int T, int H, int W,
+                           int pt, int pb, int pl, int pr, int mode, int ld, void* stream);
+
+/*
+ * Channel LayerNorm at every pixel (credit/models/crossformer.py:182-192):
+ *   y = (x - mean) / sqrt(var_biased + eps) * g + b   over the d channels of each of M pixels.
+ */
+int wxf_layernorm(const float* x, int ldx, float* y, int ldy, const float* g, const float* b,
+                  int64_t M, int d, float eps, void* stream);
+
+/*
+ * Implicit-GEMM convolution, exact fp32 FMA.  One descriptor covers
+ *   - Conv2d kxk stride s zero-pad p        (CrossEmbedLayer, crossformer.py:139-152; UpBlock 3x3, :96-99)
+ *   - 1x1 Conv2d                           (to_qkv/to_out :229-230, FeedForward :198-204)
+ *   - ConvTranspose2d k2 s2 and k4 s2 p1   (crossformer.py:92, :572-574) as `phases` = 4 output-parity
+ *     classes, each an ordinary small convolution scattered to (oy*out_scale + phase/2, ox*out_scale + phase%2).
+ * For GEMM row m = (b, oy, ox) over the [B, Ho, Wo] grid and phase z:
+ *   acc[n] = sum_{t<T} sum_{c<Cin} in[b, oy*stride + taps[z][t].dy, ox*stride + taps[z][t].dx, c]
+ *                                  * w[z][n][t*Cin + c]          (out-of-range pixels read as 0)
+ *   v = acc[n] + bias[n];  v = act(v);  v += res[pixel, n] (if res);  out[pixel, c_off + n] = v
+ */
+typedef struct WxfConvDesc {
+  const float* in;   /* [B, Hi, Wi, lda] */
+  const float* w;    /* [phases, N, T*Cin] */
+  const int32_t* taps; /* [phases, T, 2] = (dy, dx), padding already subtracted */
+  const float* bias; /* [N] or NULL */
+  const float* res;  /* residual, same pixel grid as out, or NULL */
+  float* out;        /* [B, Ho*out_scale, Wo*out_scale, ldc] */
+  int32_t B, Hi, Wi, lda, Cin;
+  int32_t N, T, stride;
+  int32_t Ho, Wo;
+  int32_t phases, out_scale;
+  int32_t ldc, c_off;
+  int32_t ldr, r_off;
+  int32_t act;
+} WxfConvDesc;
+
+int wxf_conv_igemm_f32(const WxfConvDesc* desc, void* stream);
+
+/*
+ * Cross-scale window attention core (credit/models/crossformer.py:261-296, 301-314) for all windows
+ * and heads of one Attention block, on the pixel-major output of the to_qkv 1x1 conv:
+ *   qkv   : [B, H, W, ldq] with q = [0,d), k = [d,2d), v = [2d,3d); head h = channels h*dh..h*dh+dh-1
+ *   biasT : [L, L] transposed position bias, biasT[j*L + i] = bias[i][j]  (L = wsz*wsz)
+ *   out   : [B, H, W, ldo] channel h*dh + e   (input of to_out)
+ * S = (q*scale) k^T + bias; P = softmax(S); out = P v.   kind: WXF_ATTN_SHORT tiles wsz x wsz blocks,
+ * WXF_ATTN_LONG groups the dilated tokens (l1*(H/wsz)+gh, l2*(W/wsz)+gw).   dh must be 32, L <= 128.
+ */
+int wxf_window_attention_f32(const float* qkv, int ldq, const float* biasT, float* out, int ldo,
+                             int B, int H, int W, int d, int dh, int wsz, int kind, float scale, void* stream);
+
+/*
+ * GroupNorm + SiLU on a pixel-major field (UpBlock residual stack, crossformer.py:96-116).
+ * Two calls: statistics (deterministic two-level reduction, fp64 final combine) then apply.
+ *   stats : [B, G, 2] fp32 (mean, rstd);   scratch: >= wxf_groupnorm_scratch_bytes(...) bytes.
+ *   apply : y = silu((x - mean) * rstd * gamma + beta) (+ res if res != NULL)
+ */
+int64_t wxf_groupnorm_scratch_bytes(int B, int64_t HW, int C);
+int wxf_groupnorm_stats(const float* x, int ldx, float* stats, void* scratch, int B, int64_t HW, int C, int G,
+                        float eps, void* stream);
+int wxf_groupnorm_silu(const float* x, int ldx, const float* stats, const float* gamma, const float* beta,
+                       const float* res, int ldr, float* y, int ldy, int B, int64_t HW, int C, int G, void* stream);
+
+/*
+ * Un-pad + bilinear resize (align_corners = False) + pixel-major -> NCHW
+ * (TensorPadding.unpad, boundary_padding.py:35-48; F.interpolate, crossformer.py:628-635).
+ *   y   : [B, Hd, Wd, ld]; the crop is rows [top, top+Hc), cols [left, left+Wc)
+ *   out : [B, C, Ho, Wo] fp32 contiguous (C = base_output_channels*output_frames)
+ */
+int wxf_unpad_resize_to_nchw(const float* y, int ld, float* out, int B, int C, int Hd, int Wd, int top, int left,
+                             int Hc, int Wc, int Ho, int Wo, void* stream);
+
+/*
+ * Autoregressive state update (update_x, credit/datasets/gen_2/channel_utils.py:253-291):
+ * for every group g < n_groups: dst[:, dst_c0[g] : dst_c0[g]+len[g]] = src[:, src_c0[g] : src_c0[g]+len[g]]
+ * on [B, C, plane] tensors (plane = T*H*W elements per channel).
+ */
+int wxf_copy_channels(float* dst, int dst_C, const float* src, int src_C, int B, int64_t plane,
+                      const int32_t* dst_c0, const int32_t* src_c0, const int32_t* len, int n_groups, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WXFORMER_B200_H */

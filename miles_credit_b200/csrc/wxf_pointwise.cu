@@ -1,0 +1,377 @@
+// HBM-bound passes of the forecast step: boundary pad (+NCHW->pixel-major), channel LayerNorm,
+// GroupNorm+SiLU, un-pad + bilinear resize (+pixel-major->NCHW), rollout channel copy.
+// Each is one coalesced read and one coalesced write of its tensor; see DESIGN.md for the byte counts.
+#include "wxf_common.cuh"
+
+thread_local char wxf_err_buf[512] = "";
+
+extern "C" int wxf_abi_version(void) { return WXF_ABI_VERSION; }
+extern "C" const char* wxf_last_error(void) { return wxf_err_buf; }
+
+// ------------------------------------------------------------------------------------------------
+// boundary pad + transpose.  Index map of TensorPadding._earth_padding (boundary_padding.py:50-72):
+// padded (r, c): j = (c - pl) mod W; r < pt -> x[pt-1-r, (j - W/2) mod W]; pt <= r < pt+H -> x[r-pt, j];
+// else x[H-1-(r-pt-H), (j - W/2) mod W].  mirror (:98-117): circular lon, reflect lat (no edge repeat).
+
+__global__ void __launch_bounds__(256) pad_to_pixel_major_kernel(const float* __restrict__ x, float* __restrict__ xp,
+                                                                  int CT, int H, int W, int pt, int pl, int mode,
+                                                                  int ld, int Hp, int Wp, int cgroups) {
+  __shared__ float tile[32][33];  // [channel][column]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int b = blockIdx.z / cgroups, cg = blockIdx.z % cgroups;
+  const int r = blockIdx.y;
+  const int c0 = blockIdx.x * 32;
+
+  int sr;
+  bool roll = false;
+  if (mode == WXF_PAD_EARTH) {
+    if (r < pt) {
+      sr = pt - 1 - r;
+      roll = true;
+    } else if (r < pt + H) {
+      sr = r - pt;
+    } else {
+      sr = H - 1 - (r - pt - H);
+      roll = true;
+    }
+  } else {
+    sr = r - pt;
+    if (sr < 0) sr = -sr;
+    if (sr >= H) sr = 2 * (H - 1) - sr;
+  }
+
+  const int col = c0 + tx;
+  int sc = -1;
+  if (col < Wp) {
+    int j = (col - pl) % W;
+    if (j < 0) j += W;
+    if (roll) {
+      j -= W / 2;
+      if (j < 0) j += W;
+    }
+    sc = j;
+  }
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int ch = cg * 32 + i;
+    float v = 0.f;
+    if (ch < CT && sc >= 0) v = __ldg(x + ((size_t)(b * CT + ch) * H + sr) * W + sc);
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  const int ch = cg * 32 + tx;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int cw = c0 + i;
+    if (cw < Wp && ch < ld) xp[((size_t)(b * Hp + r) * Wp + cw) * ld + ch] = tile[tx][i];
+  }
+}
+
+extern "C" int wxf_pad_to_pixel_major(const float* x, float* xp, int B, int C, int T, int H, int W, int pt, int pb,
+                                      int pl, int pr, int mode, int ld, void* stream) {
+  if (B <= 0 || C <= 0 || T <= 0 || H <= 0 || W <= 0 || pt < 0 || pb < 0 || pl < 0 || pr < 0)
+    WXF_FAIL(WXF_EINVAL, "pad: bad dims");
+  if (ld < C * T) WXF_FAIL(WXF_EINVAL, "pad: ld %d < C*T %d", ld, C * T);
+  if (mode != WXF_PAD_EARTH && mode != WXF_PAD_MIRROR) WXF_FAIL(WXF_EINVAL, "pad: bad mode %d", mode);
+  if (mode == WXF_PAD_EARTH && (pt > H || pb > H)) WXF_FAIL(WXF_EINVAL, "pad: earth pad_lat larger than H");
+  if (mode == WXF_PAD_MIRROR && (pt >= H || pb >= H)) WXF_FAIL(WXF_EINVAL, "pad: mirror pad_lat must be < H");
+  const int Hp = H + pt + pb, Wp = W + pl + pr;
+  const int cgroups = (ld + 31) / 32;
+  if (Hp > 65535 || (int64_t)B * cgroups > 65535) WXF_FAIL(WXF_EINVAL, "pad: grid too large");
+  dim3 grid((Wp + 31) / 32, Hp, B * cgroups), block(32, 8);
+  pad_to_pixel_major_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, xp, C * T, H, W, pt, pl, mode, ld, Hp, Wp,
+                                                                       cgroups);
+  WXF_CHECK_LAUNCH("pad_to_pixel_major");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel LayerNorm (crossformer.py:182-192): one warp per pixel, row cached in registers.
+
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y,
+                                                         int ldy, const float* __restrict__ g,
+                                                         const float* __restrict__ bta, int64_t M, int d, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* xr = x + row * ldx;
+  float v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane + 32 * k;
+    v[k] = (c < d) ? xr[c] : 0.f;
+    s += v[k];
+  }
+  const float mean = wxf_warp_sum(s) / (float)d;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane + 32 * k;
+    const float t = (c < d) ? v[k] - mean : 0.f;
+    ss += t * t;
+  }
+  const float var = wxf_warp_sum(ss) / (float)d;
+  const float den = sqrtf(var + eps);
+  float* yr = y + row * ldy;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane + 32 * k;
+    if (c < d) yr[c] = (v[k] - mean) / den * __ldg(g + c) + __ldg(bta + c);
+  }
+}
+
+extern "C" int wxf_layernorm(const float* x, int ldx, float* y, int ldy, const float* g, const float* b, int64_t M,
+                             int d, float eps, void* stream) {
+  if (M <= 0 || d <= 0 || ldx < d || ldy < d) WXF_FAIL(WXF_EINVAL, "layernorm: bad dims");
+  if (d > 1024) WXF_FAIL(WXF_EUNSUPPORTED, "layernorm: d=%d > 1024", d);
+  const int nv = (d + 31) / 32;
+  const unsigned blocks = (unsigned)((M + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LN_CASE(NV)                                                                  \
+  if (nv <= NV) {                                                                    \
+    layernorm_kernel<NV><<<blocks, 256, 0, st>>>(x, ldx, y, ldy, g, b, M, d, eps);  \
+    WXF_CHECK_LAUNCH("layernorm");                                                   \
+    return 0;                                                                        \
+  }
+  LN_CASE(1) LN_CASE(2) LN_CASE(4) LN_CASE(8) LN_CASE(16) LN_CASE(32)
+#undef LN_CASE
+  return WXF_EUNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm + SiLU (nn.GroupNorm(num_groups, C) + nn.SiLU, crossformer.py:96-100).
+// Pass 1: per-block partial (sum, sumsq) per group -> scratch;  pass 2: fp64 combine -> (mean, rstd);
+// pass 3: normalise + affine + SiLU (+ UpBlock shortcut).
+
+static constexpr int GN_PIX_PER_BLOCK = 512;
+
+__global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, int ldx, float2* __restrict__ part,
+                                                          int64_t HW, int C, int G, int nchunk) {
+  // channel slot of this thread: TC = min(C, 256) channels in flight, 256/TC pixel lanes
+  __shared__ float rs[1024], rq[1024];
+  const int tid = threadIdx.x;
+  const int TC = C < 256 ? C : 256;
+  const int lanes = 256 / TC;  // TC divides 256 (checked on host) or TC == 256
+  const int KS = C / TC;       // channel slots per thread (<= 4)
+  const int tc = tid % TC, pl = tid / TC;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int64_t p0 = (int64_t)chunk * GN_PIX_PER_BLOCK;
+  int64_t p1 = p0 + GN_PIX_PER_BLOCK;
+  if (p1 > HW) p1 = HW;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (pl < lanes) {
+    for (int64_t p = p0 + pl; p < p1; p += lanes) {
+      const float* xr = x + ((int64_t)b * HW + p) * ldx;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < KS) {
+          const float v = xr[tc + k * TC];
+          s[k] += v;
+          q[k] += v * v;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    rs[tid + 256 * k] = s[k];
+    rq[tid + 256 * k] = q[k];
+  }
+  __syncthreads();
+  // per-channel totals across pixel lanes: channel c = tc + k*TC lives at rs[pl*TC + tc + 256*k]
+  const int cpg = C / G;
+  for (int gidx = tid; gidx < G; gidx += 256) {
+    float ts = 0.f, tq = 0.f;
+    for (int cc = 0; cc < cpg; ++cc) {
+      const int c = gidx * cpg + cc;
+      const int k = c / TC, t = c % TC;
+      for (int l = 0; l < lanes; ++l) {
+        ts += rs[l * TC + t + 256 * k];
+        tq += rq[l * TC + t + 256 * k];
+      }
+    }
+    part[((int64_t)b * nchunk + chunk) * G + gidx] = make_float2(ts, tq);
+  }
+}
+
+__global__ void gn_finalize_kernel(const float2* __restrict__ part, float* __restrict__ stats, int B, int G, int nchunk,
+                                   double count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * G) return;
+  const int b = i / G, g = i % G;
+  double s = 0.0, q = 0.0;
+  for (int c = 0; c < nchunk; ++c) {
+    const float2 p = part[((int64_t)b * nchunk + c) * G + g];
+    s += (double)p.x;
+    q += (double)p.y;
+  }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[2 * i] = (float)mean;
+  stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ x, int ldx,
+                                                       const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float* __restrict__ res,
+                                                       int ldr, float* __restrict__ y, int ldy, int64_t HW, int C,
+                                                       int cpg, int G, int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = idx / C;
+    const int c = (int)(idx - pix * C);
+    const int b = (int)(pix / HW);
+    const int g = c / cpg;
+    const float mean = __ldg(stats + 2 * (b * G + g)), rstd = __ldg(stats + 2 * (b * G + g) + 1);
+    float v = (x[pix * ldx + c] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    v = wxf_silu(v);
+    if (res) v += res[pix * ldr + c];
+    y[pix * ldy + c] = v;
+  }
+}
+
+extern "C" int64_t wxf_groupnorm_scratch_bytes(int B, int64_t HW, int C) {
+  const int64_t nchunk = (HW + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK;
+  return (int64_t)B * nchunk * C * (int64_t)sizeof(float2);  // G <= C
+}
+
+extern "C" int wxf_groupnorm_stats(const float* x, int ldx, float* stats, void* scratch, int B, int64_t HW, int C,
+                                   int G, float eps, void* stream) {
+  if (B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G) WXF_FAIL(WXF_EINVAL, "groupnorm: bad dims");
+  if (C > 1024 || !((C <= 256 && 256 % C == 0) || (C % 256 == 0)))
+    WXF_FAIL(WXF_EUNSUPPORTED, "groupnorm: C=%d must divide 256 or be a multiple of 256 (<=1024)", C);
+  const int nchunk = (int)((HW + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK);
+  cudaStream_t st = (cudaStream_t)stream;
+  gn_partial_kernel<<<dim3(nchunk, B), 256, 0, st>>>(x, ldx, (float2*)scratch, HW, C, G, nchunk);
+  WXF_CHECK_LAUNCH("gn_partial");
+  gn_finalize_kernel<<<(B * G + 127) / 128, 128, 0, st>>>((const float2*)scratch, stats, B, G, nchunk,
+                                                          (double)HW * (double)(C / G), eps);
+  WXF_CHECK_LAUNCH("gn_finalize");
+  return 0;
+}
+
+extern "C" int wxf_groupnorm_silu(const float* x, int ldx, const float* stats, const float* gamma, const float* beta,
+                                  const float* res, int ldr, float* y, int ldy, int B, int64_t HW, int C, int G,
+                                  void* stream) {
+  if (B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G) WXF_FAIL(WXF_EINVAL, "groupnorm_silu: bad dims");
+  const int64_t total = (int64_t)B * HW * C;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  gn_silu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, stats, gamma, beta, res, ldr, y, ldy, HW,
+                                                                     C, C / G, G, total);
+  WXF_CHECK_LAUNCH("gn_silu");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// un-pad + bilinear (align_corners=False) + pixel-major -> NCHW.
+// src = (dst + 0.5) * in/out - 0.5 clamped at 0 (torch area_pixel_compute_source_index).
+
+__device__ __forceinline__ void bilin_axis(int dst, float scale, int n_in, int& i0, int& i1, float& l0, float& l1) {
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > n_in - 1) i0 = n_in - 1;
+  i1 = i0 + ((i0 < n_in - 1) ? 1 : 0);
+  l1 = src - (float)i0;
+  if (l1 < 0.f) l1 = 0.f;
+  if (l1 > 1.f) l1 = 1.f;
+  l0 = 1.f - l1;
+}
+
+__global__ void __launch_bounds__(256) unpad_resize_kernel(const float* __restrict__ y, int ld, float* __restrict__ out,
+                                                            int C, int Hd, int Wd, int top, int left, int Hc, int Wc,
+                                                            int Ho, int Wo, float sh, float sw, int cgroups) {
+  __shared__ float tile[32][33];  // [channel][column]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int b = blockIdx.z / cgroups, cg = blockIdx.z % cgroups;
+  const int h = blockIdx.y, w0 = blockIdx.x * 32;
+  int y0, y1;
+  float ly0, ly1;
+  bilin_axis(h, sh, Hc, y0, y1, ly0, ly1);
+  const int ch = cg * 32 + tx;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int w = w0 + i;
+    float v = 0.f;
+    if (w < Wo && ch < C) {
+      int x0, x1;
+      float lx0, lx1;
+      bilin_axis(w, sw, Wc, x0, x1, lx0, lx1);
+      const float* r0 = y + ((size_t)(b * Hd + top + y0) * Wd + left) * ld + ch;
+      const float* r1 = y + ((size_t)(b * Hd + top + y1) * Wd + left) * ld + ch;
+      const float v00 = r0[(size_t)x0 * ld], v01 = r0[(size_t)x1 * ld];
+      const float v10 = r1[(size_t)x0 * ld], v11 = r1[(size_t)x1 * ld];
+      v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+    }
+    tile[tx][i] = v;
+  }
+  __syncthreads();
+  const int w = w0 + tx;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int c = cg * 32 + i;
+    if (w < Wo && c < C) out[((size_t)(b * C + c) * Ho + h) * Wo + w] = tile[i][tx];
+  }
+}
+
+extern "C" int wxf_unpad_resize_to_nchw(const float* y, int ld, float* out, int B, int C, int Hd, int Wd, int top,
+                                        int left, int Hc, int Wc, int Ho, int Wo, void* stream) {
+  if (B <= 0 || C <= 0 || Hc <= 0 || Wc <= 0 || Ho <= 0 || Wo <= 0 || top < 0 || left < 0 || top + Hc > Hd ||
+      left + Wc > Wd || ld < C)
+    WXF_FAIL(WXF_EINVAL, "unpad_resize: bad dims");
+  const int cgroups = (C + 31) / 32;
+  if (Ho > 65535 || (int64_t)B * cgroups > 65535) WXF_FAIL(WXF_EINVAL, "unpad_resize: grid too large");
+  const float sh = (float)Hc / (float)Ho, sw = (float)Wc / (float)Wo;
+  dim3 grid((Wo + 31) / 32, Ho, B * cgroups), block(32, 8);
+  unpad_resize_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(y, ld, out, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, sh,
+                                                                 sw, cgroups);
+  WXF_CHECK_LAUNCH("unpad_resize");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rollout channel copy (update_x, datasets/gen_2/channel_utils.py:253-291)
+
+struct CopyGroups {
+  int32_t dst_c0[8], src_c0[8], len[8];
+};
+
+__global__ void __launch_bounds__(256) copy_channels_kernel(float* __restrict__ dst, int dst_C,
+                                                             const float* __restrict__ src, int src_C, int64_t plane,
+                                                             CopyGroups gr, int B) {
+  const int g = blockIdx.y / B, b = blockIdx.y % B;
+  const int64_t n = (int64_t)gr.len[g] * plane;
+  float* d = dst + ((int64_t)b * dst_C + gr.dst_c0[g]) * plane;
+  const float* s = src + ((int64_t)b * src_C + gr.src_c0[g]) * plane;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((((uintptr_t)d | (uintptr_t)s) & 15u) == 0 && (n & 3) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+    float4* d4 = reinterpret_cast<float4*>(d);
+    for (int64_t i = i0; i < (n >> 2); i += stride) d4[i] = s4[i];
+  } else {
+    for (int64_t i = i0; i < n; i += stride) d[i] = s[i];
+  }
+}
+
+extern "C" int wxf_copy_channels(float* dst, int dst_C, const float* src, int src_C, int B, int64_t plane,
+                                 const int32_t* dst_c0, const int32_t* src_c0, const int32_t* len, int n_groups,
+                                 void* stream) {
+  if (n_groups <= 0 || n_groups > 8 || B <= 0 || plane <= 0) WXF_FAIL(WXF_EINVAL, "copy_channels: bad dims");
+  CopyGroups gr;
+  for (int g = 0; g < n_groups; ++g) {
+    if (dst_c0[g] < 0 || src_c0[g] < 0 || len[g] <= 0 || dst_c0[g] + len[g] > dst_C || src_c0[g] + len[g] > src_C)
+      WXF_FAIL(WXF_EINVAL, "copy_channels: group %d out of range", g);
+    gr.dst_c0[g] = dst_c0[g];
+    gr.src_c0[g] = src_c0[g];
+    gr.len[g] = len[g];
+  }
+  dim3 grid(148 * 4, n_groups * B);
+  copy_channels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dst, dst_C, src, src_C, plane, gr, B);
+  WXF_CHECK_LAUNCH("copy_channels");
+  return 0;
+}

@@ -1,0 +1,88 @@
+"""ctypes binding of the C-ABI library (include/wxformer_b200.h).
+
+There is no fallback: if ``libwxformer_b200.so`` is missing or a call fails, a ``RuntimeError`` is raised.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
+HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
+
+WXF_ABI_VERSION = 1
+
+PAD_EARTH, PAD_MIRROR = 0, 1
+ACT_NONE, ACT_GELU = 0, 1
+ATTN_SHORT, ATTN_LONG = 0, 1
+
+
+class WxfConvDesc(Structure):
+    _fields_ = [
+        ("inp", c_void_p), ("w", c_void_p), ("taps", c_void_p), ("bias", c_void_p), ("res", c_void_p),
+        ("out", c_void_p),
+        ("B", c_int32), ("Hi", c_int32), ("Wi", c_int32), ("lda", c_int32), ("Cin", c_int32),
+        ("N", c_int32), ("T", c_int32), ("stride", c_int32),
+        ("Ho", c_int32), ("Wo", c_int32),
+        ("phases", c_int32), ("out_scale", c_int32),
+        ("ldc", c_int32), ("c_off", c_int32),
+        ("ldr", c_int32), ("r_off", c_int32),
+        ("act", c_int32),
+    ]
+
+
+_SIGNATURES = {
+    "wxf_abi_version": (c_int, []),
+    "wxf_last_error": (c_char_p, []),
+    "wxf_pad_to_pixel_major": (c_int, [c_void_p, c_void_p] + [c_int] * 11 + [c_void_p]),
+    "wxf_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
+    "wxf_conv_igemm_f32": (c_int, [POINTER(WxfConvDesc), c_void_p]),
+    "wxf_window_attention_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int] + [c_int] * 7 + [c_float, c_void_p]),
+    "wxf_groupnorm_scratch_bytes": (c_int64, [c_int, c_int64, c_int]),
+    "wxf_groupnorm_stats": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float, c_void_p]),
+    "wxf_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                   c_int, c_int64, c_int, c_int, c_void_p]),
+    "wxf_unpad_resize_to_nchw": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 10 + [c_void_p]),
+    "wxf_copy_channels": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int64, POINTER(c_int32), POINTER(c_int32),
+                                  POINTER(c_int32), c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def declared_symbols(header_path: str = HEADER_PATH):
+    """Every function name the public header declares (used by the CPU export test)."""
+    text = open(header_path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(wxf_[a-z0-9_]+)\s*\(", text)))
+
+
+def load(path: str = LIB_PATH):
+    """Load the shared library; raises if it is not built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(path):
+        raise RuntimeError(
+            f"{path} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). This package has no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    # signatures of symbols added by later ABI revisions are attached where they are declared
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = load().wxf_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed with status {status}: {msg}")

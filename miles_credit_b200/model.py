@@ -1,0 +1,345 @@
+"""``CrossFormerB200`` — drop-in replacement of ``credit.models.crossformer.CrossFormer`` for the forecast step.
+
+Same constructor keywords (crossformer.py:372-401), same ``state_dict`` keys and shapes (so reference
+checkpoints load with ``strict=True``), same tensor contract ``[B, C_in, frames, H, W] -> [B, C_out,
+output_frames, H, W]`` (crossformer.py:593-644) and the attributes other CREDIT code reads
+(``use_padding``, ``padding_opt``, ``image_height``, ``image_width``, ``use_interp``, ``channels``, ``levels``,
+``surface_channels``; trainers/trainer_gen2.py:83-89, base_model.py:44-46).  It subclasses CREDIT's
+``BaseModel`` when CREDIT is importable (so ``@register_model`` accepts it, models/__init__.py:154), else a
+local mirror of it.
+
+Inside, the forward is a fixed launch plan over hand-written sm_100a kernels reached through the C-ABI
+(include/wxformer_b200.h).  Eval-mode forward only: there is no autograd, no CPU path and no PyTorch
+fallback — a missing library or a CPU tensor raises.
+"""
+
+from __future__ import annotations
+
+import copy
+import logging
+import os
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import lib as _lib
+from . import ops
+from .geometry import Geometry, build_geometry, state_spec
+from .synth import synthetic_state_dict
+from .weights import ConvWeights, PreparedWeights, prepare
+
+logger = logging.getLogger(__name__)
+
+try:  # CREDIT present: be a real BaseModel so credit.models.register_model accepts the class
+    from credit.models.base_model import BaseModel as _Base  # type: ignore
+except Exception:  # noqa: BLE001 - CREDIT (or one of its heavy deps) absent: local mirror
+
+    class _Base(nn.Module):
+        """Mirror of credit/models/base_model.py:12-126 (checkpoint classmethods + reshape helper)."""
+
+        def __init__(self):
+            super().__init__()
+
+        def split_and_reshape(self, tensor):
+            t1 = tensor[:, : int(self.channels * self.levels), :, :, :]
+            t2 = tensor[:, -int(self.surface_channels):, :, :, :]
+            t1 = t1.view(t1.shape[0], self.channels, self.levels, t1.shape[2], t1.shape[3], t1.shape[4])
+            return t1, t2
+
+        @classmethod
+        def load_model(cls, conf):
+            conf = copy.deepcopy(conf)
+            save_loc = os.path.expandvars(conf["save_loc"])
+            ckpt = os.path.join(save_loc, "model_checkpoint.pt")
+            if not os.path.isfile(ckpt):
+                ckpt = os.path.join(save_loc, "checkpoint.pt")
+            return cls._from_checkpoint(conf, ckpt)
+
+        @classmethod
+        def load_model_name(cls, conf, model_name):
+            conf = copy.deepcopy(conf)
+            return cls._from_checkpoint(conf, os.path.join(os.path.expandvars(conf["save_loc"]), model_name))
+
+        @classmethod
+        def _from_checkpoint(cls, conf, ckpt):
+            if not os.path.isfile(ckpt):
+                raise ValueError("No saved checkpoint exists. You must train a model first. Exiting.")
+            checkpoint = torch.load(ckpt, map_location="cpu" if not torch.cuda.is_available() else None)
+            conf["model"].pop("type", None)
+            model = cls(**conf["model"])
+            sd = checkpoint["model_state_dict"] if "model_state_dict" in checkpoint else checkpoint
+            msg = model.load_state_dict(sd, strict=False)
+            if msg.unexpected_keys:  # models/checkpoint.py:25-31: unexpected keys raise, missing keys warn
+                raise RuntimeError(str(msg))
+            if msg.missing_keys:
+                logger.warning(f"Loaded partial model {msg}")
+            return model
+
+        def save_model(self, conf):
+            save_loc = os.path.expandvars(conf["save_loc"])
+            torch.save({"model_state_dict": self.state_dict()}, os.path.join(save_loc, "checkpoint.pt"))
+
+
+class _Holder(nn.Module):
+    """Parameter container; exists only so state-dict keys equal the reference's module paths."""
+
+
+class PaddingView:
+    """``model.padding_opt`` as CREDIT code expects it (pad/unpad on [..., H, W]; boundary_padding.py:20-48).
+
+    ``pad`` runs the same CUDA kernel as the forward and returns the reference's NCHW layout.
+    """
+
+    def __init__(self, geo: Geometry):
+        self.mode = geo.padding.mode
+        self.pad_NS = list(geo.padding.pad_lat)
+        self.pad_WE = list(geo.padding.pad_lon)
+
+    def pad(self, x: torch.Tensor) -> torch.Tensor:
+        shape = x.shape
+        x5 = x.reshape(-1, 1, 1, shape[-2], shape[-1]) if x.dim() != 5 else x
+        b, c, t = x5.shape[:3]
+        pm = ops.pad_to_pixel_major(x5.float(), self.pad_NS, self.pad_WE, self.mode, c * t)
+        out = pm.permute(0, 3, 1, 2).reshape(b, c, t, pm.shape[1], pm.shape[2])
+        return out.reshape(*shape[:-2], pm.shape[1], pm.shape[2]).contiguous()
+
+    def unpad(self, x: torch.Tensor) -> torch.Tensor:
+        h, w = x.shape[-2:]
+        return x[..., self.pad_NS[0]: h - self.pad_NS[1], self.pad_WE[0]: w - self.pad_WE[1]]
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+class _Plan:
+    """Workspace + ordered kernel launches of one forward for a fixed batch size."""
+
+    def __init__(self, geo: Geometry, wts: PreparedWeights, batch: int, device):
+        self.geo, self.batch = geo, batch
+        f32 = dict(device=device, dtype=torch.float32)
+        B = batch
+        g = geo
+        self.ld0 = wts.cin0_pad
+        self.xp = torch.empty((B, g.h_pad, g.w_pad, self.ld0), **f32)
+        st0 = g.stages[0]
+        m0 = B * st0.h * st0.w
+        big = max(B * s.h * s.w * s.dim for s in g.stages)
+        big = max(big, max(4 * B * u.h_in * u.w_in * u.c_out for u in g.ups))
+        self.ln = torch.empty(big, **f32)
+        y_elems = B * g.h_dec * g.w_dec * g.output_channels
+        self.scratch = torch.empty(max(4 * big, 2 * big + y_elems), **f32)
+        # residual streams: stages 0..2 live in the upper half of their skip-concat buffer
+        self.cat = [torch.empty((B, s.h, s.w, 2 * s.dim), **f32) for s in g.stages[:3]]
+        self.x3 = torch.empty((B, g.stages[3].h, g.stages[3].w, g.stages[3].dim), **f32)
+        self.gn_stats = torch.empty((B, g.dim[0], 2), **f32)
+        gn_bytes = max(ops.groupnorm_scratch_bytes(B, 4 * u.h_in * u.w_in, u.c_out) for u in g.ups)
+        self.gn_scratch = torch.empty(gn_bytes // 4 + 4, **f32)
+        self.steps: List[tuple] = []
+        self._build(wts)
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _add(self, fn, args, tag, flops=0.0, nbytes=0.0):
+        self.steps.append((fn, args, tag, float(flops), float(nbytes)))
+
+    def _conv(self, inp, wts: ConvWeights, out, tag="conv", **kw):
+        desc = ops.make_conv_desc(inp, wts, out, **kw)
+        m = kw["B"] * kw["Ho"] * kw["Wo"]
+        flops = 2.0 * m * wts.n * wts.t * wts.cin * wts.phases
+        self._add(ops.conv_igemm_f32, (desc,), tag, flops)
+
+    def _build(self, wts: PreparedWeights):
+        g, B = self.geo, self.batch
+        add = self._add
+        src, src_ld, src_h, src_w = self.xp, self.ld0, g.h_pad, g.w_pad
+        for st in g.stages:
+            s, d = st.index, st.dim
+            if s < 3:
+                xbuf, ld, xoff = self.cat[s], 2 * d, d
+            else:
+                xbuf, ld, xoff = self.x3, d, 0
+            xv = xbuf[..., xoff:]  # view: data_ptr carries the channel offset
+            m = B * st.h * st.w
+            for br, bw in zip(st.branches, wts.embeds[s]):
+                self._conv(src, bw, xbuf, tag=f"embed{s}.k{br.kernel}", B=B, Hi=src_h, Wi=src_w, lda=src_ld, Ho=st.h,
+                           Wo=st.w, ldc=ld, c_off=xoff + br.c_off)
+            ln = self.ln[: m * d]
+            wide = self.scratch[: m * 4 * d]
+            for layer in wts.blocks[s]:
+                for att, ff in ((layer[0], layer[1]), (layer[2], layer[3])):
+                    L = att.wsz * att.wsz
+                    add(ops.layernorm, (xv, ld, ln, d, att.ln_g, att.ln_b, m, d), "layernorm", 0, 8.0 * m * d)
+                    self._conv(ln, att.qkv, wide, tag="qkv", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=3 * d)
+                    add(ops.window_attention_f32, (wide, 3 * d, att.bias_t, ln, d, B, st.h, st.w, d, g.dim_head,
+                                                   att.wsz, att.kind, float(g.dim_head) ** -0.5), "attention",
+                        4.0 * m * L * d, 16.0 * m * d)
+                    self._conv(ln, att.out, xv, tag="out_proj", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=ld,
+                               res=xv, ldr=ld)
+                    add(ops.layernorm, (xv, ld, ln, d, ff.ln_g, ff.ln_b, m, d), "layernorm", 0, 8.0 * m * d)
+                    self._conv(ln, ff.fc1, wide, tag="ff1", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=4 * d,
+                               act=_lib.ACT_GELU)
+                    self._conv(wide, ff.fc2, xv, tag="ff2", B=B, Hi=st.h, Wi=st.w, lda=4 * d, Ho=st.h, Wo=st.w, ldc=ld,
+                               res=xv, ldr=ld)
+            src, src_ld, src_h, src_w = xv, ld, st.h, st.w
+
+        # decoder: UpBlock x3 (crossformer.py:107-122), outputs land in the lower half of the skip buffers
+        dec_in, dec_ld = self.x3, g.stages[3].dim
+        for up, uw, skip in zip(g.ups, wts.ups, (2, 1, 0)):
+            ho, wo, c = 2 * up.h_in, 2 * up.w_in, up.c_out
+            n = B * ho * wo * c
+            short = self.ln[:n]
+            a, b = self.scratch[:n], self.scratch[n: 2 * n]
+            self._conv(dec_in, uw.up, short, tag="dec_up", B=B, Hi=up.h_in, Wi=up.w_in, lda=dec_ld, Ho=up.h_in,
+                       Wo=up.w_in, ldc=c)
+            self._conv(short, uw.convs[0], a, tag="dec_conv3x3", B=B, Hi=ho, Wi=wo, lda=c, Ho=ho, Wo=wo, ldc=c)
+            add(ops.groupnorm_silu, (a, c, self.gn_stats, self.gn_scratch, uw.gn_w[0], uw.gn_b[0], None, 0, b, c, B,
+                                     ho * wo, c, up.groups), "groupnorm_silu", 0, 12.0 * n)
+            self._conv(b, uw.convs[1], a, tag="dec_conv3x3", B=B, Hi=ho, Wi=wo, lda=c, Ho=ho, Wo=wo, ldc=c)
+            dst = self.cat[skip]
+            add(ops.groupnorm_silu, (a, c, self.gn_stats, self.gn_scratch, uw.gn_w[1], uw.gn_b[1], short, c, dst,
+                                     2 * c, B, ho * wo, c, up.groups), "groupnorm_silu", 0, 16.0 * n)
+            dec_in, dec_ld = dst, 2 * c
+        st0 = g.stages[0]
+        big2 = 2 * (B * st0.h * st0.w * st0.dim)
+        self.y_dec = self.scratch[big2: big2 + B * g.h_dec * g.w_dec * g.output_channels]
+        self._conv(dec_in, wts.head, self.y_dec, tag="dec_head", B=B, Hi=st0.h, Wi=st0.w, lda=dec_ld, Ho=st0.h,
+                   Wo=st0.w, ldc=g.output_channels)
+
+    def _pad(self, x):
+        g = self.geo
+        if g.padding.activate:
+            ops.pad_to_pixel_major(x, g.padding.pad_lat, g.padding.pad_lon, g.padding.mode, self.ld0, out=self.xp)
+        else:
+            ops.pad_to_pixel_major(x, (0, 0), (0, 0), "earth", self.ld0, out=self.xp)
+
+    def _unpad(self, out):
+        g, B = self.geo, self.batch
+        pt, pl = (g.padding.pad_lat[0], g.padding.pad_lon[0]) if g.padding.activate else (0, 0)
+        ops.unpad_resize_to_nchw(self.y_dec, g.output_channels, out, B, g.output_channels, g.h_dec, g.w_dec, pt, pl,
+                                 g.h_crop, g.w_crop, g.h_out, g.w_out)
+
+    def run(self, x: torch.Tensor) -> torch.Tensor:
+        g, B = self.geo, self.batch
+        self._pad(x)
+        for fn, args, _tag, _fl, _by in self.steps:
+            fn(*args)
+        out = torch.empty((B, g.base_output_channels, g.output_frames, g.h_out, g.w_out), device=x.device,
+                          dtype=torch.float32)
+        self._unpad(out)
+        return out
+
+    def run_profiled(self, x: torch.Tensor):
+        """One forward with a CUDA-event pair around every launch: [(tag, ms, flops, bytes)] (bench.py roofline)."""
+        g, B = self.geo, self.batch
+        recs = []
+
+        def timed(tag, flops, nbytes, fn, *args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*args)
+            e1.record()
+            recs.append([tag, (e0, e1), flops, nbytes])
+
+        n_in = float(x.numel()) * 4
+        timed("pad", 0.0, n_in + 4.0 * self.xp.numel(), self._pad, x)
+        for fn, args, tag, fl, by in self.steps:
+            timed(tag, fl, by, fn, *args)
+        out = torch.empty((B, g.base_output_channels, g.output_frames, g.h_out, g.w_out), device=x.device,
+                          dtype=torch.float32)
+        timed("unpad_resize", 0.0, 8.0 * out.numel(), self._unpad, out)
+        torch.cuda.synchronize()
+        return out, [(t, ev[0].elapsed_time(ev[1]), fl, by) for t, ev, fl, by in recs]
+
+
+class CrossFormerB200(_Base):
+    """WXFormer/CrossFormer forecast step on B200.  Constructor = reference keywords (crossformer.py:372-401)."""
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.geometry = geo = build_geometry(**kwargs)
+        # attributes CREDIT reads off the model
+        self.image_height, self.image_width = geo.image_height, geo.image_width
+        self.patch_height = self.patch_width = 1
+        self.frames, self.output_frames = geo.frames, geo.output_frames
+        self.channels, self.levels, self.surface_channels = geo.channels, geo.levels, geo.surface_channels
+        self.input_only_channels = geo.input_only_channels
+        self.base_input_channels, self.input_channels = geo.base_input_channels, geo.input_channels
+        self.base_output_channels, self.output_channels = geo.base_output_channels, geo.output_channels
+        self.use_spectral_norm = geo.use_spectral_norm
+        self.use_interp = geo.interp
+        self.use_padding = geo.padding.activate
+        self.use_post_block = False
+        self.upsample_v_conv = False
+        if self.use_padding:
+            self.padding_opt = PaddingView(geo)
+        # parameters: same dotted names as the reference module tree
+        init = synthetic_state_dict(geo, seed=int(torch.initial_seed() % (2**31)), sn_iters=5)
+        for key, (shape, role) in state_spec(geo).items():
+            parts = key.split(".")
+            mod = self
+            for p in parts[:-1]:
+                if p not in mod._modules:
+                    mod.add_module(p, _Holder())
+                mod = mod._modules[p]
+            if role in ("u", "v"):
+                mod.register_buffer(parts[-1], init[key])
+            else:
+                mod.register_parameter(parts[-1], nn.Parameter(init[key], requires_grad=False))
+        self._prepared: Optional[PreparedWeights] = None
+        self._prepared_sig = None
+        self._plans: Dict[tuple, _Plan] = {}
+
+    # -- weight folding ------------------------------------------------------------------------------
+    def _signature(self):
+        ver = 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            ver += t._version
+        first = next(self.parameters())
+        return (ver, first.data_ptr(), str(first.device))
+
+    def refresh_weights(self):
+        """Re-fold spectral norm / position bias and re-lay weights (automatic when parameters change)."""
+        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("CrossFormerB200 parameters must live on a CUDA device (call .cuda()/.to('cuda'))")
+        self._prepared = prepare(sd, self.geometry, _round_up(self.geometry.input_channels, 4))
+        self._prepared_sig = self._signature()
+        self._plans.clear()
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._prepared = None
+        self._plans = {}
+        return out
+
+    # -- forward ---------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise NotImplementedError("CrossFormerB200 implements the eval-mode forecast forward only: call .eval()")
+        geo = self.geometry
+        if x.dim() != 5 or tuple(x.shape[1:]) != geo.in_shape:
+            raise ValueError(f"expected input [B, {', '.join(map(str, geo.in_shape))}], got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("CrossFormerB200 has no CPU path: pass a CUDA tensor")
+        if x.dtype != torch.float32:
+            x = x.float()
+        if self._prepared is None or self._prepared_sig != self._signature():
+            self.refresh_weights()
+        key = (int(x.shape[0]), x.device.index)
+        plan = self._plans.get(key)
+        if plan is None:
+            with torch.cuda.device(x.device):
+                plan = self._plans[key] = _Plan(geo, self._prepared, int(x.shape[0]), x.device)
+        with torch.cuda.device(x.device):
+            return plan.run(x.contiguous())
+
+
+def register_with_credit(key: str = "crossformer_b200", message: Optional[str] = None):
+    """Register under CREDIT's model registry (credit/models/__init__.py:128-161) so ``type: crossformer_b200``
+    selects this class from YAML; needs CREDIT importable."""
+    from credit.models import register_model  # type: ignore
+
+    return register_model(key, message or "Loading the B200-native CrossFormer forecast step ...")(CrossFormerB200)

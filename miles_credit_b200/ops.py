@@ -1,0 +1,143 @@
+"""Thin tensor-level wrappers over the C-ABI entry points (one Python function per exported kernel).
+
+PyTorch only supplies device memory and the current CUDA stream; every function enqueues exactly the
+kernels of its entry point and raises ``RuntimeError`` on a non-zero status.  ``LAUNCHES`` counts the
+kernels this package has enqueued (bench.py reports it as ``gpu_launches``).
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import lib as _lib
+from .lib import WxfConvDesc
+from .weights import ConvWeights
+
+LAUNCHES = 0
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: miles_credit_b200 has no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def pad_to_pixel_major(x: torch.Tensor, pad_lat, pad_lon, mode: str, ld: int, out: Optional[torch.Tensor] = None):
+    """[B, C, T, H, W] -> padded pixel-major [B, Hp, Wp, ld] (channel c*T + t)."""
+    global LAUNCHES
+    _req(x, "x")
+    x = x.contiguous()
+    b, c, t, h, w = x.shape
+    hp, wp = h + pad_lat[0] + pad_lat[1], w + pad_lon[0] + pad_lon[1]
+    if out is None:
+        out = torch.empty((b, hp, wp, ld), device=x.device, dtype=torch.float32)
+    m = _lib.PAD_EARTH if mode == "earth" else _lib.PAD_MIRROR
+    st = _lib.load().wxf_pad_to_pixel_major(x.data_ptr(), out.data_ptr(), b, c, t, h, w, pad_lat[0], pad_lat[1],
+                                            pad_lon[0], pad_lon[1], m, ld, _stream())
+    _lib.check(st, "wxf_pad_to_pixel_major")
+    LAUNCHES += 1
+    return out
+
+
+def layernorm(x: torch.Tensor, ldx: int, y: torch.Tensor, ldy: int, g: torch.Tensor, b: torch.Tensor, m: int, d: int,
+              eps: float = 1e-5):
+    global LAUNCHES
+    st = _lib.load().wxf_layernorm(x.data_ptr(), ldx, y.data_ptr(), ldy, g.data_ptr(), b.data_ptr(), m, d, eps, _stream())
+    _lib.check(st, "wxf_layernorm")
+    LAUNCHES += 1
+
+
+def make_conv_desc(inp: torch.Tensor, wts: ConvWeights, out: torch.Tensor, *, B: int, Hi: int, Wi: int, lda: int,
+                   Ho: int, Wo: int, ldc: int, c_off: int = 0, res: Optional[torch.Tensor] = None, ldr: int = 0,
+                   r_off: int = 0, act: int = 0, in_off: int = 0) -> WxfConvDesc:
+    """Descriptor of one implicit-GEMM launch.  ``in_off``: element offset of the first input channel."""
+    d = WxfConvDesc()
+    d.inp = inp.data_ptr() + 4 * in_off
+    d.w = wts.w.data_ptr()
+    d.taps = wts.taps.data_ptr()
+    d.bias = _ptr(wts.bias)
+    d.res = _ptr(res)
+    d.out = out.data_ptr()
+    d.B, d.Hi, d.Wi, d.lda, d.Cin = B, Hi, Wi, lda, wts.cin
+    d.N, d.T, d.stride = wts.n, wts.t, wts.stride
+    d.Ho, d.Wo = Ho, Wo
+    d.phases, d.out_scale = wts.phases, wts.out_scale
+    d.ldc, d.c_off, d.ldr, d.r_off, d.act = ldc, c_off, ldr, r_off, act
+    return d
+
+
+def conv_igemm_f32(desc: WxfConvDesc):
+    global LAUNCHES
+    st = _lib.load().wxf_conv_igemm_f32(ctypes.byref(desc), _stream())
+    _lib.check(st, "wxf_conv_igemm_f32")
+    LAUNCHES += 1
+
+
+def window_attention_f32(qkv: torch.Tensor, ldq: int, bias_t: torch.Tensor, out: torch.Tensor, ldo: int, B: int, H: int,
+                         W: int, d: int, dh: int, wsz: int, kind: int, scale: float):
+    global LAUNCHES
+    st = _lib.load().wxf_window_attention_f32(qkv.data_ptr(), ldq, bias_t.data_ptr(), out.data_ptr(), ldo, B, H, W, d, dh,
+                                              wsz, kind, scale, _stream())
+    _lib.check(st, "wxf_window_attention_f32")
+    LAUNCHES += 1
+
+
+def groupnorm_scratch_bytes(B: int, HW: int, C: int) -> int:
+    return int(_lib.load().wxf_groupnorm_scratch_bytes(B, HW, C))
+
+
+def groupnorm_silu(x: torch.Tensor, ldx: int, stats: torch.Tensor, scratch: torch.Tensor, gamma: torch.Tensor,
+                   beta: torch.Tensor, res: Optional[torch.Tensor], ldr: int, y: torch.Tensor, ldy: int, B: int, HW: int,
+                   C: int, G: int, eps: float = 1e-5):
+    """GroupNorm statistics + normalise/affine/SiLU (+ residual)."""
+    global LAUNCHES
+    L = _lib.load()
+    st = L.wxf_groupnorm_stats(x.data_ptr(), ldx, stats.data_ptr(), scratch.data_ptr(), B, HW, C, G, eps, _stream())
+    _lib.check(st, "wxf_groupnorm_stats")
+    st = L.wxf_groupnorm_silu(x.data_ptr(), ldx, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(res), ldr,
+                              y.data_ptr(), ldy, B, HW, C, G, _stream())
+    _lib.check(st, "wxf_groupnorm_silu")
+    LAUNCHES += 3
+
+
+def unpad_resize_to_nchw(y: torch.Tensor, ld: int, out: torch.Tensor, B: int, C: int, Hd: int, Wd: int, top: int,
+                         left: int, Hc: int, Wc: int, Ho: int, Wo: int):
+    global LAUNCHES
+    st = _lib.load().wxf_unpad_resize_to_nchw(y.data_ptr(), ld, out.data_ptr(), B, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo,
+                                              _stream())
+    _lib.check(st, "wxf_unpad_resize_to_nchw")
+    LAUNCHES += 1
+
+
+def copy_channels(dst: torch.Tensor, src: torch.Tensor, groups):
+    """dst[:, d0:d0+n] = src[:, s0:s0+n] for (d0, s0, n) in groups; tensors are [B, C, ...] contiguous."""
+    global LAUNCHES
+    _req(dst, "dst")
+    _req(src, "src")
+    if not (dst.is_contiguous() and src.is_contiguous()):
+        raise ValueError("copy_channels needs contiguous tensors")
+    B, dc = dst.shape[:2]
+    sc = src.shape[1]
+    plane = dst[0, 0].numel()
+    if src[0, 0].numel() != plane or src.shape[0] != B:
+        raise ValueError("copy_channels: plane/batch mismatch")
+    n = len(groups)
+    arr = ctypes.c_int32 * n
+    d0 = arr(*[g[0] for g in groups])
+    s0 = arr(*[g[1] for g in groups])
+    ln = arr(*[g[2] for g in groups])
+    st = _lib.load().wxf_copy_channels(dst.data_ptr(), dc, src.data_ptr(), sc, B, plane, d0, s0, ln, n, _stream())
+    _lib.check(st, "wxf_copy_channels")
+    LAUNCHES += 1

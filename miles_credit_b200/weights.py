@@ -1,0 +1,193 @@
+"""Load-time weight preparation: everything input-independent is folded once, not per forward.
+
+* spectral norm: ``W = weight_orig / (u . W_mat v)`` (eval-mode torch.nn.utils.spectral_norm; the reference
+  recomputes it on every forward for 84 modules, crossformer.py:23-26, 576-578)
+* dynamic position bias: the [L, L] table of every Attention (crossformer.py:158-176, 238-245, 279-286),
+  including the reference's (2w-1)-stride index quirk
+* weight re-layout for the implicit-GEMM kernels: [N, taps*Cin] with the channel index fastest, transposed-conv
+  weights split into 4 output-parity phases, plus the (dy, dx) tap tables.
+
+This runs in PyTorch on whatever device the parameters live on; it is not part of the per-step path.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from .geometry import Geometry
+
+
+def fold_spectral_norm(sd: Dict[str, torch.Tensor], prefix: str, sn_dim: int = 0) -> torch.Tensor:
+    if prefix + ".weight_orig" not in sd:
+        return sd[prefix + ".weight"].float()
+    w = sd[prefix + ".weight_orig"].float()
+    wm = w if sn_dim == 0 else w.transpose(0, sn_dim)
+    wm = wm.reshape(wm.shape[0], -1)
+    sigma = torch.dot(sd[prefix + ".weight_u"].float(), torch.mv(wm, sd[prefix + ".weight_v"].float()))
+    return w / sigma
+
+
+def position_bias_table(sd, prefix: str, wsz: int) -> torch.Tensor:
+    """bias[i, j] for tokens i, j of a wsz x wsz window (fp32, [L, L])."""
+    dev = sd[prefix + ".dpb.layers.0.bias"].device
+    pos = torch.arange(-wsz, wsz + 1, device=dev, dtype=torch.float32)
+    t = torch.stack(torch.meshgrid(pos, pos, indexing="ij"), dim=-1).reshape(-1, 2)
+    for lin, ln in ((0, 1), (3, 4), (6, 7)):
+        t = F.linear(t, fold_spectral_norm(sd, f"{prefix}.dpb.layers.{lin}"), sd[f"{prefix}.dpb.layers.{lin}.bias"].float())
+        t = F.layer_norm(t, (t.shape[-1],), sd[f"{prefix}.dpb.layers.{ln}.weight"].float(),
+                         sd[f"{prefix}.dpb.layers.{ln}.bias"].float(), 1e-5)
+        t = torch.relu(t)
+    t = F.linear(t, fold_spectral_norm(sd, f"{prefix}.dpb.layers.9"), sd[f"{prefix}.dpb.layers.9.bias"].float())
+    t = t.reshape(-1)
+    p = torch.arange(wsz, device=dev)
+    tok = torch.stack(torch.meshgrid(p, p, indexing="ij"), dim=-1).reshape(-1, 2)
+    rel = tok[:, None, :] - tok[None, :, :] + (wsz - 1)
+    idx = rel[..., 0] * (2 * wsz - 1) + rel[..., 1]  # reference stride quirk kept
+    return t[idx]
+
+
+@dataclass
+class ConvWeights:
+    """One implicit-GEMM contraction: weights [phases, N, T*Cin], taps [phases, T, 2], bias [N] or None."""
+
+    w: torch.Tensor
+    taps: torch.Tensor
+    bias: Optional[torch.Tensor]
+    n: int
+    t: int
+    cin: int
+    stride: int = 1
+    phases: int = 1
+    out_scale: int = 1
+
+
+def _pad_cin(w_ntc: torch.Tensor, cin_pad: int) -> torch.Tensor:
+    """[N, T, Cin] -> [N, T, cin_pad] zero padded."""
+    n, t, c = w_ntc.shape
+    if cin_pad == c:
+        return w_ntc
+    out = w_ntc.new_zeros((n, t, cin_pad))
+    out[:, :, :c] = w_ntc
+    return out
+
+
+def conv_weights(w: torch.Tensor, bias, stride: int, pad: int, cin_pad: Optional[int] = None) -> ConvWeights:
+    """Conv2d weight [N, Cin, k, k] -> implicit-GEMM layout; taps carry (ky - pad, kx - pad)."""
+    n, c, kh, kw = w.shape
+    cin_pad = cin_pad or c
+    w_ntc = w.permute(0, 2, 3, 1).reshape(n, kh * kw, c)
+    w_ntc = _pad_cin(w_ntc, cin_pad)
+    ky, kx = torch.meshgrid(torch.arange(kh), torch.arange(kw), indexing="ij")
+    taps = torch.stack([ky.reshape(-1) - pad, kx.reshape(-1) - pad], dim=-1).to(torch.int32)
+    return ConvWeights(w_ntc.reshape(1, n, kh * kw * cin_pad).contiguous(), taps.reshape(1, kh * kw, 2).contiguous().to(w.device),
+                       None if bias is None else bias.float().contiguous(), n, kh * kw, cin_pad, stride)
+
+
+def convt_k2s2_weights(w: torch.Tensor, bias) -> ConvWeights:
+    """ConvTranspose2d(k=2, s=2) weight [Cin, Cout, 2, 2]: phase (dy, dx) is a 1x1 conv to output (2y+dy, 2x+dx)."""
+    cin, cout = w.shape[:2]
+    wz = w.permute(2, 3, 1, 0).reshape(4, cout, cin).contiguous()  # [(dy,dx), co, ci]
+    taps = torch.zeros((4, 1, 2), dtype=torch.int32, device=w.device)
+    return ConvWeights(wz, taps, bias.float().contiguous(), cout, 1, cin, 1, 4, 2)
+
+
+def convt_k4s2p1_weights(w: torch.Tensor, bias) -> ConvWeights:
+    """ConvTranspose2d(k=4, s=2, p=1) weight [Cin, Cout, 4, 4] as 4 output-parity 2x2 convolutions.
+
+    oy = 2*iy - 1 + ky.  Even oy = 2y: (ky, iy) in {(1, y), (3, y-1)}; odd oy = 2y+1: {(0, y+1), (2, y)}.
+    """
+    cin, cout = w.shape[:2]
+    sel = {0: ((1, 0), (3, -1)), 1: ((0, 1), (2, 0))}  # parity -> ((k, d), (k, d))
+    wz = w.new_zeros((4, cout, 4, cin))
+    taps = torch.zeros((4, 4, 2), dtype=torch.int32)
+    for py in (0, 1):
+        for px in (0, 1):
+            z = py * 2 + px
+            for ty, (ky, dy) in enumerate(sel[py]):
+                for tx, (kx, dx) in enumerate(sel[px]):
+                    t = ty * 2 + tx
+                    wz[z, :, t, :] = w[:, :, ky, kx].t()
+                    taps[z, t, 0], taps[z, t, 1] = dy, dx
+    return ConvWeights(wz.reshape(4, cout, 4 * cin).contiguous(), taps.to(w.device), bias.float().contiguous(), cout, 4, cin, 1, 4, 2)
+
+
+@dataclass
+class AttentionWeights:
+    ln_g: torch.Tensor
+    ln_b: torch.Tensor
+    qkv: ConvWeights
+    out: ConvWeights
+    bias_t: torch.Tensor  # [L, L] transposed position bias
+    wsz: int
+    kind: int
+
+
+@dataclass
+class FeedForwardWeights:
+    ln_g: torch.Tensor
+    ln_b: torch.Tensor
+    fc1: ConvWeights
+    fc2: ConvWeights
+
+
+@dataclass
+class UpBlockWeights:
+    up: ConvWeights
+    convs: List[ConvWeights]
+    gn_w: List[torch.Tensor]
+    gn_b: List[torch.Tensor]
+
+
+@dataclass
+class PreparedWeights:
+    embeds: List[List[ConvWeights]]
+    blocks: List[List[tuple]]  # per stage, per layer: (short_attn, ff, long_attn, ff)
+    ups: List[UpBlockWeights]
+    head: ConvWeights
+    cin0_pad: int
+
+
+def prepare(sd: Dict[str, torch.Tensor], geo: Geometry, cin0_pad: int) -> PreparedWeights:
+    """Fold and re-lay every parameter of the state dict for the kernels (device of ``sd``)."""
+    with torch.no_grad():
+        embeds, blocks = [], []
+        for st in geo.stages:
+            s = st.index
+            brs = []
+            for i, br in enumerate(st.branches):
+                w = fold_spectral_norm(sd, f"layers.{s}.0.convs.{i}")
+                brs.append(conv_weights(w, sd[f"layers.{s}.0.convs.{i}.bias"], br.stride, br.pad,
+                                        cin0_pad if s == 0 else None))
+            embeds.append(brs)
+            layers = []
+            for l in range(st.depth):
+                entry = []
+                for a, kind, wsz in ((0, 0, st.local_window), (2, 1, st.global_window)):
+                    p = f"layers.{s}.1.layers.{l}.{a}"
+                    att = AttentionWeights(
+                        sd[p + ".norm.g"].float().reshape(-1).contiguous(), sd[p + ".norm.b"].float().reshape(-1).contiguous(),
+                        conv_weights(fold_spectral_norm(sd, p + ".to_qkv"), None, 1, 0),
+                        conv_weights(fold_spectral_norm(sd, p + ".to_out"), sd[p + ".to_out.bias"], 1, 0),
+                        position_bias_table(sd, p, wsz).t().contiguous(), wsz, kind)
+                    f = f"layers.{s}.1.layers.{l}.{a + 1}.layers"
+                    ff = FeedForwardWeights(
+                        sd[f + ".0.g"].float().reshape(-1).contiguous(), sd[f + ".0.b"].float().reshape(-1).contiguous(),
+                        conv_weights(fold_spectral_norm(sd, f + ".1"), sd[f + ".1.bias"], 1, 0),
+                        conv_weights(fold_spectral_norm(sd, f + ".4"), sd[f + ".4.bias"], 1, 0))
+                    entry += [att, ff]
+                layers.append(tuple(entry))
+            blocks.append(layers)
+        ups = []
+        for up in geo.ups:
+            n = up.name
+            ups.append(UpBlockWeights(
+                convt_k2s2_weights(fold_spectral_norm(sd, n + ".conv", 1), sd[n + ".conv.bias"]),
+                [conv_weights(fold_spectral_norm(sd, f"{n}.b.{ci}"), sd[f"{n}.b.{ci}.bias"], 1, 1) for ci in (0, 3)],
+                [sd[f"{n}.b.{gi}.weight"].float().contiguous() for gi in (1, 4)],
+                [sd[f"{n}.b.{gi}.bias"].float().contiguous() for gi in (1, 4)]))
+        head = convt_k4s2p1_weights(fold_spectral_norm(sd, "up_block4", 1), sd["up_block4.bias"])
+    return PreparedWeights(embeds, blocks, ups, head, cin0_pad)

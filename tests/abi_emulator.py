@@ -1,0 +1,201 @@
+"""Test double of the C-ABI library: executes the *documented semantics* of every entry point of
+include/wxformer_b200.h on CPU memory, straight from raw pointers and dims (numpy views over ctypes).
+
+It exists so the host logic (launch plan, descriptors, weight re-layout, tap tables, buffer aliasing) can be
+checked in the CPU test-suite without a GPU.  It lives under tests/ and is never importable from the product:
+``miles_credit_b200`` has no CPU path.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+
+def _arr(ptr, n):
+    if not ptr:
+        return None
+    return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), shape=(int(n),))
+
+
+def _iarr(ptr, n):
+    return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_int32)), shape=(int(n),))
+
+
+def _t(a):
+    return torch.from_numpy(a)
+
+
+class EmulatedLib:
+    """Same call signatures as the ctypes handle returned by ``miles_credit_b200.lib.load()``."""
+
+    def __init__(self):
+        self.calls = []
+
+    def wxf_abi_version(self):
+        return 1
+
+    def wxf_last_error(self):
+        return b"emulator"
+
+    def wxf_pad_to_pixel_major(self, x, xp, B, C, T, H, W, pt, pb, pl, pr, mode, ld, stream):
+        self.calls.append("pad")
+        xs = _t(_arr(x, B * C * T * H * W)).view(B, C * T, H, W)
+        Hp, Wp = H + pt + pb, W + pl + pr
+        out = _t(_arr(xp, B * Hp * Wp * ld)).view(B, Hp, Wp, ld)
+        out.zero_()
+        for r in range(Hp):
+            roll = False
+            if mode == 0:
+                if r < pt:
+                    sr, roll = pt - 1 - r, True
+                elif r < pt + H:
+                    sr = r - pt
+                else:
+                    sr, roll = H - 1 - (r - pt - H), True
+            else:
+                sr = abs(r - pt)
+                if sr >= H:
+                    sr = 2 * (H - 1) - sr
+            j = (torch.arange(Wp) - pl) % W
+            if roll:
+                j = (j - W // 2) % W
+            out[:, r, :, : C * T] = xs[:, :, sr, :][:, :, j].permute(0, 2, 1)
+        return 0
+
+    def wxf_layernorm(self, x, ldx, y, ldy, g, b, M, d, eps, stream):
+        self.calls.append("layernorm")
+        xs = _t(_arr(x, (M - 1) * ldx + d)).as_strided((M, d), (ldx, 1))
+        ys = _t(_arr(y, (M - 1) * ldy + d)).as_strided((M, d), (ldy, 1))
+        gg, bb = _t(_arr(g, d)), _t(_arr(b, d))
+        mean = xs.mean(1, keepdim=True)
+        var = ((xs - mean) ** 2).mean(1, keepdim=True)
+        ys.copy_((xs - mean) / (var + eps).sqrt() * gg + bb)
+        return 0
+
+    def wxf_conv_igemm_f32(self, dref, stream):
+        d = dref._obj
+        self.calls.append("conv")
+        B, Hi, Wi, lda, Cin, N, T, s = d.B, d.Hi, d.Wi, d.lda, d.Cin, d.N, d.T, d.stride
+        Ho, Wo, P, osc = d.Ho, d.Wo, d.phases, d.out_scale
+        n_in = ((B * Hi - 1) * Wi + Wi - 1) * lda + Cin
+        xin = _t(_arr(d.inp, n_in)).as_strided((B, Hi, Wi, Cin), (Hi * Wi * lda, Wi * lda, lda, 1))
+        w = _t(_arr(d.w, P * N * T * Cin)).view(P, N, T, Cin)
+        taps = _t(_iarr(d.taps, P * T * 2)).view(P, T, 2)
+        Hout, Wout = Ho * osc, Wo * osc
+        n_out = ((B * Hout - 1) * Wout + Wout - 1) * d.ldc + d.c_off + N
+        out = _t(_arr(d.out, n_out)).as_strided((B, Hout, Wout, N), (Hout * Wout * d.ldc, Wout * d.ldc, d.ldc, 1),
+                                                d.c_off)
+        res = None
+        if d.res:
+            n_res = ((B * Hout - 1) * Wout + Wout - 1) * d.ldr + d.r_off + N
+            res = _t(_arr(d.res, n_res)).as_strided((B, Hout, Wout, N), (Hout * Wout * d.ldr, Wout * d.ldr, d.ldr, 1),
+                                                    d.r_off).clone()
+        bias = _t(_arr(d.bias, N)) if d.bias else None
+        oy = torch.arange(Ho) * s
+        ox = torch.arange(Wo) * s
+        for z in range(P):
+            acc = torch.zeros(B, Ho, Wo, N, dtype=torch.float64)
+            for t in range(T):
+                dy, dx = int(taps[z, t, 0]), int(taps[z, t, 1])
+                iy, ix = oy + dy, ox + dx
+                vy = (iy >= 0) & (iy < Hi)
+                vx = (ix >= 0) & (ix < Wi)
+                g = xin[:, iy.clamp(0, Hi - 1)][:, :, ix.clamp(0, Wi - 1)].double()
+                g = g * (vy[:, None] & vx[None, :])[None, :, :, None]
+                acc += g @ w[z, :, t, :].double().t()
+            v = acc.float()
+            if bias is not None:
+                v = v + bias
+            if d.act == 1:
+                v = 0.5 * v * (1 + torch.erf(v * 0.7071067811865476))
+            py, px = z >> 1, z & 1
+            if res is not None:
+                v = v + res[:, py::osc, px::osc] if osc > 1 else v + res
+            if osc > 1:
+                out[:, py::osc, px::osc] = v
+            else:
+                out.copy_(v)
+        return 0
+
+    def wxf_window_attention_f32(self, qkv, ldq, biasT, outp, ldo, B, H, W, d, dh, wsz, kind, scale, stream):
+        self.calls.append("attention")
+        if dh != 32 or wsz * wsz > 128:
+            return -3
+        M = B * H * W
+        q3 = _t(_arr(qkv, (M - 1) * ldq + 3 * d)).as_strided((B, H, W, 3 * d), (H * W * ldq, W * ldq, ldq, 1)).clone()
+        out = _t(_arr(outp, (M - 1) * ldo + d)).as_strided((B, H, W, d), (H * W * ldo, W * ldo, ldo, 1))
+        L = wsz * wsz
+        bias = _t(_arr(biasT, L * L)).view(L, L).t()
+        nh, nw, heads = H // wsz, W // wsz, d // dh
+        for b in range(B):
+            for gh in range(nh):
+                for gw in range(nw):
+                    if kind == 0:
+                        ys = gh * wsz + torch.arange(wsz)
+                        xs = gw * wsz + torch.arange(wsz)
+                    else:
+                        ys = torch.arange(wsz) * nh + gh
+                        xs = torch.arange(wsz) * nw + gw
+                    tok = q3[b][ys][:, xs].reshape(L, 3, heads, dh)
+                    q, k, v = tok[:, 0].transpose(0, 1) * scale, tok[:, 1].transpose(0, 1), tok[:, 2].transpose(0, 1)
+                    p = (q @ k.transpose(1, 2) + bias).softmax(-1)
+                    o = (p @ v).transpose(0, 1).reshape(wsz, wsz, d)
+                    out[b, ys[:, None], xs[None, :]] = o
+        return 0
+
+    def wxf_groupnorm_scratch_bytes(self, B, HW, C):
+        return B * ((HW + 511) // 512) * C * 8
+
+    def wxf_groupnorm_stats(self, x, ldx, stats, scratch, B, HW, C, G, eps, stream):
+        self.calls.append("gn_stats")
+        xs = _t(_arr(x, (B * HW - 1) * ldx + C)).as_strided((B, HW, G, C // G), (HW * ldx, ldx, C // G, 1)).double()
+        st = _t(_arr(stats, B * G * 2)).view(B, G, 2)
+        mean = xs.mean(dim=(1, 3))
+        var = (xs * xs).mean(dim=(1, 3)) - mean * mean
+        st[..., 0] = mean.float()
+        st[..., 1] = (1.0 / (var + eps).sqrt()).float()
+        return 0
+
+    def wxf_groupnorm_silu(self, x, ldx, stats, gamma, beta, res, ldr, y, ldy, B, HW, C, G, stream):
+        self.calls.append("gn_silu")
+        xs = _t(_arr(x, (B * HW - 1) * ldx + C)).as_strided((B, HW, C), (HW * ldx, ldx, 1))
+        st = _t(_arr(stats, B * G * 2)).view(B, G, 2)
+        mean = st[..., 0].repeat_interleave(C // G, dim=1)[:, None, :]
+        rstd = st[..., 1].repeat_interleave(C // G, dim=1)[:, None, :]
+        v = (xs - mean) * rstd * _t(_arr(gamma, C)) + _t(_arr(beta, C))
+        v = v / (1 + torch.exp(-v))
+        if res:
+            v = v + _t(_arr(res, (B * HW - 1) * ldr + C)).as_strided((B, HW, C), (HW * ldr, ldr, 1))
+        _t(_arr(y, (B * HW - 1) * ldy + C)).as_strided((B, HW, C), (HW * ldy, ldy, 1)).copy_(v)
+        return 0
+
+    def wxf_unpad_resize_to_nchw(self, y, ld, outp, B, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, stream):
+        self.calls.append("unpad_resize")
+        ys = _t(_arr(y, (B * Hd * Wd - 1) * ld + C)).as_strided((B, Hd, Wd, C), (Hd * Wd * ld, Wd * ld, ld, 1))
+        crop = ys[:, top: top + Hc, left: left + Wc].permute(0, 3, 1, 2)
+        out = _t(_arr(outp, B * C * Ho * Wo)).view(B, C, Ho, Wo)
+
+        def axis(n_in, n_out):
+            scale = np.float32(n_in) / np.float32(n_out)
+            src = (torch.arange(n_out, dtype=torch.float32) + 0.5) * float(scale) - 0.5
+            src = src.clamp_min(0)
+            i0 = src.floor().long().clamp_max(n_in - 1)
+            i1 = (i0 + 1).clamp_max(n_in - 1)
+            l1 = (src - i0).clamp(0, 1)
+            return i0, i1, 1 - l1, l1
+
+        y0, y1, ly0, ly1 = axis(Hc, Ho)
+        x0, x1, lx0, lx1 = axis(Wc, Wo)
+        top_ = crop[:, :, y0][..., x0] * lx0 + crop[:, :, y0][..., x1] * lx1
+        bot_ = crop[:, :, y1][..., x0] * lx0 + crop[:, :, y1][..., x1] * lx1
+        out.copy_(top_ * ly0[:, None] + bot_ * ly1[:, None])
+        return 0
+
+    def wxf_copy_channels(self, dst, dst_C, src, src_C, B, plane, d0, s0, ln, n, stream):
+        self.calls.append("copy_channels")
+        dd = _t(_arr(dst, B * dst_C * plane)).view(B, dst_C, plane)
+        ss = _t(_arr(src, B * src_C * plane)).view(B, src_C, plane)
+        for g in range(n):
+            dd[:, d0[g]: d0[g] + ln[g]] = ss[:, s0[g]: s0[g] + ln[g]]
+        return 0

@@ -1,0 +1,64 @@
+"""CPU: the drop-in boundary (module surface, state-dict compatibility, C-ABI exports, loud failures)."""
+import ctypes
+import json
+import os
+
+import pytest
+import torch
+
+from miles_credit_b200 import lib as wlib
+from miles_credit_b200.geometry import build_geometry, workload
+from miles_credit_b200.model import CrossFormerB200
+from miles_credit_b200.synth import synthetic_state_dict
+
+
+def test_state_dict_is_reference_compatible(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "unit.pt"), weights_only=False)
+    model = CrossFormerB200(**fx["kwargs"])
+    assert {k: list(v.shape) for k, v in model.state_dict().items()} == fx["keys"]
+    sd = synthetic_state_dict(build_geometry(**fx["kwargs"]), seed=fx["seed"])
+    msg = model.load_state_dict(sd, strict=True)
+    assert not msg.missing_keys and not msg.unexpected_keys
+    assert torch.equal(model.state_dict()["layers.0.0.convs.3.weight_orig"], sd["layers.0.0.convs.3.weight_orig"])
+    with pytest.raises(RuntimeError):
+        model.load_state_dict(dict(sd, bogus=torch.zeros(1)), strict=True)
+
+
+def test_module_surface():
+    kw = workload("unit")
+    m = CrossFormerB200(**kw)
+    assert m.use_padding and m.padding_opt.pad_NS == [25, 27] and m.use_interp
+    assert (m.image_height, m.image_width, m.channels, m.levels, m.surface_channels) == (45, 96, 2, 3, 2)
+    assert (m.input_channels, m.output_channels) == (10, 9)
+    t1, t2 = m.split_and_reshape(torch.zeros(1, 9, 1, 45, 96))
+    assert t1.shape == (1, 2, 3, 1, 45, 96) and t2.shape == (1, 2, 1, 45, 96)
+
+
+def test_no_cpu_fallback():
+    m = CrossFormerB200(**workload("unit")).eval()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 10, 1, 45, 96))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 11, 1, 45, 96))
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 10, 1, 45, 96))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.isfile(wlib.LIB_PATH):
+        import __graft_entry__ as entry
+
+        entry.build()
+    names = wlib.declared_symbols()
+    assert "wxf_conv_igemm_f32" in names and len(names) >= 10
+    raw = ctypes.CDLL(wlib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/wxformer_b200.h but not exported"
+    L = wlib.load()
+    assert L.wxf_abi_version() == wlib.WXF_ABI_VERSION
+    assert set(wlib._SIGNATURES) <= set(names)
+
+
+def test_credit_registry_if_importable():
+    pytest.importorskip("credit.models", reason="CREDIT not on sys.path (GPU box)")
