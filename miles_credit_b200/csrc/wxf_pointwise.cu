@@ -271,7 +271,7 @@ extern "C" int wxf_groupnorm_silu(const float* x, int ldx, const float* stats, c
 // src = (dst + 0.5) * in/out - 0.5 clamped at 0 (torch area_pixel_compute_source_index).
 
 __device__ __forceinline__ void bilin_axis(int dst, float scale, int n_in, int& i0, int& i1, float& l0, float& l1) {
-  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  float src = fmaf(scale, (float)dst + 0.5f, -0.5f);  // torch's fp32 expression is FMA-contracted (CPU and CUDA)
   if (src < 0.f) src = 0.f;
   i0 = (int)src;
   if (i0 > n_in - 1) i0 = n_in - 1;

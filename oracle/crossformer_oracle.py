@@ -238,8 +238,10 @@ def bilinear_resize(x, h_out: int, w_out: int) -> torch.Tensor:
     h_in, w_in = x.shape[-2:]
 
     def axis(n_in, n_out):
-        scale = n_in / n_out
-        src = (torch.arange(n_out, dtype=torch.float32) + 0.5) * scale - 0.5
+        # torch evaluates scale*(dst+0.5)-0.5 in fp32 with a fused multiply-add (one rounding), on CPU builds
+        # and in the CUDA kernel alike; at 720->721 an unfused product moves the weights by ~3e-5.
+        scale = (torch.tensor(float(n_in), dtype=torch.float32) / torch.tensor(float(n_out), dtype=torch.float32)).double()
+        src = (scale * (torch.arange(n_out, dtype=torch.float64) + 0.5) - 0.5).float()
         src = src.clamp_min(0.0)
         i0 = src.floor().long().clamp_max(n_in - 1)
         i1 = (i0 + 1).clamp_max(n_in - 1)

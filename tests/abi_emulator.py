@@ -177,8 +177,8 @@ class EmulatedLib:
         out = _t(_arr(outp, B * C * Ho * Wo)).view(B, C, Ho, Wo)
 
         def axis(n_in, n_out):
-            scale = np.float32(n_in) / np.float32(n_out)
-            src = (torch.arange(n_out, dtype=torch.float32) + 0.5) * float(scale) - 0.5
+            scale = float(np.float32(n_in) / np.float32(n_out))
+            src = (scale * (torch.arange(n_out, dtype=torch.float64) + 0.5) - 0.5).float()  # fused multiply-add
             src = src.clamp_min(0)
             i0 = src.floor().long().clamp_max(n_in - 1)
             i1 = (i0 + 1).clamp_max(n_in - 1)

@@ -96,7 +96,7 @@ def test_conv_igemm_f32(case):
     ops.conv_igemm_f32(d)
     got = out[..., 4:].cpu()
     want = to_pm(ref) + res.cpu()
-    assert relmax(got, want) < 2e-6
+    assert relmax(got, want) < 1e-5  # fp32 accumulation over K up to 12288
     assert torch.count_nonzero(out[..., :4]) == 0
 
 
@@ -152,8 +152,8 @@ def _attention_block_reference(stage_idx, kind_idx, geo, sd, x):
 def test_attention_block(wl, stage_idx, kind_idx):
     """LN -> to_qkv -> window attention -> to_out + residual against the oracle's Attention restatement."""
     kw = workload("unit") if wl == "unit" else dict(
-        workload("unit"), image_height=40, image_width=80, local_window_size=10, global_window_size=[10, 5, 2, 1],
-        padding_conf=dict(activate=True, mode="earth", pad_lat=[20, 20], pad_lon=[40, 40]), depth=[1, 1, 1, 1])
+        workload("unit"), image_height=80, image_width=160, local_window_size=10, global_window_size=[10, 5, 2, 1],
+        padding_conf=dict(activate=True, mode="earth", pad_lat=[40, 40], pad_lon=[80, 80]), depth=[1, 1, 1, 1])
     geo = build_geometry(**kw)
     sd = synthetic_state_dict(geo, seed=7)
     st = geo.stages[stage_idx]
@@ -199,7 +199,7 @@ def test_unpad_resize(hd, wd, top, left, hc, wc, ho, wo, c):
     y = torch.randn(b, c, hd, wd)
     ref = oracle.bilinear_resize(y[..., top: top + hc, left: left + wc], ho, wo)
     tor = F.interpolate(y[..., top: top + hc, left: left + wc], size=(ho, wo), mode="bilinear")
-    assert torch.allclose(ref, tor, atol=1e-6)
+    assert torch.allclose(ref, tor, atol=2e-6)
     ld = c + 3
     ypm = torch.zeros(b, hd, wd, ld)
     ypm[..., :c] = to_pm(y)

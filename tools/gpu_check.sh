@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt
-timeout 900 python -m pytest tests -q -m gpu -x --timeout 600 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -q -m gpu --timeout 600 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
 echo "pytest exit ${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
