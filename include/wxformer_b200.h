@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 1
+#define WXF_ABI_VERSION 2
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -61,6 +61,13 @@ int wxf_pad_to_pixel_major(const float* x, float* xp, int B, int C, int T, int H
  */
 int wxf_layernorm(const float* x, int ldx, float* y, int ldy, const float* g, const float* b,
                   int64_t M, int d, float eps, void* stream);
+
+/*
+ * Same LayerNorm, result written as the two fp16 operand planes of the tensor-core GEMM
+ * (hi = fp16(y), lo = fp16(y - hi); see wxf_gemm_f16x2_tc).  y_hi / y_lo : [M, ldh] fp16.
+ */
+int wxf_layernorm_f16x2(const float* x, int ldx, void* y_hi, void* y_lo, int ldh, const float* g, const float* b,
+                        int64_t M, int d, float eps, void* stream);
 
 /*
  * Implicit-GEMM convolution, exact fp32 FMA.  One descriptor covers
@@ -102,6 +109,42 @@ int wxf_conv_igemm_f32(const WxfConvDesc* desc, void* stream);
  */
 int wxf_window_attention_f32(const float* qkv, int ldq, const float* biasT, float* out, int ldo,
                              int B, int H, int W, int d, int dh, int wsz, int kind, float scale, void* stream);
+
+/* Same attention core; the result is written as fp16 hi/lo operand planes [B*H*W, ldh] for the to_out GEMM. */
+int wxf_window_attention_f16x2(const float* qkv, int ldq, const float* biasT, void* out_hi, void* out_lo, int ldh,
+                               int B, int H, int W, int d, int dh, int wsz, int kind, float scale, void* stream);
+
+/*
+ * Pointwise (1x1 conv) GEMM on the tcgen05 tensor cores with TMA-staged operands
+ * (to_qkv / to_out, crossformer.py:229-230, 268, 297; FeedForward 1x1 convs, :198-204):
+ *     acc[m, n] = sum_k A[m, k] * W[n, k]
+ * with every fp32 operand carried as two fp16 planes (hi = fp16(x), lo = fp16(x - hi)) and three MMA passes
+ * (hi*lo + lo*hi + hi*hi) into one fp32 TMEM accumulator: 22-bit operands, fp32 accumulation.
+ *   a_hi, a_lo : [M, lda] fp16;  w_hi, w_lo : [N, K] fp16 planes of W * 2^w_scale_log2
+ *   v = acc * 2^-w_scale_log2 + bias[n];  v = act(v);  v += res[m*ldr + r_off + n]
+ *   out (fp32, optional): out[m*ldc + c_off + n] = v;  out_hi/out_lo (fp16 planes, optional): [M, ldh]
+ * K and lda must be multiples of 8; all planes 16-byte aligned.
+ */
+typedef struct WxfGemmDesc {
+  const void* a_hi;
+  const void* a_lo;
+  const void* w_hi;
+  const void* w_lo;
+  const float* bias;
+  const float* res;
+  float* out;
+  void* out_hi;
+  void* out_lo;
+  int64_t M;
+  int32_t N, K, lda;
+  int32_t ldc, c_off, ldr, r_off, ldh;
+  int32_t act, w_scale_log2;
+} WxfGemmDesc;
+
+int wxf_gemm_f16x2_tc(const WxfGemmDesc* desc, void* stream);
+
+/* Split an fp32 [M, ldx] matrix (first d columns) into fp16 hi/lo planes [M, ldh] (test/utility pass). */
+int wxf_split_f16x2(const float* x, int ldx, void* hi, void* lo, int ldh, int64_t M, int d, void* stream);
 
 /*
  * GroupNorm + SiLU on a pixel-major field (UpBlock residual stack, crossformer.py:96-116).

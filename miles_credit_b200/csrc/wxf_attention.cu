@@ -28,8 +28,10 @@ __device__ __forceinline__ int64_t token_pixel(int64_t win, int i, int H, int W,
   return ((int64_t)b * H + y) * W + x;
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(ATT_THREADS) window_attention_kernel(
-    const float* __restrict__ qkv, int ldq, const float* __restrict__ biasT, float* __restrict__ out, int ldo, int H,
+    const float* __restrict__ qkv, int ldq, const float* __restrict__ biasT, float* __restrict__ out,
+    __half* __restrict__ out_hi, __half* __restrict__ out_lo, int ldo, int H,
     int W, int d, int heads, int wsz, int kind, float scale, int L, int G, int64_t npairs) {
   extern __shared__ float4 smem4[];
   float4* Ks = smem4;
@@ -124,16 +126,30 @@ __global__ void __launch_bounds__(ATT_THREADS) window_attention_kernel(
     mrun = mnew;
   }
   const float inv = 1.0f / lrun;
-  float4* op = reinterpret_cast<float4*>(out + pix * ldo + head * DH);
+  if constexpr (SPLIT) {
+    uint4* hp = reinterpret_cast<uint4*>(out_hi + pix * ldo + head * DH);
+    uint4* lp = reinterpret_cast<uint4*>(out_lo + pix * ldo + head * DH);
 #pragma unroll
-  for (int c = 0; c < DH / 4; ++c)
-    op[c] = make_float4(o[4 * c + 0] * inv, o[4 * c + 1] * inv, o[4 * c + 2] * inv, o[4 * c + 3] * inv);
+    for (int c = 0; c < DH / 8; ++c) {
+      __align__(16) __half h8[8];
+      __align__(16) __half l8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) wxf_split_f16x2(o[8 * c + e] * inv, h8[e], l8[e]);
+      hp[c] = *reinterpret_cast<const uint4*>(h8);
+      lp[c] = *reinterpret_cast<const uint4*>(l8);
+    }
+  } else {
+    float4* op = reinterpret_cast<float4*>(out + pix * ldo + head * DH);
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c)
+      op[c] = make_float4(o[4 * c + 0] * inv, o[4 * c + 1] * inv, o[4 * c + 2] * inv, o[4 * c + 3] * inv);
+  }
 }
 
 }  // namespace
 
-extern "C" int wxf_window_attention_f32(const float* qkv, int ldq, const float* biasT, float* out, int ldo, int B,
-                                        int H, int W, int d, int dh, int wsz, int kind, float scale, void* stream) {
+static int attention_launch(const float* qkv, int ldq, const float* biasT, float* out, void* out_hi, void* out_lo,
+                            int ldo, int B, int H, int W, int d, int dh, int wsz, int kind, float scale, void* stream) {
   if (B <= 0 || H <= 0 || W <= 0 || d <= 0 || wsz <= 0) WXF_FAIL(WXF_EINVAL, "attention: bad dims");
   if (dh != DH) WXF_FAIL(WXF_EUNSUPPORTED, "attention: dim_head must be 32, got %d", dh);
   if (d % dh) WXF_FAIL(WXF_EINVAL, "attention: d %% dh != 0");
@@ -141,15 +157,35 @@ extern "C" int wxf_window_attention_f32(const float* qkv, int ldq, const float* 
   if (kind != WXF_ATTN_SHORT && kind != WXF_ATTN_LONG) WXF_FAIL(WXF_EINVAL, "attention: bad kind");
   const int L = wsz * wsz;
   if (L > ATT_THREADS) WXF_FAIL(WXF_EUNSUPPORTED, "attention: window %d (L=%d) > %d tokens", wsz, L, ATT_THREADS);
-  if (ldq < 3 * d || ldo < d || (ldq & 3) || (ldo & 3) || !wxf_aligned16(qkv) || !wxf_aligned16(out))
+  const bool split = out_hi != nullptr;
+  if (ldq < 3 * d || ldo < d || (ldq & 3) || (ldo & (split ? 7 : 3)) || !wxf_aligned16(qkv) ||
+      !(split ? (wxf_aligned16(out_hi) && wxf_aligned16(out_lo)) : wxf_aligned16(out)))
     WXF_FAIL(WXF_EALIGN, "attention: strides/pointers must be 16-byte aligned");
   const int heads = d / dh;
   const int G = ATT_THREADS / L;
   const int64_t npairs = (int64_t)B * (H / wsz) * (W / wsz) * heads;
   const int64_t blocks = (npairs + G - 1) / G;
   const size_t smem = (size_t)G * L * DH * sizeof(float) * 2;
-  window_attention_kernel<<<(unsigned)blocks, ATT_THREADS, smem, (cudaStream_t)stream>>>(
-      qkv, ldq, biasT, out, ldo, H, W, d, heads, wsz, kind, scale, L, G, npairs);
-  WXF_CHECK_LAUNCH("window_attention_f32");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (split)
+    window_attention_kernel<true><<<(unsigned)blocks, ATT_THREADS, smem, st>>>(
+        qkv, ldq, biasT, nullptr, (__half*)out_hi, (__half*)out_lo, ldo, H, W, d, heads, wsz, kind, scale, L, G, npairs);
+  else
+    window_attention_kernel<false><<<(unsigned)blocks, ATT_THREADS, smem, st>>>(
+        qkv, ldq, biasT, out, nullptr, nullptr, ldo, H, W, d, heads, wsz, kind, scale, L, G, npairs);
+  WXF_CHECK_LAUNCH("window_attention");
   return 0;
+}
+
+extern "C" int wxf_window_attention_f32(const float* qkv, int ldq, const float* biasT, float* out, int ldo, int B,
+                                        int H, int W, int d, int dh, int wsz, int kind, float scale, void* stream) {
+  if (!out) WXF_FAIL(WXF_EINVAL, "attention: null output");
+  return attention_launch(qkv, ldq, biasT, out, nullptr, nullptr, ldo, B, H, W, d, dh, wsz, kind, scale, stream);
+}
+
+extern "C" int wxf_window_attention_f16x2(const float* qkv, int ldq, const float* biasT, void* out_hi, void* out_lo,
+                                          int ldh, int B, int H, int W, int d, int dh, int wsz, int kind, float scale,
+                                          void* stream) {
+  if (!out_hi || !out_lo) WXF_FAIL(WXF_EINVAL, "attention: null output planes");
+  return attention_launch(qkv, ldq, biasT, nullptr, out_hi, out_lo, ldh, B, H, W, d, dh, wsz, kind, scale, stream);
 }

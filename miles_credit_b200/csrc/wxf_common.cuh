@@ -1,5 +1,6 @@
 // Shared host/device helpers of the wxformer_b200 C-ABI library.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -33,3 +34,10 @@ __device__ __forceinline__ float wxf_warp_sum(float v) {
 
 __device__ __forceinline__ float wxf_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float wxf_silu(float x) { return x / (1.0f + expf(-x)); }
+
+// fp32 -> (hi, lo) fp16 operand planes of the f16x2 tensor-core scheme (22 significant bits; hi saturates)
+__device__ __forceinline__ void wxf_split_f16x2(float v, __half& hi, __half& lo) {
+  const float c = fminf(fmaxf(v, -65504.f), 65504.f);
+  hi = __float2half_rn(c);
+  lo = __float2half_rn(v - __half2float(hi));
+}

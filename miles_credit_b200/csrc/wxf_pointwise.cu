@@ -88,10 +88,11 @@ extern "C" int wxf_pad_to_pixel_major(const float* x, float* xp, int B, int C, i
 // ------------------------------------------------------------------------------------------------
 // channel LayerNorm (crossformer.py:182-192): one warp per pixel, row cached in registers.
 
-template <int NV>
+template <int NV, bool SPLIT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y,
-                                                         int ldy, const float* __restrict__ g,
-                                                         const float* __restrict__ bta, int64_t M, int d, float eps) {
+                                                         int ldy, __half* __restrict__ y_hi, __half* __restrict__ y_lo,
+                                                         const float* __restrict__ g, const float* __restrict__ bta,
+                                                         int64_t M, int d, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -114,30 +115,73 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
   const float var = wxf_warp_sum(ss) / (float)d;
   const float den = sqrtf(var + eps);
-  float* yr = y + row * ldy;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int c = lane + 32 * k;
-    if (c < d) yr[c] = (v[k] - mean) / den * __ldg(g + c) + __ldg(bta + c);
+    if (c < d) {
+      const float o = (v[k] - mean) / den * __ldg(g + c) + __ldg(bta + c);
+      if constexpr (SPLIT) {
+        __half hi, lo;
+        wxf_split_f16x2(o, hi, lo);
+        y_hi[row * ldy + c] = hi;
+        y_lo[row * ldy + c] = lo;
+      } else {
+        y[row * ldy + c] = o;
+      }
+    }
   }
 }
 
-extern "C" int wxf_layernorm(const float* x, int ldx, float* y, int ldy, const float* g, const float* b, int64_t M,
-                             int d, float eps, void* stream) {
+template <bool SPLIT>
+static int layernorm_launch(const float* x, int ldx, float* y, int ldy, void* y_hi, void* y_lo, const float* g,
+                            const float* b, int64_t M, int d, float eps, void* stream) {
   if (M <= 0 || d <= 0 || ldx < d || ldy < d) WXF_FAIL(WXF_EINVAL, "layernorm: bad dims");
   if (d > 1024) WXF_FAIL(WXF_EUNSUPPORTED, "layernorm: d=%d > 1024", d);
   const int nv = (d + 31) / 32;
   const unsigned blocks = (unsigned)((M + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_CASE(NV)                                                                  \
-  if (nv <= NV) {                                                                    \
-    layernorm_kernel<NV><<<blocks, 256, 0, st>>>(x, ldx, y, ldy, g, b, M, d, eps);  \
-    WXF_CHECK_LAUNCH("layernorm");                                                   \
-    return 0;                                                                        \
+#define LN_CASE(NV)                                                                                         \
+  if (nv <= NV) {                                                                                           \
+    layernorm_kernel<NV, SPLIT><<<blocks, 256, 0, st>>>(x, ldx, y, ldy, (__half*)y_hi, (__half*)y_lo, g, b, M, d, eps); \
+    WXF_CHECK_LAUNCH("layernorm");                                                                          \
+    return 0;                                                                                               \
   }
   LN_CASE(1) LN_CASE(2) LN_CASE(4) LN_CASE(8) LN_CASE(16) LN_CASE(32)
 #undef LN_CASE
   return WXF_EUNSUPPORTED;
+}
+
+extern "C" int wxf_layernorm(const float* x, int ldx, float* y, int ldy, const float* g, const float* b, int64_t M,
+                             int d, float eps, void* stream) {
+  return layernorm_launch<false>(x, ldx, y, ldy, nullptr, nullptr, g, b, M, d, eps, stream);
+}
+
+extern "C" int wxf_layernorm_f16x2(const float* x, int ldx, void* y_hi, void* y_lo, int ldh, const float* g,
+                                   const float* b, int64_t M, int d, float eps, void* stream) {
+  if (!y_hi || !y_lo) WXF_FAIL(WXF_EINVAL, "layernorm_f16x2: null planes");
+  return layernorm_launch<true>(x, ldx, nullptr, ldh, y_hi, y_lo, g, b, M, d, eps, stream);
+}
+
+__global__ void __launch_bounds__(256) split_f16x2_kernel(const float* __restrict__ x, int ldx, __half* __restrict__ hi,
+                                                           __half* __restrict__ lo, int ldh, int64_t M, int d) {
+  const int64_t total = M * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d;
+    const int c = (int)(i - r * d);
+    __half h, l;
+    wxf_split_f16x2(x[r * ldx + c], h, l);
+    hi[r * ldh + c] = h;
+    lo[r * ldh + c] = l;
+  }
+}
+
+extern "C" int wxf_split_f16x2(const float* x, int ldx, void* hi, void* lo, int ldh, int64_t M, int d, void* stream) {
+  if (M <= 0 || d <= 0 || ldx < d || ldh < d || !hi || !lo) WXF_FAIL(WXF_EINVAL, "split_f16x2: bad args");
+  int64_t blocks = (M * d + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split_f16x2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, (__half*)hi, (__half*)lo, ldh, M, d);
+  WXF_CHECK_LAUNCH("split_f16x2");
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -116,8 +116,9 @@ def _round_up(v: int, m: int) -> int:
 class _Plan:
     """Workspace + ordered kernel launches of one forward for a fixed batch size."""
 
-    def __init__(self, geo: Geometry, wts: PreparedWeights, batch: int, device):
+    def __init__(self, geo: Geometry, wts: PreparedWeights, batch: int, device, tensor_cores: bool = True):
         self.geo, self.batch = geo, batch
+        self.tensor_cores = tensor_cores
         f32 = dict(device=device, dtype=torch.float32)
         B = batch
         g = geo
@@ -127,9 +128,12 @@ class _Plan:
         m0 = B * st0.h * st0.w
         big = max(B * s.h * s.w * s.dim for s in g.stages)
         big = max(big, max(4 * B * u.h_in * u.w_in * u.c_out for u in g.ups))
+        big = _round_up(big, 8)
         self.ln = torch.empty(big, **f32)
         y_elems = B * g.h_dec * g.w_dec * g.output_channels
-        self.scratch = torch.empty(max(4 * big, 2 * big + y_elems), **f32)
+        self.scratch = torch.empty(_round_up(max(4 * big, 2 * big + y_elems), 8), **f32)
+        self.ln16 = self.ln.view(torch.float16)            # [hi plane | lo plane], each ln.numel() halves
+        self.scratch16 = self.scratch.view(torch.float16)  # [hi plane | lo plane], each scratch.numel() halves
         # residual streams: stages 0..2 live in the upper half of their skip-concat buffer
         self.cat = [torch.empty((B, s.h, s.w, 2 * s.dim), **f32) for s in g.stages[:3]]
         self.x3 = torch.empty((B, g.stages[3].h, g.stages[3].w, g.stages[3].dim), **f32)
@@ -149,6 +153,10 @@ class _Plan:
         flops = 2.0 * m * wts.n * wts.t * wts.cin * wts.phases
         self._add(ops.conv_igemm_f32, (desc,), tag, flops)
 
+    def _gemm(self, a_hi, a_lo, wts, tag, **kw):
+        desc = ops.make_gemm_desc(a_hi, a_lo, wts, **kw)
+        self._add(ops.gemm_f16x2_tc, (desc,), tag, 2.0 * kw["M"] * wts.n * wts.k)
+
     def _build(self, wts: PreparedWeights):
         g, B = self.geo, self.batch
         add = self._add
@@ -166,14 +174,32 @@ class _Plan:
                            Wo=st.w, ldc=ld, c_off=xoff + br.c_off)
             ln = self.ln[: m * d]
             wide = self.scratch[: m * 4 * d]
+            # fp16 operand planes alias the same workspaces (2 planes x 2 bytes = the fp32 footprint)
+            ln_hi, ln_lo = self.ln16[: m * d], self.ln16[self.ln.numel(): self.ln.numel() + m * d]
+            hid_off = self.scratch.numel()
+            hid_hi, hid_lo = self.scratch16[: m * 4 * d], self.scratch16[hid_off: hid_off + m * 4 * d]
+            scale = float(g.dim_head) ** -0.5
             for layer in wts.blocks[s]:
                 for att, ff in ((layer[0], layer[1]), (layer[2], layer[3])):
                     L = att.wsz * att.wsz
+                    attn_cost = (4.0 * m * L * d, 16.0 * m * d)
+                    if self.tensor_cores:
+                        add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, att.ln_g, att.ln_b, m, d), "layernorm", 0,
+                            8.0 * m * d)
+                        self._gemm(ln_hi, ln_lo, att.qkv_tc, "qkv", M=m, lda=d, out=wide, ldc=3 * d)
+                        add(ops.window_attention_f16x2, (wide, 3 * d, att.bias_t, ln_hi, ln_lo, d, B, st.h, st.w, d,
+                                                         g.dim_head, att.wsz, att.kind, scale), "attention", *attn_cost)
+                        self._gemm(ln_hi, ln_lo, att.out_tc, "out_proj", M=m, lda=d, out=xv, ldc=ld, res=xv, ldr=ld)
+                        add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, ff.ln_g, ff.ln_b, m, d), "layernorm", 0,
+                            8.0 * m * d)
+                        self._gemm(ln_hi, ln_lo, ff.fc1_tc, "ff1", M=m, lda=d, out_hi=hid_hi, out_lo=hid_lo, ldh=4 * d,
+                                   act=_lib.ACT_GELU)
+                        self._gemm(hid_hi, hid_lo, ff.fc2_tc, "ff2", M=m, lda=4 * d, out=xv, ldc=ld, res=xv, ldr=ld)
+                        continue
                     add(ops.layernorm, (xv, ld, ln, d, att.ln_g, att.ln_b, m, d), "layernorm", 0, 8.0 * m * d)
                     self._conv(ln, att.qkv, wide, tag="qkv", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=3 * d)
                     add(ops.window_attention_f32, (wide, 3 * d, att.bias_t, ln, d, B, st.h, st.w, d, g.dim_head,
-                                                   att.wsz, att.kind, float(g.dim_head) ** -0.5), "attention",
-                        4.0 * m * L * d, 16.0 * m * d)
+                                                   att.wsz, att.kind, scale), "attention", *attn_cost)
                     self._conv(ln, att.out, xv, tag="out_proj", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=ld,
                                res=xv, ldr=ld)
                     add(ops.layernorm, (xv, ld, ln, d, ff.ln_g, ff.ln_b, m, d), "layernorm", 0, 8.0 * m * d)
@@ -286,6 +312,8 @@ class CrossFormerB200(_Base):
                 mod.register_buffer(parts[-1], init[key])
             else:
                 mod.register_parameter(parts[-1], nn.Parameter(init[key], requires_grad=False))
+        # exact-fp32 CUDA-core contractions instead of the f16x2 tensor-core GEMMs (validation aid, ~5x slower)
+        self.exact_fp32 = os.environ.get("WXF_EXACT_FP32", "0") == "1"
         self._prepared: Optional[PreparedWeights] = None
         self._prepared_sig = None
         self._plans: Dict[tuple, _Plan] = {}
@@ -328,11 +356,11 @@ class CrossFormerB200(_Base):
             x = x.float()
         if self._prepared is None or self._prepared_sig != self._signature():
             self.refresh_weights()
-        key = (int(x.shape[0]), x.device.index)
+        key = (int(x.shape[0]), x.device.index, self.exact_fp32)
         plan = self._plans.get(key)
         if plan is None:
             with torch.cuda.device(x.device):
-                plan = self._plans[key] = _Plan(geo, self._prepared, int(x.shape[0]), x.device)
+                plan = self._plans[key] = _Plan(geo, self._prepared, int(x.shape[0]), x.device, not self.exact_fp32)
         with torch.cuda.device(x.device):
             return plan.run(x.contiguous())
 

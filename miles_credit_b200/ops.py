@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import lib as _lib
-from .lib import WxfConvDesc
+from .lib import WxfConvDesc, WxfGemmDesc
 from .weights import ConvWeights
 
 LAUNCHES = 0
@@ -56,6 +56,55 @@ def layernorm(x: torch.Tensor, ldx: int, y: torch.Tensor, ldy: int, g: torch.Ten
     global LAUNCHES
     st = _lib.load().wxf_layernorm(x.data_ptr(), ldx, y.data_ptr(), ldy, g.data_ptr(), b.data_ptr(), m, d, eps, _stream())
     _lib.check(st, "wxf_layernorm")
+    LAUNCHES += 1
+
+
+def layernorm_f16x2(x: torch.Tensor, ldx: int, y_hi: torch.Tensor, y_lo: torch.Tensor, ldh: int, g: torch.Tensor,
+                    b: torch.Tensor, m: int, d: int, eps: float = 1e-5):
+    """LayerNorm whose result is written as fp16 hi/lo operand planes."""
+    global LAUNCHES
+    st = _lib.load().wxf_layernorm_f16x2(x.data_ptr(), ldx, y_hi.data_ptr(), y_lo.data_ptr(), ldh, g.data_ptr(),
+                                         b.data_ptr(), m, d, eps, _stream())
+    _lib.check(st, "wxf_layernorm_f16x2")
+    LAUNCHES += 1
+
+
+def split_f16x2(x: torch.Tensor, ldx: int, hi: torch.Tensor, lo: torch.Tensor, ldh: int, m: int, d: int):
+    global LAUNCHES
+    st = _lib.load().wxf_split_f16x2(x.data_ptr(), ldx, hi.data_ptr(), lo.data_ptr(), ldh, m, d, _stream())
+    _lib.check(st, "wxf_split_f16x2")
+    LAUNCHES += 1
+
+
+def make_gemm_desc(a_hi: torch.Tensor, a_lo: torch.Tensor, wts, *, M: int, lda: int, out: Optional[torch.Tensor] = None,
+                   ldc: int = 0, c_off: int = 0, res: Optional[torch.Tensor] = None, ldr: int = 0, r_off: int = 0,
+                   out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None, ldh: int = 0,
+                   act: int = 0) -> WxfGemmDesc:
+    """Descriptor of one tensor-core GEMM launch; ``wts`` is a weights.GemmWeights (fp16 hi/lo planes)."""
+    d = WxfGemmDesc()
+    d.a_hi, d.a_lo = a_hi.data_ptr(), a_lo.data_ptr()
+    d.w_hi, d.w_lo = wts.w_hi.data_ptr(), wts.w_lo.data_ptr()
+    d.bias, d.res, d.out = _ptr(wts.bias), _ptr(res), _ptr(out)
+    d.out_hi, d.out_lo = _ptr(out_hi), _ptr(out_lo)
+    d.M, d.N, d.K, d.lda = M, wts.n, wts.k, lda
+    d.ldc, d.c_off, d.ldr, d.r_off, d.ldh = ldc, c_off, ldr, r_off, ldh
+    d.act, d.w_scale_log2 = act, wts.scale_log2
+    return d
+
+
+def gemm_f16x2_tc(desc: WxfGemmDesc):
+    global LAUNCHES
+    st = _lib.load().wxf_gemm_f16x2_tc(ctypes.byref(desc), _stream())
+    _lib.check(st, "wxf_gemm_f16x2_tc")
+    LAUNCHES += 1
+
+
+def window_attention_f16x2(qkv: torch.Tensor, ldq: int, bias_t: torch.Tensor, out_hi: torch.Tensor, out_lo: torch.Tensor,
+                           ldh: int, B: int, H: int, W: int, d: int, dh: int, wsz: int, kind: int, scale: float):
+    global LAUNCHES
+    st = _lib.load().wxf_window_attention_f16x2(qkv.data_ptr(), ldq, bias_t.data_ptr(), out_hi.data_ptr(),
+                                                out_lo.data_ptr(), ldh, B, H, W, d, dh, wsz, kind, scale, _stream())
+    _lib.check(st, "wxf_window_attention_f16x2")
     LAUNCHES += 1
 
 

@@ -12,6 +12,7 @@ This runs in PyTorch on whatever device the parameters live on; it is not part o
 
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -116,6 +117,35 @@ def convt_k4s2p1_weights(w: torch.Tensor, bias) -> ConvWeights:
 
 
 @dataclass
+class GemmWeights:
+    """Tensor-core operand planes of a 1x1-conv weight: fp16 hi/lo of W * 2^scale_log2, [N, K] row-major."""
+
+    w_hi: torch.Tensor
+    w_lo: torch.Tensor
+    bias: Optional[torch.Tensor]
+    n: int
+    k: int
+    scale_log2: int
+
+
+def gemm_weights(w: torch.Tensor, bias) -> GemmWeights:
+    """Split a [N, K(,1,1)] fp32 weight into fp16 hi/lo planes after a power-of-two pre-scale.
+
+    The scale puts max|W| in [512, 1024) so the lo plane stays in fp16's normal range for every element within
+    2^-13 of the largest; the GEMM epilogue multiplies by the exact inverse.
+    """
+    w2 = w.reshape(w.shape[0], -1).float()
+    amax = float(w2.abs().max())
+    k = 0 if amax == 0.0 else int(math.floor(math.log2(1024.0 / amax)))
+    k = max(min(k, 24), -24)
+    ws = w2 * (2.0 ** k)
+    hi = ws.half()
+    lo = (ws - hi.float()).half()
+    return GemmWeights(hi.contiguous(), lo.contiguous(), None if bias is None else bias.float().contiguous(),
+                       w2.shape[0], w2.shape[1], k)
+
+
+@dataclass
 class AttentionWeights:
     ln_g: torch.Tensor
     ln_b: torch.Tensor
@@ -124,6 +154,8 @@ class AttentionWeights:
     bias_t: torch.Tensor  # [L, L] transposed position bias
     wsz: int
     kind: int
+    qkv_tc: Optional[GemmWeights] = None
+    out_tc: Optional[GemmWeights] = None
 
 
 @dataclass
@@ -132,6 +164,8 @@ class FeedForwardWeights:
     ln_b: torch.Tensor
     fc1: ConvWeights
     fc2: ConvWeights
+    fc1_tc: Optional[GemmWeights] = None
+    fc2_tc: Optional[GemmWeights] = None
 
 
 @dataclass
@@ -168,16 +202,20 @@ def prepare(sd: Dict[str, torch.Tensor], geo: Geometry, cin0_pad: int) -> Prepar
                 entry = []
                 for a, kind, wsz in ((0, 0, st.local_window), (2, 1, st.global_window)):
                     p = f"layers.{s}.1.layers.{l}.{a}"
+                    w_qkv, w_out = fold_spectral_norm(sd, p + ".to_qkv"), fold_spectral_norm(sd, p + ".to_out")
                     att = AttentionWeights(
                         sd[p + ".norm.g"].float().reshape(-1).contiguous(), sd[p + ".norm.b"].float().reshape(-1).contiguous(),
-                        conv_weights(fold_spectral_norm(sd, p + ".to_qkv"), None, 1, 0),
-                        conv_weights(fold_spectral_norm(sd, p + ".to_out"), sd[p + ".to_out.bias"], 1, 0),
-                        position_bias_table(sd, p, wsz).t().contiguous(), wsz, kind)
+                        conv_weights(w_qkv, None, 1, 0),
+                        conv_weights(w_out, sd[p + ".to_out.bias"], 1, 0),
+                        position_bias_table(sd, p, wsz).t().contiguous(), wsz, kind,
+                        gemm_weights(w_qkv, None), gemm_weights(w_out, sd[p + ".to_out.bias"]))
                     f = f"layers.{s}.1.layers.{l}.{a + 1}.layers"
+                    w1, w2 = fold_spectral_norm(sd, f + ".1"), fold_spectral_norm(sd, f + ".4")
                     ff = FeedForwardWeights(
                         sd[f + ".0.g"].float().reshape(-1).contiguous(), sd[f + ".0.b"].float().reshape(-1).contiguous(),
-                        conv_weights(fold_spectral_norm(sd, f + ".1"), sd[f + ".1.bias"], 1, 0),
-                        conv_weights(fold_spectral_norm(sd, f + ".4"), sd[f + ".4.bias"], 1, 0))
+                        conv_weights(w1, sd[f + ".1.bias"], 1, 0),
+                        conv_weights(w2, sd[f + ".4.bias"], 1, 0),
+                        gemm_weights(w1, sd[f + ".1.bias"]), gemm_weights(w2, sd[f + ".4.bias"]))
                     entry += [att, ff]
                 layers.append(tuple(entry))
             blocks.append(layers)

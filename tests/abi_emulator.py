@@ -33,7 +33,7 @@ class EmulatedLib:
         self.calls = []
 
     def wxf_abi_version(self):
-        return 1
+        return 2
 
     def wxf_last_error(self):
         return b"emulator"
@@ -71,6 +71,71 @@ class EmulatedLib:
         mean = xs.mean(1, keepdim=True)
         var = ((xs - mean) ** 2).mean(1, keepdim=True)
         ys.copy_((xs - mean) / (var + eps).sqrt() * gg + bb)
+        return 0
+
+    @staticmethod
+    def _harr(ptr, n):
+        return torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint16)), shape=(int(n),))
+                                .view(np.float16))
+
+    @staticmethod
+    def _split(v):
+        hi = v.clamp(-65504.0, 65504.0).half()
+        lo = (v - hi.float()).half()
+        return hi, lo
+
+    def wxf_layernorm_f16x2(self, x, ldx, y_hi, y_lo, ldh, g, b, M, d, eps, stream):
+        self.calls.append("layernorm_f16x2")
+        xs = _t(_arr(x, (M - 1) * ldx + d)).as_strided((M, d), (ldx, 1))
+        gg, bb = _t(_arr(g, d)), _t(_arr(b, d))
+        mean = xs.mean(1, keepdim=True)
+        var = ((xs - mean) ** 2).mean(1, keepdim=True)
+        hi, lo = self._split((xs - mean) / (var + eps).sqrt() * gg + bb)
+        self._harr(y_hi, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(hi)
+        self._harr(y_lo, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(lo)
+        return 0
+
+    def wxf_split_f16x2(self, x, ldx, hi_p, lo_p, ldh, M, d, stream):
+        self.calls.append("split")
+        xs = _t(_arr(x, (M - 1) * ldx + d)).as_strided((M, d), (ldx, 1))
+        hi, lo = self._split(xs)
+        self._harr(hi_p, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(hi)
+        self._harr(lo_p, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(lo)
+        return 0
+
+    def wxf_gemm_f16x2_tc(self, dref, stream):
+        d = dref._obj
+        self.calls.append("gemm_tc")
+        M, N, K = d.M, d.N, d.K
+        a_hi = self._harr(d.a_hi, (M - 1) * d.lda + K).as_strided((M, K), (d.lda, 1)).double()
+        a_lo = self._harr(d.a_lo, (M - 1) * d.lda + K).as_strided((M, K), (d.lda, 1)).double()
+        w_hi = self._harr(d.w_hi, N * K).view(N, K).double()
+        w_lo = self._harr(d.w_lo, N * K).view(N, K).double()
+        acc = (a_hi @ w_lo.t() + a_lo @ w_hi.t() + a_hi @ w_hi.t()).float()
+        v = acc * (2.0 ** -d.w_scale_log2)
+        if d.bias:
+            v = v + _t(_arr(d.bias, N))
+        if d.act == 1:
+            v = 0.5 * v * (1 + torch.erf(v * 0.7071067811865476))
+        if d.res:
+            v = v + _t(_arr(d.res, (M - 1) * d.ldr + d.r_off + N)).as_strided((M, N), (d.ldr, 1), d.r_off)
+        if d.out:
+            _t(_arr(d.out, (M - 1) * d.ldc + d.c_off + N)).as_strided((M, N), (d.ldc, 1), d.c_off).copy_(v)
+        if d.out_hi:
+            hi, lo = self._split(v)
+            self._harr(d.out_hi, (M - 1) * d.ldh + N).as_strided((M, N), (d.ldh, 1)).copy_(hi)
+            self._harr(d.out_lo, (M - 1) * d.ldh + N).as_strided((M, N), (d.ldh, 1)).copy_(lo)
+        return 0
+
+    def wxf_window_attention_f16x2(self, qkv, ldq, biasT, out_hi, out_lo, ldh, B, H, W, d, dh, wsz, kind, scale, stream):
+        M = B * H * W
+        tmp = np.zeros(M * d, dtype=np.float32)
+        rc = self.wxf_window_attention_f32(qkv, ldq, biasT, tmp.ctypes.data, d, B, H, W, d, dh, wsz, kind, scale, stream)
+        if rc:
+            return rc
+        hi, lo = self._split(torch.from_numpy(tmp).view(M, d))
+        self._harr(out_hi, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(hi)
+        self._harr(out_lo, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(lo)
         return 0
 
     def wxf_conv_igemm_f32(self, dref, stream):

@@ -17,11 +17,13 @@ def relmax(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
+@pytest.mark.parametrize("exact", [False, True], ids=["tensorcore", "exactfp32"])
 @pytest.mark.parametrize("case", ["unit", "unit_mirror_f2"])
-def test_forward_matches_reference_golden(golden_dir, case):
+def test_forward_matches_reference_golden(golden_dir, case, exact):
     fx = torch.load(os.path.join(golden_dir, f"{case}.pt"), weights_only=False)
     geo = build_geometry(**fx["kwargs"])
     model = CrossFormerB200(**fx["kwargs"])
+    model.exact_fp32 = exact
     model.load_state_dict(synthetic_state_dict(geo, seed=fx["seed"]), strict=True)
     model = model.cuda().eval()
     x = synthetic_input(geo, batch=fx["batch"], seed=fx["seed"])
