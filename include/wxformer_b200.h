@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 2
+#define WXF_ABI_VERSION 3
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -143,6 +143,40 @@ typedef struct WxfGemmDesc {
 
 int wxf_gemm_f16x2_tc(const WxfGemmDesc* desc, void* stream);
 
+/*
+ * Convolution as an implicit GEMM on the tcgen05 tensor cores (same f16x2 scheme and epilogue as
+ * wxf_gemm_f16x2_tc).  Covers the same operators as wxf_conv_igemm_f32 (Conv2d k x k stride 1/2 with zero
+ * padding; ConvTranspose2d k2 s2 / k4 s2 p1 as 4 output-parity phases): CrossEmbedLayer stages 1-3
+ * (crossformer.py:139-152), UpBlock (crossformer.py:92-116), up_block4 (crossformer.py:572-574).
+ * The A tile of one K-step (one tap, 64 channels) is a single 4-D TMA box of the pixel-major fp16 planes;
+ * out-of-image pixels are TMA zero fill.
+ *   in_hi, in_lo : [B, Hi, Wi, lda] fp16 planes;   w_hi, w_lo : [phases, N, T*cin_pad] planes of W * 2^w_scale_log2
+ *   taps         : HOST pointer, [phases, T, 2] = (dy, dx) with padding already subtracted, T <= 64
+ *   epilogue     : v = acc*2^-w_scale_log2 + bias[n]; act; + res[pixel*ldr + r_off + n];
+ *                  out[pixel*ldc + c_off + n] (fp32, optional), out_hi/lo[pixel*ldh + h_off + n] (optional)
+ * N % 4 == 0, lda % 8 == 0, cin_pad % 64 == 0 (weights zero-padded per tap), stride in {1, 2}.
+ */
+typedef struct WxfConvTcDesc {
+  const void* in_hi;
+  const void* in_lo;
+  const void* w_hi;
+  const void* w_lo;
+  const int32_t* taps;
+  const float* bias;
+  const float* res;
+  float* out;
+  void* out_hi;
+  void* out_lo;
+  int32_t B, Hi, Wi, lda, Cin, cin_pad;
+  int32_t N, T, stride;
+  int32_t Ho, Wo;
+  int32_t phases, out_scale;
+  int32_t ldc, c_off, ldr, r_off, ldh, h_off;
+  int32_t act, w_scale_log2;
+} WxfConvTcDesc;
+
+int wxf_conv_f16x2_tc(const WxfConvTcDesc* desc, void* stream);
+
 /* Split an fp32 [M, ldx] matrix (first d columns) into fp16 hi/lo planes [M, ldh] (test/utility pass). */
 int wxf_split_f16x2(const float* x, int ldx, void* hi, void* lo, int ldh, int64_t M, int d, void* stream);
 
@@ -157,6 +191,10 @@ int wxf_groupnorm_stats(const float* x, int ldx, float* stats, void* scratch, in
                         float eps, void* stream);
 int wxf_groupnorm_silu(const float* x, int ldx, const float* stats, const float* gamma, const float* beta,
                        const float* res, int ldr, float* y, int ldy, int B, int64_t HW, int C, int G, void* stream);
+/* Same apply pass, result written as fp16 hi/lo operand planes: y_hi/y_lo[pixel*ldh + h_off + c]. */
+int wxf_groupnorm_silu_f16x2(const float* x, int ldx, const float* stats, const float* gamma, const float* beta,
+                             const float* res, int ldr, void* y_hi, void* y_lo, int ldh, int h_off, int B, int64_t HW,
+                             int C, int G, void* stream);
 
 /*
  * Un-pad + bilinear resize (align_corners = False) + pixel-major -> NCHW

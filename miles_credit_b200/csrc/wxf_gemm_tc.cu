@@ -1,15 +1,22 @@
-// Pointwise (1x1-conv) GEMM on the 5th-generation tensor cores: C[M,N] = epi(A[M,K] * W[N,K]^T).
+// Contractions on the 5th-generation tensor cores (tcgen05 + TMEM), operands staged by TMA.
+//
+//   GEMM mode : C[M,N] = epi(A[M,K] * W[N,K]^T)                       (1x1 convs: to_qkv, to_out, FeedForward)
+//   CONV mode : implicit GEMM over (tap, channel-block) K-steps; the A tile of a K-step is ONE 4-D TMA box
+//               {64 channels, bw pixels (element stride s), bh rows (element stride s), 1 image} of the
+//               pixel-major input, so there is no im2col buffer and zero padding is TMA's out-of-bounds fill.
+//               Transposed convolutions run as 4 output-parity phases (gridDim.z).
 //
 // Precision scheme "f16x2": every fp32 operand is carried as two fp16 planes (hi = fp16(x), lo = fp16(x - hi),
-// 22 significant bits) and the product is three tcgen05.mma passes into one fp32 TMEM accumulator:
-//     A W^T ~= A_hi W_lo^T + A_lo W_hi^T + A_hi W_hi^T          (the lo*lo term is below fp32 resolution)
-// Measured end to end this stays within 4e-6 rel-max of the fp32 reference forward (budget 1e-4), where a
-// single tf32/fp16 pass is at 1e-3.  Operand planes cost the same HBM bytes as fp32.
+// 22 significant bits); a product is three tcgen05.mma passes  A_hi W_lo + A_lo W_hi + A_hi W_hi  with fp32
+// accumulation in TMEM.  The tensor-core accumulator truncates on every accumulate (measured: 1.8e-5 rel at
+// K=4096 with one accumulator), so the small cross terms go to their own accumulator and the main term is
+// spread over several accumulators along K; they are summed in fp32 (round-to-nearest) in the epilogue.
 //
-// Kernel shape: one CTA per 128 x BN output tile (BN = 128 or 256), 192 threads:
-//   warp 0    : TMA producer  (cp.async.bulk.tensor 2D, 128B swizzle, 3/2-stage mbarrier ring)
+// CTA = 128 x BN output tile, 192 threads:
+//   warp 0    : TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier ring)
 //   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16 per instruction)
-//   warps 2-5 : epilogue, tcgen05.ld 32 lanes x 32 columns -> registers -> scale/bias/GELU/residual -> global
+//   warps 2-5 : epilogue: tcgen05.ld -> registers -> padded smem transpose -> bias/GELU/residual ->
+//               coalesced 128-byte row segments (fp32 and/or fp16 hi/lo planes)
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -21,22 +28,32 @@
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;                       // 64 fp16 = one 128-byte swizzle row
+constexpr int BLOCK_K = 64;                        // 64 fp16 = one 128-byte swizzle row
 constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB: one 128-row operand plane of one stage
 constexpr int NUM_THREADS = 192;
+constexpr int STG_LD = 36;                         // floats per staged row (32 + 4 pad: conflict-free float4)
+constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;     // 4 epilogue warps
 constexpr uint32_t SPIN_LIMIT = 1u << 22;          // mbarrier waits trap instead of hanging the GPU
+constexpr int MAX_TAPS = 64;
 
-struct GemmTcParams {
+struct TcParams {
   const float* bias;
   const float* res;
   float* out;
   __half* out_hi;
   __half* out_lo;
-  int64_t M;
-  int N, K;
+  int64_t M;          // GEMM mode: rows
+  int N, num_ksteps;  // K-steps of 64
   int ldc, ldr, ldh;
   int act;
-  float w_scale;  // 2^-k: undoes the power-of-two pre-scale of the weight planes
+  float w_scale;      // 2^-k: undoes the power-of-two pre-scale of the weight planes
+  // conv mode
+  int cblocks;        // channel blocks of 64 per tap
+  int cin_pad;        // weight K stride per tap
+  int bw, bh, tiles_x, tiles_y;
+  int Ho, Wo, stride, out_scale;
+  uint32_t a_bytes;   // bytes of one A plane box
+  int16_t taps[4][MAX_TAPS][2];  // [phase][tap] = (dy, dx); only [0] used when phases == 1
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -61,7 +78,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (done) break;
     if (++spins > SPIN_LIMIT) {
-      printf("wxf_gemm_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      printf("wxf tc kernel: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
       __trap();
     }
   }
@@ -70,6 +88,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar,
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -109,16 +135,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return d;
 }
 
-
 // ---- kernel --------------------------------------------------------------------------------------
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_f16x2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                     const GemmTcParams p) {
+tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                   const __grid_constant__ TcParams p) {
   constexpr int W_BYTES = BN * BLOCK_K * 2;
   constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * W_BYTES;
+  constexpr int NACC = 512 / BN;        // TMEM accumulators: [0] cross terms, [1..] main term split along K
+  constexpr int NMAIN = NACC - 1;
   // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 
@@ -126,16 +153,30 @@ gemm_f16x2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle-128B atoms need 1024-byte alignment
   uint8_t* gen = smem_raw + (base - raw);
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+  float* staging = reinterpret_cast<float*>(gen + STAGES * STAGE_BYTES);
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES + STG_BYTES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + STAGES * STAGE_BYTES + STG_BYTES + 8 * (2 * STAGES + 1));
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
-  const int64_t m0 = (int64_t)blockIdx.y * BLOCK_M;
-  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int z = blockIdx.z;
+  const int num_k = p.num_ksteps;
+
+  // tile origin
+  int64_t m0 = 0;
+  int tb = 0, oy0 = 0, ox0 = 0;
+  if constexpr (CONV) {
+    const int per_img = p.tiles_x * p.tiles_y;
+    tb = blockIdx.y / per_img;
+    const int rem = blockIdx.y - tb * per_img;
+    oy0 = (rem / p.tiles_x) * p.bh;
+    ox0 = (rem % p.tiles_x) * p.bw;
+  } else {
+    m0 = (int64_t)blockIdx.y * BLOCK_M;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -145,8 +186,8 @@ gemm_f16x2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: BN fp32 accumulator columns x 128 lanes
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN)
+  if (warp == 1) {  // all 512 TMEM columns: NACC accumulators of BN fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -157,111 +198,140 @@ gemm_f16x2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      const uint32_t stage_tx = CONV ? (2u * p.a_bytes + 2u * W_BYTES) : (uint32_t)STAGE_BYTES;
+      for (int ks = 0; ks < num_k; ++ks) {
+        const int s = ks % STAGES;
+        const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t st = base + s * STAGE_BYTES;
-        mbar_expect_tx(full_bar(s), STAGE_BYTES);
-        tma_load_2d(&tmA_hi, full_bar(s), st, kb * BLOCK_K, (int)m0);
-        tma_load_2d(&tmA_lo, full_bar(s), st + TILE_BYTES, kb * BLOCK_K, (int)m0);
-        tma_load_2d(&tmW_hi, full_bar(s), st + 2 * TILE_BYTES, kb * BLOCK_K, n0);
-        tma_load_2d(&tmW_lo, full_bar(s), st + 2 * TILE_BYTES + W_BYTES, kb * BLOCK_K, n0);
+        mbar_expect_tx(full_bar(s), stage_tx);
+        int wk;
+        if constexpr (CONV) {
+          const int t = ks / p.cblocks, cb = ks - t * p.cblocks;
+          const int iy = oy0 * p.stride + p.taps[z][t][0], ix = ox0 * p.stride + p.taps[z][t][1];
+          tma_load_4d(&tmA_hi, full_bar(s), st, cb * BLOCK_K, ix, iy, tb);
+          tma_load_4d(&tmA_lo, full_bar(s), st + TILE_BYTES, cb * BLOCK_K, ix, iy, tb);
+          wk = t * p.cin_pad + cb * BLOCK_K;
+        } else {
+          tma_load_2d(&tmA_hi, full_bar(s), st, ks * BLOCK_K, (int)m0);
+          tma_load_2d(&tmA_lo, full_bar(s), st + TILE_BYTES, ks * BLOCK_K, (int)m0);
+          wk = ks * BLOCK_K;
+        }
+        tma_load_2d(&tmW_hi, full_bar(s), st + 2 * TILE_BYTES, wk, z * p.N + n0);
+        tma_load_2d(&tmW_lo, full_bar(s), st + 2 * TILE_BYTES + W_BYTES, wk, z * p.N + n0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      uint32_t started = 0;  // bit a: accumulator a already holds data
+      for (int ks = 0; ks < num_k; ++ks) {
+        const int s = ks % STAGES;
+        const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t st = base + s * STAGE_BYTES;
+        const int am = 1 + (int)(((int64_t)ks * NMAIN) / num_k);  // main accumulator of this K-step
+        const uint32_t d_cross = tmem_base, d_main = tmem_base + (uint32_t)(am * BN);
 #pragma unroll
         for (int k = 0; k < BLOCK_K / 16; ++k) {
           const uint64_t a_hi = umma_desc_sw128(st + k * 32);
           const uint64_t a_lo = umma_desc_sw128(st + TILE_BYTES + k * 32);
           const uint64_t w_hi = umma_desc_sw128(st + 2 * TILE_BYTES + k * 32);
           const uint64_t w_lo = umma_desc_sw128(st + 2 * TILE_BYTES + W_BYTES + k * 32);
-          tc_mma_f16(tmem_base, a_hi, w_lo, IDESC, (kb | k) ? 1u : 0u);
-          tc_mma_f16(tmem_base, a_lo, w_hi, IDESC, 1u);
-          tc_mma_f16(tmem_base, a_hi, w_hi, IDESC, 1u);
+          tc_mma_f16(d_cross, a_hi, w_lo, IDESC, started & 1u);
+          started |= 1u;
+          tc_mma_f16(d_cross, a_lo, w_hi, IDESC, 1u);
+          tc_mma_f16(d_main, a_hi, w_hi, IDESC, (started >> am) & 1u);
+          started |= 1u << am;
         }
         tc_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
       }
-      tc_commit(tmem_full_bar);   // accumulator complete
+      tc_commit(tmem_full_bar);   // accumulators complete
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) ----
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const int64_t m = m0 + row;
+    float* stg = staging + quarter * (32 * STG_LD);
+    const int r4 = lane >> 3, c4 = lane & 7;
+    const int used_main = num_k < NMAIN ? num_k : NMAIN;
+
+    // output pixel of the 8 rows this lane stores (row = it*4 + r4 of this warp's 32-row slab)
+    int64_t opix[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = quarter * 32 + it * 4 + r4;
+      if constexpr (CONV) {
+        const int i = row / p.bw, j = row - i * p.bw;
+        const int oy = oy0 + i, ox = ox0 + j;
+        if (i < p.bh && oy < p.Ho && ox < p.Wo) {
+          const int Hout = p.Ho * p.out_scale, Wout = p.Wo * p.out_scale;
+          opix[it] = ((int64_t)tb * Hout + oy * p.out_scale + (z >> 1)) * Wout + ox * p.out_scale + (z & 1);
+        } else {
+          opix[it] = -1;
+        }
+      } else {
+        const int64_t m = m0 + row;
+        opix[it] = m < p.M ? m : -1;
+      }
+    }
+
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const bool vec4 = ((p.ldc & 3) == 0) && (!p.res || (p.ldr & 3) == 0) && ((p.N & 3) == 0);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
-      if (n0 + c * 32 >= p.N) break;  // warp-uniform
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
-      if (m < p.M) {
-        float v[32];
+      const int nb = n0 + c * 32;
+      if (nb >= p.N) break;  // warp-uniform
+      float v[32];
+      {
+        uint32_t r[32];
+        tmem_ld32(lane_base + (uint32_t)(c * 32), r);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c * 32 + j;
-          float t = __uint_as_float(r[j]) * p.w_scale;
-          if (n < p.N) {
-            if (p.bias) t += __ldg(p.bias + n);
-            if (p.act == WXF_ACT_GELU_ERF) t = wxf_gelu_erf(t);
-          }
-          v[j] = t;
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+#pragma unroll 1
+        for (int a = 1; a <= used_main; ++a) {
+          tmem_ld32(lane_base + (uint32_t)(a * BN + c * 32), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
         }
-        const int nb = n0 + c * 32;
-        if (p.res) {
-          const float* rr = p.res + m * p.ldr + nb;
-          if (vec4 && nb + 32 <= p.N) {
+      }
+      // lane = row: write the 32 columns of this row into the padded staging slab
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 q = *reinterpret_cast<const float4*>(rr + j);
-              v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
-            }
-          } else {
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stg + lane * STG_LD + j) =
+            make_float4(v[j] * p.w_scale, v[j + 1] * p.w_scale, v[j + 2] * p.w_scale, v[j + 3] * p.w_scale);
+      __syncwarp();
+      // transposed pass: 8 lanes cover one row's 32 columns (128 B), 4 rows per instruction
+      const int n = nb + c4 * 4;
+      if (n < p.N) {
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) v[j] += rr[j];
+        for (int it = 0; it < 8; ++it) {
+          if (opix[it] < 0) continue;
+          float4 t = *reinterpret_cast<const float4*>(stg + (it * 4 + r4) * STG_LD + c4 * 4);
+          t.x += bias4.x; t.y += bias4.y; t.z += bias4.z; t.w += bias4.w;
+          if (p.act == WXF_ACT_GELU_ERF) {
+            t.x = wxf_gelu_erf(t.x); t.y = wxf_gelu_erf(t.y); t.z = wxf_gelu_erf(t.z); t.w = wxf_gelu_erf(t.w);
           }
-        }
-        if (p.out) {
-          float* oo = p.out + m * p.ldc + nb;
-          if (vec4 && nb + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(oo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) oo[j] = v[j];
+          if (p.res) {
+            const float4 q = *reinterpret_cast<const float4*>(p.res + opix[it] * p.ldr + n);
+            t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
           }
-        }
-        if (p.out_hi) {
-          __half* hh = p.out_hi + m * p.ldh + nb;
-          __half* ll = p.out_lo + m * p.ldh + nb;
-          if ((p.ldh & 7) == 0 && nb + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __align__(16) __half h8[8];
-              __align__(16) __half l8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) wxf_split_f16x2(v[j + e], h8[e], l8[e]);
-              *reinterpret_cast<uint4*>(hh + j) = *reinterpret_cast<const uint4*>(h8);
-              *reinterpret_cast<uint4*>(ll + j) = *reinterpret_cast<const uint4*>(l8);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) wxf_split_f16x2(v[j], hh[j], ll[j]);
+          if (p.out) *reinterpret_cast<float4*>(p.out + opix[it] * p.ldc + n) = t;
+          if (p.out_hi) {
+            __align__(8) __half h4[4];
+            __align__(8) __half l4[4];
+            wxf_split_f16x2(t.x, h4[0], l4[0]);
+            wxf_split_f16x2(t.y, h4[1], l4[1]);
+            wxf_split_f16x2(t.z, h4[2], l4[2]);
+            wxf_split_f16x2(t.w, h4[3], l4[3]);
+            *reinterpret_cast<uint2*>(p.out_hi + opix[it] * p.ldh + n) = *reinterpret_cast<const uint2*>(h4);
+            *reinterpret_cast<uint2*>(p.out_lo + opix[it] * p.ldh + n) = *reinterpret_cast<const uint2*>(l4);
           }
         }
       }
+      __syncwarp();
     }
   }
 
@@ -270,7 +340,7 @@ gemm_f16x2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -295,25 +365,40 @@ EncodeTiledFn encode_fn() {
 
 struct MapKey {
   const void* ptr;
-  uint64_t rows, cols, ld;
-  uint32_t box_rows;
+  uint64_t d[4], s[3];
+  uint32_t box[4], es[4], rank;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    if (ptr != o.ptr || rank != o.rank) return false;
+    for (int i = 0; i < 4; ++i)
+      if (d[i] != o.d[i] || box[i] != o.box[i] || es[i] != o.es[i]) return false;
+    for (int i = 0; i < 3; ++i)
+      if (s[i] != o.s[i]) return false;
+    return true;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
-    size_t h = std::hash<const void*>()(k.ptr);
-    h ^= std::hash<uint64_t>()(k.rows * 1315423911ull + k.cols * 2654435761ull + k.ld * 97ull + k.box_rows);
-    return h;
+    uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull + k.rank;
+    for (int i = 0; i < 4; ++i) h = (h ^ (k.d[i] * 1315423911ull + k.box[i] * 2654435761ull + k.es[i])) * 0x100000001B3ull;
+    for (int i = 0; i < 3; ++i) h = (h ^ k.s[i]) * 0x100000001B3ull;
+    return (size_t)h;
   }
 };
 
-// fp16 [rows, cols] row-major with row stride ld elements; box = box_rows x 64 columns, 128B swizzle, zero OOB fill
-int make_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// fp16 tensor map, 128B swizzle, zero OOB fill; dims innermost-first, strides in bytes for dims 1..rank-1
+int make_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims, const uint64_t* strides,
+             const uint32_t* box, const uint32_t* estr) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  const MapKey key{ptr, rows, cols, ld, box_rows};
+  MapKey key{};
+  key.ptr = ptr;
+  key.rank = rank;
+  for (uint32_t i = 0; i < rank; ++i) {
+    key.d[i] = dims[i];
+    key.box[i] = box[i];
+    key.es[i] = estr[i];
+    if (i + 1 < rank) key.s[i] = strides[i];
+  }
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -323,49 +408,65 @@ int make_map(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, ui
     }
   }
   EncodeTiledFn fn = encode_fn();
-  if (!fn) WXF_FAIL(WXF_EUNSUPPORTED, "gemm_tc: cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  if (!fn) WXF_FAIL(WXF_EUNSUPPORTED, "tc: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t b[4], e[4];
+  for (uint32_t i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    b[i] = box[i];
+    e[i] = estr[i];
+    if (i + 1 < rank) gstr[i] = strides[i];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, b, e,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) WXF_FAIL(WXF_EINVAL, "gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  if (r != CUDA_SUCCESS) WXF_FAIL(WXF_EINVAL, "tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
   std::lock_guard<std::mutex> g(mu);
   if (cache.size() > 4096) cache.clear();
   cache.emplace(key, *out);
   return 0;
 }
 
+int make_map_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows}, strides[1] = {ld * 2};
+  const uint32_t box[2] = {(uint32_t)BLOCK_K, box_rows}, es[2] = {1, 1};
+  return make_map(out, ptr, 2, dims, strides, box, es);
+}
+
 template <int BN, int STAGES>
-int launch(const WxfGemmDesc* d, cudaStream_t st) {
-  constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * BN * BLOCK_K * 2;
-  constexpr int SMEM = STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1) + 16 + 1024;
+constexpr int smem_bytes() {
+  return STAGES * (2 * TILE_BYTES + 2 * BN * BLOCK_K * 2) + STG_BYTES + 8 * (2 * STAGES + 1) + 16 + 1024;
+}
+
+template <int BN, int STAGES, bool CONV>
+int launch(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
+           const TcParams& p, dim3 grid, cudaStream_t st) {
+  constexpr int SMEM = smem_bytes<BN, STAGES>();
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16x2_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) WXF_FAIL((int)e, "gemm_tc: cannot opt in to %d bytes of shared memory: %s", SMEM, cudaGetErrorString(e));
+    cudaError_t e =
+        cudaFuncSetAttribute(tc_contract_kernel<BN, STAGES, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", SMEM, cudaGetErrorString(e));
     attr_set = true;
   }
-  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
-  int rc;
-  if ((rc = make_map(&ta_hi, d->a_hi, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, BLOCK_M))) return rc;
-  if ((rc = make_map(&ta_lo, d->a_lo, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, BLOCK_M))) return rc;
-  if ((rc = make_map(&tw_hi, d->w_hi, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K, BN))) return rc;
-  if ((rc = make_map(&tw_lo, d->w_lo, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K, BN))) return rc;
-  GemmTcParams p;
-  p.bias = d->bias;
-  p.res = d->res ? d->res + d->r_off : nullptr;
-  p.out = d->out ? d->out + d->c_off : nullptr;
-  p.out_hi = reinterpret_cast<__half*>(d->out_hi);
-  p.out_lo = reinterpret_cast<__half*>(d->out_lo);
-  p.M = d->M; p.N = d->N; p.K = d->K;
-  p.ldc = d->ldc; p.ldr = d->ldr; p.ldh = d->ldh; p.act = d->act;
-  p.w_scale = ldexpf(1.0f, -d->w_scale_log2);
-  dim3 grid((unsigned)((d->N + BN - 1) / BN), (unsigned)((d->M + BLOCK_M - 1) / BLOCK_M));
-  gemm_f16x2_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
-  WXF_CHECK_LAUNCH("gemm_f16x2_tc");
+  tc_contract_kernel<BN, STAGES, CONV><<<grid, NUM_THREADS, SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
+  WXF_CHECK_LAUNCH("tc_contract");
+  return 0;
+}
+
+int check_epilogue(const char* who, int N, const float* bias, const float* res, const float* out, const void* out_hi,
+                   const void* out_lo, int ldc, int c_off, int ldr, int r_off, int ldh, int h_off) {
+  if (!out && !out_hi) WXF_FAIL(WXF_EINVAL, "%s: no output", who);
+  if ((out_hi == nullptr) != (out_lo == nullptr)) WXF_FAIL(WXF_EINVAL, "%s: out_hi/out_lo must come together", who);
+  if (N & 3) WXF_FAIL(WXF_EUNSUPPORTED, "%s: N=%d must be a multiple of 4", who, N);
+  if (out && (ldc < c_off + N || (ldc & 3) || (c_off & 3) || !wxf_aligned16(out)))
+    WXF_FAIL(WXF_EALIGN, "%s: out stride/alignment", who);
+  if (res && (ldr < r_off + N || (ldr & 3) || (r_off & 3) || !wxf_aligned16(res)))
+    WXF_FAIL(WXF_EALIGN, "%s: res stride/alignment", who);
+  if (out_hi && (ldh < h_off + N || (ldh & 3) || (h_off & 3) || (reinterpret_cast<uintptr_t>(out_hi) & 7) ||
+                 (reinterpret_cast<uintptr_t>(out_lo) & 7)))
+    WXF_FAIL(WXF_EALIGN, "%s: plane stride/alignment", who);
+  if (bias && !wxf_aligned16(bias)) WXF_FAIL(WXF_EALIGN, "%s: bias alignment", who);
   return 0;
 }
 
@@ -373,20 +474,111 @@ int launch(const WxfGemmDesc* d, cudaStream_t st) {
 
 extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
   if (!d || !d->a_hi || !d->a_lo || !d->w_hi || !d->w_lo) WXF_FAIL(WXF_EINVAL, "gemm_tc: null operand");
-  if (!d->out && !d->out_hi) WXF_FAIL(WXF_EINVAL, "gemm_tc: no output");
-  if ((d->out_hi == nullptr) != (d->out_lo == nullptr)) WXF_FAIL(WXF_EINVAL, "gemm_tc: out_hi/out_lo must come together");
   if (d->M <= 0 || d->N <= 0 || d->K <= 0 || d->lda < d->K) WXF_FAIL(WXF_EINVAL, "gemm_tc: bad dims");
   if ((d->lda & 7) || (d->K & 7)) WXF_FAIL(WXF_EALIGN, "gemm_tc: K and lda must be multiples of 8 (16-byte TMA rows)");
   if (!wxf_aligned16(d->a_hi) || !wxf_aligned16(d->a_lo) || !wxf_aligned16(d->w_hi) || !wxf_aligned16(d->w_lo))
     WXF_FAIL(WXF_EALIGN, "gemm_tc: operand planes must be 16-byte aligned");
-  if (d->out && (d->ldc < d->c_off + d->N)) WXF_FAIL(WXF_EINVAL, "gemm_tc: ldc");
-  if (d->res && (d->ldr < d->r_off + d->N)) WXF_FAIL(WXF_EINVAL, "gemm_tc: ldr");
-  if (d->out_hi && d->ldh < d->N) WXF_FAIL(WXF_EINVAL, "gemm_tc: ldh");
-  if (d->out_hi && (!wxf_aligned16(d->out_hi) || !wxf_aligned16(d->out_lo))) WXF_FAIL(WXF_EALIGN, "gemm_tc: out planes alignment");
-  if (d->out && ((d->c_off & 3) || !wxf_aligned16(d->out))) WXF_FAIL(WXF_EALIGN, "gemm_tc: out alignment");
-  if (d->res && ((d->r_off & 3) || !wxf_aligned16(d->res))) WXF_FAIL(WXF_EALIGN, "gemm_tc: res alignment");
+  int rc = check_epilogue("gemm_tc", d->N, d->bias, d->res, d->out, d->out_hi, d->out_lo, d->ldc, d->c_off, d->ldr,
+                          d->r_off, d->ldh, 0);
+  if (rc) return rc;
   if (d->M > (int64_t)65535 * BLOCK_M) WXF_FAIL(WXF_EINVAL, "gemm_tc: M too large for one launch");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->N > 128) return launch<256, 2>(d, st);
-  return launch<128, 3>(d, st);
+  const int BN = d->N > 128 ? 256 : 128;
+  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  if ((rc = make_map_2d(&ta_hi, d->a_hi, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, BLOCK_M))) return rc;
+  if ((rc = make_map_2d(&ta_lo, d->a_lo, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, BLOCK_M))) return rc;
+  if ((rc = make_map_2d(&tw_hi, d->w_hi, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K, BN))) return rc;
+  if ((rc = make_map_2d(&tw_lo, d->w_lo, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K, BN))) return rc;
+  TcParams p{};
+  p.bias = d->bias;
+  p.res = d->res ? d->res + d->r_off : nullptr;
+  p.out = d->out ? d->out + d->c_off : nullptr;
+  p.out_hi = reinterpret_cast<__half*>(d->out_hi);
+  p.out_lo = reinterpret_cast<__half*>(d->out_lo);
+  p.M = d->M; p.N = d->N; p.num_ksteps = (d->K + BLOCK_K - 1) / BLOCK_K;
+  p.ldc = d->ldc; p.ldr = d->ldr; p.ldh = d->ldh; p.act = d->act;
+  p.w_scale = ldexpf(1.0f, -d->w_scale_log2);
+  dim3 grid((unsigned)((d->N + BN - 1) / BN), (unsigned)((d->M + BLOCK_M - 1) / BLOCK_M), 1);
+  if (BN == 256) return launch<256, 2, false>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
+  return launch<128, 3, false>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
+}
+
+extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
+  if (!d || !d->in_hi || !d->in_lo || !d->w_hi || !d->w_lo || !d->taps) WXF_FAIL(WXF_EINVAL, "conv_tc: null operand");
+  if (d->B <= 0 || d->Hi <= 0 || d->Wi <= 0 || d->Cin <= 0 || d->N <= 0 || d->T <= 0 || d->Ho <= 0 || d->Wo <= 0 ||
+      d->lda < d->Cin)
+    WXF_FAIL(WXF_EINVAL, "conv_tc: bad dims");
+  if (d->T > MAX_TAPS) WXF_FAIL(WXF_EUNSUPPORTED, "conv_tc: %d taps > %d", d->T, MAX_TAPS);
+  if (d->stride != 1 && d->stride != 2) WXF_FAIL(WXF_EUNSUPPORTED, "conv_tc: stride must be 1 or 2");
+  if (d->phases != 1 && d->phases != 4) WXF_FAIL(WXF_EINVAL, "conv_tc: phases must be 1 or 4");
+  if ((d->phases == 4) != (d->out_scale == 2) || (d->phases == 1 && d->out_scale != 1))
+    WXF_FAIL(WXF_EINVAL, "conv_tc: phases/out_scale mismatch");
+  if ((d->lda & 7) || (d->cin_pad & 63) || d->cin_pad < d->Cin) WXF_FAIL(WXF_EALIGN, "conv_tc: lda %% 8, cin_pad %% 64");
+  if (!wxf_aligned16(d->in_hi) || !wxf_aligned16(d->in_lo) || !wxf_aligned16(d->w_hi) || !wxf_aligned16(d->w_lo))
+    WXF_FAIL(WXF_EALIGN, "conv_tc: operand planes must be 16-byte aligned");
+  int rc = check_epilogue("conv_tc", d->N, d->bias, d->res, d->out, d->out_hi, d->out_lo, d->ldc, d->c_off, d->ldr,
+                          d->r_off, d->ldh, d->h_off);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  // M tile = bh x bw output pixels (<= 128) chosen to minimise the number of tiles
+  const int s = d->stride;
+  int best_bw = 1, best_bh = 1;
+  int64_t best_tiles = INT64_MAX;
+  for (int bw = (d->Wo < 128 ? d->Wo : 128); bw >= 1; --bw) {
+    int bh = 128 / bw;
+    if (bh > d->Ho) bh = d->Ho;
+    if (bh * s > 256 || bw * s > 256) continue;
+    const int64_t tiles = (int64_t)((d->Wo + bw - 1) / bw) * ((d->Ho + bh - 1) / bh);
+    if (tiles < best_tiles) {
+      best_tiles = tiles;
+      best_bw = bw;
+      best_bh = bh;
+    }
+  }
+  const int bw = best_bw, bh = best_bh;
+  const int BN = d->N > 128 ? 256 : 128;
+  const int K = d->T * d->cin_pad;
+
+  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  {
+    const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Wi, (uint64_t)d->Hi, (uint64_t)d->B};
+    const uint64_t strides[3] = {(uint64_t)d->lda * 2, (uint64_t)d->Wi * d->lda * 2,
+                                 (uint64_t)d->Hi * d->Wi * d->lda * 2};
+    // with an element stride s TMA loads ceil(boxDim/s) elements: boxDim = n*s picks n (driver API documentation)
+    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)(bw * s), (uint32_t)(bh * s), 1};
+    const uint32_t es[4] = {1, (uint32_t)s, (uint32_t)s, 1};
+    if ((rc = make_map(&ta_hi, d->in_hi, 4, dims, strides, box, es))) return rc;
+    if ((rc = make_map(&ta_lo, d->in_lo, 4, dims, strides, box, es))) return rc;
+  }
+  if ((rc = make_map_2d(&tw_hi, d->w_hi, (uint64_t)d->phases * d->N, (uint64_t)K, (uint64_t)K, BN))) return rc;
+  if ((rc = make_map_2d(&tw_lo, d->w_lo, (uint64_t)d->phases * d->N, (uint64_t)K, (uint64_t)K, BN))) return rc;
+
+  TcParams p{};
+  p.bias = d->bias;
+  p.res = d->res ? d->res + d->r_off : nullptr;
+  p.out = d->out ? d->out + d->c_off : nullptr;
+  p.out_hi = d->out_hi ? reinterpret_cast<__half*>(d->out_hi) + d->h_off : nullptr;
+  p.out_lo = d->out_lo ? reinterpret_cast<__half*>(d->out_lo) + d->h_off : nullptr;
+  p.M = 0; p.N = d->N;
+  p.cblocks = d->cin_pad / BLOCK_K;
+  p.cin_pad = d->cin_pad;
+  p.num_ksteps = d->T * p.cblocks;
+  p.ldc = d->ldc; p.ldr = d->ldr; p.ldh = d->ldh; p.act = d->act;
+  p.w_scale = ldexpf(1.0f, -d->w_scale_log2);
+  p.bw = bw; p.bh = bh;
+  p.tiles_x = (d->Wo + bw - 1) / bw;
+  p.tiles_y = (d->Ho + bh - 1) / bh;
+  p.Ho = d->Ho; p.Wo = d->Wo; p.stride = s; p.out_scale = d->out_scale;
+  p.a_bytes = (uint32_t)(bw * bh * BLOCK_K * 2);
+  for (int z = 0; z < d->phases; ++z)
+    for (int t = 0; t < d->T; ++t) {
+      p.taps[z][t][0] = (int16_t)d->taps[(z * d->T + t) * 2];
+      p.taps[z][t][1] = (int16_t)d->taps[(z * d->T + t) * 2 + 1];
+    }
+  const int64_t ntiles = (int64_t)d->B * p.tiles_x * p.tiles_y;
+  if (ntiles > 65535) WXF_FAIL(WXF_EINVAL, "conv_tc: too many tiles for one launch");
+  dim3 grid((unsigned)((d->N + BN - 1) / BN), (unsigned)ntiles, (unsigned)d->phases);
+  if (BN == 256) return launch<256, 2, true>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
+  return launch<128, 3, true>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
 }

@@ -258,11 +258,13 @@ __global__ void gn_finalize_kernel(const float2* __restrict__ part, float* __res
   stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ x, int ldx,
                                                        const float* __restrict__ stats, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float* __restrict__ res,
-                                                       int ldr, float* __restrict__ y, int ldy, int64_t HW, int C,
-                                                       int cpg, int G, int64_t total) {
+                                                       int ldr, float* __restrict__ y, __half* __restrict__ y_hi,
+                                                       __half* __restrict__ y_lo, int ldy, int64_t HW, int C, int cpg,
+                                                       int G, int64_t total) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pix = idx / C;
@@ -273,7 +275,14 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ 
     float v = (x[pix * ldx + c] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
     v = wxf_silu(v);
     if (res) v += res[pix * ldr + c];
-    y[pix * ldy + c] = v;
+    if constexpr (SPLIT) {
+      __half hi, lo;
+      wxf_split_f16x2(v, hi, lo);
+      y_hi[pix * ldy + c] = hi;
+      y_lo[pix * ldy + c] = lo;
+    } else {
+      y[pix * ldy + c] = v;
+    }
   }
 }
 
@@ -297,17 +306,37 @@ extern "C" int wxf_groupnorm_stats(const float* x, int ldx, float* stats, void* 
   return 0;
 }
 
-extern "C" int wxf_groupnorm_silu(const float* x, int ldx, const float* stats, const float* gamma, const float* beta,
-                                  const float* res, int ldr, float* y, int ldy, int B, int64_t HW, int C, int G,
-                                  void* stream) {
+static int gn_silu_launch(const float* x, int ldx, const float* stats, const float* gamma, const float* beta,
+                          const float* res, int ldr, float* y, void* y_hi, void* y_lo, int ldy, int B, int64_t HW,
+                          int C, int G, void* stream) {
   if (B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G) WXF_FAIL(WXF_EINVAL, "groupnorm_silu: bad dims");
   const int64_t total = (int64_t)B * HW * C;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  gn_silu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, stats, gamma, beta, res, ldr, y, ldy, HW,
-                                                                     C, C / G, G, total);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (y_hi)
+    gn_silu_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, stats, gamma, beta, res, ldr, nullptr, (__half*)y_hi,
+                                                           (__half*)y_lo, ldy, HW, C, C / G, G, total);
+  else
+    gn_silu_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, stats, gamma, beta, res, ldr, y, nullptr, nullptr,
+                                                            ldy, HW, C, C / G, G, total);
   WXF_CHECK_LAUNCH("gn_silu");
   return 0;
+}
+
+extern "C" int wxf_groupnorm_silu(const float* x, int ldx, const float* stats, const float* gamma, const float* beta,
+                                  const float* res, int ldr, float* y, int ldy, int B, int64_t HW, int C, int G,
+                                  void* stream) {
+  if (!y) WXF_FAIL(WXF_EINVAL, "groupnorm_silu: null output");
+  return gn_silu_launch(x, ldx, stats, gamma, beta, res, ldr, y, nullptr, nullptr, ldy, B, HW, C, G, stream);
+}
+
+extern "C" int wxf_groupnorm_silu_f16x2(const float* x, int ldx, const float* stats, const float* gamma,
+                                        const float* beta, const float* res, int ldr, void* y_hi, void* y_lo, int ldh,
+                                        int h_off, int B, int64_t HW, int C, int G, void* stream) {
+  if (!y_hi || !y_lo || h_off < 0 || ldh < h_off + C) WXF_FAIL(WXF_EINVAL, "groupnorm_silu_f16x2: bad planes");
+  return gn_silu_launch(x, ldx, stats, gamma, beta, res, ldr, nullptr, (__half*)y_hi + h_off, (__half*)y_lo + h_off, ldh,
+                        B, HW, C, G, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 2
+WXF_ABI_VERSION = 3
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -47,6 +47,19 @@ class WxfGemmDesc(Structure):
     ]
 
 
+class WxfConvTcDesc(Structure):
+    _fields_ = [
+        ("in_hi", c_void_p), ("in_lo", c_void_p), ("w_hi", c_void_p), ("w_lo", c_void_p), ("taps", c_void_p),
+        ("bias", c_void_p), ("res", c_void_p), ("out", c_void_p), ("out_hi", c_void_p), ("out_lo", c_void_p),
+        ("B", c_int32), ("Hi", c_int32), ("Wi", c_int32), ("lda", c_int32), ("Cin", c_int32), ("cin_pad", c_int32),
+        ("N", c_int32), ("T", c_int32), ("stride", c_int32),
+        ("Ho", c_int32), ("Wo", c_int32),
+        ("phases", c_int32), ("out_scale", c_int32),
+        ("ldc", c_int32), ("c_off", c_int32), ("ldr", c_int32), ("r_off", c_int32), ("ldh", c_int32), ("h_off", c_int32),
+        ("act", c_int32), ("w_scale_log2", c_int32),
+    ]
+
+
 _SIGNATURES = {
     "wxf_abi_version": (c_int, []),
     "wxf_last_error": (c_char_p, []),
@@ -56,6 +69,9 @@ _SIGNATURES = {
                                     c_void_p]),
     "wxf_conv_igemm_f32": (c_int, [POINTER(WxfConvDesc), c_void_p]),
     "wxf_gemm_f16x2_tc": (c_int, [POINTER(WxfGemmDesc), c_void_p]),
+    "wxf_conv_f16x2_tc": (c_int, [POINTER(WxfConvTcDesc), c_void_p]),
+    "wxf_groupnorm_silu_f16x2": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                         c_int, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
     "wxf_split_f16x2": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "wxf_window_attention_f16x2": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int] + [c_int] * 7
                                    + [c_float, c_void_p]),

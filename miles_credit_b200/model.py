@@ -114,18 +114,28 @@ def _round_up(v: int, m: int) -> int:
 
 
 class _Plan:
-    """Workspace + ordered kernel launches of one forward for a fixed batch size."""
+    """Workspace + ordered kernel launches of one forward for a fixed batch size.
+
+    ``tensor_cores=True``: contractions run on tcgen05 (f16x2 operand planes); every producer writes the planes its
+    consumer needs, the fp32 residual stream stays fp32.  ``False``: every contraction on the exact-fp32 CUDA-core
+    kernel (validation path).
+    """
 
     def __init__(self, geo: Geometry, wts: PreparedWeights, batch: int, device, tensor_cores: bool = True):
         self.geo, self.batch = geo, batch
+        if tensor_cores:
+            ok = all(c is not None for brs in wts.embeds_tc[1:] for c in brs) and \
+                all(u.up.n % 4 == 0 for u in wts.ups)
+            if not ok:
+                logger.warning("channel counts not multiples of 4: using the exact-fp32 CUDA-core path")
+                tensor_cores = False
         self.tensor_cores = tensor_cores
         f32 = dict(device=device, dtype=torch.float32)
+        f16 = dict(device=device, dtype=torch.float16)
         B = batch
         g = geo
         self.ld0 = wts.cin0_pad
         self.xp = torch.empty((B, g.h_pad, g.w_pad, self.ld0), **f32)
-        st0 = g.stages[0]
-        m0 = B * st0.h * st0.w
         big = max(B * s.h * s.w * s.dim for s in g.stages)
         big = max(big, max(4 * B * u.h_in * u.w_in * u.c_out for u in g.ups))
         big = _round_up(big, 8)
@@ -137,6 +147,13 @@ class _Plan:
         # residual streams: stages 0..2 live in the upper half of their skip-concat buffer
         self.cat = [torch.empty((B, s.h, s.w, 2 * s.dim), **f32) for s in g.stages[:3]]
         self.x3 = torch.empty((B, g.stages[3].h, g.stages[3].w, g.stages[3].dim), **f32)
+        if tensor_cores:
+            self.catp = [(torch.empty((B, s.h, s.w, 2 * s.dim), **f16), torch.empty((B, s.h, s.w, 2 * s.dim), **f16))
+                         for s in g.stages[:3]]
+            s3 = g.stages[3]
+            self.x3p = (torch.empty((B, s3.h, s3.w, s3.dim), **f16), torch.empty((B, s3.h, s3.w, s3.dim), **f16))
+            nmax = max(4 * B * u.h_in * u.w_in * u.c_out for u in g.ups)
+            self.shortp = (torch.empty(nmax, **f16), torch.empty(nmax, **f16))
         self.gn_stats = torch.empty((B, g.dim[0], 2), **f32)
         gn_bytes = max(ops.groupnorm_scratch_bytes(B, 4 * u.h_in * u.w_in, u.c_out) for u in g.ups)
         self.gn_scratch = torch.empty(gn_bytes // 4 + 4, **f32)
@@ -157,10 +174,18 @@ class _Plan:
         desc = ops.make_gemm_desc(a_hi, a_lo, wts, **kw)
         self._add(ops.gemm_f16x2_tc, (desc,), tag, 2.0 * kw["M"] * wts.n * wts.k)
 
+    def _conv_tc(self, in_hi, in_lo, wts, tag, **kw):
+        desc = ops.make_conv_tc_desc(in_hi, in_lo, wts, **kw)
+        m = kw["B"] * kw["Ho"] * kw["Wo"]
+        self._add(ops.conv_f16x2_tc, (desc,), tag, 2.0 * m * wts.n * wts.t * wts.cin * wts.phases)
+
     def _build(self, wts: PreparedWeights):
         g, B = self.geo, self.batch
         add = self._add
+        tc = self.tensor_cores
         src, src_ld, src_h, src_w = self.xp, self.ld0, g.h_pad, g.w_pad
+        src_planes = None
+        scale = float(g.dim_head) ** -0.5
         for st in g.stages:
             s, d = st.index, st.dim
             if s < 3:
@@ -169,21 +194,32 @@ class _Plan:
                 xbuf, ld, xoff = self.x3, d, 0
             xv = xbuf[..., xoff:]  # view: data_ptr carries the channel offset
             m = B * st.h * st.w
-            for br, bw in zip(st.branches, wts.embeds[s]):
-                self._conv(src, bw, xbuf, tag=f"embed{s}.k{br.kernel}", B=B, Hi=src_h, Wi=src_w, lda=src_ld, Ho=st.h,
-                           Wo=st.w, ldc=ld, c_off=xoff + br.c_off)
+            if tc:
+                if s < 3:
+                    xp_hi, xp_lo, pld = self.catp[s][0][..., d:], self.catp[s][1][..., d:], 2 * d
+                else:
+                    xp_hi, xp_lo, pld = self.x3p[0], self.x3p[1], d
+            for bi, (br, bw) in enumerate(zip(st.branches, wts.embeds[s])):
+                if tc and s > 0:
+                    self._conv_tc(src_planes[0], src_planes[1], wts.embeds_tc[s][bi], f"embed{s}.k{br.kernel}", B=B,
+                                  Hi=src_h, Wi=src_w, lda=src_ld, Ho=st.h, Wo=st.w, out=xbuf, ldc=ld,
+                                  c_off=xoff + br.c_off)
+                else:
+                    self._conv(src, bw, xbuf, tag=f"embed{s}.k{br.kernel}", B=B, Hi=src_h, Wi=src_w, lda=src_ld,
+                               Ho=st.h, Wo=st.w, ldc=ld, c_off=xoff + br.c_off)
             ln = self.ln[: m * d]
             wide = self.scratch[: m * 4 * d]
             # fp16 operand planes alias the same workspaces (2 planes x 2 bytes = the fp32 footprint)
             ln_hi, ln_lo = self.ln16[: m * d], self.ln16[self.ln.numel(): self.ln.numel() + m * d]
             hid_off = self.scratch.numel()
             hid_hi, hid_lo = self.scratch16[: m * 4 * d], self.scratch16[hid_off: hid_off + m * 4 * d]
-            scale = float(g.dim_head) ** -0.5
-            for layer in wts.blocks[s]:
-                for att, ff in ((layer[0], layer[1]), (layer[2], layer[3])):
+            n_layers = len(wts.blocks[s])
+            for li, layer in enumerate(wts.blocks[s]):
+                for half, (att, ff) in enumerate(((layer[0], layer[1]), (layer[2], layer[3]))):
                     L = att.wsz * att.wsz
                     attn_cost = (4.0 * m * L * d, 16.0 * m * d)
-                    if self.tensor_cores:
+                    last = li == n_layers - 1 and half == 1
+                    if tc:
                         add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, att.ln_g, att.ln_b, m, d), "layernorm", 0,
                             8.0 * m * d)
                         self._gemm(ln_hi, ln_lo, att.qkv_tc, "qkv", M=m, lda=d, out=wide, ldc=3 * d)
@@ -194,7 +230,11 @@ class _Plan:
                             8.0 * m * d)
                         self._gemm(ln_hi, ln_lo, ff.fc1_tc, "ff1", M=m, lda=d, out_hi=hid_hi, out_lo=hid_lo, ldh=4 * d,
                                    act=_lib.ACT_GELU)
-                        self._gemm(hid_hi, hid_lo, ff.fc2_tc, "ff2", M=m, lda=4 * d, out=xv, ldc=ld, res=xv, ldr=ld)
+                        if last:  # the stage output also feeds the next cross-embed / the decoder: emit its planes
+                            self._gemm(hid_hi, hid_lo, ff.fc2_tc, "ff2", M=m, lda=4 * d, out=xv, ldc=ld, res=xv, ldr=ld,
+                                       out_hi=xp_hi, out_lo=xp_lo, ldh=pld)
+                        else:
+                            self._gemm(hid_hi, hid_lo, ff.fc2_tc, "ff2", M=m, lda=4 * d, out=xv, ldc=ld, res=xv, ldr=ld)
                         continue
                     add(ops.layernorm, (xv, ld, ln, d, att.ln_g, att.ln_b, m, d), "layernorm", 0, 8.0 * m * d)
                     self._conv(ln, att.qkv, wide, tag="qkv", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=3 * d)
@@ -208,29 +248,58 @@ class _Plan:
                     self._conv(wide, ff.fc2, xv, tag="ff2", B=B, Hi=st.h, Wi=st.w, lda=4 * d, Ho=st.h, Wo=st.w, ldc=ld,
                                res=xv, ldr=ld)
             src, src_ld, src_h, src_w = xv, ld, st.h, st.w
+            if tc:
+                src_planes = (xp_hi, xp_lo)
 
-        # decoder: UpBlock x3 (crossformer.py:107-122), outputs land in the lower half of the skip buffers
+        # decoder: UpBlock x3 (crossformer.py:107-122); outputs land in the lower half of the skip buffers
+        st0 = g.stages[0]
+        big2 = 2 * (B * st0.h * st0.w * st0.dim)
+        self.y_dec = self.scratch[big2: big2 + B * g.h_dec * g.w_dec * g.output_channels]
+        head_tc = tc and wts.head_tc is not None
         dec_in, dec_ld = self.x3, g.stages[3].dim
+        dec_planes = self.x3p if tc else None
         for up, uw, skip in zip(g.ups, wts.ups, (2, 1, 0)):
             ho, wo, c = 2 * up.h_in, 2 * up.w_in, up.c_out
             n = B * ho * wo * c
             short = self.ln[:n]
             a, b = self.scratch[:n], self.scratch[n: 2 * n]
+            dst = self.cat[skip]
+            if tc:
+                sp_hi, sp_lo = self.shortp[0][:n], self.shortp[1][:n]
+                b_hi, b_lo = self.scratch16[2 * n: 3 * n], self.scratch16[3 * n: 4 * n]
+                self._conv_tc(dec_planes[0], dec_planes[1], uw.up_tc, "dec_up", B=B, Hi=up.h_in, Wi=up.w_in, lda=dec_ld,
+                              Ho=up.h_in, Wo=up.w_in, out=short, ldc=c, out_hi=sp_hi, out_lo=sp_lo, ldh=c)
+                self._conv_tc(sp_hi, sp_lo, uw.convs_tc[0], "dec_conv3x3", B=B, Hi=ho, Wi=wo, lda=c, Ho=ho, Wo=wo, out=a,
+                              ldc=c)
+                add(ops.groupnorm_silu_f16x2, (a, c, self.gn_stats, self.gn_scratch, uw.gn_w[0], uw.gn_b[0], None, 0,
+                                               b_hi, b_lo, c, 0, B, ho * wo, c, up.groups), "groupnorm_silu", 0, 8.0 * n)
+                self._conv_tc(b_hi, b_lo, uw.convs_tc[1], "dec_conv3x3", B=B, Hi=ho, Wi=wo, lda=c, Ho=ho, Wo=wo, out=a,
+                              ldc=c)
+                if skip == 0 and not head_tc:  # fp32 head (odd channel count): keep the fp32 concat buffer
+                    add(ops.groupnorm_silu, (a, c, self.gn_stats, self.gn_scratch, uw.gn_w[1], uw.gn_b[1], short, c,
+                                             dst, 2 * c, B, ho * wo, c, up.groups), "groupnorm_silu", 0, 16.0 * n)
+                else:
+                    add(ops.groupnorm_silu_f16x2, (a, c, self.gn_stats, self.gn_scratch, uw.gn_w[1], uw.gn_b[1], short,
+                                                   c, self.catp[skip][0], self.catp[skip][1], 2 * c, 0, B, ho * wo, c,
+                                                   up.groups), "groupnorm_silu", 0, 12.0 * n)
+                dec_planes, dec_ld = self.catp[skip], 2 * c
+                dec_in = dst
+                continue
             self._conv(dec_in, uw.up, short, tag="dec_up", B=B, Hi=up.h_in, Wi=up.w_in, lda=dec_ld, Ho=up.h_in,
                        Wo=up.w_in, ldc=c)
             self._conv(short, uw.convs[0], a, tag="dec_conv3x3", B=B, Hi=ho, Wi=wo, lda=c, Ho=ho, Wo=wo, ldc=c)
             add(ops.groupnorm_silu, (a, c, self.gn_stats, self.gn_scratch, uw.gn_w[0], uw.gn_b[0], None, 0, b, c, B,
                                      ho * wo, c, up.groups), "groupnorm_silu", 0, 12.0 * n)
             self._conv(b, uw.convs[1], a, tag="dec_conv3x3", B=B, Hi=ho, Wi=wo, lda=c, Ho=ho, Wo=wo, ldc=c)
-            dst = self.cat[skip]
             add(ops.groupnorm_silu, (a, c, self.gn_stats, self.gn_scratch, uw.gn_w[1], uw.gn_b[1], short, c, dst,
                                      2 * c, B, ho * wo, c, up.groups), "groupnorm_silu", 0, 16.0 * n)
             dec_in, dec_ld = dst, 2 * c
-        st0 = g.stages[0]
-        big2 = 2 * (B * st0.h * st0.w * st0.dim)
-        self.y_dec = self.scratch[big2: big2 + B * g.h_dec * g.w_dec * g.output_channels]
-        self._conv(dec_in, wts.head, self.y_dec, tag="dec_head", B=B, Hi=st0.h, Wi=st0.w, lda=dec_ld, Ho=st0.h,
-                   Wo=st0.w, ldc=g.output_channels)
+        if head_tc:
+            self._conv_tc(dec_planes[0], dec_planes[1], wts.head_tc, "dec_head", B=B, Hi=st0.h, Wi=st0.w, lda=dec_ld,
+                          Ho=st0.h, Wo=st0.w, out=self.y_dec, ldc=g.output_channels)
+        else:
+            self._conv(dec_in, wts.head, self.y_dec, tag="dec_head", B=B, Hi=st0.h, Wi=st0.w, lda=dec_ld, Ho=st0.h,
+                       Wo=st0.w, ldc=g.output_channels)
 
     def _pad(self, x):
         g = self.geo

@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import lib as _lib
-from .lib import WxfConvDesc, WxfGemmDesc
+from .lib import WxfConvDesc, WxfConvTcDesc, WxfGemmDesc
 from .weights import ConvWeights
 
 LAUNCHES = 0
@@ -97,6 +97,49 @@ def gemm_f16x2_tc(desc: WxfGemmDesc):
     st = _lib.load().wxf_gemm_f16x2_tc(ctypes.byref(desc), _stream())
     _lib.check(st, "wxf_gemm_f16x2_tc")
     LAUNCHES += 1
+
+
+def make_conv_tc_desc(in_hi: torch.Tensor, in_lo: torch.Tensor, wts, *, B: int, Hi: int, Wi: int, lda: int, Ho: int,
+                      Wo: int, out: Optional[torch.Tensor] = None, ldc: int = 0, c_off: int = 0,
+                      res: Optional[torch.Tensor] = None, ldr: int = 0, r_off: int = 0,
+                      out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None, ldh: int = 0,
+                      h_off: int = 0, act: int = 0) -> WxfConvTcDesc:
+    """Descriptor of one tensor-core implicit-GEMM convolution; ``wts`` is a weights.ConvTcWeights."""
+    d = WxfConvTcDesc()
+    d.in_hi, d.in_lo = in_hi.data_ptr(), in_lo.data_ptr()
+    d.w_hi, d.w_lo = wts.w_hi.data_ptr(), wts.w_lo.data_ptr()
+    d.taps = ctypes.addressof(wts.taps_host)
+    d.bias, d.res, d.out = _ptr(wts.bias), _ptr(res), _ptr(out)
+    d.out_hi, d.out_lo = _ptr(out_hi), _ptr(out_lo)
+    d.B, d.Hi, d.Wi, d.lda, d.Cin, d.cin_pad = B, Hi, Wi, lda, wts.cin, wts.cin_pad
+    d.N, d.T, d.stride = wts.n, wts.t, wts.stride
+    d.Ho, d.Wo = Ho, Wo
+    d.phases, d.out_scale = wts.phases, wts.out_scale
+    d.ldc, d.c_off, d.ldr, d.r_off, d.ldh, d.h_off = ldc, c_off, ldr, r_off, ldh, h_off
+    d.act, d.w_scale_log2 = act, wts.scale_log2
+    d._keep = wts  # the host tap table must outlive the descriptor
+    return d
+
+
+def conv_f16x2_tc(desc: WxfConvTcDesc):
+    global LAUNCHES
+    st = _lib.load().wxf_conv_f16x2_tc(ctypes.byref(desc), _stream())
+    _lib.check(st, "wxf_conv_f16x2_tc")
+    LAUNCHES += 1
+
+
+def groupnorm_silu_f16x2(x: torch.Tensor, ldx: int, stats: torch.Tensor, scratch: torch.Tensor, gamma: torch.Tensor,
+                         beta: torch.Tensor, res: Optional[torch.Tensor], ldr: int, y_hi: torch.Tensor,
+                         y_lo: torch.Tensor, ldh: int, h_off: int, B: int, HW: int, C: int, G: int, eps: float = 1e-5):
+    """GroupNorm statistics + normalise/affine/SiLU (+ residual), result as fp16 hi/lo operand planes."""
+    global LAUNCHES
+    L = _lib.load()
+    st = L.wxf_groupnorm_stats(x.data_ptr(), ldx, stats.data_ptr(), scratch.data_ptr(), B, HW, C, G, eps, _stream())
+    _lib.check(st, "wxf_groupnorm_stats")
+    st = L.wxf_groupnorm_silu_f16x2(x.data_ptr(), ldx, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(res), ldr,
+                                    y_hi.data_ptr(), y_lo.data_ptr(), ldh, h_off, B, HW, C, G, _stream())
+    _lib.check(st, "wxf_groupnorm_silu_f16x2")
+    LAUNCHES += 3
 
 
 def window_attention_f16x2(qkv: torch.Tensor, ldq: int, bias_t: torch.Tensor, out_hi: torch.Tensor, out_lo: torch.Tensor,

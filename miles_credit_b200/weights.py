@@ -146,6 +146,46 @@ def gemm_weights(w: torch.Tensor, bias) -> GemmWeights:
 
 
 @dataclass
+class ConvTcWeights:
+    """Tensor-core operand planes of a convolution: [phases, N, T*cin_pad] fp16 hi/lo of W * 2^scale_log2."""
+
+    w_hi: torch.Tensor
+    w_lo: torch.Tensor
+    taps_host: object  # ctypes int32 array [phases*T*2], read by the host at launch
+    bias: Optional[torch.Tensor]
+    n: int
+    t: int
+    cin: int
+    cin_pad: int
+    stride: int
+    phases: int
+    out_scale: int
+    scale_log2: int
+
+
+def conv_tc_weights(cw: "ConvWeights") -> ConvTcWeights:
+    """Re-lay a ConvWeights ([phases, N, T*Cin] fp32) as channel-padded, pre-scaled fp16 hi/lo planes."""
+    import ctypes
+
+    cin_pad = (cw.cin + 63) // 64 * 64
+    w = cw.w.reshape(cw.phases, cw.n, cw.t, cw.cin).float()
+    if cin_pad != cw.cin:
+        wp = w.new_zeros((cw.phases, cw.n, cw.t, cin_pad))
+        wp[..., : cw.cin] = w
+        w = wp
+    amax = float(w.abs().max())
+    k = 0 if amax == 0.0 else int(math.floor(math.log2(1024.0 / amax)))
+    k = max(min(k, 24), -24)
+    ws = (w * (2.0 ** k)).reshape(cw.phases, cw.n, cw.t * cin_pad)
+    hi = ws.half()
+    lo = (ws - hi.float()).half()
+    flat = [int(v) for v in cw.taps.reshape(-1).cpu().tolist()]
+    taps = (ctypes.c_int32 * len(flat))(*flat)
+    return ConvTcWeights(hi.contiguous(), lo.contiguous(), taps, cw.bias, cw.n, cw.t, cw.cin, cin_pad, cw.stride, cw.phases,
+                         cw.out_scale, k)
+
+
+@dataclass
 class AttentionWeights:
     ln_g: torch.Tensor
     ln_b: torch.Tensor
@@ -174,6 +214,8 @@ class UpBlockWeights:
     convs: List[ConvWeights]
     gn_w: List[torch.Tensor]
     gn_b: List[torch.Tensor]
+    up_tc: Optional[ConvTcWeights] = None
+    convs_tc: Optional[List[ConvTcWeights]] = None
 
 
 @dataclass
@@ -183,6 +225,8 @@ class PreparedWeights:
     ups: List[UpBlockWeights]
     head: ConvWeights
     cin0_pad: int
+    embeds_tc: Optional[List[List[Optional[ConvTcWeights]]]] = None
+    head_tc: Optional[ConvTcWeights] = None
 
 
 def prepare(sd: Dict[str, torch.Tensor], geo: Geometry, cin0_pad: int) -> PreparedWeights:
@@ -228,4 +272,11 @@ def prepare(sd: Dict[str, torch.Tensor], geo: Geometry, cin0_pad: int) -> Prepar
                 [sd[f"{n}.b.{gi}.weight"].float().contiguous() for gi in (1, 4)],
                 [sd[f"{n}.b.{gi}.bias"].float().contiguous() for gi in (1, 4)]))
         head = convt_k4s2p1_weights(fold_spectral_norm(sd, "up_block4", 1), sd["up_block4.bias"])
-    return PreparedWeights(embeds, blocks, ups, head, cin0_pad)
+        # tensor-core planes for every convolution whose output-channel count suits the epilogue (N % 4 == 0)
+        for uw in ups:
+            uw.up_tc = conv_tc_weights(uw.up)
+            uw.convs_tc = [conv_tc_weights(c) for c in uw.convs]
+        embeds_tc = [[(conv_tc_weights(c) if (s > 0 and c.n % 4 == 0 and c.t <= 64) else None) for c in brs]
+                     for s, brs in enumerate(embeds)]
+        head_tc = conv_tc_weights(head) if head.n % 4 == 0 else None
+    return PreparedWeights(embeds, blocks, ups, head, cin0_pad, embeds_tc, head_tc)

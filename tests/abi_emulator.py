@@ -33,7 +33,7 @@ class EmulatedLib:
         self.calls = []
 
     def wxf_abi_version(self):
-        return 2
+        return 3
 
     def wxf_last_error(self):
         return b"emulator"
@@ -125,6 +125,65 @@ class EmulatedLib:
             hi, lo = self._split(v)
             self._harr(d.out_hi, (M - 1) * d.ldh + N).as_strided((M, N), (d.ldh, 1)).copy_(hi)
             self._harr(d.out_lo, (M - 1) * d.ldh + N).as_strided((M, N), (d.ldh, 1)).copy_(lo)
+        return 0
+
+    def wxf_conv_f16x2_tc(self, dref, stream):
+        d = dref._obj
+        self.calls.append("conv_tc")
+        if d.N % 4 or d.cin_pad % 64 or d.T > 64:
+            return -3
+        B, Hi, Wi, lda, Cin, cp, N, T, s = d.B, d.Hi, d.Wi, d.lda, d.Cin, d.cin_pad, d.N, d.T, d.stride
+        Ho, Wo, P, osc = d.Ho, d.Wo, d.phases, d.out_scale
+        n_in = ((B * Hi - 1) * Wi + Wi - 1) * lda + Cin
+        shape, strides = (B, Hi, Wi, Cin), (Hi * Wi * lda, Wi * lda, lda, 1)
+        x_hi = self._harr(d.in_hi, n_in).as_strided(shape, strides).double()
+        x_lo = self._harr(d.in_lo, n_in).as_strided(shape, strides).double()
+        w_hi = self._harr(d.w_hi, P * N * T * cp).view(P, N, T, cp)[..., :Cin].double()
+        w_lo = self._harr(d.w_lo, P * N * T * cp).view(P, N, T, cp)[..., :Cin].double()
+        taps = _t(_iarr(d.taps, P * T * 2)).view(P, T, 2)
+        Hout, Wout = Ho * osc, Wo * osc
+
+        def view(ptr, ld, off, harr=False):
+            n_el = ((B * Hout - 1) * Wout + Wout - 1) * ld + off + N
+            base = self._harr(ptr, n_el) if harr else _t(_arr(ptr, n_el))
+            return base.as_strided((B, Hout, Wout, N), (Hout * Wout * ld, Wout * ld, ld, 1), off)
+
+        res = view(d.res, d.ldr, d.r_off).clone() if d.res else None
+        bias = _t(_arr(d.bias, N)) if d.bias else None
+        oy, ox = torch.arange(Ho) * s, torch.arange(Wo) * s
+        for z in range(P):
+            acc = torch.zeros(B, Ho, Wo, N, dtype=torch.float64)
+            for t in range(T):
+                dy, dx = int(taps[z, t, 0]), int(taps[z, t, 1])
+                iy, ix = oy + dy, ox + dx
+                mask = ((iy >= 0) & (iy < Hi))[:, None] & ((ix >= 0) & (ix < Wi))[None, :]
+                gh = x_hi[:, iy.clamp(0, Hi - 1)][:, :, ix.clamp(0, Wi - 1)] * mask[None, :, :, None]
+                gl = x_lo[:, iy.clamp(0, Hi - 1)][:, :, ix.clamp(0, Wi - 1)] * mask[None, :, :, None]
+                acc += gh @ w_lo[z, :, t].t() + gl @ w_hi[z, :, t].t() + gh @ w_hi[z, :, t].t()
+            v = acc.float() * (2.0 ** -d.w_scale_log2)
+            if bias is not None:
+                v = v + bias
+            if d.act == 1:
+                v = 0.5 * v * (1 + torch.erf(v * 0.7071067811865476))
+            py, px = z >> 1, z & 1
+            sl = (slice(None), slice(py, None, osc), slice(px, None, osc)) if osc > 1 else (slice(None),) * 3
+            if res is not None:
+                v = v + res[sl]
+            if d.out:
+                view(d.out, d.ldc, d.c_off)[sl] = v
+            if d.out_hi:
+                hi, lo = self._split(v)
+                view(d.out_hi, d.ldh, d.h_off, True)[sl] = hi
+                view(d.out_lo, d.ldh, d.h_off, True)[sl] = lo
+        return 0
+
+    def wxf_groupnorm_silu_f16x2(self, x, ldx, stats, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, B, HW, C, G, stream):
+        tmp = np.zeros(B * HW * C, dtype=np.float32)
+        self.wxf_groupnorm_silu(x, ldx, stats, gamma, beta, res, ldr, tmp.ctypes.data, C, B, HW, C, G, stream)
+        hi, lo = self._split(torch.from_numpy(tmp).view(B * HW, C))
+        n_el = (B * HW - 1) * ldh + h_off + C
+        self._harr(y_hi, n_el).as_strided((B * HW, C), (ldh, 1), h_off).copy_(hi)
+        self._harr(y_lo, n_el).as_strided((B * HW, C), (ldh, 1), h_off).copy_(lo)
         return 0
 
     def wxf_window_attention_f16x2(self, qkv, ldq, biasT, out_hi, out_lo, ldh, B, H, W, d, dh, wsz, kind, scale, stream):

@@ -80,3 +80,22 @@ def test_rollout_two_steps_vs_oracle():
         assert relmax(y.cpu(), yo) < TOL
         xo = oracle.rollout_update(xo, yo, geo)
     assert relmax(xs.cpu(), xo) < TOL
+
+
+@pytest.mark.parametrize("exact", [False, True], ids=["tensorcore", "exactfp32"])
+def test_forward_wxformer_6h_1deg_vs_oracle(exact):
+    """BASELINE config[1]: the 0.25-degree architecture (dims 128..1024, depth 2/2/8/2, lws 10) on the 181x360 grid."""
+    kw = workload("wxformer_6h_1deg")
+    geo = build_geometry(**kw)
+    sd = synthetic_state_dict(geo, seed=1000, sn_iters=5)
+    x = synthetic_input(geo, batch=1, seed=1000)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    with torch.no_grad():
+        ref = oracle.forward(x, sd, geo)
+    model = CrossFormerB200(**kw)
+    model.exact_fp32 = exact
+    model.load_state_dict(sd, strict=True)
+    y = model.cuda().eval()(x.cuda())
+    err = relmax(y.cpu(), ref)
+    print(f"wxformer_6h_1deg ({'exact fp32' if exact else 'tensor cores'}): rel-max vs oracle = {err:.3e}")
+    assert err < TOL

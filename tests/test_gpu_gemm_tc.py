@@ -55,7 +55,7 @@ def test_gemm_tc_plain(m, n, k):
     err = float((got - ref).abs().max() / ref.abs().max())
     print(f"gemm_tc {m}x{n}x{k}: rel-max {err:.3e}")
     assert torch.isfinite(got).all()
-    assert err < 3e-6
+    assert err < 4e-6
 
 
 def test_gemm_tc_epilogues_match_exact_kernel():

@@ -44,3 +44,24 @@ def test_plan_through_emulated_abi_matches_reference(golden_dir, emulated, case,
     assert float((s0 - fx["taps"]["s0.out"]).abs().max() / fx["taps"]["s0.out"].abs().max()) < 1e-5
     assert emulated.calls.count("attention") == 2 * sum(geo.depth)
     assert (emulated.calls.count("gemm_tc") == 8 * sum(geo.depth)) == tensor_cores
+    if tensor_cores:  # stage 1-3 cross-embed (6) + decoder (3 x 3) run as tensor-core convolutions
+        assert emulated.calls.count("conv_tc") >= 15
+
+
+def test_plan_tensor_core_head_vs_oracle(emulated):
+    """Output channel count divisible by 4: the k4s2p1 transposed-conv head also runs as a tensor-core conv."""
+    from miles_credit_b200.geometry import workload
+    from oracle import crossformer_oracle as oracle
+
+    kw = dict(workload("unit"), output_only_channels=4, depth=[1, 1, 1, 1])
+    geo = build_geometry(**kw)
+    sd = synthetic_state_dict(geo, seed=11)
+    wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
+    assert wts.head_tc is not None
+    plan = wmodel._Plan(geo, wts, 1, torch.device("cpu"), True)
+    x = synthetic_input(geo, batch=1, seed=11)
+    y = plan.run(x)
+    with torch.no_grad():
+        ref = oracle.forward(x, sd, geo)
+    assert float((y - ref).abs().max() / ref.abs().max()) < 2e-5
+    assert emulated.calls.count("conv_tc") == 6 + 9 + 1

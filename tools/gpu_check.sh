@@ -3,9 +3,9 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt
-timeout 600 python -m pytest tests/test_gpu_gemm_tc.py -q -m gpu -s --timeout 300 2>&1 | tail -60 > gpurun_out/pytest_gemm_tc.log
+timeout 600 python -m pytest tests/test_gpu_gemm_tc.py tests/test_gpu_conv_tc.py -q -m gpu -s --timeout 300 2>&1 | tail -60 > gpurun_out/pytest_gemm_tc.log
 echo "pytest gemm_tc exit ${PIPESTATUS[0]}" >> gpurun_out/pytest_gemm_tc.log
-timeout 900 python -m pytest tests -q -m gpu --timeout 600 --deselect tests/test_gpu_gemm_tc.py -s 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -q -m gpu --timeout 600 --deselect tests/test_gpu_gemm_tc.py --deselect tests/test_gpu_conv_tc.py -s 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
 echo "pytest exit ${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
