@@ -60,5 +60,33 @@ def test_library_exports_every_declared_symbol():
     assert set(wlib._SIGNATURES) <= set(names)
 
 
-def test_credit_registry_if_importable():
-    pytest.importorskip("credit.models", reason="CREDIT not on sys.path (GPU box)")
+def test_credit_registry_plugin(tmp_path):
+    """With CREDIT present (build container): `type: crossformer_b200` + custom_models goes through load_model()."""
+    import subprocess
+    import sys
+
+    if not os.path.isdir("/root/reference/credit"):
+        pytest.skip("CREDIT sources not mounted (GPU box)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import sys, types, torch
+from torch import nn
+sys.path.insert(0, "/root/reference"); sys.path.insert(0, {root!r})
+stub = types.ModuleType("credit.postblock.gen1")
+class PostBlock(nn.Module): pass
+stub.PostBlock = PostBlock
+sys.modules["credit.postblock.gen1"] = stub
+from credit.models import load_model
+from credit.models.base_model import BaseModel
+from miles_credit_b200.geometry import workload
+conf = {{"custom_models": [{os.path.join(root, "miles_credit_b200", "credit_plugin.py")!r}],
+        "model": dict(workload("unit"), type="crossformer_b200")}}
+m = load_model(conf)
+assert isinstance(m, BaseModel) and type(m).__name__ == "CrossFormerB200", type(m)
+ref = load_model({{"model": dict(workload("unit"), type="crossformer")}})
+assert {{k: tuple(v.shape) for k, v in ref.state_dict().items()}} == {{k: tuple(v.shape) for k, v in m.state_dict().items()}}
+m.load_state_dict(ref.state_dict(), strict=True)
+print("ok")
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
