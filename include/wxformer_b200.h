@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 3
+#define WXF_ABI_VERSION 4
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -54,6 +54,9 @@ const char* wxf_last_error(void);
  */
 int wxf_pad_to_pixel_major(const float* x, float* xp, int B, int C, int T, int H, int W,
                            int pt, int pb, int pl, int pr, int mode, int ld, void* stream);
+/* Same pass, result written as fp16 hi/lo operand planes [B, Hp, Wp, ld] (input of the stage-0 cross-embed). */
+int wxf_pad_to_pixel_major_f16x2(const float* x, void* xp_hi, void* xp_lo, int B, int C, int T, int H, int W,
+                                 int pt, int pb, int pl, int pr, int mode, int ld, void* stream);
 
 /*
  * Channel LayerNorm at every pixel (credit/models/crossformer.py:182-192):
@@ -176,6 +179,32 @@ typedef struct WxfConvTcDesc {
 } WxfConvTcDesc;
 
 int wxf_conv_f16x2_tc(const WxfConvTcDesc* desc, void* stream);
+
+/*
+ * Stage-0 CrossEmbedLayer branch (Conv2d k x k, stride 2, zero pad p = (k-2)/2, few output channels;
+ * crossformer.py:139-152) as a Toeplitz-lifted implicit GEMM on the tensor cores: the kernel column
+ * kx = 2j + r is split and j is folded into the GEMM's N dimension,
+ *     P[oy, m, (j, c)] = sum_{ky, r, ci} in[2 oy + ky - p, 2 m + r - p, ci] * W[c, ci, ky, 2j + r]
+ *     out[oy, ox, c]   = bias[c] + sum_j P[oy, ox + j, (j, c)]
+ * so N = (k/2)*ch instead of ch.  in planes: [B, Hi, Wi, lda] fp16 (Cin <= 64, zero-padded to 64 by TMA);
+ * w planes: [(k/2)*ch, 2k*64] fp16 with row (j, c), column (ky, r, ci), pre-scaled by 2^w_scale_log2;
+ * out: fp32 out[pixel*ldc + c_off + c].  Requires k even, (k/2)*ch <= 256, ch % 4 == 0.
+ */
+typedef struct WxfToeplitzDesc {
+  const void* in_hi;
+  const void* in_lo;
+  const void* w_hi;
+  const void* w_lo;
+  const float* bias;
+  float* out;
+  int32_t B, Hi, Wi, lda, Cin, cin_pad;
+  int32_t ch, kernel, pad;
+  int32_t Ho, Wo;
+  int32_t ldc, c_off;
+  int32_t w_scale_log2;
+} WxfToeplitzDesc;
+
+int wxf_cross_embed_toeplitz_tc(const WxfToeplitzDesc* desc, void* stream);
 
 /* Split an fp32 [M, ldx] matrix (first d columns) into fp16 hi/lo planes [M, ldh] (test/utility pass). */
 int wxf_split_f16x2(const float* x, int ldx, void* hi, void* lo, int ldh, int64_t M, int d, void* stream);

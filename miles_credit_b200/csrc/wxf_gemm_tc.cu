@@ -5,6 +5,14 @@
 //               {64 channels, bw pixels (element stride s), bh rows (element stride s), 1 image} of the
 //               pixel-major input, so there is no im2col buffer and zero padding is TMA's out-of-bounds fill.
 //               Transposed convolutions run as 4 output-parity phases (gridDim.z).
+//   TOEP mode : the stage-0 cross-embed (k in {4,8,16,32}, stride 2, only 16..64 output channels).  A direct
+//               implicit GEMM would have N = 16: the tensor core idles on operand traffic.  Instead the kernel
+//               column kx = 2j + r is split; the tap index j is folded into the GEMM's N dimension:
+//                   P[oy, m, (j, c)] = sum_{ky, r, ci} X[2 oy + ky - p, 2 m + r - p, ci] * W[c, ci, ky, 2j + r]
+//                   out[oy, ox, c]   = sum_j P[oy, ox + j, (j, c)]
+//               so N = (k/2) * channels (128..256), K-steps = 2k taps (ky, r) of 64 channels, and the A tile of a
+//               K-step is again one TMA box (128 pixels at element stride 2).  The epilogue stages P in shared
+//               memory (reusing the operand ring) and does the diagonal sum over j.
 //
 // Precision scheme "f16x2": every fp32 operand is carried as two fp16 planes (hi = fp16(x), lo = fp16(x - hi),
 // 22 significant bits); a product is three tcgen05.mma passes  A_hi W_lo + A_lo W_hi + A_hi W_hi  with fp32
@@ -35,6 +43,7 @@ constexpr int STG_LD = 36;                         // floats per staged row (32 
 constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;     // 4 epilogue warps
 constexpr uint32_t SPIN_LIMIT = 1u << 22;          // mbarrier waits trap instead of hanging the GPU
 constexpr int MAX_TAPS = 64;
+constexpr int MODE_GEMM = 0, MODE_CONV = 1, MODE_TOEP = 2;
 
 struct TcParams {
   const float* bias;
@@ -53,6 +62,7 @@ struct TcParams {
   int bw, bh, tiles_x, tiles_y;
   int Ho, Wo, stride, out_scale;
   uint32_t a_bytes;   // bytes of one A plane box
+  int step, J, ch;    // Toeplitz mode: tile step along x (128 - (J-1)), taps folded into N, channels of the branch
   int16_t taps[4][MAX_TAPS][2];  // [phase][tap] = (dy, dx); only [0] used when phases == 1
 };
 
@@ -137,7 +147,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 
 // ---- kernel --------------------------------------------------------------------------------------
 
-template <int BN, int STAGES, bool CONV>
+template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
@@ -146,6 +156,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * W_BYTES;
   constexpr int NACC = 512 / BN;        // TMEM accumulators: [0] cross terms, [1..] main term split along K
   constexpr int NMAIN = NACC - 1;
+  constexpr bool CONV = MODE != MODE_GEMM;   // operand staging of TOEP is the conv staging (taps = (ky, r))
   // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 
@@ -173,7 +184,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     tb = blockIdx.y / per_img;
     const int rem = blockIdx.y - tb * per_img;
     oy0 = (rem / p.tiles_x) * p.bh;
-    ox0 = (rem % p.tiles_x) * p.bw;
+    ox0 = (rem % p.tiles_x) * (MODE == MODE_TOEP ? p.step : p.bw);
   } else {
     m0 = (int64_t)blockIdx.y * BLOCK_M;
   }
@@ -250,6 +261,51 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     }
   } else {
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) ----
+    if constexpr (MODE == MODE_TOEP) {
+      const int quarter = warp & 3;
+      const int used_main = num_k < NMAIN ? num_k : NMAIN;
+      constexpr int SLD = BN + 4;
+      float* S = reinterpret_cast<float*>(gen);  // the operand ring is idle once the accumulators are complete
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const int trow = quarter * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c * 32 >= p.N) break;
+        float v[32];
+        uint32_t r[32];
+        tmem_ld32(lane_base + (uint32_t)(c * 32), r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+#pragma unroll 1
+        for (int a = 1; a <= used_main; ++a) {
+          tmem_ld32(lane_base + (uint32_t)(a * BN + c * 32), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(S + trow * SLD + c * 32 + j) =
+              make_float4(v[j] * p.w_scale, v[j + 1] * p.w_scale, v[j + 2] * p.w_scale, v[j + 3] * p.w_scale);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+      // diagonal sum: out[ox0 + i, c] = sum_j P[i + j, j*ch + c]
+      const int i = trow;
+      const int ox = ox0 + i;
+      if (i < p.step && ox < p.Wo) {
+        const int64_t pix = ((int64_t)tb * p.Ho + oy0) * p.Wo + ox;
+        float* orow = p.out + pix * p.ldc;
+        for (int c4 = 0; c4 < p.ch; c4 += 4) {
+          float4 acc = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < p.J; ++j) {
+            const float4 t = *reinterpret_cast<const float4*>(S + (i + j) * SLD + j * p.ch + c4);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
+          *reinterpret_cast<float4*>(orow + c4) = acc;
+        }
+      }
+    } else {
     const int quarter = warp & 3;
     float* stg = staging + quarter * (32 * STG_LD);
     const int r4 = lane >> 3, c4 = lane & 7;
@@ -332,6 +388,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         }
       }
       __syncwarp();
+    }
     }
   }
 
@@ -438,18 +495,18 @@ constexpr int smem_bytes() {
   return STAGES * (2 * TILE_BYTES + 2 * BN * BLOCK_K * 2) + STG_BYTES + 8 * (2 * STAGES + 1) + 16 + 1024;
 }
 
-template <int BN, int STAGES, bool CONV>
+template <int BN, int STAGES, int MODE>
 int launch(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
            const TcParams& p, dim3 grid, cudaStream_t st) {
   constexpr int SMEM = smem_bytes<BN, STAGES>();
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
-        cudaFuncSetAttribute(tc_contract_kernel<BN, STAGES, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaFuncSetAttribute(tc_contract_kernel<BN, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", SMEM, cudaGetErrorString(e));
     attr_set = true;
   }
-  tc_contract_kernel<BN, STAGES, CONV><<<grid, NUM_THREADS, SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
+  tc_contract_kernel<BN, STAGES, MODE><<<grid, NUM_THREADS, SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
   WXF_CHECK_LAUNCH("tc_contract");
   return 0;
 }
@@ -499,8 +556,8 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
   p.ldc = d->ldc; p.ldr = d->ldr; p.ldh = d->ldh; p.act = d->act;
   p.w_scale = ldexpf(1.0f, -d->w_scale_log2);
   dim3 grid((unsigned)((d->N + BN - 1) / BN), (unsigned)((d->M + BLOCK_M - 1) / BLOCK_M), 1);
-  if (BN == 256) return launch<256, 2, false>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
-  return launch<128, 3, false>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
+  if (BN == 256) return launch<256, 2, MODE_GEMM>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
+  return launch<128, 3, MODE_GEMM>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
 }
 
 extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
@@ -579,6 +636,66 @@ extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
   const int64_t ntiles = (int64_t)d->B * p.tiles_x * p.tiles_y;
   if (ntiles > 65535) WXF_FAIL(WXF_EINVAL, "conv_tc: too many tiles for one launch");
   dim3 grid((unsigned)((d->N + BN - 1) / BN), (unsigned)ntiles, (unsigned)d->phases);
-  if (BN == 256) return launch<256, 2, true>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
-  return launch<128, 3, true>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
+  if (BN == 256) return launch<256, 2, MODE_CONV>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
+  return launch<128, 3, MODE_CONV>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
+}
+
+extern "C" int wxf_cross_embed_toeplitz_tc(const WxfToeplitzDesc* d, void* stream) {
+  if (!d || !d->in_hi || !d->in_lo || !d->w_hi || !d->w_lo || !d->out) WXF_FAIL(WXF_EINVAL, "toeplitz: null pointer");
+  if (d->B <= 0 || d->Hi <= 0 || d->Wi <= 0 || d->Cin <= 0 || d->ch <= 0 || d->kernel <= 0 || d->Ho <= 0 || d->Wo <= 0 ||
+      d->lda < d->Cin || d->pad < 0)
+    WXF_FAIL(WXF_EINVAL, "toeplitz: bad dims");
+  if (d->kernel & 1) WXF_FAIL(WXF_EUNSUPPORTED, "toeplitz: kernel size must be even (stride 2)");
+  const int J = d->kernel / 2, T = 2 * d->kernel, N = J * d->ch;
+  if (T > MAX_TAPS) WXF_FAIL(WXF_EUNSUPPORTED, "toeplitz: kernel %d too large", d->kernel);
+  if (N > 256 || (d->ch & 3)) WXF_FAIL(WXF_EUNSUPPORTED, "toeplitz: (k/2)*channels = %d must be <= 256, channels %% 4 == 0", N);
+  if (d->cin_pad != 64 || d->Cin > 64) WXF_FAIL(WXF_EUNSUPPORTED, "toeplitz: at most 64 input channels (cin_pad = 64)");
+  if ((d->lda & 7)) WXF_FAIL(WXF_EALIGN, "toeplitz: lda %% 8");
+  if (!wxf_aligned16(d->in_hi) || !wxf_aligned16(d->in_lo) || !wxf_aligned16(d->w_hi) || !wxf_aligned16(d->w_lo))
+    WXF_FAIL(WXF_EALIGN, "toeplitz: operand planes must be 16-byte aligned");
+  if (d->ldc < d->c_off + d->ch || (d->ldc & 3) || (d->c_off & 3) || !wxf_aligned16(d->out) ||
+      (d->bias && !wxf_aligned16(d->bias)))
+    WXF_FAIL(WXF_EALIGN, "toeplitz: output stride/alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int BN = N > 128 ? 256 : 128;
+  const int K = T * 64;
+  int rc;
+  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  {
+    const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Wi, (uint64_t)d->Hi, (uint64_t)d->B};
+    const uint64_t strides[3] = {(uint64_t)d->lda * 2, (uint64_t)d->Wi * d->lda * 2,
+                                 (uint64_t)d->Hi * d->Wi * d->lda * 2};
+    const uint32_t box[4] = {(uint32_t)BLOCK_K, 256, 1, 1};  // 128 pixels at element stride 2
+    const uint32_t es[4] = {1, 2, 1, 1};
+    if ((rc = make_map(&ta_hi, d->in_hi, 4, dims, strides, box, es))) return rc;
+    if ((rc = make_map(&ta_lo, d->in_lo, 4, dims, strides, box, es))) return rc;
+  }
+  if ((rc = make_map_2d(&tw_hi, d->w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN))) return rc;
+  if ((rc = make_map_2d(&tw_lo, d->w_lo, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN))) return rc;
+  TcParams p{};
+  p.bias = d->bias;
+  p.out = d->out + d->c_off;
+  p.N = N;
+  p.cblocks = 1;
+  p.cin_pad = 64;
+  p.num_ksteps = T;
+  p.ldc = d->ldc;
+  p.w_scale = ldexpf(1.0f, -d->w_scale_log2);
+  p.bw = 128; p.bh = 1;
+  p.step = 128 - (J - 1);
+  p.J = J; p.ch = d->ch;
+  p.tiles_x = (d->Wo + p.step - 1) / p.step;
+  p.tiles_y = d->Ho;
+  p.Ho = d->Ho; p.Wo = d->Wo; p.stride = 2; p.out_scale = 1;
+  p.a_bytes = (uint32_t)TILE_BYTES;
+  for (int ky = 0; ky < d->kernel; ++ky)
+    for (int r = 0; r < 2; ++r) {
+      p.taps[0][ky * 2 + r][0] = (int16_t)(ky - d->pad);
+      p.taps[0][ky * 2 + r][1] = (int16_t)(r - d->pad);
+    }
+  const int64_t ntiles = (int64_t)d->B * p.tiles_x * p.tiles_y;
+  if (ntiles > 65535) WXF_FAIL(WXF_EINVAL, "toeplitz: too many tiles for one launch");
+  dim3 grid(1, (unsigned)ntiles, 1);
+  if (BN == 256) return launch<256, 2, MODE_TOEP>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
+  return launch<128, 3, MODE_TOEP>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
 }

@@ -13,7 +13,9 @@ extern "C" const char* wxf_last_error(void) { return wxf_err_buf; }
 // padded (r, c): j = (c - pl) mod W; r < pt -> x[pt-1-r, (j - W/2) mod W]; pt <= r < pt+H -> x[r-pt, j];
 // else x[H-1-(r-pt-H), (j - W/2) mod W].  mirror (:98-117): circular lon, reflect lat (no edge repeat).
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) pad_to_pixel_major_kernel(const float* __restrict__ x, float* __restrict__ xp,
+                                                                  __half* __restrict__ xp_hi, __half* __restrict__ xp_lo,
                                                                   int CT, int H, int W, int pt, int pl, int mode,
                                                                   int ld, int Hp, int Wp, int cgroups) {
   __shared__ float tile[32][33];  // [channel][column]
@@ -63,12 +65,22 @@ __global__ void __launch_bounds__(256) pad_to_pixel_major_kernel(const float* __
 #pragma unroll
   for (int i = ty; i < 32; i += 8) {
     const int cw = c0 + i;
-    if (cw < Wp && ch < ld) xp[((size_t)(b * Hp + r) * Wp + cw) * ld + ch] = tile[tx][i];
+    if (cw < Wp && ch < ld) {
+      const size_t o = ((size_t)(b * Hp + r) * Wp + cw) * ld + ch;
+      if constexpr (SPLIT) {
+        __half hi, lo;
+        wxf_split_f16x2(tile[tx][i], hi, lo);
+        xp_hi[o] = hi;
+        xp_lo[o] = lo;
+      } else {
+        xp[o] = tile[tx][i];
+      }
+    }
   }
 }
 
-extern "C" int wxf_pad_to_pixel_major(const float* x, float* xp, int B, int C, int T, int H, int W, int pt, int pb,
-                                      int pl, int pr, int mode, int ld, void* stream) {
+static int pad_launch(const float* x, float* xp, void* xp_hi, void* xp_lo, int B, int C, int T, int H, int W, int pt,
+                      int pb, int pl, int pr, int mode, int ld, void* stream) {
   if (B <= 0 || C <= 0 || T <= 0 || H <= 0 || W <= 0 || pt < 0 || pb < 0 || pl < 0 || pr < 0)
     WXF_FAIL(WXF_EINVAL, "pad: bad dims");
   if (ld < C * T) WXF_FAIL(WXF_EINVAL, "pad: ld %d < C*T %d", ld, C * T);
@@ -79,10 +91,27 @@ extern "C" int wxf_pad_to_pixel_major(const float* x, float* xp, int B, int C, i
   const int cgroups = (ld + 31) / 32;
   if (Hp > 65535 || (int64_t)B * cgroups > 65535) WXF_FAIL(WXF_EINVAL, "pad: grid too large");
   dim3 grid((Wp + 31) / 32, Hp, B * cgroups), block(32, 8);
-  pad_to_pixel_major_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, xp, C * T, H, W, pt, pl, mode, ld, Hp, Wp,
-                                                                       cgroups);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (xp_hi)
+    pad_to_pixel_major_kernel<true><<<grid, block, 0, st>>>(x, nullptr, (__half*)xp_hi, (__half*)xp_lo, C * T, H, W, pt,
+                                                            pl, mode, ld, Hp, Wp, cgroups);
+  else
+    pad_to_pixel_major_kernel<false><<<grid, block, 0, st>>>(x, xp, nullptr, nullptr, C * T, H, W, pt, pl, mode, ld, Hp,
+                                                             Wp, cgroups);
   WXF_CHECK_LAUNCH("pad_to_pixel_major");
   return 0;
+}
+
+extern "C" int wxf_pad_to_pixel_major(const float* x, float* xp, int B, int C, int T, int H, int W, int pt, int pb,
+                                      int pl, int pr, int mode, int ld, void* stream) {
+  if (!xp) WXF_FAIL(WXF_EINVAL, "pad: null output");
+  return pad_launch(x, xp, nullptr, nullptr, B, C, T, H, W, pt, pb, pl, pr, mode, ld, stream);
+}
+
+extern "C" int wxf_pad_to_pixel_major_f16x2(const float* x, void* xp_hi, void* xp_lo, int B, int C, int T, int H, int W,
+                                            int pt, int pb, int pl, int pr, int mode, int ld, void* stream) {
+  if (!xp_hi || !xp_lo) WXF_FAIL(WXF_EINVAL, "pad: null output planes");
+  return pad_launch(x, nullptr, xp_hi, xp_lo, B, C, T, H, W, pt, pb, pl, pr, mode, ld, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

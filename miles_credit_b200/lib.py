@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 3
+WXF_ABI_VERSION = 4
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -60,10 +60,24 @@ class WxfConvTcDesc(Structure):
     ]
 
 
+class WxfToeplitzDesc(Structure):
+    _fields_ = [
+        ("in_hi", c_void_p), ("in_lo", c_void_p), ("w_hi", c_void_p), ("w_lo", c_void_p), ("bias", c_void_p),
+        ("out", c_void_p),
+        ("B", c_int32), ("Hi", c_int32), ("Wi", c_int32), ("lda", c_int32), ("Cin", c_int32), ("cin_pad", c_int32),
+        ("ch", c_int32), ("kernel", c_int32), ("pad", c_int32),
+        ("Ho", c_int32), ("Wo", c_int32),
+        ("ldc", c_int32), ("c_off", c_int32),
+        ("w_scale_log2", c_int32),
+    ]
+
+
 _SIGNATURES = {
     "wxf_abi_version": (c_int, []),
     "wxf_last_error": (c_char_p, []),
     "wxf_pad_to_pixel_major": (c_int, [c_void_p, c_void_p] + [c_int] * 11 + [c_void_p]),
+    "wxf_pad_to_pixel_major_f16x2": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 11 + [c_void_p]),
+    "wxf_cross_embed_toeplitz_tc": (c_int, [POINTER(WxfToeplitzDesc), c_void_p]),
     "wxf_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
     "wxf_layernorm_f16x2": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float,
                                     c_void_p]),

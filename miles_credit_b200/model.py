@@ -134,8 +134,14 @@ class _Plan:
         f16 = dict(device=device, dtype=torch.float16)
         B = batch
         g = geo
-        self.ld0 = wts.cin0_pad
-        self.xp = torch.empty((B, g.h_pad, g.w_pad, self.ld0), **f32)
+        self.toeplitz = tensor_cores and wts.embed0_toep is not None
+        if self.toeplitz:  # stage-0 input as fp16 operand planes, channels padded to 64 (zero) for the 128-byte TMA rows
+            self.ld0 = 64
+            self.xp = None
+            self.xp_planes = (torch.empty((B, g.h_pad, g.w_pad, 64), **f16), torch.empty((B, g.h_pad, g.w_pad, 64), **f16))
+        else:
+            self.ld0 = wts.cin0_pad
+            self.xp = torch.empty((B, g.h_pad, g.w_pad, self.ld0), **f32)
         big = max(B * s.h * s.w * s.dim for s in g.stages)
         big = max(big, max(4 * B * u.h_in * u.w_in * u.c_out for u in g.ups))
         big = _round_up(big, 8)
@@ -200,7 +206,13 @@ class _Plan:
                 else:
                     xp_hi, xp_lo, pld = self.x3p[0], self.x3p[1], d
             for bi, (br, bw) in enumerate(zip(st.branches, wts.embeds[s])):
-                if tc and s > 0:
+                if s == 0 and self.toeplitz:
+                    tw = wts.embed0_toep[bi]
+                    desc = ops.make_toeplitz_desc(self.xp_planes[0], self.xp_planes[1], tw, xbuf, B=B, Hi=src_h, Wi=src_w,
+                                                  lda=64, Ho=st.h, Wo=st.w, ldc=ld, c_off=xoff + br.c_off)
+                    self._add(ops.cross_embed_toeplitz_tc, (desc,), f"embed0.k{br.kernel}",
+                              2.0 * m * br.c_out * st.c_in * br.kernel * br.kernel)
+                elif tc and s > 0:
                     self._conv_tc(src_planes[0], src_planes[1], wts.embeds_tc[s][bi], f"embed{s}.k{br.kernel}", B=B,
                                   Hi=src_h, Wi=src_w, lda=src_ld, Ho=st.h, Wo=st.w, out=xbuf, ldc=ld,
                                   c_off=xoff + br.c_off)
@@ -303,10 +315,12 @@ class _Plan:
 
     def _pad(self, x):
         g = self.geo
-        if g.padding.activate:
-            ops.pad_to_pixel_major(x, g.padding.pad_lat, g.padding.pad_lon, g.padding.mode, self.ld0, out=self.xp)
+        lat, lon, mode = ((g.padding.pad_lat, g.padding.pad_lon, g.padding.mode) if g.padding.activate
+                          else ((0, 0), (0, 0), "earth"))
+        if self.toeplitz:
+            ops.pad_to_pixel_major_f16x2(x, lat, lon, mode, 64, self.xp_planes[0], self.xp_planes[1])
         else:
-            ops.pad_to_pixel_major(x, (0, 0), (0, 0), "earth", self.ld0, out=self.xp)
+            ops.pad_to_pixel_major(x, lat, lon, mode, self.ld0, out=self.xp)
 
     def _unpad(self, out):
         g, B = self.geo, self.batch
@@ -337,7 +351,8 @@ class _Plan:
             recs.append([tag, (e0, e1), flops, nbytes])
 
         n_in = float(x.numel()) * 4
-        timed("pad", 0.0, n_in + 4.0 * self.xp.numel(), self._pad, x)
+        n_pad = 4.0 * (self.xp.numel() if self.xp is not None else self.xp_planes[0].numel())
+        timed("pad", 0.0, n_in + n_pad, self._pad, x)
         for fn, args, tag, fl, by in self.steps:
             timed(tag, fl, by, fn, *args)
         out = torch.empty((B, g.base_output_channels, g.output_frames, g.h_out, g.w_out), device=x.device,

@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import lib as _lib
-from .lib import WxfConvDesc, WxfConvTcDesc, WxfGemmDesc
+from .lib import WxfConvDesc, WxfConvTcDesc, WxfGemmDesc, WxfToeplitzDesc
 from .weights import ConvWeights
 
 LAUNCHES = 0
@@ -49,6 +49,41 @@ def pad_to_pixel_major(x: torch.Tensor, pad_lat, pad_lon, mode: str, ld: int, ou
     _lib.check(st, "wxf_pad_to_pixel_major")
     LAUNCHES += 1
     return out
+
+
+def pad_to_pixel_major_f16x2(x: torch.Tensor, pad_lat, pad_lon, mode: str, ld: int, out_hi: torch.Tensor,
+                             out_lo: torch.Tensor):
+    """[B, C, T, H, W] fp32 -> padded pixel-major fp16 hi/lo planes [B, Hp, Wp, ld]."""
+    global LAUNCHES
+    _req(x, "x")
+    x = x.contiguous()
+    b, c, t, h, w = x.shape
+    m = _lib.PAD_EARTH if mode == "earth" else _lib.PAD_MIRROR
+    st = _lib.load().wxf_pad_to_pixel_major_f16x2(x.data_ptr(), out_hi.data_ptr(), out_lo.data_ptr(), b, c, t, h, w,
+                                                  pad_lat[0], pad_lat[1], pad_lon[0], pad_lon[1], m, ld, _stream())
+    _lib.check(st, "wxf_pad_to_pixel_major_f16x2")
+    LAUNCHES += 1
+
+
+def make_toeplitz_desc(in_hi: torch.Tensor, in_lo: torch.Tensor, wts, out: torch.Tensor, *, B: int, Hi: int, Wi: int,
+                       lda: int, Ho: int, Wo: int, ldc: int, c_off: int = 0) -> WxfToeplitzDesc:
+    """Descriptor of one stage-0 cross-embed branch; ``wts`` is a weights.ToeplitzWeights."""
+    d = WxfToeplitzDesc()
+    d.in_hi, d.in_lo = in_hi.data_ptr(), in_lo.data_ptr()
+    d.w_hi, d.w_lo = wts.w_hi.data_ptr(), wts.w_lo.data_ptr()
+    d.bias, d.out = _ptr(wts.bias), out.data_ptr()
+    d.B, d.Hi, d.Wi, d.lda, d.Cin, d.cin_pad = B, Hi, Wi, lda, wts.cin, 64
+    d.ch, d.kernel, d.pad = wts.ch, wts.kernel, wts.pad
+    d.Ho, d.Wo, d.ldc, d.c_off = Ho, Wo, ldc, c_off
+    d.w_scale_log2 = wts.scale_log2
+    return d
+
+
+def cross_embed_toeplitz_tc(desc: WxfToeplitzDesc):
+    global LAUNCHES
+    st = _lib.load().wxf_cross_embed_toeplitz_tc(ctypes.byref(desc), _stream())
+    _lib.check(st, "wxf_cross_embed_toeplitz_tc")
+    LAUNCHES += 1
 
 
 def layernorm(x: torch.Tensor, ldx: int, y: torch.Tensor, ldy: int, g: torch.Tensor, b: torch.Tensor, m: int, d: int,

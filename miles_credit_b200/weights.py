@@ -186,6 +186,42 @@ def conv_tc_weights(cw: "ConvWeights") -> ConvTcWeights:
 
 
 @dataclass
+class ToeplitzWeights:
+    """Stage-0 cross-embed branch for wxf_cross_embed_toeplitz_tc: rows (j, c), columns (ky, r, ci<64)."""
+
+    w_hi: torch.Tensor
+    w_lo: torch.Tensor
+    bias: Optional[torch.Tensor]
+    ch: int
+    cin: int
+    kernel: int
+    pad: int
+    scale_log2: int
+
+
+def toeplitz_eligible(c_out: int, c_in: int, kernel: int, stride: int) -> bool:
+    return (stride == 2 and kernel % 2 == 0 and 2 * kernel <= 64 and (kernel // 2) * c_out <= 256 and c_out % 4 == 0
+            and c_in <= 64)
+
+
+def toeplitz_weights(w: torch.Tensor, bias, pad: int) -> ToeplitzWeights:
+    """Conv2d weight [ch, Cin, k, k] (stride 2) -> Wt[j*ch + c, (ky*2 + r)*64 + ci] = w[c, ci, ky, 2j + r]."""
+    ch, cin, k, _ = w.shape
+    J = k // 2
+    w5 = w.float().reshape(ch, cin, k, J, 2).permute(3, 0, 2, 4, 1)  # j, c, ky, r, ci
+    wp = w5.new_zeros((J, ch, k, 2, 64))
+    wp[..., :cin] = w5
+    amax = float(wp.abs().max())
+    kk = 0 if amax == 0.0 else int(math.floor(math.log2(1024.0 / amax)))
+    kk = max(min(kk, 24), -24)
+    ws = (wp * (2.0 ** kk)).reshape(J * ch, k * 2 * 64)
+    hi = ws.half()
+    lo = (ws - hi.float()).half()
+    return ToeplitzWeights(hi.contiguous(), lo.contiguous(), None if bias is None else bias.float().contiguous(), ch, cin, k,
+                           pad, kk)
+
+
+@dataclass
 class AttentionWeights:
     ln_g: torch.Tensor
     ln_b: torch.Tensor
@@ -227,6 +263,7 @@ class PreparedWeights:
     cin0_pad: int
     embeds_tc: Optional[List[List[Optional[ConvTcWeights]]]] = None
     head_tc: Optional[ConvTcWeights] = None
+    embed0_toep: Optional[List[ToeplitzWeights]] = None  # None unless every stage-0 branch is eligible
 
 
 def prepare(sd: Dict[str, torch.Tensor], geo: Geometry, cin0_pad: int) -> PreparedWeights:
@@ -279,4 +316,9 @@ def prepare(sd: Dict[str, torch.Tensor], geo: Geometry, cin0_pad: int) -> Prepar
         embeds_tc = [[(conv_tc_weights(c) if (s > 0 and c.n % 4 == 0 and c.t <= 64) else None) for c in brs]
                      for s, brs in enumerate(embeds)]
         head_tc = conv_tc_weights(head) if head.n % 4 == 0 else None
-    return PreparedWeights(embeds, blocks, ups, head, cin0_pad, embeds_tc, head_tc)
+        st0 = geo.stages[0]
+        toep = None
+        if all(toeplitz_eligible(br.c_out, st0.c_in, br.kernel, br.stride) for br in st0.branches):
+            toep = [toeplitz_weights(fold_spectral_norm(sd, f"layers.0.0.convs.{i}"), sd[f"layers.0.0.convs.{i}.bias"],
+                                     br.pad) for i, br in enumerate(st0.branches)]
+    return PreparedWeights(embeds, blocks, ups, head, cin0_pad, embeds_tc, head_tc, toep)

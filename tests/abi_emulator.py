@@ -33,7 +33,7 @@ class EmulatedLib:
         self.calls = []
 
     def wxf_abi_version(self):
-        return 3
+        return 4
 
     def wxf_last_error(self):
         return b"emulator"
@@ -61,6 +61,50 @@ class EmulatedLib:
             if roll:
                 j = (j - W // 2) % W
             out[:, r, :, : C * T] = xs[:, :, sr, :][:, :, j].permute(0, 2, 1)
+        return 0
+
+    def wxf_pad_to_pixel_major_f16x2(self, x, xp_hi, xp_lo, B, C, T, H, W, pt, pb, pl, pr, mode, ld, stream):
+        Hp, Wp = H + pt + pb, W + pl + pr
+        tmp = np.zeros(B * Hp * Wp * ld, dtype=np.float32)
+        self.wxf_pad_to_pixel_major(x, tmp.ctypes.data, B, C, T, H, W, pt, pb, pl, pr, mode, ld, stream)
+        hi, lo = self._split(torch.from_numpy(tmp))
+        self._harr(xp_hi, tmp.size).copy_(hi)
+        self._harr(xp_lo, tmp.size).copy_(lo)
+        return 0
+
+    def wxf_cross_embed_toeplitz_tc(self, dref, stream):
+        d = dref._obj
+        self.calls.append("toeplitz")
+        k, p_, ch, J = d.kernel, d.pad, d.ch, d.kernel // 2
+        N = J * ch
+        if k % 2 or N > 256 or ch % 4 or d.cin_pad != 64 or d.Cin > 64:
+            return -3
+        B, Hi, Wi, lda, Cin, Ho, Wo = d.B, d.Hi, d.Wi, d.lda, d.Cin, d.Ho, d.Wo
+        n_in = ((B * Hi - 1) * Wi + Wi - 1) * lda + Cin
+        shape, strides = (B, Hi, Wi, Cin), (Hi * Wi * lda, Wi * lda, lda, 1)
+        x_hi = self._harr(d.in_hi, n_in).as_strided(shape, strides).double()
+        x_lo = self._harr(d.in_lo, n_in).as_strided(shape, strides).double()
+        w_hi = self._harr(d.w_hi, N * 2 * k * 64).view(N, 2 * k, 64)[..., :Cin].double()
+        w_lo = self._harr(d.w_lo, N * 2 * k * 64).view(N, 2 * k, 64)[..., :Cin].double()
+        Mx = Wo + J - 1
+        P = torch.zeros(B, Ho, Mx, N, dtype=torch.float64)
+        oy, mm = torch.arange(Ho) * 2, torch.arange(Mx) * 2
+        for ky in range(k):
+            for r in range(2):
+                iy, ix = oy + ky - p_, mm + r - p_
+                mask = ((iy >= 0) & (iy < Hi))[:, None] & ((ix >= 0) & (ix < Wi))[None, :]
+                gh = x_hi[:, iy.clamp(0, Hi - 1)][:, :, ix.clamp(0, Wi - 1)] * mask[None, :, :, None]
+                gl = x_lo[:, iy.clamp(0, Hi - 1)][:, :, ix.clamp(0, Wi - 1)] * mask[None, :, :, None]
+                ks = ky * 2 + r
+                P += gh @ w_lo[:, ks].t() + gl @ w_hi[:, ks].t() + gh @ w_hi[:, ks].t()
+        P = P.float() * (2.0 ** -d.w_scale_log2)
+        out_v = torch.zeros(B, Ho, Wo, ch)
+        if d.bias:
+            out_v += _t(_arr(d.bias, ch))
+        for j in range(J):
+            out_v += P[:, :, j: j + Wo, j * ch: (j + 1) * ch]
+        n_out = ((B * Ho - 1) * Wo + Wo - 1) * d.ldc + d.c_off + ch
+        _t(_arr(d.out, n_out)).as_strided((B, Ho, Wo, ch), (Ho * Wo * d.ldc, Wo * d.ldc, d.ldc, 1), d.c_off).copy_(out_v)
         return 0
 
     def wxf_layernorm(self, x, ldx, y, ldy, g, b, M, d, eps, stream):

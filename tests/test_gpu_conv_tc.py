@@ -109,3 +109,42 @@ def test_conv_tc_channel_slice_input():
     ops.conv_f16x2_tc(ops.make_conv_tc_desc(hi[..., c:], lo[..., c:], tw, B=1, Hi=h, Wi=w, lda=2 * c, Ho=h // 2, Wo=w // 2,
                                             out=out, ldc=128))
     assert relmax(out.cpu(), to_pm(ref)) < 3e-6
+
+
+@pytest.mark.parametrize("cin,ch,k,h,w,b", [(60, 16, 32, 97, 300, 1), (60, 16, 16, 97, 300, 1), (60, 32, 8, 45, 130, 2),
+                                            (60, 64, 4, 45, 130, 2), (10, 4, 32, 97, 144, 1), (24, 8, 8, 33, 64, 1)])
+def test_cross_embed_toeplitz_tc(cin, ch, k, h, w, b):
+    """Stage-0 cross-embed branch (stride 2, pad (k-2)/2) as the Toeplitz-lifted tensor-core GEMM vs fp64 conv2d."""
+    from miles_credit_b200.weights import toeplitz_weights
+
+    torch.manual_seed(cin * k + ch)
+    x = torch.randn(b, cin, h, w)
+    wt = torch.randn(ch, cin, k, k) / (cin * k * k) ** 0.5
+    bias = torch.randn(ch)
+    p = (k - 2) // 2
+    ref = F.conv2d(x.double(), wt.double(), bias.double(), stride=2, padding=p).float()
+    ho, wo = ref.shape[-2:]
+    xpm = torch.zeros(b, h, w, 64)
+    xpm[..., :cin] = to_pm(x)
+    hi, lo = planes_of(xpm.to(DEV))
+    tw = toeplitz_weights(wt.to(DEV), bias.to(DEV), p)
+    ldc = 2 * ch + 8
+    out = torch.zeros(b, ho, wo, ldc, device=DEV)
+    ops.cross_embed_toeplitz_tc(ops.make_toeplitz_desc(hi, lo, tw, out, B=b, Hi=h, Wi=w, lda=64, Ho=ho, Wo=wo, ldc=ldc,
+                                                       c_off=8))
+    torch.cuda.synchronize()
+    err = relmax(out[..., 8: 8 + ch].cpu(), to_pm(ref))
+    print(f"toeplitz cin={cin} ch={ch} k={k}: rel-max {err:.3e}")
+    assert err < 3e-6
+    assert torch.count_nonzero(out[..., :8]) == 0 and torch.count_nonzero(out[..., 8 + ch:]) == 0
+
+
+def test_pad_planes_match_fp32_pad():
+    torch.manual_seed(4)
+    x = torch.randn(2, 5, 2, 9, 16, device=DEV)
+    ref = ops.pad_to_pixel_major(x, (3, 4), (5, 2), "earth", 64)
+    hi = torch.empty(2, 16, 23, 64, device=DEV, dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    ops.pad_to_pixel_major_f16x2(x, (3, 4), (5, 2), "earth", 64, hi, lo)
+    assert torch.equal(hi, ref.half())
+    assert float((hi.float() + lo.float() - ref).abs().max()) < 1e-6

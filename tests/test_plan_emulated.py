@@ -46,6 +46,7 @@ def test_plan_through_emulated_abi_matches_reference(golden_dir, emulated, case,
     assert (emulated.calls.count("gemm_tc") == 8 * sum(geo.depth)) == tensor_cores
     if tensor_cores:  # stage 1-3 cross-embed (6) + decoder (3 x 3) run as tensor-core convolutions
         assert emulated.calls.count("conv_tc") >= 15
+        assert emulated.calls.count("toeplitz") == 4  # the four stage-0 cross-embed branches
 
 
 def test_plan_tensor_core_head_vs_oracle(emulated):
