@@ -135,7 +135,7 @@ def test_cross_embed_toeplitz_tc(cin, ch, k, h, w, b):
     torch.cuda.synchronize()
     err = relmax(out[..., 8: 8 + ch].cpu(), to_pm(ref))
     print(f"toeplitz cin={cin} ch={ch} k={k}: rel-max {err:.3e}")
-    assert err < 3e-6
+    assert err < 6e-6  # K = 2k*64 up to 4096 with two accumulators (see test_gpu_gemm_tc)
     assert torch.count_nonzero(out[..., :8]) == 0 and torch.count_nonzero(out[..., 8 + ch:]) == 0
 
 
