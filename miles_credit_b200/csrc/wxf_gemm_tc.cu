@@ -28,6 +28,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -401,6 +403,263 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   }
 }
 
+
+// ---- persistent kernel: one CTA per SM loops over output tiles; TMEM holds two accumulator slots so the epilogue of
+//      tile i overlaps the TMA loads and MMAs of tile i+1; 8 epilogue warps (two per TMEM lane quarter) -------------
+
+constexpr int P_BN = 128;
+constexpr int P_STAGES = 3;
+constexpr int P_THREADS = 64 + 256;
+constexpr int P_STAGE_BYTES = 2 * TILE_BYTES + 2 * P_BN * BLOCK_K * 2;  // 64 KB
+constexpr int P_STG_LD = 20;                                            // 16 columns + 4 pad per staged row
+constexpr int P_STG_BYTES = 8 * 32 * P_STG_LD * 4;                      // 8 epilogue warps
+constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + P_STG_BYTES + 8 * (2 * P_STAGES + 4) + 16 + 1024;
+
+template <int MODE>
+__global__ void __launch_bounds__(P_THREADS, 1)
+tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                     const __grid_constant__ TcParams p, const int n_tiles, const int m_tiles, const int total_tiles) {
+  constexpr bool CONV = MODE == MODE_CONV;
+  constexpr int BN = P_BN, STAGES = P_STAGES, STAGE_BYTES = P_STAGE_BYTES, W_BYTES = P_BN * BLOCK_K * 2;
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  float* staging = reinterpret_cast<float*>(gen + STAGES * STAGE_BYTES);
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES + P_STG_BYTES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + STAGES * STAGE_BYTES + P_STG_BYTES + 8 * (2 * STAGES + 4));
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = p.num_ksteps;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile t -> (n tile, m tile, phase); n fastest so CTAs running concurrently share the A tile in L2
+  auto decode = [&](int t, int& n0, int& z, int64_t& m0, int& tb, int& oy0, int& ox0) {
+    const int nt = t % n_tiles;
+    const int rest = t / n_tiles;
+    const int mt = rest % m_tiles;
+    z = rest / m_tiles;
+    n0 = nt * BN;
+    m0 = 0; tb = 0; oy0 = 0; ox0 = 0;
+    if constexpr (CONV) {
+      const int per_img = p.tiles_x * p.tiles_y;
+      tb = mt / per_img;
+      const int rem = mt - tb * per_img;
+      oy0 = (rem / p.tiles_x) * p.bh;
+      ox0 = (rem % p.tiles_x) * p.bw;
+    } else {
+      m0 = (int64_t)mt * BLOCK_M;
+    }
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t stage_tx = CONV ? (2u * p.a_bytes + 2u * W_BYTES) : (uint32_t)STAGE_BYTES;
+      uint32_t g = 0;  // K-steps issued so far (ring position)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int n0, z, tb, oy0, ox0;
+        int64_t m0;
+        decode(t, n0, z, m0, tb, oy0, ox0);
+        for (int ks = 0; ks < num_k; ++ks, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (g / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t st = base + s * STAGE_BYTES;
+          mbar_expect_tx(full_bar(s), stage_tx);
+          int wk;
+          if constexpr (CONV) {
+            const int tp = ks / p.cblocks, cb = ks - tp * p.cblocks;
+            const int iy = oy0 * p.stride + p.taps[z][tp][0], ix = ox0 * p.stride + p.taps[z][tp][1];
+            tma_load_4d(&tmA_hi, full_bar(s), st, cb * BLOCK_K, ix, iy, tb);
+            tma_load_4d(&tmA_lo, full_bar(s), st + TILE_BYTES, cb * BLOCK_K, ix, iy, tb);
+            wk = tp * p.cin_pad + cb * BLOCK_K;
+          } else {
+            tma_load_2d(&tmA_hi, full_bar(s), st, ks * BLOCK_K, (int)m0);
+            tma_load_2d(&tmA_lo, full_bar(s), st + TILE_BYTES, ks * BLOCK_K, (int)m0);
+            wk = ks * BLOCK_K;
+          }
+          tma_load_2d(&tmW_hi, full_bar(s), st + 2 * TILE_BYTES, wk, z * p.N + n0);
+          tma_load_2d(&tmW_lo, full_bar(s), st + 2 * TILE_BYTES + W_BYTES, wk, z * p.N + n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      int i = 0;  // local tile counter
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        const int slot = i & 1;
+        mbar_wait(tempty_bar(slot), (((uint32_t)i >> 1) & 1u) ^ 1u);  // epilogue has drained this slot
+        tc_fence_after();
+        const uint32_t d_cross = tmem_base + (uint32_t)(slot * 2 * BN), d_main = d_cross + BN;
+        for (int ks = 0; ks < num_k; ++ks, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (g / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t a_hi = umma_desc_sw128(st + k * 32);
+            const uint64_t a_lo = umma_desc_sw128(st + TILE_BYTES + k * 32);
+            const uint64_t w_hi = umma_desc_sw128(st + 2 * TILE_BYTES + k * 32);
+            const uint64_t w_lo = umma_desc_sw128(st + 2 * TILE_BYTES + W_BYTES + k * 32);
+            const uint32_t acc = (ks | k) ? 1u : 0u;
+            tc_mma_f16(d_cross, a_hi, w_lo, IDESC, acc);
+            tc_mma_f16(d_cross, a_lo, w_hi, IDESC, 1u);
+            tc_mma_f16(d_main, a_hi, w_hi, IDESC, acc);
+          }
+          tc_commit(empty_bar(s));
+        }
+        tc_commit(tfull_bar(slot));
+      }
+    }
+  } else {
+    // ---- 8 epilogue warps: quarter = TMEM lane quarter, half = which 64 of the 128 columns ----
+    const int ew = warp - 2;
+    const int quarter = warp & 3, half = ew >> 2;
+    float* stg = staging + ew * (32 * P_STG_LD);
+    const int r8 = lane >> 2, c4 = lane & 3;  // transposed pass: 8 rows x 4 float4 (16 columns) per instruction
+    int i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      const int slot = i & 1;
+      int n0, z, tb, oy0, ox0;
+      int64_t m0;
+      decode(t, n0, z, m0, tb, oy0, ox0);
+      const int nb0 = n0 + half * 64;
+
+      int64_t opix[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = quarter * 32 + it * 8 + r8;
+        if constexpr (CONV) {
+          const int ii = row / p.bw, jj = row - ii * p.bw;
+          const int oy = oy0 + ii, ox = ox0 + jj;
+          if (ii < p.bh && oy < p.Ho && ox < p.Wo) {
+            const int Hout = p.Ho * p.out_scale, Wout = p.Wo * p.out_scale;
+            opix[it] = ((int64_t)tb * Hout + oy * p.out_scale + (z >> 1)) * Wout + ox * p.out_scale + (z & 1);
+          } else {
+            opix[it] = -1;
+          }
+        } else {
+          const int64_t m = m0 + row;
+          opix[it] = m < p.M ? m : -1;
+        }
+      }
+      // residual prefetch: issued before waiting for the accumulator so it overlaps the main loop
+      float4 rres[4][4];
+      if (p.res) {
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          const int n = nb0 + sub * 16 + c4 * 4;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            rres[sub][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < p.N && opix[it] >= 0) rres[sub][it] = *reinterpret_cast<const float4*>(p.res + opix[it] * p.ldr + n);
+          }
+        }
+      }
+
+      mbar_wait(tfull_bar(slot), ((uint32_t)i >> 1) & 1u);
+      tc_fence_after();
+      float v[64];
+      {
+        const uint32_t tb_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 2 * BN + half * 64);
+        uint32_t r[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(tb_addr + (uint32_t)(c * 32), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(r[j]);
+          tmem_ld32(tb_addr + (uint32_t)(BN + c * 32), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[c * 32 + j] += __uint_as_float(r[j]);
+        }
+      }
+      // this warp no longer needs the TMEM slot: release it before the (slow) global stores
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(slot)) : "memory");
+
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) {
+        const int nb = nb0 + sub * 16;
+        if (nb >= p.N) break;  // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * P_STG_LD + j) =
+              make_float4(v[sub * 16 + j] * p.w_scale, v[sub * 16 + j + 1] * p.w_scale, v[sub * 16 + j + 2] * p.w_scale,
+                          v[sub * 16 + j + 3] * p.w_scale);
+        __syncwarp();
+        const int n = nb + c4 * 4;
+        if (n < p.N) {
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            if (opix[it] < 0) continue;
+            float4 tt = *reinterpret_cast<const float4*>(stg + (it * 8 + r8) * P_STG_LD + c4 * 4);
+            tt.x += bias4.x; tt.y += bias4.y; tt.z += bias4.z; tt.w += bias4.w;
+            if (p.act == WXF_ACT_GELU_ERF) {
+              tt.x = wxf_gelu_erf(tt.x); tt.y = wxf_gelu_erf(tt.y); tt.z = wxf_gelu_erf(tt.z); tt.w = wxf_gelu_erf(tt.w);
+            }
+            if (p.res) {
+              tt.x += rres[sub][it].x; tt.y += rres[sub][it].y; tt.z += rres[sub][it].z; tt.w += rres[sub][it].w;
+            }
+            if (p.out) *reinterpret_cast<float4*>(p.out + opix[it] * p.ldc + n) = tt;
+            if (p.out_hi) {
+              __align__(8) __half h4[4];
+              __align__(8) __half l4[4];
+              wxf_split_f16x2(tt.x, h4[0], l4[0]);
+              wxf_split_f16x2(tt.y, h4[1], l4[1]);
+              wxf_split_f16x2(tt.z, h4[2], l4[2]);
+              wxf_split_f16x2(tt.w, h4[3], l4[3]);
+              *reinterpret_cast<uint2*>(p.out_hi + opix[it] * p.ldh + n) = *reinterpret_cast<const uint2*>(h4);
+              *reinterpret_cast<uint2*>(p.out_lo + opix[it] * p.ldh + n) = *reinterpret_cast<const uint2*>(l4);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ---- host side: TMA descriptors -----------------------------------------------------------------------------
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -511,6 +770,43 @@ int launch(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap
   return 0;
 }
 
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+bool persistent_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXF_TC_PERSISTENT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int MODE>
+int launch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
+                      const TcParams& p, int n_tiles, int m_tiles, int phases, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_persistent_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    if (e != cudaSuccess) WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", P_SMEM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int64_t total = (int64_t)n_tiles * m_tiles * phases;
+  if (total > INT32_MAX) WXF_FAIL(WXF_EINVAL, "tc: too many tiles");
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  tc_persistent_kernel<MODE><<<grid, P_THREADS, P_SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p, n_tiles, m_tiles, (int)total);
+  WXF_CHECK_LAUNCH("tc_persistent");
+  return 0;
+}
+
 int check_epilogue(const char* who, int N, const float* bias, const float* res, const float* out, const void* out_hi,
                    const void* out_lo, int ldc, int c_off, int ldr, int r_off, int ldh, int h_off) {
   if (!out && !out_hi) WXF_FAIL(WXF_EINVAL, "%s: no output", who);
@@ -540,7 +836,8 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
   if (rc) return rc;
   if (d->M > (int64_t)65535 * BLOCK_M) WXF_FAIL(WXF_EINVAL, "gemm_tc: M too large for one launch");
   cudaStream_t st = (cudaStream_t)stream;
-  const int BN = d->N > 128 ? 256 : 128;
+  const bool persistent = persistent_enabled();
+  const int BN = (!persistent && d->N > 128) ? 256 : 128;
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
   if ((rc = make_map_2d(&ta_hi, d->a_hi, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, BLOCK_M))) return rc;
   if ((rc = make_map_2d(&ta_lo, d->a_lo, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, BLOCK_M))) return rc;
@@ -555,6 +852,9 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
   p.M = d->M; p.N = d->N; p.num_ksteps = (d->K + BLOCK_K - 1) / BLOCK_K;
   p.ldc = d->ldc; p.ldr = d->ldr; p.ldh = d->ldh; p.act = d->act;
   p.w_scale = ldexpf(1.0f, -d->w_scale_log2);
+  if (persistent)
+    return launch_persistent<MODE_GEMM>(ta_hi, ta_lo, tw_hi, tw_lo, p, (d->N + BN - 1) / BN,
+                                        (int)((d->M + BLOCK_M - 1) / BLOCK_M), 1, st);
   dim3 grid((unsigned)((d->N + BN - 1) / BN), (unsigned)((d->M + BLOCK_M - 1) / BLOCK_M), 1);
   if (BN == 256) return launch<256, 2, MODE_GEMM>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
   return launch<128, 3, MODE_GEMM>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
@@ -594,7 +894,8 @@ extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
     }
   }
   const int bw = best_bw, bh = best_bh;
-  const int BN = d->N > 128 ? 256 : 128;
+  const bool persistent = persistent_enabled();
+  const int BN = (!persistent && d->N > 128) ? 256 : 128;
   const int K = d->T * d->cin_pad;
 
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
@@ -634,6 +935,8 @@ extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
       p.taps[z][t][1] = (int16_t)d->taps[(z * d->T + t) * 2 + 1];
     }
   const int64_t ntiles = (int64_t)d->B * p.tiles_x * p.tiles_y;
+  if (persistent)
+    return launch_persistent<MODE_CONV>(ta_hi, ta_lo, tw_hi, tw_lo, p, (d->N + BN - 1) / BN, (int)ntiles, d->phases, st);
   if (ntiles > 65535) WXF_FAIL(WXF_EINVAL, "conv_tc: too many tiles for one launch");
   dim3 grid((unsigned)((d->N + BN - 1) / BN), (unsigned)ntiles, (unsigned)d->phases);
   if (BN == 256) return launch<256, 2, MODE_CONV>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);

@@ -11,4 +11,9 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 echo "smoke exit $?" >> gpurun_out/smoke.log
 timeout 900 python bench.py --steps ${STEPS:-5} --warmup 3 --profile-out gpurun_out/bench_profile.json ${BENCH_EXTRA:-} > gpurun_out/bench.log 2> gpurun_out/bench.err
 echo "bench exit $?" >> gpurun_out/bench.err
+if [ -n "${AB:-}" ]; then
+  WXF_TC_PERSISTENT=0 timeout 600 python -m pytest tests/test_gpu_gemm_tc.py tests/test_gpu_conv_tc.py -q -m gpu --timeout 300 2>&1 | tail -5 > gpurun_out/pytest_tc_nonpersistent.log
+  WXF_TC_PERSISTENT=0 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --profile-out gpurun_out/bench_profile_np.json > gpurun_out/bench_np.log 2>> gpurun_out/bench.err
+  tail -3 gpurun_out/pytest_tc_nonpersistent.log; python -c "import json;d=json.loads(open('gpurun_out/bench_np.log').read());print('non-persistent ms/step',d['ms_per_step'],{k:v['ms'] for k,v in d['kernel_families'].items()})"
+fi
 tail -25 gpurun_out/pytest_gemm_tc.log; tail -8 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; cat gpurun_out/bench.log; tail -5 gpurun_out/bench.err
