@@ -25,15 +25,15 @@
 //   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16 per instruction)
 //   warps 2-5 : epilogue: tcgen05.ld -> registers -> padded smem transpose -> bias/GELU/residual ->
 //               coalesced 128-byte row segments (fp32 and/or fp16 hi/lo planes)
-#include <cuda.h>
-#include <cuda_fp16.h>
-
 #include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
 
-#include "wxf_common.cuh"
+#include "wxf_tc_host.cuh"
+#include "wxf_tc_ptx.cuh"
+
+using namespace wxf_tc;
 
 namespace {
 
@@ -43,7 +43,6 @@ constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB: one 128-row operand
 constexpr int NUM_THREADS = 192;
 constexpr int STG_LD = 36;                         // floats per staged row (32 + 4 pad: conflict-free float4)
 constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;     // 4 epilogue warps
-constexpr uint32_t SPIN_LIMIT = 1u << 22;          // mbarrier waits trap instead of hanging the GPU
 constexpr int MAX_TAPS = 64;
 constexpr int MODE_GEMM = 0, MODE_CONV = 1, MODE_TOEP = 2;
 
@@ -67,85 +66,6 @@ struct TcParams {
   int step, J, ch;    // Toeplitz mode: tile step along x (128 - (J-1)), taps folded into N, channels of the branch
   int16_t taps[4][MAX_TAPS][2];  // [phase][tap] = (dy, dx); only [0] used when phases == 1
 };
-
-// ---- PTX wrappers ------------------------------------------------------------------------------
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > SPIN_LIMIT) {
-      printf("wxf tc kernel: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          dst),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row atoms 1024 B apart)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
-  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                    // descriptor version 1 (sm_100)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-  return d;
-}
 
 // ---- kernel --------------------------------------------------------------------------------------
 
@@ -661,93 +581,6 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 }
 
 // ---- host side: TMA descriptors -----------------------------------------------------------------------------
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(f);
-  });
-  return fn;
-}
-
-struct MapKey {
-  const void* ptr;
-  uint64_t d[4], s[3];
-  uint32_t box[4], es[4], rank;
-  bool operator==(const MapKey& o) const {
-    if (ptr != o.ptr || rank != o.rank) return false;
-    for (int i = 0; i < 4; ++i)
-      if (d[i] != o.d[i] || box[i] != o.box[i] || es[i] != o.es[i]) return false;
-    for (int i = 0; i < 3; ++i)
-      if (s[i] != o.s[i]) return false;
-    return true;
-  }
-};
-struct MapKeyHash {
-  size_t operator()(const MapKey& k) const {
-    uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull + k.rank;
-    for (int i = 0; i < 4; ++i) h = (h ^ (k.d[i] * 1315423911ull + k.box[i] * 2654435761ull + k.es[i])) * 0x100000001B3ull;
-    for (int i = 0; i < 3; ++i) h = (h ^ k.s[i]) * 0x100000001B3ull;
-    return (size_t)h;
-  }
-};
-
-// fp16 tensor map, 128B swizzle, zero OOB fill; dims innermost-first, strides in bytes for dims 1..rank-1
-int make_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims, const uint64_t* strides,
-             const uint32_t* box, const uint32_t* estr) {
-  static std::mutex mu;
-  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{};
-  key.ptr = ptr;
-  key.rank = rank;
-  for (uint32_t i = 0; i < rank; ++i) {
-    key.d[i] = dims[i];
-    key.box[i] = box[i];
-    key.es[i] = estr[i];
-    if (i + 1 < rank) key.s[i] = strides[i];
-  }
-  {
-    std::lock_guard<std::mutex> g(mu);
-    auto it = cache.find(key);
-    if (it != cache.end()) {
-      *out = it->second;
-      return 0;
-    }
-  }
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) WXF_FAIL(WXF_EUNSUPPORTED, "tc: cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t gdim[4], gstr[3];
-  cuuint32_t b[4], e[4];
-  for (uint32_t i = 0; i < rank; ++i) {
-    gdim[i] = dims[i];
-    b[i] = box[i];
-    e[i] = estr[i];
-    if (i + 1 < rank) gstr[i] = strides[i];
-  }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, b, e,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) WXF_FAIL(WXF_EINVAL, "tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  std::lock_guard<std::mutex> g(mu);
-  if (cache.size() > 4096) cache.clear();
-  cache.emplace(key, *out);
-  return 0;
-}
-
-int make_map_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
-  const uint64_t dims[2] = {cols, rows}, strides[1] = {ld * 2};
-  const uint32_t box[2] = {(uint32_t)BLOCK_K, box_rows}, es[2] = {1, 1};
-  return make_map(out, ptr, 2, dims, strides, box, es);
-}
 
 template <int BN, int STAGES>
 constexpr int smem_bytes() {
