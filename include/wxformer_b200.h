@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 4
+#define WXF_ABI_VERSION 5
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -116,6 +116,16 @@ int wxf_window_attention_f32(const float* qkv, int ldq, const float* biasT, floa
 /* Same attention core; the result is written as fp16 hi/lo operand planes [B*H*W, ldh] for the to_out GEMM. */
 int wxf_window_attention_f16x2(const float* qkv, int ldq, const float* biasT, void* out_hi, void* out_lo, int ldh,
                                int B, int H, int W, int d, int dh, int wsz, int kind, float scale, void* stream);
+
+/*
+ * The same attention core on the tcgen05 tensor cores: Q, K, V gathered by TMA from the fp16 hi/lo planes of the
+ * to_qkv output ([B, H, W, ldq]; short windows as 4-D boxes, dilated long groups as 5-D boxes), S = QK^T and O = PV as
+ * f16x2 three-pass MMAs with TMEM accumulators, windows of the same head packed block-diagonally into 128-row tiles,
+ * softmax in fp32 registers.  Output: fp16 hi/lo planes [B*H*W, ldh].  dh must be 32, L <= 128, ldq % 8 == 0.
+ */
+int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, int ldq, const float* biasT, void* out_hi,
+                            void* out_lo, int ldh, int B, int H, int W, int d, int dh, int wsz, int kind, float scale,
+                            void* stream);
 
 /*
  * Pointwise (1x1 conv) GEMM on the tcgen05 tensor cores with TMA-staged operands

@@ -1,0 +1,295 @@
+// Cross-scale window attention on the tensor cores (tcgen05 + TMEM), operands gathered by TMA.
+// Reference arithmetic: credit/models/crossformer.py:261-296, 301-314 (window / dilated token gather, q*scale,
+// QK^T + dynamic position bias, softmax, PV, inverse gather).
+//
+// One CTA = one (window group, head) tile of up to 128 query rows: G = 128 / Lp windows of the same head are packed
+// block-diagonally (Lp = L rounded up to 2 so every TMA box lands 128-byte aligned).  All operands are f16x2 planes:
+//   TMA   : per window 6 boxes (Q, K, V) x (hi, lo) of the qkv planes [B, H, W, 3d]; short windows are a 4-D box
+//           {32 ch, wsz, wsz, 1}; the dilated "long" groups are a 5-D box over the (l1, gh, l2, gw) view of the grid,
+//           so the strided gather costs nothing.  64-byte rows, SWIZZLE_64B.
+//   MMA 1 : S[128 x 128] = Q K^T, 3 passes x 2 K-steps (K-major A and B), accumulator in TMEM columns [0, 128)
+//   soft  : thread = row; two TMEM passes (max, then exp / sum); only the row's own window columns are kept, the
+//           rest of the block-diagonal tile is written as exact zeros; P goes to shared memory as fp16 hi/lo planes in
+//           the K-major SWIZZLE_128B layout the second MMA reads
+//   MMA 2 : O[128 x 32] = P V, 3 passes x 8 K-steps; V is read as an MN-major B operand straight from the TMA tile
+//   epi   : O / rowsum -> fp16 hi/lo planes of the attention output at the token's pixel (the inverse gather)
+#include "wxf_tc_host.cuh"
+#include "wxf_tc_ptx.cuh"
+
+using namespace wxf_tc;
+
+namespace {
+
+constexpr int DH = 32;
+constexpr int AT_THREADS = 192;
+constexpr int ROWS = 128;
+constexpr int QKV_PLANE = ROWS * 64;       // 8 KB: 128 rows x 64 B
+constexpr int P_ATOM = ROWS * 128;         // 16 KB: 128 rows x 64 fp16
+// K, V: hi plane then lo plane.  Q aliases the first 16 KB of the P area: Q is dead once S = Q K^T has completed,
+// which is exactly when the softmax warps start writing P (2 CTAs of 97 KB fit one SM).
+constexpr int OFF_K = 0, OFF_V = 2 * QKV_PLANE;
+constexpr int OFF_P = 4 * QKV_PLANE;       // P_hi (2 atoms) then P_lo (2 atoms)
+constexpr int OFF_Q = OFF_P;
+constexpr int OFF_BAR = OFF_P + 4 * P_ATOM;
+constexpr int AT_SMEM = OFF_BAR + 64 + 1024;
+constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t IDESC_O = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+struct AttnParams {
+  const float* biasT;
+  __half* out_hi;
+  __half* out_lo;
+  int ldh;
+  int H, W, d, heads, wsz, kind;
+  float scale;
+  int L, Lp, G, nh, nw;
+  int64_t nwin;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                           const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t bar_load = base + OFF_BAR, bar_s = bar_load + 8, bar_p = bar_load + 16, bar_o = bar_load + 24;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + OFF_BAR + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.x % p.heads;
+  const int64_t group = blockIdx.x / p.heads;
+  const int64_t w0 = group * p.G;
+  const int nv = (int)((p.nwin - w0) < p.G ? (p.nwin - w0) : p.G);  // windows present in this tile
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // rows the TMA boxes do not cover must be finite zeros (0 * garbage could be NaN in P V)
+  {
+    uint4* z = reinterpret_cast<uint4*>(gen);
+    for (int i = threadIdx.x; i < (6 * QKV_PLANE) / 16; i += AT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, (uint32_t)(nv * 6 * p.L * 64));
+      const int per_img = p.nh * p.nw;
+      for (int g = 0; g < nv; ++g) {
+        const int64_t w = w0 + g;
+        const int b = (int)(w / per_img);
+        const int rem = (int)(w - (int64_t)b * per_img);
+        const int gh = rem / p.nw, gw = rem - gh * p.nw;
+        const uint32_t row_off = (uint32_t)(g * p.Lp * 64);
+#pragma unroll
+        for (int which = 0; which < 3; ++which) {  // q, k, v
+          const int c0 = which * p.d + head * DH;
+          const uint32_t dst = base + (uint32_t)(which == 0 ? OFF_Q : (which == 1 ? OFF_K : OFF_V)) + row_off;
+          if (p.kind == WXF_ATTN_SHORT) {
+            tma_load_4d(&tm_hi, bar_load, dst, c0, gw * p.wsz, gh * p.wsz, b);
+            tma_load_4d(&tm_lo, bar_load, dst + QKV_PLANE, c0, gw * p.wsz, gh * p.wsz, b);
+          } else {
+            tma_load_5d(&tm_hi, bar_load, dst, c0, gw, 0, gh, b * p.wsz);
+            tma_load_5d(&tm_lo, bar_load, dst + QKV_PLANE, c0, gw, 0, gh, b * p.wsz);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(bar_load, 0);
+      tc_fence_after();
+      const uint32_t q_hi = base + OFF_Q, q_lo = q_hi + QKV_PLANE, k_hi = base + OFF_K, k_lo = k_hi + QKV_PLANE;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {  // dh = 32 = two K=16 steps (32 bytes each inside the 64-byte row)
+        tc_mma_f16(tmem_base, umma_desc_sw64_kmajor(q_hi + k * 32), umma_desc_sw64_kmajor(k_lo + k * 32), IDESC_S, k ? 1u : 0u);
+        tc_mma_f16(tmem_base, umma_desc_sw64_kmajor(q_lo + k * 32), umma_desc_sw64_kmajor(k_hi + k * 32), IDESC_S, 1u);
+        tc_mma_f16(tmem_base, umma_desc_sw64_kmajor(q_hi + k * 32), umma_desc_sw64_kmajor(k_hi + k * 32), IDESC_S, 1u);
+      }
+      tc_commit(bar_s);
+      mbar_wait(bar_p, 0);  // P planes written by the softmax warps
+      tc_fence_after();
+      const uint32_t p_hi = base + OFF_P, p_lo = p_hi + 2 * P_ATOM, v_hi = base + OFF_V, v_lo = v_hi + QKV_PLANE;
+      const uint32_t d_o = tmem_base + 128;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {  // 128 key rows = eight K=16 steps
+        const uint32_t pa = (uint32_t)((ks >> 2) * P_ATOM + (ks & 3) * 32);
+        const uint32_t va = (uint32_t)(ks * 16 * 64);
+        tc_mma_f16(d_o, umma_desc_sw128(p_hi + pa), umma_desc_sw64_mnmajor(v_lo + va), IDESC_O, ks ? 1u : 0u);
+        tc_mma_f16(d_o, umma_desc_sw128(p_lo + pa), umma_desc_sw64_mnmajor(v_hi + va), IDESC_O, 1u);
+        tc_mma_f16(d_o, umma_desc_sw128(p_hi + pa), umma_desc_sw64_mnmajor(v_hi + va), IDESC_O, 1u);
+      }
+      tc_commit(bar_o);
+    }
+  } else {
+    // ---- softmax + epilogue: thread = query row ----
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int g = r / p.Lp, i = r - g * p.Lp;
+    const bool valid = g < nv && i < p.L;
+    const int lo_c = valid ? g * p.Lp : 0, hi_c = valid ? lo_c + p.L : 0;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float* brow = p.biasT + i;  // biasT[j*L + i]
+
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float mx = -3.0e38f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t rr[32];
+      tmem_ld32(lane_base + (uint32_t)(c * 32), rr);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = c * 32 + j;
+        if (col >= lo_c && col < hi_c) {
+          const float sv = fmaf(__uint_as_float(rr[j]), p.scale, __ldg(brow + (size_t)(col - lo_c) * p.L));
+          mx = fmaxf(mx, sv);
+        }
+      }
+    }
+    float lsum = 0.f;
+    uint8_t* prow_hi = gen + OFF_P + r * 128;
+    uint8_t* prow_lo = prow_hi + 2 * P_ATOM;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t rr[32];
+      tmem_ld32(lane_base + (uint32_t)(c * 32), rr);
+#pragma unroll
+      for (int q8 = 0; q8 < 4; ++q8) {  // 8 columns = one 16-byte chunk of the swizzled row
+        __align__(16) __half h8[8];
+        __align__(16) __half l8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int col = c * 32 + q8 * 8 + e;
+          float pv = 0.f;
+          if (col >= lo_c && col < hi_c) {
+            const float sv = fmaf(__uint_as_float(rr[q8 * 8 + e]), p.scale, __ldg(brow + (size_t)(col - lo_c) * p.L));
+            pv = expf(sv - mx);
+          }
+          lsum += pv;
+          h8[e] = __float2half_rn(pv);
+          l8[e] = __float2half_rn(pv - __half2float(h8[e]));
+        }
+        const int cc = (c & 1) * 4 + q8;                 // 16-byte chunk index inside the 64-column atom
+        const int off = (c >> 1) * P_ATOM + ((cc ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(prow_hi + off) = *reinterpret_cast<const uint4*>(h8);
+        *reinterpret_cast<uint4*>(prow_lo + off) = *reinterpret_cast<const uint4*>(l8);
+      }
+    }
+    fence_proxy_async();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    mbar_arrive(bar_p);
+
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    uint32_t oo[32];
+    tmem_ld32(lane_base + 128u, oo);
+    if (valid) {
+      const int64_t w = w0 + g;
+      const int per_img = p.nh * p.nw;
+      const int b = (int)(w / per_img);
+      const int rem = (int)(w - (int64_t)b * per_img);
+      const int gh = rem / p.nw, gw = rem - gh * p.nw;
+      const int ty = i / p.wsz, tx = i - ty * p.wsz;
+      int y, x;
+      if (p.kind == WXF_ATTN_SHORT) {
+        y = gh * p.wsz + ty;
+        x = gw * p.wsz + tx;
+      } else {
+        y = ty * p.nh + gh;
+        x = tx * p.nw + gw;
+      }
+      const int64_t pix = ((int64_t)b * p.H + y) * p.W + x;
+      const float inv = 1.0f / lsum;
+      uint4* hp = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldh + head * DH);
+      uint4* lp = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldh + head * DH);
+#pragma unroll
+      for (int c = 0; c < DH / 8; ++c) {
+        __align__(16) __half h8[8];
+        __align__(16) __half l8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) wxf_split_f16x2(__uint_as_float(oo[8 * c + e]) * inv, h8[e], l8[e]);
+        hp[c] = *reinterpret_cast<const uint4*>(h8);
+        lp[c] = *reinterpret_cast<const uint4*>(l8);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+}  // namespace
+
+extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, int ldq, const float* biasT, void* out_hi,
+                                       void* out_lo, int ldh, int B, int H, int W, int d, int dh, int wsz, int kind,
+                                       float scale, void* stream) {
+  if (!qkv_hi || !qkv_lo || !biasT || !out_hi || !out_lo) WXF_FAIL(WXF_EINVAL, "attention_tc: null pointer");
+  if (B <= 0 || H <= 0 || W <= 0 || d <= 0 || wsz <= 0) WXF_FAIL(WXF_EINVAL, "attention_tc: bad dims");
+  if (dh != DH) WXF_FAIL(WXF_EUNSUPPORTED, "attention_tc: dim_head must be 32, got %d", dh);
+  if (d % dh) WXF_FAIL(WXF_EINVAL, "attention_tc: d %% dh != 0");
+  if (H % wsz || W % wsz) WXF_FAIL(WXF_EINVAL, "attention_tc: grid %dx%d not divisible by window %d", H, W, wsz);
+  if (kind != WXF_ATTN_SHORT && kind != WXF_ATTN_LONG) WXF_FAIL(WXF_EINVAL, "attention_tc: bad kind");
+  const int L = wsz * wsz;
+  if (L > ROWS) WXF_FAIL(WXF_EUNSUPPORTED, "attention_tc: window %d (L=%d) > %d tokens", wsz, L, ROWS);
+  if (ldq < 3 * d || (ldq & 7) || ldh < d || (ldh & 7) || !wxf_aligned16(qkv_hi) || !wxf_aligned16(qkv_lo) ||
+      !wxf_aligned16(out_hi) || !wxf_aligned16(out_lo))
+    WXF_FAIL(WXF_EALIGN, "attention_tc: strides must be multiples of 8 and planes 16-byte aligned");
+  const int nh = H / wsz, nw = W / wsz;
+  const uint64_t ldb = (uint64_t)ldq * 2;
+  CUtensorMap tm_hi, tm_lo;
+  int rc;
+  if (kind == WXF_ATTN_SHORT) {
+    const uint64_t dims[4] = {(uint64_t)3 * d, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {ldb, (uint64_t)W * ldb, (uint64_t)H * W * ldb};
+    const uint32_t box[4] = {(uint32_t)DH, (uint32_t)wsz, (uint32_t)wsz, 1}, es[4] = {1, 1, 1, 1};
+    if ((rc = make_map(&tm_hi, qkv_hi, 4, dims, strides, box, es, 64))) return rc;
+    if ((rc = make_map(&tm_lo, qkv_lo, 4, dims, strides, box, es, 64))) return rc;
+  } else {
+    // pixel (y, x) = (l1*nh + gh, l2*nw + gw): dims (c, gw, l2, gh, (b, l1)); a group's tokens are one box
+    const uint64_t dims[5] = {(uint64_t)3 * d, (uint64_t)nw, (uint64_t)wsz, (uint64_t)nh, (uint64_t)B * wsz};
+    const uint64_t strides[4] = {ldb, (uint64_t)nw * ldb, (uint64_t)W * ldb, (uint64_t)nh * W * ldb};
+    const uint32_t box[5] = {(uint32_t)DH, 1, (uint32_t)wsz, 1, (uint32_t)wsz}, es[5] = {1, 1, 1, 1, 1};
+    if ((rc = make_map(&tm_hi, qkv_hi, 5, dims, strides, box, es, 64))) return rc;
+    if ((rc = make_map(&tm_lo, qkv_lo, 5, dims, strides, box, es, 64))) return rc;
+  }
+  AttnParams p{};
+  p.biasT = biasT;
+  p.out_hi = reinterpret_cast<__half*>(out_hi);
+  p.out_lo = reinterpret_cast<__half*>(out_lo);
+  p.ldh = ldh;
+  p.H = H; p.W = W; p.d = d; p.heads = d / dh; p.wsz = wsz; p.kind = kind; p.scale = scale;
+  p.L = L; p.Lp = (L + 1) & ~1; p.G = ROWS / p.Lp; p.nh = nh; p.nw = nw;
+  p.nwin = (int64_t)B * nh * nw;
+  const int64_t groups = (p.nwin + p.G - 1) / p.G;
+  const int64_t blocks = groups * p.heads;
+  if (blocks > INT32_MAX) WXF_FAIL(WXF_EINVAL, "attention_tc: too many tiles");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e != cudaSuccess) WXF_FAIL((int)e, "attention_tc: cannot opt in to %d bytes of shared memory", AT_SMEM);
+    attr_set = true;
+  }
+  window_attention_tc_kernel<<<(unsigned)blocks, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tm_hi, tm_lo, p);
+  WXF_CHECK_LAUNCH("window_attention_tc");
+  return 0;
+}

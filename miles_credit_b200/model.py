@@ -130,6 +130,7 @@ class _Plan:
                 logger.warning("channel counts not multiples of 4: using the exact-fp32 CUDA-core path")
                 tensor_cores = False
         self.tensor_cores = tensor_cores
+        self.attention_tc = tensor_cores and os.environ.get("WXF_ATTN_TC", "1") != "0"
         f32 = dict(device=device, dtype=torch.float32)
         f16 = dict(device=device, dtype=torch.float16)
         B = batch
@@ -234,9 +235,17 @@ class _Plan:
                     if tc:
                         add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, att.ln_g, att.ln_b, m, d), "layernorm", 0,
                             8.0 * m * d)
-                        self._gemm(ln_hi, ln_lo, att.qkv_tc, "qkv", M=m, lda=d, out=wide, ldc=3 * d)
-                        add(ops.window_attention_f16x2, (wide, 3 * d, att.bias_t, ln_hi, ln_lo, d, B, st.h, st.w, d,
-                                                         g.dim_head, att.wsz, att.kind, scale), "attention", *attn_cost)
+                        if self.attention_tc and L <= 128:
+                            q_hi, q_lo = self.scratch16[: m * 3 * d], self.scratch16[hid_off: hid_off + m * 3 * d]
+                            self._gemm(ln_hi, ln_lo, att.qkv_tc, "qkv", M=m, lda=d, out_hi=q_hi, out_lo=q_lo, ldh=3 * d)
+                            add(ops.window_attention_tc, (q_hi, q_lo, 3 * d, att.bias_t, ln_hi, ln_lo, d, B, st.h, st.w,
+                                                          d, g.dim_head, att.wsz, att.kind, scale), "attention",
+                                *attn_cost)
+                        else:
+                            self._gemm(ln_hi, ln_lo, att.qkv_tc, "qkv", M=m, lda=d, out=wide, ldc=3 * d)
+                            add(ops.window_attention_f16x2, (wide, 3 * d, att.bias_t, ln_hi, ln_lo, d, B, st.h, st.w, d,
+                                                             g.dim_head, att.wsz, att.kind, scale), "attention",
+                                *attn_cost)
                         self._gemm(ln_hi, ln_lo, att.out_tc, "out_proj", M=m, lda=d, out=xv, ldc=ld, res=xv, ldr=ld)
                         add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, ff.ln_g, ff.ln_b, m, d), "layernorm", 0,
                             8.0 * m * d)

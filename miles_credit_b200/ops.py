@@ -186,6 +186,18 @@ def window_attention_f16x2(qkv: torch.Tensor, ldq: int, bias_t: torch.Tensor, ou
     LAUNCHES += 1
 
 
+def window_attention_tc(qkv_hi: torch.Tensor, qkv_lo: torch.Tensor, ldq: int, bias_t: torch.Tensor, out_hi: torch.Tensor,
+                        out_lo: torch.Tensor, ldh: int, B: int, H: int, W: int, d: int, dh: int, wsz: int, kind: int,
+                        scale: float):
+    """Window attention on the tensor cores: fp16 hi/lo planes of qkv in, planes of the attention output out."""
+    global LAUNCHES
+    st = _lib.load().wxf_window_attention_tc(qkv_hi.data_ptr(), qkv_lo.data_ptr(), ldq, bias_t.data_ptr(),
+                                             out_hi.data_ptr(), out_lo.data_ptr(), ldh, B, H, W, d, dh, wsz, kind, scale,
+                                             _stream())
+    _lib.check(st, "wxf_window_attention_tc")
+    LAUNCHES += 1
+
+
 def make_conv_desc(inp: torch.Tensor, wts: ConvWeights, out: torch.Tensor, *, B: int, Hi: int, Wi: int, lda: int,
                    Ho: int, Wo: int, ldc: int, c_off: int = 0, res: Optional[torch.Tensor] = None, ldr: int = 0,
                    r_off: int = 0, act: int = 0, in_off: int = 0) -> WxfConvDesc:

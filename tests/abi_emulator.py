@@ -33,7 +33,7 @@ class EmulatedLib:
         self.calls = []
 
     def wxf_abi_version(self):
-        return 4
+        return 5
 
     def wxf_last_error(self):
         return b"emulator"
@@ -239,6 +239,43 @@ class EmulatedLib:
         hi, lo = self._split(torch.from_numpy(tmp).view(M, d))
         self._harr(out_hi, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(hi)
         self._harr(out_lo, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(lo)
+        return 0
+
+    def wxf_window_attention_tc(self, qkv_hi, qkv_lo, ldq, biasT, out_hi, out_lo, ldh, B, H, W, d, dh, wsz, kind, scale,
+                                stream):
+        """f16x2 semantics: operands are hi+lo (22 bits), the lo*lo products are dropped, softmax in fp32."""
+        self.calls.append("attention_tc")
+        if dh != 32 or wsz * wsz > 128 or ldq % 8:
+            return -3
+        M = B * H * W
+        n_el = (M - 1) * ldq + 3 * d
+        hi = self._harr(qkv_hi, n_el).as_strided((B, H, W, 3 * d), (H * W * ldq, W * ldq, ldq, 1)).float()
+        lo = self._harr(qkv_lo, n_el).as_strided((B, H, W, 3 * d), (H * W * ldq, W * ldq, ldq, 1)).float()
+        L = wsz * wsz
+        bias = _t(_arr(biasT, L * L)).view(L, L).t()
+        nh, nw, heads = H // wsz, W // wsz, d // dh
+        res = torch.zeros(B, H, W, d)
+        for b in range(B):
+            for gh in range(nh):
+                for gw in range(nw):
+                    if kind == 0:
+                        ys, xs = gh * wsz + torch.arange(wsz), gw * wsz + torch.arange(wsz)
+                    else:
+                        ys, xs = torch.arange(wsz) * nh + gh, torch.arange(wsz) * nw + gw
+                    th = hi[b][ys][:, xs].reshape(L, 3, heads, dh).double()
+                    tl = lo[b][ys][:, xs].reshape(L, 3, heads, dh).double()
+                    qh, kh, vh = (th[:, i].transpose(0, 1) for i in range(3))
+                    ql, kl, vl = (tl[:, i].transpose(0, 1) for i in range(3))
+                    s_ = (qh @ kl.transpose(1, 2) + ql @ kh.transpose(1, 2) + qh @ kh.transpose(1, 2)).float()
+                    s_ = s_ * scale + bias
+                    pe = torch.exp(s_ - s_.max(-1, keepdim=True).values)
+                    ph = pe.half().float()
+                    pl = (pe - ph).half().float()
+                    o = (ph.double() @ vl + pl.double() @ vh + ph.double() @ vh).float() / pe.sum(-1, keepdim=True)
+                    res[b, ys[:, None], xs[None, :]] = o.transpose(0, 1).reshape(wsz, wsz, d)
+        oh, ol = self._split(res.view(M, d))
+        self._harr(out_hi, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(oh)
+        self._harr(out_lo, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(ol)
         return 0
 
     def wxf_conv_igemm_f32(self, dref, stream):

@@ -42,7 +42,7 @@ def test_plan_through_emulated_abi_matches_reference(golden_dir, emulated, case,
     d0 = geo.stages[0].dim
     s0 = plan.cat[0][..., d0:].permute(0, 3, 1, 2)
     assert float((s0 - fx["taps"]["s0.out"]).abs().max() / fx["taps"]["s0.out"].abs().max()) < 1e-5
-    assert emulated.calls.count("attention") == 2 * sum(geo.depth)
+    assert emulated.calls.count("attention_tc" if tensor_cores else "attention") == 2 * sum(geo.depth)
     assert (emulated.calls.count("gemm_tc") == 8 * sum(geo.depth)) == tensor_cores
     if tensor_cores:  # stage 1-3 cross-embed (6) + decoder (3 x 3) run as tensor-core convolutions
         assert emulated.calls.count("conv_tc") >= 15
