@@ -43,7 +43,7 @@ struct AttnParams {
   int H, W, d, heads, wsz, kind;
   float scale;
   int L, Lp, G, nh, nw;
-  int64_t nwin;
+  int64_t nwin, ntiles;
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -57,10 +57,6 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + OFF_BAR + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.x % p.heads;
-  const int64_t group = blockIdx.x / p.heads;
-  const int64_t w0 = group * p.G;
-  const int nv = (int)((p.nwin - w0) < p.G ? (p.nwin - w0) : p.G);  // windows present in this tile
 
   if (threadIdx.x == 0) {
     mbar_init(bar_load, 1);
@@ -85,8 +81,18 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // persistent: each CTA (two per SM) walks tiles = (window group, head); every barrier completes once per tile, so
+  // the wait parity is the tile iteration's low bit.  Stale rows of a previous tile are finite, masked data.
+  for (int64_t tile = blockIdx.x, it = 0; tile < p.ntiles; tile += gridDim.x, ++it) {
+  const uint32_t par = (uint32_t)it & 1u;
+  const int head = (int)(tile % p.heads);
+  const int64_t group = tile / p.heads;
+  const int64_t w0 = group * p.G;
+  const int nv = (int)((p.nwin - w0) < p.G ? (p.nwin - w0) : p.G);  // windows present in this tile
+
   if (warp == 0) {
     if (lane == 0) {
+      if (it > 0) mbar_wait(bar_o, par ^ 1u);  // previous tile's P V has finished reading this CTA's shared memory
       mbar_expect_tx(bar_load, (uint32_t)(nv * 6 * p.L * 64));
       const int per_img = p.nh * p.nw;
       for (int g = 0; g < nv; ++g) {
@@ -111,7 +117,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      mbar_wait(bar_load, 0);
+      mbar_wait(bar_load, par);
       tc_fence_after();
       const uint32_t q_hi = base + OFF_Q, q_lo = q_hi + QKV_PLANE, k_hi = base + OFF_K, k_lo = k_hi + QKV_PLANE;
 #pragma unroll
@@ -121,7 +127,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
         tc_mma_f16(tmem_base, umma_desc_sw64_kmajor(q_hi + k * 32), umma_desc_sw64_kmajor(k_hi + k * 32), IDESC_S, 1u);
       }
       tc_commit(bar_s);
-      mbar_wait(bar_p, 0);  // P planes written by the softmax warps
+      mbar_wait(bar_p, par);  // P planes written by the softmax warps
       tc_fence_after();
       const uint32_t p_hi = base + OFF_P, p_lo = p_hi + 2 * P_ATOM, v_hi = base + OFF_V, v_lo = v_hi + QKV_PLANE;
       const uint32_t d_o = tmem_base + 128;
@@ -145,7 +151,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float* brow = p.biasT + i;  // biasT[j*L + i]
 
-    mbar_wait(bar_s, 0);
+    mbar_wait(bar_s, par);
     tc_fence_after();
     float mx = -3.0e38f;
 #pragma unroll 1
@@ -194,7 +200,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     tc_fence_before();
     mbar_arrive(bar_p);
 
-    mbar_wait(bar_o, 0);
+    mbar_wait(bar_o, par);
     tc_fence_after();
     uint32_t oo[32];
     tmem_ld32(lane_base + 128u, oo);
@@ -227,7 +233,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
         lp[c] = *reinterpret_cast<const uint4*>(l8);
       }
     }
+    tc_fence_before();  // this row's TMEM reads are done before the next tile's MMAs overwrite S / O
   }
+  }  // tile loop
 
   tc_fence_before();
   __syncthreads();
@@ -281,8 +289,11 @@ extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, i
   p.L = L; p.Lp = (L + 1) & ~1; p.G = ROWS / p.Lp; p.nh = nh; p.nw = nw;
   p.nwin = (int64_t)B * nh * nw;
   const int64_t groups = (p.nwin + p.G - 1) / p.G;
-  const int64_t blocks = groups * p.heads;
-  if (blocks > INT32_MAX) WXF_FAIL(WXF_EINVAL, "attention_tc: too many tiles");
+  p.ntiles = groups * p.heads;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t blocks = p.ntiles < 2 * (int64_t)sms ? p.ntiles : 2 * (int64_t)sms;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);

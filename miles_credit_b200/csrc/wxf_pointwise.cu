@@ -161,6 +161,57 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// vectorised variant for d % 128 == 0: each lane owns float4 chunks, 16-byte loads, 8/16-byte stores
+template <int NV4, bool SPLIT>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y,
+                                                             int ldy, __half* __restrict__ y_hi, __half* __restrict__ y_lo,
+                                                             const float* __restrict__ g, const float* __restrict__ bta,
+                                                             int64_t M, float eps) {
+  constexpr int d = NV4 * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[NV4];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV4; ++k) {
+    v[k] = xr[lane + 32 * k];
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  const float mean = wxf_warp_sum(s) / (float)d;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV4; ++k) {
+    const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, e = v[k].w - mean;
+    ss += (a * a + b * b) + (c * c + e * e);
+  }
+  const float var = wxf_warp_sum(ss) / (float)d;
+  const float den = sqrtf(var + eps);
+#pragma unroll
+  for (int k = 0; k < NV4; ++k) {
+    const int c4 = lane + 32 * k;
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + c4), bb = __ldg(reinterpret_cast<const float4*>(bta) + c4);
+    float4 o;
+    o.x = (v[k].x - mean) / den * gg.x + bb.x;
+    o.y = (v[k].y - mean) / den * gg.y + bb.y;
+    o.z = (v[k].z - mean) / den * gg.z + bb.z;
+    o.w = (v[k].w - mean) / den * gg.w + bb.w;
+    if constexpr (SPLIT) {
+      __align__(8) __half h4[4];
+      __align__(8) __half l4[4];
+      wxf_split_f16x2(o.x, h4[0], l4[0]);
+      wxf_split_f16x2(o.y, h4[1], l4[1]);
+      wxf_split_f16x2(o.z, h4[2], l4[2]);
+      wxf_split_f16x2(o.w, h4[3], l4[3]);
+      *reinterpret_cast<uint2*>(y_hi + row * ldy + 4 * c4) = *reinterpret_cast<const uint2*>(h4);
+      *reinterpret_cast<uint2*>(y_lo + row * ldy + 4 * c4) = *reinterpret_cast<const uint2*>(l4);
+    } else {
+      *reinterpret_cast<float4*>(y + row * ldy + 4 * c4) = o;
+    }
+  }
+}
+
 template <bool SPLIT>
 static int layernorm_launch(const float* x, int ldx, float* y, int ldy, void* y_hi, void* y_lo, const float* g,
                             const float* b, int64_t M, int d, float eps, void* stream) {
@@ -169,6 +220,19 @@ static int layernorm_launch(const float* x, int ldx, float* y, int ldy, void* y_
   const int nv = (d + 31) / 32;
   const unsigned blocks = (unsigned)((M + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (d % 128 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && wxf_aligned16(x) && wxf_aligned16(g) &&
+                   wxf_aligned16(b) && (SPLIT ? ((reinterpret_cast<uintptr_t>(y_hi) | reinterpret_cast<uintptr_t>(y_lo)) % 8 == 0)
+                                              : wxf_aligned16(y));
+  if (vec) {
+#define LN_VEC(NV4)                                                                                                   \
+  if (d == NV4 * 128) {                                                                                               \
+    layernorm_vec_kernel<NV4, SPLIT><<<blocks, 256, 0, st>>>(x, ldx, y, ldy, (__half*)y_hi, (__half*)y_lo, g, b, M, eps); \
+    WXF_CHECK_LAUNCH("layernorm");                                                                                    \
+    return 0;                                                                                                         \
+  }
+    LN_VEC(1) LN_VEC(2) LN_VEC(3) LN_VEC(4) LN_VEC(6) LN_VEC(8)
+#undef LN_VEC
+  }
 #define LN_CASE(NV)                                                                                         \
   if (nv <= NV) {                                                                                           \
     layernorm_kernel<NV, SPLIT><<<blocks, 256, 0, st>>>(x, ldx, y, ldy, (__half*)y_hi, (__half*)y_lo, g, b, M, d, eps); \
@@ -218,10 +282,53 @@ extern "C" int wxf_split_f16x2(const float* x, int ldx, void* hi, void* lo, int 
 // Pass 1: per-block partial (sum, sumsq) per group -> scratch;  pass 2: fp64 combine -> (mean, rstd);
 // pass 3: normalise + affine + SiLU (+ UpBlock shortcut).
 
-static constexpr int GN_PIX_PER_BLOCK = 512;
+// Pixels per statistics block: enough blocks to fill the GPU (>= ~4 per SM) but at least 32 pixels each.
+static inline int gn_pix_per_block(int64_t HW) {
+  int64_t ppb = HW / 592;
+  if (ppb < 32) ppb = 32;
+  if (ppb > 512) ppb = 512;
+  return (int)ppb;
+}
+
+// partial (sum, sumsq) per group for a chunk of pixels; C % 4 == 0 and C/4 divides 256: float4 loads
+__global__ void __launch_bounds__(256) gn_partial_vec_kernel(const float* __restrict__ x, int ldx, float2* __restrict__ part,
+                                                              int64_t HW, int C, int G, int nchunk, int ppb) {
+  __shared__ float4 rs[256], rq[256];
+  const int tid = threadIdx.x;
+  const int TC = C >> 2;          // float4 columns
+  const int lanes = 256 / TC;     // pixel lanes
+  const int tc = tid % TC, pl = tid / TC;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int64_t p0 = (int64_t)chunk * ppb;
+  int64_t p1 = p0 + ppb;
+  if (p1 > HW) p1 = HW;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  for (int64_t p = p0 + pl; p < p1; p += lanes) {
+    const float4 v = *reinterpret_cast<const float4*>(x + ((int64_t)b * HW + p) * ldx + 4 * tc);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+  }
+  rs[tid] = s;
+  rq[tid] = q;
+  __syncthreads();
+  const int cpg = C / G;
+  const float* fs = reinterpret_cast<const float*>(rs);
+  const float* fq = reinterpret_cast<const float*>(rq);
+  for (int gidx = tid; gidx < G; gidx += 256) {
+    float ts = 0.f, tq = 0.f;
+    for (int cc = 0; cc < cpg; ++cc) {
+      const int c = gidx * cpg + cc;
+      for (int l = 0; l < lanes; ++l) {
+        ts += fs[(l * TC + (c >> 2)) * 4 + (c & 3)];
+        tq += fq[(l * TC + (c >> 2)) * 4 + (c & 3)];
+      }
+    }
+    part[((int64_t)b * nchunk + chunk) * G + gidx] = make_float2(ts, tq);
+  }
+}
 
 __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, int ldx, float2* __restrict__ part,
-                                                          int64_t HW, int C, int G, int nchunk) {
+                                                          int64_t HW, int C, int G, int nchunk, int ppb) {
   // channel slot of this thread: TC = min(C, 256) channels in flight, 256/TC pixel lanes
   __shared__ float rs[1024], rq[1024];
   const int tid = threadIdx.x;
@@ -230,8 +337,8 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict
   const int KS = C / TC;       // channel slots per thread (<= 4)
   const int tc = tid % TC, pl = tid / TC;
   const int b = blockIdx.y, chunk = blockIdx.x;
-  const int64_t p0 = (int64_t)chunk * GN_PIX_PER_BLOCK;
-  int64_t p1 = p0 + GN_PIX_PER_BLOCK;
+  const int64_t p0 = (int64_t)chunk * ppb;
+  int64_t p1 = p0 + ppb;
   if (p1 > HW) p1 = HW;
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   if (pl < lanes) {
@@ -315,8 +422,61 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ 
   }
 }
 
+// vectorised apply: one image per blockIdx.y, per-channel scale/shift staged in shared memory, float4 in / out
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) gn_silu_vec_kernel(const float* __restrict__ x, int ldx,
+                                                           const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, const float* __restrict__ res,
+                                                           int ldr, float* __restrict__ y, __half* __restrict__ y_hi,
+                                                           __half* __restrict__ y_lo, int ldy, int64_t HW, int C, int cpg,
+                                                           int G) {
+  __shared__ __align__(16) float sa[1024], sb[1024];
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int g = c / cpg;
+    const float mean = stats[2 * (b * G + g)], rstd = stats[2 * (b * G + g) + 1];
+    sa[c] = rstd * gamma[c];
+    sb[c] = beta[c];
+  }
+  __shared__ float smean[1024];
+  for (int c = threadIdx.x; c < C; c += 256) smean[c] = stats[2 * (b * G + c / cpg)];
+  __syncthreads();
+  const int C4 = C >> 2;
+  const int64_t total = HW * C4;
+  for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+    const int64_t pl = idx / C4;
+    const int c = (int)(idx - pl * C4) * 4;
+    const int64_t pix = (int64_t)b * HW + pl;
+    const float4 v = *reinterpret_cast<const float4*>(x + pix * ldx + c);
+    const float4 a = *reinterpret_cast<const float4*>(sa + c), bb = *reinterpret_cast<const float4*>(sb + c);
+    const float4 mm = *reinterpret_cast<const float4*>(smean + c);
+    float4 o;
+    o.x = wxf_silu((v.x - mm.x) * a.x + bb.x);
+    o.y = wxf_silu((v.y - mm.y) * a.y + bb.y);
+    o.z = wxf_silu((v.z - mm.z) * a.z + bb.z);
+    o.w = wxf_silu((v.w - mm.w) * a.w + bb.w);
+    if (res) {
+      const float4 r = *reinterpret_cast<const float4*>(res + pix * ldr + c);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    if constexpr (SPLIT) {
+      __align__(8) __half h4[4];
+      __align__(8) __half l4[4];
+      wxf_split_f16x2(o.x, h4[0], l4[0]);
+      wxf_split_f16x2(o.y, h4[1], l4[1]);
+      wxf_split_f16x2(o.z, h4[2], l4[2]);
+      wxf_split_f16x2(o.w, h4[3], l4[3]);
+      *reinterpret_cast<uint2*>(y_hi + pix * ldy + c) = *reinterpret_cast<const uint2*>(h4);
+      *reinterpret_cast<uint2*>(y_lo + pix * ldy + c) = *reinterpret_cast<const uint2*>(l4);
+    } else {
+      *reinterpret_cast<float4*>(y + pix * ldy + c) = o;
+    }
+  }
+}
+
 extern "C" int64_t wxf_groupnorm_scratch_bytes(int B, int64_t HW, int C) {
-  const int64_t nchunk = (HW + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK;
+  const int ppb = gn_pix_per_block(HW);
+  const int64_t nchunk = (HW + ppb - 1) / ppb;
   return (int64_t)B * nchunk * C * (int64_t)sizeof(float2);  // G <= C
 }
 
@@ -325,9 +485,14 @@ extern "C" int wxf_groupnorm_stats(const float* x, int ldx, float* stats, void* 
   if (B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G) WXF_FAIL(WXF_EINVAL, "groupnorm: bad dims");
   if (C > 1024 || !((C <= 256 && 256 % C == 0) || (C % 256 == 0)))
     WXF_FAIL(WXF_EUNSUPPORTED, "groupnorm: C=%d must divide 256 or be a multiple of 256 (<=1024)", C);
-  const int nchunk = (int)((HW + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK);
+  const int ppb = gn_pix_per_block(HW);
+  const int nchunk = (int)((HW + ppb - 1) / ppb);
   cudaStream_t st = (cudaStream_t)stream;
-  gn_partial_kernel<<<dim3(nchunk, B), 256, 0, st>>>(x, ldx, (float2*)scratch, HW, C, G, nchunk);
+  const bool vec = (C % 4 == 0) && (256 % (C / 4) == 0) && (ldx % 4 == 0) && wxf_aligned16(x);
+  if (vec)
+    gn_partial_vec_kernel<<<dim3(nchunk, B), 256, 0, st>>>(x, ldx, (float2*)scratch, HW, C, G, nchunk, ppb);
+  else
+    gn_partial_kernel<<<dim3(nchunk, B), 256, 0, st>>>(x, ldx, (float2*)scratch, HW, C, G, nchunk, ppb);
   WXF_CHECK_LAUNCH("gn_partial");
   gn_finalize_kernel<<<(B * G + 127) / 128, 128, 0, st>>>((const float2*)scratch, stats, B, G, nchunk,
                                                           (double)HW * (double)(C / G), eps);
@@ -339,10 +504,27 @@ static int gn_silu_launch(const float* x, int ldx, const float* stats, const flo
                           const float* res, int ldr, float* y, void* y_hi, void* y_lo, int ldy, int B, int64_t HW,
                           int C, int G, void* stream) {
   if (B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G) WXF_FAIL(WXF_EINVAL, "groupnorm_silu: bad dims");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (C % 4 == 0) && C <= 1024 && (ldx % 4 == 0) && (ldy % 4 == 0) && wxf_aligned16(x) &&
+                   (!res || ((ldr % 4 == 0) && wxf_aligned16(res))) && B <= 65535 &&
+                   (y_hi ? ((reinterpret_cast<uintptr_t>(y_hi) | reinterpret_cast<uintptr_t>(y_lo)) % 8 == 0) : wxf_aligned16(y));
+  if (vec) {
+    int64_t blocks = (HW * (C / 4) + 255) / 256;
+    const int64_t cap = (148 * 16 + B - 1) / B;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)B);
+    if (y_hi)
+      gn_silu_vec_kernel<true><<<grid, 256, 0, st>>>(x, ldx, stats, gamma, beta, res, ldr, nullptr, (__half*)y_hi,
+                                                     (__half*)y_lo, ldy, HW, C, C / G, G);
+    else
+      gn_silu_vec_kernel<false><<<grid, 256, 0, st>>>(x, ldx, stats, gamma, beta, res, ldr, y, nullptr, nullptr, ldy, HW,
+                                                      C, C / G, G);
+    WXF_CHECK_LAUNCH("gn_silu");
+    return 0;
+  }
   const int64_t total = (int64_t)B * HW * C;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  cudaStream_t st = (cudaStream_t)stream;
   if (y_hi)
     gn_silu_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, stats, gamma, beta, res, ldr, nullptr, (__half*)y_hi,
                                                            (__half*)y_lo, ldy, HW, C, C / G, G, total);
