@@ -269,7 +269,7 @@ def main():
     _, recs = plan.run_profiled(x)
     fam = {}
     for tag, ms, fl, by in recs:
-        key = "embed" if tag.startswith("embed") else tag
+        key = "embed" if tag.startswith("embed") else tag.split(".")[0]
         f = fam.setdefault(key, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
         f["ms"] += ms
         f["flops"] += fl

@@ -8,10 +8,13 @@
 //           {32 ch, wsz, wsz, 1}; the dilated "long" groups are a 5-D box over the (l1, gh, l2, gw) view of the grid,
 //           so the strided gather costs nothing.  64-byte rows, SWIZZLE_64B.
 //   MMA 1 : S[128 x 128] = Q K^T, 3 passes x 2 K-steps (K-major A and B), accumulator in TMEM columns [0, 128)
+//   bias  : the block-diagonal position-bias tile is identical for every tile of a launch: each CTA writes it once into
+//           TMEM columns [128, 256) (tcgen05.st) and reads it back next to S - no global or shared traffic per tile
 //   soft  : thread = row; two TMEM passes (max, then exp / sum); only the row's own window columns are kept, the
 //           rest of the block-diagonal tile is written as exact zeros; P goes to shared memory as fp16 hi/lo planes in
 //           the K-major SWIZZLE_128B layout the second MMA reads
-//   MMA 2 : O[128 x 32] = P V, 3 passes x 8 K-steps; V is read as an MN-major B operand straight from the TMA tile
+//   MMA 2 : O[128 x 32] = P V, 3 passes x 8 K-steps; V is read as an MN-major B operand straight from the TMA tile;
+//           O reuses the first 32 TMEM columns of S (dead once P is written), so two CTAs of 256 columns share an SM
 //   epi   : O / rowsum -> fp16 hi/lo planes of the attention output at the token's pixel (the inverse gather)
 #include "wxf_tc_host.cuh"
 #include "wxf_tc_ptx.cuh"
@@ -53,8 +56,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw);
-  const uint32_t bar_load = base + OFF_BAR, bar_s = bar_load + 8, bar_p = bar_load + 16, bar_o = bar_load + 24;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + OFF_BAR + 32);
+  const uint32_t bar_load = base + OFF_BAR, bar_s = bar_load + 8, bar_p = bar_load + 16, bar_o = bar_load + 24,
+                 bar_e = bar_load + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + OFF_BAR + 40);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -63,6 +67,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 128);
     mbar_init(bar_o, 1);
+    mbar_init(bar_e, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -80,6 +85,27 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // position-bias tile -> TMEM columns [128, 256): row r, column c holds bias[i(r)][c - window start] inside the row's
+  // own window and 0 elsewhere (those columns are masked anyway)
+  if (warp >= 2) {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int g = r / p.Lp, i = r - g * p.Lp;
+    const bool in_tile = g < p.G && i < p.L;
+    const int lo_c = g * p.Lp;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t bb[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int jj = c * 32 + j - lo_c;
+        bb[j] = (in_tile && jj >= 0 && jj < p.L) ? __float_as_uint(__ldg(p.biasT + (size_t)jj * p.L + i)) : 0u;
+      }
+      tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + 128u + (uint32_t)(c * 32), bb);
+    }
+    tc_fence_before();
+  }
 
   // persistent: each CTA (two per SM) walks tiles = (window group, head); every barrier completes once per tile, so
   // the wait parity is the tile iteration's low bit.  Stale rows of a previous tile are finite, masked data.
@@ -118,6 +144,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   } else if (warp == 1) {
     if (lane == 0) {
       mbar_wait(bar_load, par);
+      if (it > 0) mbar_wait(bar_e, par ^ 1u);  // previous tile's O (aliases S columns 0-31) has been read
       tc_fence_after();
       const uint32_t q_hi = base + OFF_Q, q_lo = q_hi + QKV_PLANE, k_hi = base + OFF_K, k_lo = k_hi + QKV_PLANE;
 #pragma unroll
@@ -130,7 +157,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
       mbar_wait(bar_p, par);  // P planes written by the softmax warps
       tc_fence_after();
       const uint32_t p_hi = base + OFF_P, p_lo = p_hi + 2 * P_ATOM, v_hi = base + OFF_V, v_lo = v_hi + QKV_PLANE;
-      const uint32_t d_o = tmem_base + 128;
+      const uint32_t d_o = tmem_base;  // O aliases S[:, 0:32]
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {  // 128 key rows = eight K=16 steps
         const uint32_t pa = (uint32_t)((ks >> 2) * P_ATOM + (ks & 3) * 32);
@@ -149,22 +176,20 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     const bool valid = g < nv && i < p.L;
     const int lo_c = valid ? g * p.Lp : 0, hi_c = valid ? lo_c + p.L : 0;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const float* brow = p.biasT + i;  // biasT[j*L + i]
 
     mbar_wait(bar_s, par);
     tc_fence_after();
     float mx = -3.0e38f;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
-      uint32_t rr[32];
+      uint32_t rr[32], bb[32];
       tmem_ld32(lane_base + (uint32_t)(c * 32), rr);
+      tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), bb);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = c * 32 + j;
-        if (col >= lo_c && col < hi_c) {
-          const float sv = fmaf(__uint_as_float(rr[j]), p.scale, __ldg(brow + (size_t)(col - lo_c) * p.L));
-          mx = fmaxf(mx, sv);
-        }
+        const float sv = fmaf(__uint_as_float(rr[j]), p.scale, __uint_as_float(bb[j]));
+        if (col >= lo_c && col < hi_c) mx = fmaxf(mx, sv);
       }
     }
     float lsum = 0.f;
@@ -172,8 +197,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     uint8_t* prow_lo = prow_hi + 2 * P_ATOM;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
-      uint32_t rr[32];
+      uint32_t rr[32], bb[32];
       tmem_ld32(lane_base + (uint32_t)(c * 32), rr);
+      tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), bb);
 #pragma unroll
       for (int q8 = 0; q8 < 4; ++q8) {  // 8 columns = one 16-byte chunk of the swizzled row
         __align__(16) __half h8[8];
@@ -183,7 +209,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
           const int col = c * 32 + q8 * 8 + e;
           float pv = 0.f;
           if (col >= lo_c && col < hi_c) {
-            const float sv = fmaf(__uint_as_float(rr[q8 * 8 + e]), p.scale, __ldg(brow + (size_t)(col - lo_c) * p.L));
+            const float sv = fmaf(__uint_as_float(rr[q8 * 8 + e]), p.scale, __uint_as_float(bb[q8 * 8 + e]));
             pv = expf(sv - mx);
           }
           lsum += pv;
@@ -203,7 +229,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     mbar_wait(bar_o, par);
     tc_fence_after();
     uint32_t oo[32];
-    tmem_ld32(lane_base + 128u, oo);
+    tmem_ld32(lane_base, oo);
+    tc_fence_before();
+    mbar_arrive(bar_e);  // O consumed: the next tile's QK^T may overwrite these TMEM columns
     if (valid) {
       const int64_t w = w0 + g;
       const int per_img = p.nh * p.nw;

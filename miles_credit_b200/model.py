@@ -233,40 +233,40 @@ class _Plan:
                     attn_cost = (4.0 * m * L * d, 16.0 * m * d)
                     last = li == n_layers - 1 and half == 1
                     if tc:
-                        add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, att.ln_g, att.ln_b, m, d), "layernorm", 0,
+                        add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, att.ln_g, att.ln_b, m, d), f"layernorm.s{s}", 0,
                             8.0 * m * d)
                         if self.attention_tc and L <= 128:
                             q_hi, q_lo = self.scratch16[: m * 3 * d], self.scratch16[hid_off: hid_off + m * 3 * d]
-                            self._gemm(ln_hi, ln_lo, att.qkv_tc, "qkv", M=m, lda=d, out_hi=q_hi, out_lo=q_lo, ldh=3 * d)
+                            self._gemm(ln_hi, ln_lo, att.qkv_tc, f"qkv.s{s}", M=m, lda=d, out_hi=q_hi, out_lo=q_lo, ldh=3 * d)
                             add(ops.window_attention_tc, (q_hi, q_lo, 3 * d, att.bias_t, ln_hi, ln_lo, d, B, st.h, st.w,
-                                                          d, g.dim_head, att.wsz, att.kind, scale), "attention",
+                                                          d, g.dim_head, att.wsz, att.kind, scale), f"attention.s{s}",
                                 *attn_cost)
                         else:
-                            self._gemm(ln_hi, ln_lo, att.qkv_tc, "qkv", M=m, lda=d, out=wide, ldc=3 * d)
+                            self._gemm(ln_hi, ln_lo, att.qkv_tc, f"qkv.s{s}", M=m, lda=d, out=wide, ldc=3 * d)
                             add(ops.window_attention_f16x2, (wide, 3 * d, att.bias_t, ln_hi, ln_lo, d, B, st.h, st.w, d,
-                                                             g.dim_head, att.wsz, att.kind, scale), "attention",
+                                                             g.dim_head, att.wsz, att.kind, scale), f"attention.s{s}",
                                 *attn_cost)
-                        self._gemm(ln_hi, ln_lo, att.out_tc, "out_proj", M=m, lda=d, out=xv, ldc=ld, res=xv, ldr=ld)
-                        add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, ff.ln_g, ff.ln_b, m, d), "layernorm", 0,
+                        self._gemm(ln_hi, ln_lo, att.out_tc, f"out_proj.s{s}", M=m, lda=d, out=xv, ldc=ld, res=xv, ldr=ld)
+                        add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, ff.ln_g, ff.ln_b, m, d), f"layernorm.s{s}", 0,
                             8.0 * m * d)
-                        self._gemm(ln_hi, ln_lo, ff.fc1_tc, "ff1", M=m, lda=d, out_hi=hid_hi, out_lo=hid_lo, ldh=4 * d,
+                        self._gemm(ln_hi, ln_lo, ff.fc1_tc, f"ff1.s{s}", M=m, lda=d, out_hi=hid_hi, out_lo=hid_lo, ldh=4 * d,
                                    act=_lib.ACT_GELU)
                         if last:  # the stage output also feeds the next cross-embed / the decoder: emit its planes
-                            self._gemm(hid_hi, hid_lo, ff.fc2_tc, "ff2", M=m, lda=4 * d, out=xv, ldc=ld, res=xv, ldr=ld,
+                            self._gemm(hid_hi, hid_lo, ff.fc2_tc, f"ff2.s{s}", M=m, lda=4 * d, out=xv, ldc=ld, res=xv, ldr=ld,
                                        out_hi=xp_hi, out_lo=xp_lo, ldh=pld)
                         else:
-                            self._gemm(hid_hi, hid_lo, ff.fc2_tc, "ff2", M=m, lda=4 * d, out=xv, ldc=ld, res=xv, ldr=ld)
+                            self._gemm(hid_hi, hid_lo, ff.fc2_tc, f"ff2.s{s}", M=m, lda=4 * d, out=xv, ldc=ld, res=xv, ldr=ld)
                         continue
-                    add(ops.layernorm, (xv, ld, ln, d, att.ln_g, att.ln_b, m, d), "layernorm", 0, 8.0 * m * d)
-                    self._conv(ln, att.qkv, wide, tag="qkv", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=3 * d)
+                    add(ops.layernorm, (xv, ld, ln, d, att.ln_g, att.ln_b, m, d), f"layernorm.s{s}", 0, 8.0 * m * d)
+                    self._conv(ln, att.qkv, wide, tag=f"qkv.s{s}", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=3 * d)
                     add(ops.window_attention_f32, (wide, 3 * d, att.bias_t, ln, d, B, st.h, st.w, d, g.dim_head,
-                                                   att.wsz, att.kind, scale), "attention", *attn_cost)
-                    self._conv(ln, att.out, xv, tag="out_proj", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=ld,
+                                                   att.wsz, att.kind, scale), f"attention.s{s}", *attn_cost)
+                    self._conv(ln, att.out, xv, tag=f"out_proj.s{s}", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=ld,
                                res=xv, ldr=ld)
-                    add(ops.layernorm, (xv, ld, ln, d, ff.ln_g, ff.ln_b, m, d), "layernorm", 0, 8.0 * m * d)
-                    self._conv(ln, ff.fc1, wide, tag="ff1", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=4 * d,
+                    add(ops.layernorm, (xv, ld, ln, d, ff.ln_g, ff.ln_b, m, d), f"layernorm.s{s}", 0, 8.0 * m * d)
+                    self._conv(ln, ff.fc1, wide, tag=f"ff1.s{s}", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=4 * d,
                                act=_lib.ACT_GELU)
-                    self._conv(wide, ff.fc2, xv, tag="ff2", B=B, Hi=st.h, Wi=st.w, lda=4 * d, Ho=st.h, Wo=st.w, ldc=ld,
+                    self._conv(wide, ff.fc2, xv, tag=f"ff2.s{s}", B=B, Hi=st.h, Wi=st.w, lda=4 * d, Ho=st.h, Wo=st.w, ldc=ld,
                                res=xv, ldr=ld)
             src, src_ld, src_h, src_w = xv, ld, st.h, st.w
             if tc:
