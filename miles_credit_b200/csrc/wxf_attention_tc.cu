@@ -46,8 +46,22 @@ struct AttnParams {
   int H, W, d, heads, wsz, kind;
   float scale;
   int L, Lp, G, nh, nw;
+  int inter;          // 1: long windows packed interleaved (row = token*G + window), one TMA box per plane
+  int gpr;            // interleaved: tiles (groups of G consecutive gw) per window row
+  float scale2;       // scale * log2(e): softmax runs in base 2
   int64_t nwin, ntiles;
 };
+
+// Row r of a tile -> (window slot g, token i).  Window-major packing: rows [g*Lp, g*Lp + L); interleaved: r = i*G + g.
+__device__ __forceinline__ void row_slot(const AttnParams& p, int r, int& g, int& i) {
+  if (p.inter) {
+    i = r / p.G;
+    g = r - i * p.G;
+  } else {
+    g = r / p.Lp;
+    i = r - g * p.Lp;
+  }
+}
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
 window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
@@ -91,16 +105,18 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   if (warp >= 2) {
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const int g = r / p.Lp, i = r - g * p.Lp;
+    int g, i;
+    row_slot(p, r, g, i);
     const bool in_tile = g < p.G && i < p.L;
-    const int lo_c = g * p.Lp;
+    const float log2e = 1.4426950408889634f;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t bb[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int jj = c * 32 + j - lo_c;
-        bb[j] = (in_tile && jj >= 0 && jj < p.L) ? __float_as_uint(__ldg(p.biasT + (size_t)jj * p.L + i)) : 0u;
+        int gc, jc;
+        row_slot(p, c * 32 + j, gc, jc);
+        bb[j] = (in_tile && gc == g && jc < p.L) ? __float_as_uint(__ldg(p.biasT + (size_t)jc * p.L + i) * log2e) : 0u;
       }
       tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + 128u + (uint32_t)(c * 32), bb);
     }
@@ -113,14 +129,39 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   const uint32_t par = (uint32_t)it & 1u;
   const int head = (int)(tile % p.heads);
   const int64_t group = tile / p.heads;
-  const int64_t w0 = group * p.G;
-  const int nv = (int)((p.nwin - w0) < p.G ? (p.nwin - w0) : p.G);  // windows present in this tile
+  // first window of the tile and number of windows present
+  int64_t w0;
+  int nv;
+  if (p.inter) {  // G consecutive gw of one (b, gh) row of groups
+    const int64_t rowi = group / p.gpr;
+    const int gw0 = (int)(group - rowi * p.gpr) * p.G;
+    w0 = rowi * p.nw + gw0;
+    nv = (p.nw - gw0) < p.G ? (p.nw - gw0) : p.G;
+  } else {
+    w0 = group * p.G;
+    nv = (int)((p.nwin - w0) < p.G ? (p.nwin - w0) : p.G);
+  }
 
   if (warp == 0) {
     if (lane == 0) {
       if (it > 0) mbar_wait(bar_o, par ^ 1u);  // previous tile's P V has finished reading this CTA's shared memory
-      mbar_expect_tx(bar_load, (uint32_t)(nv * 6 * p.L * 64));
       const int per_img = p.nh * p.nw;
+      if (p.inter) {
+        // one 5-D box {32 ch, G windows (gw), wsz (l2), 1, wsz (l1)} per plane: rows come out as token*G + window;
+        // windows past the grid edge are TMA zero fill (the full box is always counted)
+        mbar_expect_tx(bar_load, (uint32_t)(6 * p.L * p.G * 64));
+        const int b = (int)(w0 / per_img);
+        const int rem = (int)(w0 - (int64_t)b * per_img);
+        const int gh = rem / p.nw, gw = rem - gh * p.nw;
+#pragma unroll
+        for (int which = 0; which < 3; ++which) {
+          const int c0 = which * p.d + head * DH;
+          const uint32_t dst = base + (uint32_t)(which == 0 ? OFF_Q : (which == 1 ? OFF_K : OFF_V));
+          tma_load_5d(&tm_hi, bar_load, dst, c0, gw, 0, gh, b * p.wsz);
+          tma_load_5d(&tm_lo, bar_load, dst + QKV_PLANE, c0, gw, 0, gh, b * p.wsz);
+        }
+      } else {
+      mbar_expect_tx(bar_load, (uint32_t)(nv * 6 * p.L * 64));
       for (int g = 0; g < nv; ++g) {
         const int64_t w = w0 + g;
         const int b = (int)(w / per_img);
@@ -139,6 +180,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
             tma_load_5d(&tm_lo, bar_load, dst + QKV_PLANE, c0, gw, 0, gh, b * p.wsz);
           }
         }
+      }
       }
     }
   } else if (warp == 1) {
@@ -172,9 +214,15 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     // ---- softmax + epilogue: thread = query row ----
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const int g = r / p.Lp, i = r - g * p.Lp;
+    int g, i;
+    row_slot(p, r, g, i);
     const bool valid = g < nv && i < p.L;
-    const int lo_c = valid ? g * p.Lp : 0, hi_c = valid ? lo_c + p.L : 0;
+    // columns of this row's own window: window-major -> [lo_c, hi_c); interleaved -> c % G == g (c < L*G)
+    const int lo_c = (valid && !p.inter) ? g * p.Lp : 0, hi_c = (valid && !p.inter) ? lo_c + p.L : 0;
+    const int imod = (valid && p.inter) ? p.G : 0, ilim = p.L * p.G;
+    auto mine = [&](int col) -> bool {
+      return imod ? (col < ilim && (col % imod) == g) : (col >= lo_c && col < hi_c);
+    };
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
     mbar_wait(bar_s, par);
@@ -188,8 +236,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = c * 32 + j;
-        const float sv = fmaf(__uint_as_float(rr[j]), p.scale, __uint_as_float(bb[j]));
-        if (col >= lo_c && col < hi_c) mx = fmaxf(mx, sv);
+        const float sv = fmaf(__uint_as_float(rr[j]), p.scale2, __uint_as_float(bb[j]));
+        if (mine(col)) mx = fmaxf(mx, sv);
       }
     }
     float lsum = 0.f;
@@ -208,9 +256,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
         for (int e = 0; e < 8; ++e) {
           const int col = c * 32 + q8 * 8 + e;
           float pv = 0.f;
-          if (col >= lo_c && col < hi_c) {
-            const float sv = fmaf(__uint_as_float(rr[q8 * 8 + e]), p.scale, __uint_as_float(bb[q8 * 8 + e]));
-            pv = expf(sv - mx);
+          if (mine(col)) {
+            const float sv = fmaf(__uint_as_float(rr[q8 * 8 + e]), p.scale2, __uint_as_float(bb[q8 * 8 + e]));
+            pv = exp2f(sv - mx);
           }
           lsum += pv;
           h8[e] = __float2half_rn(pv);
@@ -304,7 +352,8 @@ extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, i
     // pixel (y, x) = (l1*nh + gh, l2*nw + gw): dims (c, gw, l2, gh, (b, l1)); a group's tokens are one box
     const uint64_t dims[5] = {(uint64_t)3 * d, (uint64_t)nw, (uint64_t)wsz, (uint64_t)nh, (uint64_t)B * wsz};
     const uint64_t strides[4] = {ldb, (uint64_t)nw * ldb, (uint64_t)W * ldb, (uint64_t)nh * W * ldb};
-    const uint32_t box[5] = {(uint32_t)DH, 1, (uint32_t)wsz, 1, (uint32_t)wsz}, es[5] = {1, 1, 1, 1, 1};
+    const int Gw = (ROWS / L >= 2) ? (ROWS / L < nw ? ROWS / L : nw) : 1;
+    const uint32_t box[5] = {(uint32_t)DH, (uint32_t)Gw, (uint32_t)wsz, 1, (uint32_t)wsz}, es[5] = {1, 1, 1, 1, 1};
     if ((rc = make_map(&tm_hi, qkv_hi, 5, dims, strides, box, es, 64))) return rc;
     if ((rc = make_map(&tm_lo, qkv_lo, 5, dims, strides, box, es, 64))) return rc;
   }
@@ -315,8 +364,17 @@ extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, i
   p.ldh = ldh;
   p.H = H; p.W = W; p.d = d; p.heads = d / dh; p.wsz = wsz; p.kind = kind; p.scale = scale;
   p.L = L; p.Lp = (L + 1) & ~1; p.G = ROWS / p.Lp; p.nh = nh; p.nw = nw;
+  p.scale2 = scale * 1.4426950408889634f;
   p.nwin = (int64_t)B * nh * nw;
-  const int64_t groups = (p.nwin + p.G - 1) / p.G;
+  p.inter = (kind == WXF_ATTN_LONG && ROWS / L >= 2) ? 1 : 0;
+  int64_t groups;
+  if (p.inter) {
+    p.G = ROWS / L < nw ? ROWS / L : nw;
+    p.gpr = (nw + p.G - 1) / p.G;
+    groups = (int64_t)B * nh * p.gpr;
+  } else {
+    groups = (p.nwin + p.G - 1) / p.G;
+  }
   p.ntiles = groups * p.heads;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
