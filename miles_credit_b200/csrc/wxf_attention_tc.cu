@@ -116,7 +116,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
       for (int j = 0; j < 32; ++j) {
         int gc, jc;
         row_slot(p, c * 32 + j, gc, jc);
-        bb[j] = (in_tile && gc == g && jc < p.L) ? __float_as_uint(__ldg(p.biasT + (size_t)jc * p.L + i) * log2e) : 0u;
+        // columns outside the row's own window carry -1e30: exp2 of them is exactly 0, no per-element masks needed
+        bb[j] = __float_as_uint((in_tile && gc == g && jc < p.L) ? __ldg(p.biasT + (size_t)jc * p.L + i) * log2e : -1.0e30f);
       }
       tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + 128u + (uint32_t)(c * 32), bb);
     }
@@ -217,16 +218,11 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     int g, i;
     row_slot(p, r, g, i);
     const bool valid = g < nv && i < p.L;
-    // columns of this row's own window: window-major -> [lo_c, hi_c); interleaved -> c % G == g (c < L*G)
-    const int lo_c = (valid && !p.inter) ? g * p.Lp : 0, hi_c = (valid && !p.inter) ? lo_c + p.L : 0;
-    const int imod = (valid && p.inter) ? p.G : 0, ilim = p.L * p.G;
-    auto mine = [&](int col) -> bool {
-      return imod ? (col < ilim && (col % imod) == g) : (col >= lo_c && col < hi_c);
-    };
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
     mbar_wait(bar_s, par);
     tc_fence_after();
+    // s2 = S * (scale*log2 e) + bias*log2 e (masked columns: -1e30); p = 2^(s2 - max)
     float mx = -3.0e38f;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
@@ -234,11 +230,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
       tmem_ld32(lane_base + (uint32_t)(c * 32), rr);
       tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), bb);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = c * 32 + j;
-        const float sv = fmaf(__uint_as_float(rr[j]), p.scale2, __uint_as_float(bb[j]));
-        if (mine(col)) mx = fmaxf(mx, sv);
-      }
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(rr[j]), p.scale2, __uint_as_float(bb[j])));
     }
     float lsum = 0.f;
     uint8_t* prow_hi = gen + OFF_P + r * 128;
@@ -250,24 +242,22 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
       tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), bb);
 #pragma unroll
       for (int q8 = 0; q8 < 4; ++q8) {  // 8 columns = one 16-byte chunk of the swizzled row
-        __align__(16) __half h8[8];
-        __align__(16) __half l8[8];
+        __align__(16) __half2 h2[4];
+        __align__(16) __half2 l2[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int col = c * 32 + q8 * 8 + e;
-          float pv = 0.f;
-          if (mine(col)) {
-            const float sv = fmaf(__uint_as_float(rr[q8 * 8 + e]), p.scale2, __uint_as_float(bb[q8 * 8 + e]));
-            pv = exp2f(sv - mx);
-          }
-          lsum += pv;
-          h8[e] = __float2half_rn(pv);
-          l8[e] = __float2half_rn(pv - __half2float(h8[e]));
+        for (int e = 0; e < 4; ++e) {
+          const int j = q8 * 8 + 2 * e;
+          const float p0 = exp2f(fmaf(__uint_as_float(rr[j]), p.scale2, __uint_as_float(bb[j])) - mx);
+          const float p1 = exp2f(fmaf(__uint_as_float(rr[j + 1]), p.scale2, __uint_as_float(bb[j + 1])) - mx);
+          lsum += p0 + p1;
+          h2[e] = __floats2half2_rn(p0, p1);
+          const float2 back = __half22float2(h2[e]);
+          l2[e] = __floats2half2_rn(p0 - back.x, p1 - back.y);
         }
         const int cc = (c & 1) * 4 + q8;                 // 16-byte chunk index inside the 64-column atom
         const int off = (c >> 1) * P_ATOM + ((cc ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(prow_hi + off) = *reinterpret_cast<const uint4*>(h8);
-        *reinterpret_cast<uint4*>(prow_lo + off) = *reinterpret_cast<const uint4*>(l8);
+        *reinterpret_cast<uint4*>(prow_hi + off) = *reinterpret_cast<const uint4*>(h2);
+        *reinterpret_cast<uint4*>(prow_lo + off) = *reinterpret_cast<const uint4*>(l2);
       }
     }
     fence_proxy_async();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
