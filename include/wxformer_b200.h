@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 5
+#define WXF_ABI_VERSION 6
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -122,8 +122,11 @@ int wxf_window_attention_f16x2(const float* qkv, int ldq, const float* biasT, vo
  * to_qkv output ([B, H, W, ldq]; short windows as 4-D boxes, dilated long groups as 5-D boxes), S = QK^T and O = PV as
  * f16x2 three-pass MMAs with TMEM accumulators, windows of the same head packed block-diagonally into 128-row tiles,
  * softmax in fp32 registers.  Output: fp16 hi/lo planes [B*H*W, ldh].  dh must be 32, L <= 128, ldq % 8 == 0.
+ * bias_tile: the [128 x 128] fp32 tile wxf_attention_bias_tile() builds once per layer from the transposed position
+ * bias (bias * log2 e inside a row's own window, -1e30 elsewhere; the kernel keeps it in TMEM).
  */
-int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, int ldq, const float* biasT, void* out_hi,
+int wxf_attention_bias_tile(const float* biasT, float* tile, int W, int wsz, int kind, void* stream);
+int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, int ldq, const float* bias_tile, void* out_hi,
                             void* out_lo, int ldh, int B, int H, int W, int d, int dh, int wsz, int kind, float scale,
                             void* stream);
 

@@ -39,7 +39,7 @@ constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32
 constexpr uint32_t IDESC_O = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 struct AttnParams {
-  const float* biasT;
+  const float* bias_tile;  // [128 columns][128 rows] fp32: bias*log2(e) inside the row's window, -1e30 elsewhere
   __half* out_hi;
   __half* out_lo;
   int ldh;
@@ -100,25 +100,15 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // position-bias tile -> TMEM columns [128, 256): row r, column c holds bias[i(r)][c - window start] inside the row's
-  // own window and 0 elsewhere (those columns are masked anyway)
+  // position-bias tile (identical for every tile of the launch) -> TMEM columns [128, 256)
   if (warp >= 2) {
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    int g, i;
-    row_slot(p, r, g, i);
-    const bool in_tile = g < p.G && i < p.L;
-    const float log2e = 1.4426950408889634f;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t bb[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        int gc, jc;
-        row_slot(p, c * 32 + j, gc, jc);
-        // columns outside the row's own window carry -1e30: exp2 of them is exactly 0, no per-element masks needed
-        bb[j] = __float_as_uint((in_tile && gc == g && jc < p.L) ? __ldg(p.biasT + (size_t)jc * p.L + i) * log2e : -1.0e30f);
-      }
+      for (int j = 0; j < 32; ++j) bb[j] = __float_as_uint(__ldg(p.bias_tile + (size_t)(c * 32 + j) * ROWS + r));
       tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + 128u + (uint32_t)(c * 32), bb);
     }
     tc_fence_before();
@@ -312,12 +302,46 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   }
 }
 
+// tile[c*128 + r] = bias[i(r)][j(c)] * log2(e) if row r and column c belong to the same window slot, else -1e30
+__global__ void attention_bias_tile_kernel(const float* __restrict__ biasT, float* __restrict__ tile, AttnParams p) {
+  const int c = blockIdx.x, r = threadIdx.x;
+  int g, i, gc, jc;
+  row_slot(p, r, g, i);
+  row_slot(p, c, gc, jc);
+  const bool ok = g < p.G && i < p.L && gc == g && jc < p.L;
+  tile[c * ROWS + r] = ok ? biasT[(size_t)jc * p.L + i] * 1.4426950408889634f : -1.0e30f;
+}
+
+// how windows are packed into a 128-row tile (shared by the tile builder and the attention launch)
+void attn_packing(AttnParams& p, int wsz, int kind, int nw) {
+  const int L = wsz * wsz;
+  p.wsz = wsz; p.kind = kind; p.nw = nw;
+  p.L = L; p.Lp = (L + 1) & ~1; p.G = ROWS / p.Lp;
+  p.inter = (kind == WXF_ATTN_LONG && ROWS / L >= 2) ? 1 : 0;
+  p.gpr = 1;
+  if (p.inter) {
+    p.G = ROWS / L < nw ? ROWS / L : nw;
+    p.gpr = (nw + p.G - 1) / p.G;
+  }
+}
+
 }  // namespace
 
-extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, int ldq, const float* biasT, void* out_hi,
+extern "C" int wxf_attention_bias_tile(const float* biasT, float* tile, int W, int wsz, int kind, void* stream) {
+  if (!biasT || !tile || wsz <= 0 || W <= 0 || W % wsz) WXF_FAIL(WXF_EINVAL, "attention_bias_tile: bad arguments");
+  if (wsz * wsz > ROWS) WXF_FAIL(WXF_EUNSUPPORTED, "attention_bias_tile: window %d too large", wsz);
+  if (kind != WXF_ATTN_SHORT && kind != WXF_ATTN_LONG) WXF_FAIL(WXF_EINVAL, "attention_bias_tile: bad kind");
+  AttnParams p{};
+  attn_packing(p, wsz, kind, W / wsz);
+  attention_bias_tile_kernel<<<ROWS, ROWS, 0, (cudaStream_t)stream>>>(biasT, tile, p);
+  WXF_CHECK_LAUNCH("attention_bias_tile");
+  return 0;
+}
+
+extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, int ldq, const float* bias_tile, void* out_hi,
                                        void* out_lo, int ldh, int B, int H, int W, int d, int dh, int wsz, int kind,
                                        float scale, void* stream) {
-  if (!qkv_hi || !qkv_lo || !biasT || !out_hi || !out_lo) WXF_FAIL(WXF_EINVAL, "attention_tc: null pointer");
+  if (!qkv_hi || !qkv_lo || !bias_tile || !out_hi || !out_lo) WXF_FAIL(WXF_EINVAL, "attention_tc: null pointer");
   if (B <= 0 || H <= 0 || W <= 0 || d <= 0 || wsz <= 0) WXF_FAIL(WXF_EINVAL, "attention_tc: bad dims");
   if (dh != DH) WXF_FAIL(WXF_EUNSUPPORTED, "attention_tc: dim_head must be 32, got %d", dh);
   if (d % dh) WXF_FAIL(WXF_EINVAL, "attention_tc: d %% dh != 0");
@@ -348,23 +372,16 @@ extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, i
     if ((rc = make_map(&tm_lo, qkv_lo, 5, dims, strides, box, es, 64))) return rc;
   }
   AttnParams p{};
-  p.biasT = biasT;
+  attn_packing(p, wsz, kind, nw);
+  p.bias_tile = bias_tile;
   p.out_hi = reinterpret_cast<__half*>(out_hi);
   p.out_lo = reinterpret_cast<__half*>(out_lo);
   p.ldh = ldh;
-  p.H = H; p.W = W; p.d = d; p.heads = d / dh; p.wsz = wsz; p.kind = kind; p.scale = scale;
-  p.L = L; p.Lp = (L + 1) & ~1; p.G = ROWS / p.Lp; p.nh = nh; p.nw = nw;
+  p.H = H; p.W = W; p.d = d; p.heads = d / dh; p.scale = scale;
+  p.nh = nh;
   p.scale2 = scale * 1.4426950408889634f;
   p.nwin = (int64_t)B * nh * nw;
-  p.inter = (kind == WXF_ATTN_LONG && ROWS / L >= 2) ? 1 : 0;
-  int64_t groups;
-  if (p.inter) {
-    p.G = ROWS / L < nw ? ROWS / L : nw;
-    p.gpr = (nw + p.G - 1) / p.G;
-    groups = (int64_t)B * nh * p.gpr;
-  } else {
-    groups = (p.nwin + p.G - 1) / p.G;
-  }
+  const int64_t groups = p.inter ? (int64_t)B * nh * p.gpr : (p.nwin + p.G - 1) / p.G;
   p.ntiles = groups * p.heads;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

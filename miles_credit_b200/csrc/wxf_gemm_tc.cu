@@ -298,12 +298,10 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           }
           if (p.out) *reinterpret_cast<float4*>(p.out + opix[it] * p.ldc + n) = t;
           if (p.out_hi) {
-            __align__(8) __half h4[4];
-            __align__(8) __half l4[4];
-            wxf_split_f16x2(t.x, h4[0], l4[0]);
-            wxf_split_f16x2(t.y, h4[1], l4[1]);
-            wxf_split_f16x2(t.z, h4[2], l4[2]);
-            wxf_split_f16x2(t.w, h4[3], l4[3]);
+            __align__(8) __half2 h4[2];
+            __align__(8) __half2 l4[2];
+            wxf_split2_f16x2(t.x, t.y, h4[0], l4[0]);
+            wxf_split2_f16x2(t.z, t.w, h4[1], l4[1]);
             *reinterpret_cast<uint2*>(p.out_hi + opix[it] * p.ldh + n) = *reinterpret_cast<const uint2*>(h4);
             *reinterpret_cast<uint2*>(p.out_lo + opix[it] * p.ldh + n) = *reinterpret_cast<const uint2*>(l4);
           }
@@ -555,12 +553,10 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
             }
             if (p.out) *reinterpret_cast<float4*>(p.out + opix[it] * p.ldc + n) = tt;
             if (p.out_hi) {
-              __align__(8) __half h4[4];
-              __align__(8) __half l4[4];
-              wxf_split_f16x2(tt.x, h4[0], l4[0]);
-              wxf_split_f16x2(tt.y, h4[1], l4[1]);
-              wxf_split_f16x2(tt.z, h4[2], l4[2]);
-              wxf_split_f16x2(tt.w, h4[3], l4[3]);
+              __align__(8) __half2 h4[2];
+              __align__(8) __half2 l4[2];
+              wxf_split2_f16x2(tt.x, tt.y, h4[0], l4[0]);
+              wxf_split2_f16x2(tt.z, tt.w, h4[1], l4[1]);
               *reinterpret_cast<uint2*>(p.out_hi + opix[it] * p.ldh + n) = *reinterpret_cast<const uint2*>(h4);
               *reinterpret_cast<uint2*>(p.out_lo + opix[it] * p.ldh + n) = *reinterpret_cast<const uint2*>(l4);
             }

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 5
+WXF_ABI_VERSION = 6
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -90,6 +90,7 @@ _SIGNATURES = {
     "wxf_window_attention_f16x2": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int] + [c_int] * 7
                                    + [c_float, c_void_p]),
     "wxf_window_attention_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int] + [c_int] * 7 + [c_float, c_void_p]),
+    "wxf_attention_bias_tile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "wxf_window_attention_tc": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int] + [c_int] * 7
                                 + [c_float, c_void_p]),
     "wxf_groupnorm_scratch_bytes": (c_int64, [c_int, c_int64, c_int]),

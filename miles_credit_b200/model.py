@@ -165,6 +165,7 @@ class _Plan:
         gn_bytes = max(ops.groupnorm_scratch_bytes(B, 4 * u.h_in * u.w_in, u.c_out) for u in g.ups)
         self.gn_scratch = torch.empty(gn_bytes // 4 + 4, **f32)
         self.steps: List[tuple] = []
+        self.bias_tiles: List[torch.Tensor] = []
         self._build(wts)
 
     # -- helpers -------------------------------------------------------------------------------
@@ -238,7 +239,9 @@ class _Plan:
                         if self.attention_tc and L <= 128:
                             q_hi, q_lo = self.scratch16[: m * 3 * d], self.scratch16[hid_off: hid_off + m * 3 * d]
                             self._gemm(ln_hi, ln_lo, att.qkv_tc, f"qkv.s{s}", M=m, lda=d, out_hi=q_hi, out_lo=q_lo, ldh=3 * d)
-                            add(ops.window_attention_tc, (q_hi, q_lo, 3 * d, att.bias_t, ln_hi, ln_lo, d, B, st.h, st.w,
+                            tile = ops.attention_bias_tile(att.bias_t, st.w, att.wsz, att.kind)
+                            self.bias_tiles.append(tile)
+                            add(ops.window_attention_tc, (q_hi, q_lo, 3 * d, tile, ln_hi, ln_lo, d, B, st.h, st.w,
                                                           d, g.dim_head, att.wsz, att.kind, scale), f"attention.s{s}",
                                 *attn_cost)
                         else:

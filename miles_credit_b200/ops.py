@@ -186,10 +186,22 @@ def window_attention_f16x2(qkv: torch.Tensor, ldq: int, bias_t: torch.Tensor, ou
     LAUNCHES += 1
 
 
+def attention_bias_tile(bias_t: torch.Tensor, W: int, wsz: int, kind: int) -> torch.Tensor:
+    """[128 x 128] fp32 bias tile of one Attention layer for wxf_window_attention_tc (built once per plan)."""
+    global LAUNCHES
+    tile = torch.empty(128 * 128, device=bias_t.device, dtype=torch.float32)
+    st = _lib.load().wxf_attention_bias_tile(bias_t.data_ptr(), tile.data_ptr(), W, wsz, kind, _stream())
+    _lib.check(st, "wxf_attention_bias_tile")
+    LAUNCHES += 1
+    return tile
+
+
 def window_attention_tc(qkv_hi: torch.Tensor, qkv_lo: torch.Tensor, ldq: int, bias_t: torch.Tensor, out_hi: torch.Tensor,
                         out_lo: torch.Tensor, ldh: int, B: int, H: int, W: int, d: int, dh: int, wsz: int, kind: int,
                         scale: float):
-    """Window attention on the tensor cores: fp16 hi/lo planes of qkv in, planes of the attention output out."""
+    """Window attention on the tensor cores: fp16 hi/lo planes of qkv in, planes of the attention output out.
+
+    ``bias_t`` here is the tile returned by :func:`attention_bias_tile`."""
     global LAUNCHES
     st = _lib.load().wxf_window_attention_tc(qkv_hi.data_ptr(), qkv_lo.data_ptr(), ldq, bias_t.data_ptr(),
                                              out_hi.data_ptr(), out_lo.data_ptr(), ldh, B, H, W, d, dh, wsz, kind, scale,

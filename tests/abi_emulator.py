@@ -33,7 +33,7 @@ class EmulatedLib:
         self.calls = []
 
     def wxf_abi_version(self):
-        return 5
+        return 6
 
     def wxf_last_error(self):
         return b"emulator"
@@ -239,6 +239,12 @@ class EmulatedLib:
         hi, lo = self._split(torch.from_numpy(tmp).view(M, d))
         self._harr(out_hi, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(hi)
         self._harr(out_lo, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(lo)
+        return 0
+
+    def wxf_attention_bias_tile(self, biasT, tile, W, wsz, kind, stream):
+        """The emulator keeps the tile opaque: it stores the plain transposed bias in the first L*L entries."""
+        L = wsz * wsz
+        _t(_arr(tile, 128 * 128))[: L * L] = _t(_arr(biasT, L * L))
         return 0
 
     def wxf_window_attention_tc(self, qkv_hi, qkv_lo, ldq, biasT, out_hi, out_lo, ldh, B, H, W, d, dh, wsz, kind, scale,

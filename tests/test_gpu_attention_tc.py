@@ -53,7 +53,8 @@ def test_window_attention_tc(wsz, kind, h, w, d, b):
     ops.split_f16x2(qkv.to(DEV), 3 * d, q_hi, q_lo, 3 * d, m, 3 * d)
     o_hi = torch.zeros(m, d, device=DEV, dtype=torch.float16)
     o_lo = torch.zeros_like(o_hi)
-    ops.window_attention_tc(q_hi, q_lo, 3 * d, bias.t().contiguous().to(DEV), o_hi, o_lo, d, b, h, w, d, 32, wsz, kind, scale)
+    tile = ops.attention_bias_tile(bias.t().contiguous().to(DEV), w, wsz, kind)
+    ops.window_attention_tc(q_hi, q_lo, 3 * d, tile, o_hi, o_lo, d, b, h, w, d, 32, wsz, kind, scale)
     torch.cuda.synchronize()
     got = (o_hi.float() + o_lo.float()).cpu().reshape(b, h, w, d)
     err = float((got - ref).abs().max() / ref.abs().max())
