@@ -330,14 +330,16 @@ constexpr int P_STAGES = 3;
 constexpr int P_THREADS = 64 + 256;
 constexpr int P_STAGE_BYTES = 2 * TILE_BYTES + 2 * P_BN * BLOCK_K * 2;  // 64 KB
 constexpr int P_STG_LD = 20;                                            // 16 columns + 4 pad per staged row
-constexpr int P_STG_BYTES = 8 * 32 * P_STG_LD * 4;                      // 8 epilogue warps
+constexpr int P_STG_BYTES = 8 * 4096;                                   // 8 epilogue warps x 4 KB (1024-byte aligned)
 constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + P_STG_BYTES + 8 * (2 * P_STAGES + 4) + 16 + 1024;
 
 template <int MODE>
 __global__ void __launch_bounds__(P_THREADS, 1)
 tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                     const __grid_constant__ TcParams p, const int n_tiles, const int m_tiles, const int total_tiles) {
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO_hi,
+                     const __grid_constant__ CUtensorMap tmO_lo, const __grid_constant__ TcParams p, const int n_tiles,
+                     const int m_tiles, const int total_tiles) {
   constexpr bool CONV = MODE == MODE_CONV;
   constexpr int BN = P_BN, STAGES = P_STAGES, STAGE_BYTES = P_STAGE_BYTES, W_BYTES = P_BN * BLOCK_K * 2;
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -463,6 +465,108 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     // ---- 8 epilogue warps: quarter = TMEM lane quarter, half = which 64 of the 128 columns ----
     const int ew = warp - 2;
     const int quarter = warp & 3, half = ew >> 2;
+    if constexpr (!CONV) {
+      // GEMM mode: lane = output row.  Accumulator row -> registers -> scale/bias/GELU/residual -> 32-column chunks
+      // staged in swizzled shared memory -> TMA store (fp32 tile and/or fp16 hi/lo plane tiles).
+      uint8_t* stg_b = reinterpret_cast<uint8_t*>(staging) + ew * 4096;
+      const uint32_t stg_a = base + STAGES * STAGE_BYTES + ew * 4096;
+      const int row = quarter * 32 + lane;
+      int i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        const int slot = i & 1;
+        int n0, z, tb, oy0, ox0;
+        int64_t m0;
+        decode(t, n0, z, m0, tb, oy0, ox0);
+        const int nb0 = n0 + half * 64;
+        const int64_t m = m0 + row;
+        // residual prefetch (the row's 64 columns), issued before waiting for the accumulator
+        float4 rres[16];
+        if (p.res) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            rres[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < p.M && nb0 + 4 * q < p.N) rres[q] = *reinterpret_cast<const float4*>(p.res + m * p.ldr + nb0 + 4 * q);
+          }
+        }
+        mbar_wait(tfull_bar(slot), ((uint32_t)i >> 1) & 1u);
+        tc_fence_after();
+        float v[64];
+        {
+          const uint32_t tb_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 2 * BN + half * 64);
+          uint32_t r[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld32(tb_addr + (uint32_t)(c * 32), r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(r[j]);
+            tmem_ld32(tb_addr + (uint32_t)(BN + c * 32), r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[c * 32 + j] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(slot));  // TMEM slot free for the MMA of tile i+2
+
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          const int nb = nb0 + cb * 32;
+          if (nb >= p.N) break;  // warp-uniform
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && nb + 4 * q < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 4 * q));
+            float* vv = v + cb * 32 + 4 * q;
+            vv[0] = fmaf(vv[0], p.w_scale, b4.x); vv[1] = fmaf(vv[1], p.w_scale, b4.y);
+            vv[2] = fmaf(vv[2], p.w_scale, b4.z); vv[3] = fmaf(vv[3], p.w_scale, b4.w);
+            if (p.act == WXF_ACT_GELU_ERF) {
+              vv[0] = wxf_gelu_erf(vv[0]); vv[1] = wxf_gelu_erf(vv[1]); vv[2] = wxf_gelu_erf(vv[2]); vv[3] = wxf_gelu_erf(vv[3]);
+            }
+            if (p.res) {
+              const float4 rr = rres[cb * 8 + q];
+              vv[0] += rr.x; vv[1] += rr.y; vv[2] += rr.z; vv[3] += rr.w;
+            }
+          }
+          if (p.out) {
+            if (lane == 0) bulk_wait_read0();  // previous TMA store has finished reading the staging buffer
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)  // fp32 row of 128 B, SWIZZLE_128B: 16-byte chunk ^= row % 8
+              *reinterpret_cast<float4*>(stg_b + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                  make_float4(v[cb * 32 + 4 * q], v[cb * 32 + 4 * q + 1], v[cb * 32 + 4 * q + 2], v[cb * 32 + 4 * q + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmO, stg_a, nb, (int)(m0 + quarter * 32));
+              bulk_commit();
+            }
+          }
+          if (p.out_hi) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // fp16 rows of 64 B, SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
+              __align__(16) __half2 h8[4];
+              __align__(16) __half2 l8[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                wxf_split2_f16x2(v[cb * 32 + 8 * q + 2 * e], v[cb * 32 + 8 * q + 2 * e + 1], h8[e], l8[e]);
+              const int off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
+              *reinterpret_cast<uint4*>(stg_b + off) = *reinterpret_cast<const uint4*>(h8);
+              *reinterpret_cast<uint4*>(stg_b + 2048 + off) = *reinterpret_cast<const uint4*>(l8);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmO_hi, stg_a, nb, (int)(m0 + quarter * 32));
+              tma_store_2d(&tmO_lo, stg_a + 2048, nb, (int)(m0 + quarter * 32));
+              bulk_commit();
+            }
+          }
+        }
+      }
+      if (lane == 0) bulk_wait0();  // all stores of this warp have landed before the CTA exits
+    } else {
     float* stg = staging + ew * (32 * P_STG_LD);
     const int r8 = lane >> 2, c4 = lane & 3;  // transposed pass: 8 rows x 4 float4 (16 columns) per instruction
     int i = 0;
@@ -565,6 +669,7 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         __syncwarp();
       }
     }
+    }  // CONV epilogue
   }
 
   tc_fence_before();
@@ -621,7 +726,8 @@ bool persistent_enabled() {
 
 template <int MODE>
 int launch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
-                      const TcParams& p, int n_tiles, int m_tiles, int phases, cudaStream_t st) {
+                      const CUtensorMap& to, const CUtensorMap& to_hi, const CUtensorMap& to_lo, const TcParams& p,
+                      int n_tiles, int m_tiles, int phases, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_persistent_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
@@ -631,7 +737,8 @@ int launch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const 
   const int64_t total = (int64_t)n_tiles * m_tiles * phases;
   if (total > INT32_MAX) WXF_FAIL(WXF_EINVAL, "tc: too many tiles");
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  tc_persistent_kernel<MODE><<<grid, P_THREADS, P_SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p, n_tiles, m_tiles, (int)total);
+  tc_persistent_kernel<MODE><<<grid, P_THREADS, P_SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, n_tiles, m_tiles,
+                                                              (int)total);
   WXF_CHECK_LAUNCH("tc_persistent");
   return 0;
 }
@@ -664,6 +771,8 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
                           d->r_off, d->ldh, 0);
   if (rc) return rc;
   if (d->M > (int64_t)65535 * BLOCK_M) WXF_FAIL(WXF_EINVAL, "gemm_tc: M too large for one launch");
+  if (d->out_hi && ((d->ldh & 7) || !wxf_aligned16(d->out_hi) || !wxf_aligned16(d->out_lo)))
+    WXF_FAIL(WXF_EALIGN, "gemm_tc: output planes need ldh %% 8 == 0 and 16-byte alignment (TMA store)");
   cudaStream_t st = (cudaStream_t)stream;
   const bool persistent = persistent_enabled();
   const int BN = (!persistent && d->N > 128) ? 256 : 128;
@@ -681,9 +790,22 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
   p.M = d->M; p.N = d->N; p.num_ksteps = (d->K + BLOCK_K - 1) / BLOCK_K;
   p.ldc = d->ldc; p.ldr = d->ldr; p.ldh = d->ldh; p.act = d->act;
   p.w_scale = ldexpf(1.0f, -d->w_scale_log2);
-  if (persistent)
-    return launch_persistent<MODE_GEMM>(ta_hi, ta_lo, tw_hi, tw_lo, p, (d->N + BN - 1) / BN,
+  if (persistent) {
+    // output tiles leave through TMA stores: 32-row x 32-column boxes of the fp32 matrix and of the fp16 planes
+    CUtensorMap to = ta_hi, to_hi = ta_hi, to_lo = ta_hi;  // placeholders when an output is absent (never dereferenced)
+    const uint32_t box[2] = {32, 32}, es[2] = {1, 1};
+    if (d->out) {
+      const uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M}, strides[1] = {(uint64_t)d->ldc * 4};
+      if ((rc = make_map(&to, d->out + d->c_off, 2, dims, strides, box, es, 128, true))) return rc;
+    }
+    if (d->out_hi) {
+      const uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M}, strides[1] = {(uint64_t)d->ldh * 2};
+      if ((rc = make_map(&to_hi, d->out_hi, 2, dims, strides, box, es, 64))) return rc;
+      if ((rc = make_map(&to_lo, d->out_lo, 2, dims, strides, box, es, 64))) return rc;
+    }
+    return launch_persistent<MODE_GEMM>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, (d->N + BN - 1) / BN,
                                         (int)((d->M + BLOCK_M - 1) / BLOCK_M), 1, st);
+  }
   dim3 grid((unsigned)((d->N + BN - 1) / BN), (unsigned)((d->M + BLOCK_M - 1) / BLOCK_M), 1);
   if (BN == 256) return launch<256, 2, MODE_GEMM>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
   return launch<128, 3, MODE_GEMM>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
@@ -765,7 +887,8 @@ extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
     }
   const int64_t ntiles = (int64_t)d->B * p.tiles_x * p.tiles_y;
   if (persistent)
-    return launch_persistent<MODE_CONV>(ta_hi, ta_lo, tw_hi, tw_lo, p, (d->N + BN - 1) / BN, (int)ntiles, d->phases, st);
+    return launch_persistent<MODE_CONV>(ta_hi, ta_lo, tw_hi, tw_lo, ta_hi, ta_hi, ta_hi, p, (d->N + BN - 1) / BN, (int)ntiles,
+                                        d->phases, st);
   if (ntiles > 65535) WXF_FAIL(WXF_EINVAL, "conv_tc: too many tiles for one launch");
   dim3 grid((unsigned)((d->N + BN - 1) / BN), (unsigned)ntiles, (unsigned)d->phases);
   if (BN == 256) return launch<256, 2, MODE_CONV>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);

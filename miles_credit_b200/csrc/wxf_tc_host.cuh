@@ -51,13 +51,13 @@ struct MapKeyHash {
 
 // fp16 tensor map (rank <= 5), 128B or 64B swizzle, zero OOB fill; dims innermost-first, strides in bytes for dims 1..
 inline int make_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint64_t* dims, const uint64_t* strides,
-             const uint32_t* box, const uint32_t* estr, uint32_t swizzle_bytes = 128) {
+             const uint32_t* box, const uint32_t* estr, uint32_t swizzle_bytes = 128, bool f32 = false) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key{};
   key.ptr = ptr;
   key.rank = rank;
-  key.swz = swizzle_bytes;
+  key.swz = swizzle_bytes + (f32 ? 1u : 0u);
   for (uint32_t i = 0; i < rank; ++i) {
     key.d[i] = dims[i];
     key.box[i] = box[i];
@@ -82,7 +82,7 @@ inline int make_map(CUtensorMap* out, const void* ptr, uint32_t rank, const uint
     e[i] = estr[i];
     if (i + 1 < rank) gstr[i] = strides[i];
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, b, e,
+  CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, b, e,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
