@@ -53,12 +53,36 @@ __device__ __forceinline__ float wxf_gelu_erf(float x) {
 }
 __device__ __forceinline__ float wxf_silu(float x) { return x / (1.0f + expf(-x)); }
 
+// Two GELUs at once on Blackwell's packed fp32 pipe (FFMA2/FMUL2): same polynomial as wxf_gelu_erf.
+__device__ __forceinline__ float2 wxf_gelu_erf2(float2 x) {
+  float2 t;
+  t.x = fminf(fabsf(x.x) * 0.70710678118654752440f, 4.0f);
+  t.y = fminf(fabsf(x.y) * 0.70710678118654752440f, 4.0f);
+  float2 q = make_float2(-1.160479314e-05f, -1.160479314e-05f);
+  q = __ffma2_rn(q, t, make_float2(1.529642177e-04f, 1.529642177e-04f));
+  q = __ffma2_rn(q, t, make_float2(-8.482338744e-04f, -8.482338744e-04f));
+  q = __ffma2_rn(q, t, make_float2(2.274784725e-03f, 2.274784725e-03f));
+  q = __ffma2_rn(q, t, make_float2(-8.480441466e-05f, -8.480441466e-05f));
+  q = __ffma2_rn(q, t, make_float2(-2.772447653e-02f, -2.772447653e-02f));
+  q = __ffma2_rn(q, t, make_float2(1.483079046e-01f, 1.483079046e-01f));
+  q = __ffma2_rn(q, t, make_float2(9.184429049e-01f, 9.184429049e-01f));
+  q = __ffma2_rn(q, t, make_float2(1.627907276e+00f, 1.627907276e+00f));
+  const float2 a = __fmul2_rn(q, t);
+  float e0, e1;
+  asm("ex2.approx.f32 %0, %1;" : "=f"(e0) : "f"(-a.x));
+  asm("ex2.approx.f32 %0, %1;" : "=f"(e1) : "f"(-a.y));
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(h, make_float2(copysignf(1.0f - e0, x.x), copysignf(1.0f - e1, x.y)), h);
+}
+
 // two values at once: packed conversions (cvt.rn.f16x2.f32)
 __device__ __forceinline__ void wxf_split2_f16x2(float a, float b, __half2& hi, __half2& lo) {
-  const float ca = fminf(fmaxf(a, -65504.f), 65504.f), cb = fminf(fmaxf(b, -65504.f), 65504.f);
-  hi = __floats2half2_rn(ca, cb);
+  uint32_t h;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));  // saturating: hi never becomes inf
+  hi = *reinterpret_cast<__half2*>(&h);
   const float2 back = __half22float2(hi);
-  lo = __floats2half2_rn(a - back.x, b - back.y);
+  const float2 d = __ffma2_rn(back, make_float2(-1.0f, -1.0f), make_float2(a, b));
+  lo = __floats2half2_rn(d.x, d.y);
 }
 
 // fp32 -> (hi, lo) fp16 operand planes of the f16x2 tensor-core scheme (22 significant bits; hi saturates)

@@ -512,19 +512,26 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         for (int cb = 0; cb < 2; ++cb) {
           const int nb = nb0 + cb * 32;
           if (nb >= p.N) break;  // warp-uniform
+          {
+            const float2 sc = make_float2(p.w_scale, p.w_scale);
+            float2* v2 = reinterpret_cast<float2*>(v + cb * 32);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias && nb + 4 * q < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 4 * q));
-            float* vv = v + cb * 32 + 4 * q;
-            vv[0] = fmaf(vv[0], p.w_scale, b4.x); vv[1] = fmaf(vv[1], p.w_scale, b4.y);
-            vv[2] = fmaf(vv[2], p.w_scale, b4.z); vv[3] = fmaf(vv[3], p.w_scale, b4.w);
-            if (p.act == WXF_ACT_GELU_ERF) {
-              vv[0] = wxf_gelu_erf(vv[0]); vv[1] = wxf_gelu_erf(vv[1]); vv[2] = wxf_gelu_erf(vv[2]); vv[3] = wxf_gelu_erf(vv[3]);
-            }
-            if (p.res) {
-              const float4 rr = rres[cb * 8 + q];
-              vv[0] += rr.x; vv[1] += rr.y; vv[2] += rr.z; vv[3] += rr.w;
+            for (int q = 0; q < 8; ++q) {  // packed fp32 math (FFMA2): scale + bias, GELU, residual
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias && nb + 4 * q < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 4 * q));
+              float2 a0 = __ffma2_rn(v2[2 * q], sc, make_float2(b4.x, b4.y));
+              float2 a1 = __ffma2_rn(v2[2 * q + 1], sc, make_float2(b4.z, b4.w));
+              if (p.act == WXF_ACT_GELU_ERF) {
+                a0 = wxf_gelu_erf2(a0);
+                a1 = wxf_gelu_erf2(a1);
+              }
+              if (p.res) {
+                const float4 rr = rres[cb * 8 + q];
+                a0 = __fadd2_rn(a0, make_float2(rr.x, rr.y));
+                a1 = __fadd2_rn(a1, make_float2(rr.z, rr.w));
+              }
+              v2[2 * q] = a0;
+              v2[2 * q + 1] = a1;
             }
           }
           if (p.out) {
