@@ -376,22 +376,31 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict
   }
 }
 
+// one warp per (image, group): lanes stride over the chunk partials, fp64 combine
 __global__ void gn_finalize_kernel(const float2* __restrict__ part, float* __restrict__ stats, int B, int G, int nchunk,
                                    double count, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= B * G) return;
   const int b = i / G, g = i % G;
   double s = 0.0, q = 0.0;
-  for (int c = 0; c < nchunk; ++c) {
+  for (int c = lane; c < nchunk; c += 32) {
     const float2 p = part[((int64_t)b * nchunk + c) * G + g];
     s += (double)p.x;
     q += (double)p.y;
   }
-  const double mean = s / count;
-  double var = q / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[2 * i] = (float)mean;
-  stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[2 * i] = (float)mean;
+    stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
 template <bool SPLIT>
@@ -494,7 +503,7 @@ extern "C" int wxf_groupnorm_stats(const float* x, int ldx, float* stats, void* 
   else
     gn_partial_kernel<<<dim3(nchunk, B), 256, 0, st>>>(x, ldx, (float2*)scratch, HW, C, G, nchunk, ppb);
   WXF_CHECK_LAUNCH("gn_partial");
-  gn_finalize_kernel<<<(B * G + 127) / 128, 128, 0, st>>>((const float2*)scratch, stats, B, G, nchunk,
+  gn_finalize_kernel<<<(B * G + 3) / 4, 128, 0, st>>>((const float2*)scratch, stats, B, G, nchunk,
                                                           (double)HW * (double)(C / G), eps);
   WXF_CHECK_LAUNCH("gn_finalize");
   return 0;
