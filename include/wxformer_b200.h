@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 6
+#define WXF_ABI_VERSION 7
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -78,6 +78,8 @@ int wxf_layernorm_f16x2(const float* x, int ldx, void* y_hi, void* y_lo, int ldh
  *   - 1x1 Conv2d                           (to_qkv/to_out :229-230, FeedForward :198-204)
  *   - ConvTranspose2d k2 s2 and k4 s2 p1   (crossformer.py:92, :572-574) as `phases` = 4 output-parity
  *     classes, each an ordinary small convolution scattered to (oy*out_scale + phase/2, ox*out_scale + phase%2).
+ *   - Conv2d 3x3 -> 4C channels + PixelShuffle(2) (wxformer/crossformer.py:143-159, 813-830): phase (dy, dx) owns the
+ *     channels 4c + 2dy + dx, same scatter, per-phase bias (bias_phase_stride = C).
  * For GEMM row m = (b, oy, ox) over the [B, Ho, Wo] grid and phase z:
  *   acc[n] = sum_{t<T} sum_{c<Cin} in[b, oy*stride + taps[z][t].dy, ox*stride + taps[z][t].dx, c]
  *                                  * w[z][n][t*Cin + c]          (out-of-range pixels read as 0)
@@ -97,6 +99,7 @@ typedef struct WxfConvDesc {
   int32_t ldc, c_off;
   int32_t ldr, r_off;
   int32_t act;
+  int32_t bias_phase_stride; /* bias index = phase*bias_phase_stride + n (0: shared; N: sub-pixel conv + PixelShuffle) */
 } WxfConvDesc;
 
 int wxf_conv_igemm_f32(const WxfConvDesc* desc, void* stream);
@@ -189,6 +192,7 @@ typedef struct WxfConvTcDesc {
   int32_t phases, out_scale;
   int32_t ldc, c_off, ldr, r_off, ldh, h_off;
   int32_t act, w_scale_log2;
+  int32_t bias_phase_stride; /* bias index = phase*bias_phase_stride + n */
 } WxfConvTcDesc;
 
 int wxf_conv_f16x2_tc(const WxfConvTcDesc* desc, void* stream);

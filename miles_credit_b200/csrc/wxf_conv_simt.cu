@@ -18,7 +18,7 @@ struct ConvP {
   int N, T, stride;
   int Ho, Wo;
   int out_scale;
-  int ldc, c_off, ldr, r_off, act;
+  int ldc, c_off, ldr, r_off, act, bias_zs;
   int K;
   int64_t M;
 };
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(NT) conv_igemm_kernel(const ConvP p) {
       for (int j = 0; j < 4; ++j) {
         float t = acc[i][g * 4 + j];
         if (n + j < p.N) {
-          if (p.bias) t += __ldg(p.bias + n + j);
+          if (p.bias) t += __ldg(p.bias + z * p.bias_zs + n + j);
           if (p.act == WXF_ACT_GELU_ERF) t = wxf_gelu_erf(t);
         }
         v[j] = t;
@@ -277,6 +277,7 @@ extern "C" int wxf_conv_igemm_f32(const WxfConvDesc* d, void* stream) {
   p.B = d->B; p.Hi = d->Hi; p.Wi = d->Wi; p.lda = d->lda; p.Cin = d->Cin;
   p.N = d->N; p.T = d->T; p.stride = d->stride; p.Ho = d->Ho; p.Wo = d->Wo; p.out_scale = d->out_scale;
   p.ldc = d->ldc; p.c_off = d->c_off; p.ldr = d->ldr; p.r_off = d->r_off; p.act = d->act;
+  p.bias_zs = d->bias_phase_stride;
   p.K = d->T * d->Cin;
   p.M = (int64_t)d->B * d->Ho * d->Wo;
   const bool vec = (d->Cin % 4 == 0) && (d->lda % 4 == 0) && wxf_aligned16(d->in) && wxf_aligned16(d->w);

@@ -63,6 +63,7 @@ struct TcParams {
   int bw, bh, tiles_x, tiles_y;
   int Ho, Wo, stride, out_scale;
   uint32_t a_bytes;   // bytes of one A plane box
+  int bias_zs;        // bias index = phase * bias_zs + n
   int step, J, ch;    // Toeplitz mode: tile step along x (128 - (J-1)), taps folded into N, channels of the branch
   int16_t taps[4][MAX_TAPS][2];  // [phase][tap] = (dy, dx); only [0] used when phases == 1
 };
@@ -283,7 +284,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       const int n = nb + c4 * 4;
       if (n < p.N) {
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + z * p.bias_zs + n));
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           if (opix[it] < 0) continue;
@@ -650,7 +651,7 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         const int n = nb + c4 * 4;
         if (n < p.N) {
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + z * p.bias_zs + n));
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             if (opix[it] < 0) continue;
@@ -829,6 +830,7 @@ extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
   if ((d->phases == 4) != (d->out_scale == 2) || (d->phases == 1 && d->out_scale != 1))
     WXF_FAIL(WXF_EINVAL, "conv_tc: phases/out_scale mismatch");
   if ((d->lda & 7) || (d->cin_pad & 63) || d->cin_pad < d->Cin) WXF_FAIL(WXF_EALIGN, "conv_tc: lda %% 8, cin_pad %% 64");
+  if (d->bias_phase_stride & 3) WXF_FAIL(WXF_EALIGN, "conv_tc: bias_phase_stride %% 4");
   if (!wxf_aligned16(d->in_hi) || !wxf_aligned16(d->in_lo) || !wxf_aligned16(d->w_hi) || !wxf_aligned16(d->w_lo))
     WXF_FAIL(WXF_EALIGN, "conv_tc: operand planes must be 16-byte aligned");
   int rc = check_epilogue("conv_tc", d->N, d->bias, d->res, d->out, d->out_hi, d->out_lo, d->ldc, d->c_off, d->ldr,
@@ -886,6 +888,7 @@ extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
   p.tiles_x = (d->Wo + bw - 1) / bw;
   p.tiles_y = (d->Ho + bh - 1) / bh;
   p.Ho = d->Ho; p.Wo = d->Wo; p.stride = s; p.out_scale = d->out_scale;
+  p.bias_zs = d->bias_phase_stride;
   p.a_bytes = (uint32_t)(bw * bh * BLOCK_K * 2);
   for (int z = 0; z < d->phases; ++z)
     for (int t = 0; t < d->T; ++t) {

@@ -120,6 +120,7 @@ class Geometry:
     w_crop: int
     h_out: int  # after optional bilinear resize
     w_out: int
+    variant: str = "crossformer"  # "crossformer": ConvTranspose decoder; "wxformer": PixelShuffle decoder
 
     @property
     def in_shape(self):
@@ -164,9 +165,15 @@ def build_geometry(
     upsample_v_conv: bool = False,
     padding_conf=None,
     post_conf=None,
+    variant: str = "crossformer",
+    upsample_with_ps: bool = True,
     **kwargs,
 ) -> Geometry:
     """Same keyword surface and defaults as ``CrossFormer.__init__`` (crossformer.py:372-401).
+
+    ``variant="wxformer"`` selects credit/models/wxformer/crossformer.py (registry keys ``wxformer`` /
+    ``wxformer_base``): same encoder, cross-embed branches wrapped in an explicit ZeroPad2d (:199-236), PixelShuffle
+    decoder (``UpBlockPS`` :137-162, ``up_block4`` :813-830); ``upsample_with_ps`` is accepted and ignored like there.
 
     Unknown keys (e.g. ``frame_patch_size``) are swallowed like the reference's ``**kwargs``.
     Features outside the forecast hot path raise ``NotImplementedError`` instead of silently
@@ -174,6 +181,8 @@ def build_geometry(
     """
     if patch_height != 1 or patch_width != 1:
         raise NotImplementedError("cube embedding (patch_height/patch_width > 1) is outside the hot path")
+    if variant not in ("crossformer", "wxformer"):
+        raise ValueError(f"unknown variant {variant!r}")
     if upsample_v_conv:
         raise NotImplementedError("upsample_v_conv=True decoder is not built (no BASELINE config uses it)")
     if attention_type is not None:
@@ -213,8 +222,12 @@ def build_geometry(
         branches, off, sizes = [], 0, set()
         for k, co in zip(ks, split):
             p = (k - strides[i]) // 2
-            ho = (h + 2 * p - k) // strides[i] + 1
-            wo = (w + 2 * p - k) // strides[i] + 1
+            if variant == "wxformer":  # ZeroPad2d(left = (k-s)//2, right = (k-s) - left) then an unpadded conv
+                ho = (h + (k - strides[i]) - k) // strides[i] + 1
+                wo = (w + (k - strides[i]) - k) // strides[i] + 1
+            else:
+                ho = (h + 2 * p - k) // strides[i] + 1
+                wo = (w + 2 * p - k) // strides[i] + 1
             sizes.add((ho, wo))
             branches.append(Branch(k, strides[i], p, co, off))
             off += co
@@ -257,7 +270,7 @@ def build_geometry(
         image_height, image_width, frames, output_frames, channels, levels, surface_channels,
         input_only_channels, output_only_channels, base_in, c_in0, base_out, c_out, dim, depth, dim_head,
         bool(use_spectral_norm), bool(interp), padding, h_pad, w_pad, tuple(stages), tuple(ups),
-        h_dec, w_dec, h_crop, w_crop, h_out, w_out,
+        h_dec, w_dec, h_crop, w_crop, h_out, w_out, variant,
     )
 
 
@@ -289,11 +302,13 @@ def _sn(spec, prefix, w_shape, sn, sn_dim=0, bias=True, bias_len=None):
 def state_spec(geo: Geometry) -> "OrderedDict[str, Tuple[Tuple[int, ...], str]]":
     """Every persistent tensor of the reference module: key -> (shape, role)."""
     sn = geo.use_spectral_norm
+    wx = geo.variant == "wxformer"
     spec: "OrderedDict[str, Tuple[Tuple[int, ...], str]]" = OrderedDict()
     for st in geo.stages:
         s = st.index
         for i, br in enumerate(st.branches):
-            _sn(spec, f"layers.{s}.0.convs.{i}", (br.c_out, st.c_in, br.kernel, br.kernel), sn)
+            # wxformer: nn.Sequential(ZeroPad2d, Conv2d) -> the conv is child "1" (tests/test_legacy_checkpoint_compat.py:24-26)
+            _sn(spec, f"layers.{s}.0.convs.{i}" + (".1" if wx else ""), (br.c_out, st.c_in, br.kernel, br.kernel), sn)
         d = st.dim
         dq = d // 4
         for l in range(st.depth):
@@ -321,13 +336,21 @@ def state_spec(geo: Geometry) -> "OrderedDict[str, Tuple[Tuple[int, ...], str]]"
     spec["cube_embedding.norm.weight"] = ((geo.dim[0],), "gain")
     spec["cube_embedding.norm.bias"] = ((geo.dim[0],), "shift")
     for up in geo.ups:
-        _sn(spec, f"{up.name}.conv", (up.c_in, up.c_out, 2, 2), sn, sn_dim=1, bias_len=up.c_out)
+        if wx:  # UpBlockPS (wxformer/crossformer.py:137-162): conv3x3 -> 4*C, PixelShuffle, sharpen conv, residual stack
+            _sn(spec, f"{up.name}.conv", (4 * up.c_out, up.c_in, 3, 3), sn)
+            _sn(spec, f"{up.name}.sharp", (up.c_out, up.c_out, 3, 3), sn)
+        else:
+            _sn(spec, f"{up.name}.conv", (up.c_in, up.c_out, 2, 2), sn, sn_dim=1, bias_len=up.c_out)
         for ci, gi in ((0, 1), (3, 4)):
             _sn(spec, f"{up.name}.b.{ci}", (up.c_out, up.c_out, 3, 3), sn)
             spec[f"{up.name}.b.{gi}.weight"] = ((up.c_out,), "gain")
             spec[f"{up.name}.b.{gi}.bias"] = ((up.c_out,), "shift")
     c4 = 2 * (geo.dim[-1] // 8)
-    _sn(spec, "up_block4", (c4, geo.output_channels, 4, 4), sn, sn_dim=1, bias_len=geo.output_channels)
+    if wx:  # up_block4 = Sequential(conv3x3 -> 4*C_out, PixelShuffle(2), conv3x3) (wxformer/crossformer.py:813-830)
+        _sn(spec, "up_block4.0", (4 * geo.output_channels, c4, 3, 3), sn)
+        _sn(spec, "up_block4.2", (geo.output_channels, geo.output_channels, 3, 3), sn)
+    else:
+        _sn(spec, "up_block4", (c4, geo.output_channels, 4, 4), sn, sn_dim=1, bias_len=geo.output_channels)
     return spec
 
 
@@ -348,13 +371,20 @@ def flops_per_forward(geo: Geometry) -> Dict[str, float]:
             out["qk"] += per * 2.0 * n * L * d
             out["pv"] += per * 2.0 * n * L * d
         out["ff"] += 2 * st.depth * 2.0 * n * d * 4 * d * 2
+    wx = geo.variant == "wxformer"
     for up in geo.ups:
         n_in = up.h_in * up.w_in
-        out["dec_up"] += 2.0 * n_in * up.c_in * up.c_out * 4
+        if wx:
+            out["dec_up"] += 2.0 * n_in * up.c_in * 4 * up.c_out * 9 + 2.0 * (4 * n_in) * up.c_out * up.c_out * 9
+        else:
+            out["dec_up"] += 2.0 * n_in * up.c_in * up.c_out * 4
         out["dec_conv3x3"] += 2 * 2.0 * (4 * n_in) * up.c_out * up.c_out * 9
     c4 = 2 * (geo.dim[-1] // 8)
     n0 = geo.stages[0].h * geo.stages[0].w
-    out["dec_up"] += 2.0 * n0 * c4 * geo.output_channels * 16
+    if wx:
+        out["dec_up"] += 2.0 * n0 * c4 * 4 * geo.output_channels * 9 + 2.0 * (4 * n0) * geo.output_channels ** 2 * 9
+    else:
+        out["dec_up"] += 2.0 * n0 * c4 * geo.output_channels * 16
     out["total"] = sum(out.values())
     return out
 

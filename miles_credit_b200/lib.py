@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 6
+WXF_ABI_VERSION = 7
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -32,7 +32,7 @@ class WxfConvDesc(Structure):
         ("phases", c_int32), ("out_scale", c_int32),
         ("ldc", c_int32), ("c_off", c_int32),
         ("ldr", c_int32), ("r_off", c_int32),
-        ("act", c_int32),
+        ("act", c_int32), ("bias_phase_stride", c_int32),
     ]
 
 
@@ -56,7 +56,7 @@ class WxfConvTcDesc(Structure):
         ("Ho", c_int32), ("Wo", c_int32),
         ("phases", c_int32), ("out_scale", c_int32),
         ("ldc", c_int32), ("c_off", c_int32), ("ldr", c_int32), ("r_off", c_int32), ("ldh", c_int32), ("h_off", c_int32),
-        ("act", c_int32), ("w_scale_log2", c_int32),
+        ("act", c_int32), ("w_scale_log2", c_int32), ("bias_phase_stride", c_int32),
     ]
 
 

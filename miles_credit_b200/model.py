@@ -148,7 +148,7 @@ class _Plan:
         big = _round_up(big, 8)
         self.ln = torch.empty(big, **f32)
         y_elems = B * g.h_dec * g.w_dec * g.output_channels
-        self.scratch = torch.empty(_round_up(max(4 * big, 2 * big + y_elems), 8), **f32)
+        self.scratch = torch.empty(_round_up(max(4 * big, 2 * big + y_elems, 2 * y_elems), 8), **f32)
         self.ln16 = self.ln.view(torch.float16)            # [hi plane | lo plane], each ln.numel() halves
         self.scratch16 = self.scratch.view(torch.float16)  # [hi plane | lo plane], each scratch.numel() halves
         # residual streams: stages 0..2 live in the upper half of their skip-concat buffer
@@ -275,11 +275,13 @@ class _Plan:
             if tc:
                 src_planes = (xp_hi, xp_lo)
 
-        # decoder: UpBlock x3 (crossformer.py:107-122); outputs land in the lower half of the skip buffers
+        # decoder: UpBlock x3 (crossformer.py:107-122) or UpBlockPS x3 (wxformer/crossformer.py:137-162);
+        # outputs land in the lower half of the skip buffers
+        wx = g.variant == "wxformer"
         st0 = g.stages[0]
         big2 = 2 * (B * st0.h * st0.w * st0.dim)
         self.y_dec = self.scratch[big2: big2 + B * g.h_dec * g.w_dec * g.output_channels]
-        head_tc = tc and wts.head_tc is not None
+        head_tc = tc and wts.head_tc is not None and (not wx or wts.head2_tc is not None)
         dec_in, dec_ld = self.x3, g.stages[3].dim
         dec_planes = self.x3p if tc else None
         for up, uw, skip in zip(g.ups, wts.ups, (2, 1, 0)):
@@ -291,8 +293,17 @@ class _Plan:
             if tc:
                 sp_hi, sp_lo = self.shortp[0][:n], self.shortp[1][:n]
                 b_hi, b_lo = self.scratch16[2 * n: 3 * n], self.scratch16[3 * n: 4 * n]
-                self._conv_tc(dec_planes[0], dec_planes[1], uw.up_tc, "dec_up", B=B, Hi=up.h_in, Wi=up.w_in, lda=dec_ld,
-                              Ho=up.h_in, Wo=up.w_in, out=short, ldc=c, out_hi=sp_hi, out_lo=sp_lo, ldh=c)
+                if wx:
+                    # sub-pixel conv + PixelShuffle -> u (fp32 in the `b` area + planes in the `a` area), then
+                    # x = u + sharp(u) -> shortcut (fp32 + planes)
+                    u_hi, u_lo = self.scratch16[:n], self.scratch16[n: 2 * n]
+                    self._conv_tc(dec_planes[0], dec_planes[1], uw.up_tc, "dec_up", B=B, Hi=up.h_in, Wi=up.w_in,
+                                  lda=dec_ld, Ho=up.h_in, Wo=up.w_in, out=b, ldc=c, out_hi=u_hi, out_lo=u_lo, ldh=c)
+                    self._conv_tc(u_hi, u_lo, uw.sharp_tc, "dec_conv3x3", B=B, Hi=ho, Wi=wo, lda=c, Ho=ho, Wo=wo,
+                                  out=short, ldc=c, res=b, ldr=c, out_hi=sp_hi, out_lo=sp_lo, ldh=c)
+                else:
+                    self._conv_tc(dec_planes[0], dec_planes[1], uw.up_tc, "dec_up", B=B, Hi=up.h_in, Wi=up.w_in,
+                                  lda=dec_ld, Ho=up.h_in, Wo=up.w_in, out=short, ldc=c, out_hi=sp_hi, out_lo=sp_lo, ldh=c)
                 self._conv_tc(sp_hi, sp_lo, uw.convs_tc[0], "dec_conv3x3", B=B, Hi=ho, Wi=wo, lda=c, Ho=ho, Wo=wo, out=a,
                               ldc=c)
                 add(ops.groupnorm_silu_f16x2, (a, c, self.gn_stats, self.gn_scratch, uw.gn_w[0], uw.gn_b[0], None, 0,
@@ -309,8 +320,14 @@ class _Plan:
                 dec_planes, dec_ld = self.catp[skip], 2 * c
                 dec_in = dst
                 continue
-            self._conv(dec_in, uw.up, short, tag="dec_up", B=B, Hi=up.h_in, Wi=up.w_in, lda=dec_ld, Ho=up.h_in,
-                       Wo=up.w_in, ldc=c)
+            if wx:
+                self._conv(dec_in, uw.up, b, tag="dec_up", B=B, Hi=up.h_in, Wi=up.w_in, lda=dec_ld, Ho=up.h_in,
+                           Wo=up.w_in, ldc=c)
+                self._conv(b, uw.sharp, short, tag="dec_conv3x3", B=B, Hi=ho, Wi=wo, lda=c, Ho=ho, Wo=wo, ldc=c, res=b,
+                           ldr=c)
+            else:
+                self._conv(dec_in, uw.up, short, tag="dec_up", B=B, Hi=up.h_in, Wi=up.w_in, lda=dec_ld, Ho=up.h_in,
+                           Wo=up.w_in, ldc=c)
             self._conv(short, uw.convs[0], a, tag="dec_conv3x3", B=B, Hi=ho, Wi=wo, lda=c, Ho=ho, Wo=wo, ldc=c)
             add(ops.groupnorm_silu, (a, c, self.gn_stats, self.gn_scratch, uw.gn_w[0], uw.gn_b[0], None, 0, b, c, B,
                                      ho * wo, c, up.groups), "groupnorm_silu", 0, 12.0 * n)
@@ -318,7 +335,21 @@ class _Plan:
             add(ops.groupnorm_silu, (a, c, self.gn_stats, self.gn_scratch, uw.gn_w[1], uw.gn_b[1], short, c, dst,
                                      2 * c, B, ho * wo, c, up.groups), "groupnorm_silu", 0, 16.0 * n)
             dec_in, dec_ld = dst, 2 * c
-        if head_tc:
+        co = g.output_channels
+        nv = B * g.h_dec * g.w_dec * co  # up_block4's PixelShuffle output (wxformer variant)
+        if wx and head_tc:
+            v_hi, v_lo = self.scratch16[:nv], self.scratch16[nv: 2 * nv]
+            self._conv_tc(dec_planes[0], dec_planes[1], wts.head_tc, "dec_head", B=B, Hi=st0.h, Wi=st0.w, lda=dec_ld,
+                          Ho=st0.h, Wo=st0.w, out_hi=v_hi, out_lo=v_lo, ldh=co)
+            self._conv_tc(v_hi, v_lo, wts.head2_tc, "dec_head", B=B, Hi=g.h_dec, Wi=g.w_dec, lda=co, Ho=g.h_dec,
+                          Wo=g.w_dec, out=self.y_dec, ldc=co)
+        elif wx:
+            v = self.scratch[:nv]
+            self._conv(dec_in, wts.head, v, tag="dec_head", B=B, Hi=st0.h, Wi=st0.w, lda=dec_ld, Ho=st0.h, Wo=st0.w,
+                       ldc=co)
+            self._conv(v, wts.head2, self.y_dec, tag="dec_head", B=B, Hi=g.h_dec, Wi=g.w_dec, lda=co, Ho=g.h_dec,
+                       Wo=g.w_dec, ldc=co)
+        elif head_tc:
             self._conv_tc(dec_planes[0], dec_planes[1], wts.head_tc, "dec_head", B=B, Hi=st0.h, Wi=st0.w, lda=dec_ld,
                           Ho=st0.h, Wo=st0.w, out=self.y_dec, ldc=g.output_channels)
         else:
@@ -377,8 +408,11 @@ class _Plan:
 class CrossFormerB200(_Base):
     """WXFormer/CrossFormer forecast step on B200.  Constructor = reference keywords (crossformer.py:372-401)."""
 
+    VARIANT = "crossformer"
+
     def __init__(self, **kwargs):
         super().__init__()
+        kwargs.setdefault("variant", self.VARIANT)
         self.geometry = geo = build_geometry(**kwargs)
         # attributes CREDIT reads off the model
         self.image_height, self.image_width = geo.image_height, geo.image_width
@@ -461,9 +495,18 @@ class CrossFormerB200(_Base):
             return plan.run(x.contiguous())
 
 
+class WXFormerB200(CrossFormerB200):
+    """Registry keys ``wxformer`` / ``wxformer_base`` of the reference (credit/models/wxformer/crossformer.py:623-904):
+    same encoder, ZeroPad2d-wrapped cross-embed branches, PixelShuffle decoder.  Constructor keywords as there
+    (``upsample_with_ps`` accepted and ignored, :669-673)."""
+
+    VARIANT = "wxformer"
+
+
 def register_with_credit(key: str = "crossformer_b200", message: Optional[str] = None):
     """Register under CREDIT's model registry (credit/models/__init__.py:128-161) so ``type: crossformer_b200``
-    selects this class from YAML; needs CREDIT importable."""
+    (and ``wxformer_b200`` for the PixelShuffle variant) selects these classes from YAML; needs CREDIT importable."""
     from credit.models import register_model  # type: ignore
 
+    register_model("wxformer_b200", "Loading the B200-native WXFormer (PixelShuffle decoder) forecast step ...")(WXFormerB200)
     return register_model(key, message or "Loading the B200-native CrossFormer forecast step ...")(CrossFormerB200)

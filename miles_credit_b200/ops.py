@@ -152,6 +152,7 @@ def make_conv_tc_desc(in_hi: torch.Tensor, in_lo: torch.Tensor, wts, *, B: int, 
     d.phases, d.out_scale = wts.phases, wts.out_scale
     d.ldc, d.c_off, d.ldr, d.r_off, d.ldh, d.h_off = ldc, c_off, ldr, r_off, ldh, h_off
     d.act, d.w_scale_log2 = act, wts.scale_log2
+    d.bias_phase_stride = wts.bias_phase_stride
     d._keep = wts  # the host tap table must outlive the descriptor
     return d
 
@@ -226,6 +227,7 @@ def make_conv_desc(inp: torch.Tensor, wts: ConvWeights, out: torch.Tensor, *, B:
     d.Ho, d.Wo = Ho, Wo
     d.phases, d.out_scale = wts.phases, wts.out_scale
     d.ldc, d.c_off, d.ldr, d.r_off, d.act = ldc, c_off, ldr, r_off, act
+    d.bias_phase_stride = wts.bias_phase_stride
     return d
 
 

@@ -64,6 +64,7 @@ class ConvWeights:
     stride: int = 1
     phases: int = 1
     out_scale: int = 1
+    bias_phase_stride: int = 0
 
 
 def _pad_cin(w_ntc: torch.Tensor, cin_pad: int) -> torch.Tensor:
@@ -161,6 +162,7 @@ class ConvTcWeights:
     phases: int
     out_scale: int
     scale_log2: int
+    bias_phase_stride: int = 0
 
 
 def conv_tc_weights(cw: "ConvWeights") -> ConvTcWeights:
@@ -182,7 +184,7 @@ def conv_tc_weights(cw: "ConvWeights") -> ConvTcWeights:
     flat = [int(v) for v in cw.taps.reshape(-1).cpu().tolist()]
     taps = (ctypes.c_int32 * len(flat))(*flat)
     return ConvTcWeights(hi.contiguous(), lo.contiguous(), taps, cw.bias, cw.n, cw.t, cw.cin, cin_pad, cw.stride, cw.phases,
-                         cw.out_scale, k)
+                         cw.out_scale, k, cw.bias_phase_stride)
 
 
 @dataclass
@@ -221,6 +223,22 @@ def toeplitz_weights(w: torch.Tensor, bias, pad: int) -> ToeplitzWeights:
                            pad, kk)
 
 
+def conv_ps_weights(w: torch.Tensor, bias) -> ConvWeights:
+    """Conv2d(Cin -> 4C, 3x3, pad 1) followed by PixelShuffle(2) (wxformer/crossformer.py:143-159, 813-830).
+
+    out[c, 2y+dy, 2x+dx] = conv[4c + 2dy + dx, y, x]: phase z = 2dy + dx is a 3x3 conv with the weight rows 4c + z,
+    scattered to (2y+dy, 2x+dx); the bias is re-ordered to [phase, C].
+    """
+    c4, cin, kh, kw = w.shape
+    c = c4 // 4
+    wz = w.reshape(c, 4, cin, kh, kw).permute(1, 0, 3, 4, 2).reshape(4, c, kh * kw * cin).contiguous()  # [z, c, (ky,kx,ci)]
+    ky, kx = torch.meshgrid(torch.arange(kh), torch.arange(kw), indexing="ij")
+    t1 = torch.stack([ky.reshape(-1) - 1, kx.reshape(-1) - 1], dim=-1).to(torch.int32)
+    taps = t1.reshape(1, kh * kw, 2).repeat(4, 1, 1).contiguous().to(w.device)
+    bz = bias.float().reshape(c, 4).t().contiguous().reshape(-1)
+    return ConvWeights(wz, taps, bz, c, kh * kw, cin, 1, 4, 2, c)
+
+
 @dataclass
 class AttentionWeights:
     ln_g: torch.Tensor
@@ -252,6 +270,8 @@ class UpBlockWeights:
     gn_b: List[torch.Tensor]
     up_tc: Optional[ConvTcWeights] = None
     convs_tc: Optional[List[ConvTcWeights]] = None
+    sharp: Optional[ConvWeights] = None          # wxformer variant: sharpening conv after the PixelShuffle
+    sharp_tc: Optional[ConvTcWeights] = None
 
 
 @dataclass
@@ -264,19 +284,22 @@ class PreparedWeights:
     embeds_tc: Optional[List[List[Optional[ConvTcWeights]]]] = None
     head_tc: Optional[ConvTcWeights] = None
     embed0_toep: Optional[List[ToeplitzWeights]] = None  # None unless every stage-0 branch is eligible
+    head2: Optional[ConvWeights] = None           # wxformer variant: conv3x3 after up_block4's PixelShuffle
+    head2_tc: Optional[ConvTcWeights] = None
 
 
 def prepare(sd: Dict[str, torch.Tensor], geo: Geometry, cin0_pad: int) -> PreparedWeights:
     """Fold and re-lay every parameter of the state dict for the kernels (device of ``sd``)."""
+    wx = geo.variant == "wxformer"
     with torch.no_grad():
         embeds, blocks = [], []
         for st in geo.stages:
             s = st.index
             brs = []
             for i, br in enumerate(st.branches):
-                w = fold_spectral_norm(sd, f"layers.{s}.0.convs.{i}")
-                brs.append(conv_weights(w, sd[f"layers.{s}.0.convs.{i}.bias"], br.stride, br.pad,
-                                        cin0_pad if s == 0 else None))
+                ck = f"layers.{s}.0.convs.{i}" + (".1" if wx else "")
+                w = fold_spectral_norm(sd, ck)
+                brs.append(conv_weights(w, sd[ck + ".bias"], br.stride, br.pad, cin0_pad if s == 0 else None))
             embeds.append(brs)
             layers = []
             for l in range(st.depth):
@@ -303,22 +326,37 @@ def prepare(sd: Dict[str, torch.Tensor], geo: Geometry, cin0_pad: int) -> Prepar
         ups = []
         for up in geo.ups:
             n = up.name
+            if wx:
+                upw = conv_ps_weights(fold_spectral_norm(sd, n + ".conv"), sd[n + ".conv.bias"])
+            else:
+                upw = convt_k2s2_weights(fold_spectral_norm(sd, n + ".conv", 1), sd[n + ".conv.bias"])
             ups.append(UpBlockWeights(
-                convt_k2s2_weights(fold_spectral_norm(sd, n + ".conv", 1), sd[n + ".conv.bias"]),
+                upw,
                 [conv_weights(fold_spectral_norm(sd, f"{n}.b.{ci}"), sd[f"{n}.b.{ci}.bias"], 1, 1) for ci in (0, 3)],
                 [sd[f"{n}.b.{gi}.weight"].float().contiguous() for gi in (1, 4)],
                 [sd[f"{n}.b.{gi}.bias"].float().contiguous() for gi in (1, 4)]))
-        head = convt_k4s2p1_weights(fold_spectral_norm(sd, "up_block4", 1), sd["up_block4.bias"])
+            if wx:
+                ups[-1].sharp = conv_weights(fold_spectral_norm(sd, n + ".sharp"), sd[n + ".sharp.bias"], 1, 1)
+        head2 = None
+        if wx:
+            head = conv_ps_weights(fold_spectral_norm(sd, "up_block4.0"), sd["up_block4.0.bias"])
+            head2 = conv_weights(fold_spectral_norm(sd, "up_block4.2"), sd["up_block4.2.bias"], 1, 1)
+        else:
+            head = convt_k4s2p1_weights(fold_spectral_norm(sd, "up_block4", 1), sd["up_block4.bias"])
         # tensor-core planes for every convolution whose output-channel count suits the epilogue (N % 4 == 0)
         for uw in ups:
             uw.up_tc = conv_tc_weights(uw.up)
             uw.convs_tc = [conv_tc_weights(c) for c in uw.convs]
+            if uw.sharp is not None:
+                uw.sharp_tc = conv_tc_weights(uw.sharp)
         embeds_tc = [[(conv_tc_weights(c) if (s > 0 and c.n % 4 == 0 and c.t <= 64) else None) for c in brs]
                      for s, brs in enumerate(embeds)]
         head_tc = conv_tc_weights(head) if head.n % 4 == 0 else None
+        head2_tc = conv_tc_weights(head2) if (head2 is not None and head2.n % 4 == 0) else None
         st0 = geo.stages[0]
         toep = None
         if all(toeplitz_eligible(br.c_out, st0.c_in, br.kernel, br.stride) for br in st0.branches):
-            toep = [toeplitz_weights(fold_spectral_norm(sd, f"layers.0.0.convs.{i}"), sd[f"layers.0.0.convs.{i}.bias"],
-                                     br.pad) for i, br in enumerate(st0.branches)]
-    return PreparedWeights(embeds, blocks, ups, head, cin0_pad, embeds_tc, head_tc, toep)
+            sfx = ".1" if wx else ""
+            toep = [toeplitz_weights(fold_spectral_norm(sd, f"layers.0.0.convs.{i}{sfx}"),
+                                     sd[f"layers.0.0.convs.{i}{sfx}.bias"], br.pad) for i, br in enumerate(st0.branches)]
+    return PreparedWeights(embeds, blocks, ups, head, cin0_pad, embeds_tc, head_tc, toep, head2, head2_tc)

@@ -150,8 +150,15 @@ def cross_embed(x, sd, prefix: str, stage) -> torch.Tensor:
     """CrossEmbedLayer.forward (crossformer.py:128-152): concat of strided convs, sorted kernels."""
     outs = []
     for i, br in enumerate(stage.branches):
-        w = effective_weight(sd, f"{prefix}.convs.{i}")
-        outs.append(F.conv2d(x, w, sd[f"{prefix}.convs.{i}.bias"], stride=br.stride, padding=br.pad))
+        if f"{prefix}.convs.{i}.1.bias" in sd:
+            # wxformer variant (wxformer/crossformer.py:199-236): ZeroPad2d(left=(k-s)//2, right=(k-s)-left) + unpadded conv
+            key = f"{prefix}.convs.{i}.1"
+            tot = br.kernel - br.stride
+            lo, hi = tot // 2, tot - tot // 2
+            outs.append(F.conv2d(F.pad(x, (lo, hi, lo, hi)), effective_weight(sd, key), sd[key + ".bias"], stride=br.stride))
+        else:
+            w = effective_weight(sd, f"{prefix}.convs.{i}")
+            outs.append(F.conv2d(x, w, sd[f"{prefix}.convs.{i}.bias"], stride=br.stride, padding=br.pad))
     return torch.cat(outs, dim=1)
 
 
@@ -230,6 +237,26 @@ def up_block(x, sd, up) -> torch.Tensor:
     return y + x
 
 
+def pixel_shuffle2(x: torch.Tensor) -> torch.Tensor:
+    """nn.PixelShuffle(2) spelled out: out[c, 2y+dy, 2x+dx] = in[4c + 2dy + dx, y, x]."""
+    b, c4, h, w = x.shape
+    c = c4 // 4
+    return x.reshape(b, c, 2, 2, h, w).permute(0, 1, 4, 2, 5, 3).reshape(b, c, 2 * h, 2 * w)
+
+
+def up_block_ps(x, sd, up) -> torch.Tensor:
+    """UpBlockPS.forward (wxformer/crossformer.py:156-162): conv3x3 -> PixelShuffle -> x + sharp(x) -> stack + skip."""
+    n = up.name
+    x = pixel_shuffle2(F.conv2d(x, effective_weight(sd, n + ".conv"), sd[n + ".conv.bias"], padding=1))
+    x = x + F.conv2d(x, effective_weight(sd, n + ".sharp"), sd[n + ".sharp.bias"], padding=1)
+    y = x
+    for ci, gi in ((0, 1), (3, 4)):
+        y = F.conv2d(y, effective_weight(sd, f"{n}.b.{ci}"), sd[f"{n}.b.{ci}.bias"], padding=1)
+        y = F.group_norm(y, up.groups, sd[f"{n}.b.{gi}.weight"], sd[f"{n}.b.{gi}.bias"], 1e-5)
+        y = F.silu(y)
+    return y + x
+
+
 def bilinear_resize(x, h_out: int, w_out: int) -> torch.Tensor:
     """``F.interpolate(mode="bilinear")`` with align_corners=False (crossformer.py:631-632), spelled out.
 
@@ -281,12 +308,17 @@ def forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], geo: Geometry, taps: O
         if taps is not None:
             taps[f"s{st.index}.out"] = x
         enc.append(x)
+    wx = geo.variant == "wxformer"
     for up, skip in zip(geo.ups, (2, 1, 0)):
-        x = up_block(x, sd, up)
+        x = up_block_ps(x, sd, up) if wx else up_block(x, sd, up)
         if taps is not None:
             taps[up.name] = x
         x = torch.cat([x, enc[skip]], dim=1)
-    x = F.conv_transpose2d(x, effective_weight(sd, "up_block4", sn_dim=1), sd["up_block4.bias"], stride=2, padding=1)
+    if wx:  # up_block4 = conv3x3 -> PixelShuffle(2) -> conv3x3 (wxformer/crossformer.py:813-830)
+        x = pixel_shuffle2(F.conv2d(x, effective_weight(sd, "up_block4.0"), sd["up_block4.0.bias"], padding=1))
+        x = F.conv2d(x, effective_weight(sd, "up_block4.2"), sd["up_block4.2.bias"], padding=1)
+    else:
+        x = F.conv_transpose2d(x, effective_weight(sd, "up_block4", sn_dim=1), sd["up_block4.bias"], stride=2, padding=1)
     if taps is not None:
         taps["up_block4"] = x
     if geo.padding.activate:

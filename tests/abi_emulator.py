@@ -33,7 +33,7 @@ class EmulatedLib:
         self.calls = []
 
     def wxf_abi_version(self):
-        return 6
+        return 7
 
     def wxf_last_error(self):
         return b"emulator"
@@ -193,9 +193,10 @@ class EmulatedLib:
             return base.as_strided((B, Hout, Wout, N), (Hout * Wout * ld, Wout * ld, ld, 1), off)
 
         res = view(d.res, d.ldr, d.r_off).clone() if d.res else None
-        bias = _t(_arr(d.bias, N)) if d.bias else None
+        bias_all = _t(_arr(d.bias, N + (P - 1) * d.bias_phase_stride)) if d.bias else None
         oy, ox = torch.arange(Ho) * s, torch.arange(Wo) * s
         for z in range(P):
+            bias = bias_all[z * d.bias_phase_stride: z * d.bias_phase_stride + N] if bias_all is not None else None
             acc = torch.zeros(B, Ho, Wo, N, dtype=torch.float64)
             for t in range(T):
                 dy, dx = int(taps[z, t, 0]), int(taps[z, t, 1])
@@ -302,10 +303,11 @@ class EmulatedLib:
             n_res = ((B * Hout - 1) * Wout + Wout - 1) * d.ldr + d.r_off + N
             res = _t(_arr(d.res, n_res)).as_strided((B, Hout, Wout, N), (Hout * Wout * d.ldr, Wout * d.ldr, d.ldr, 1),
                                                     d.r_off).clone()
-        bias = _t(_arr(d.bias, N)) if d.bias else None
+        bias_all = _t(_arr(d.bias, N + (P - 1) * d.bias_phase_stride)) if d.bias else None
         oy = torch.arange(Ho) * s
         ox = torch.arange(Wo) * s
         for z in range(P):
+            bias = bias_all[z * d.bias_phase_stride: z * d.bias_phase_stride + N] if bias_all is not None else None
             acc = torch.zeros(B, Ho, Wo, N, dtype=torch.float64)
             for t in range(T):
                 dy, dx = int(taps[z, t, 0]), int(taps[z, t, 1])

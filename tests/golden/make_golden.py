@@ -54,6 +54,8 @@ CASES = {
         interp=True, use_spectral_norm=False,
         padding_conf=dict(activate=True, mode="mirror", pad_lat=[20, 20], pad_lon=[40, 40]),
         post_conf={"activate": False}), 2),
+    # registry key "wxformer": credit/models/wxformer/crossformer.py (PixelShuffle decoder, ZeroPad2d cross-embed)
+    "unit_wxformer": (dict(workload("unit"), variant="wxformer", output_only_channels=4, depth=[1, 1, 1, 1]), 1),
 }
 TAPS = ["s0.embed", "s0.l0.short_attn", "s0.out", "s2.out", "s3.out", "up_block1", "up_block3", "up_block4"]
 
@@ -82,7 +84,8 @@ def main():
     for name, (kwargs, batch) in CASES.items():
         geo = build_geometry(**kwargs)
         sd = synthetic_state_dict(geo, seed=1000)
-        model = load_model({"model": dict(kwargs, type="crossformer")})
+        ref_kwargs = {k: v for k, v in kwargs.items() if k != "variant"}
+        model = load_model({"model": dict(ref_kwargs, type=kwargs.get("variant", "crossformer"))})
         ref_sd = model.state_dict()
         assert list(sorted(ref_sd)) == list(sorted(sd)), "state-dict key mismatch vs reference"
         for k in ref_sd:
@@ -113,13 +116,15 @@ def main():
 
     # state-dict key/shape tables of the BASELINE configs (no weights: shapes only)
     keys = {}
-    for wl in ("wxformer_6h_025deg", "smoke_1deg"):
+    for wl, variant in (("wxformer_6h_025deg", "crossformer"), ("smoke_1deg", "crossformer"),
+                        ("wxformer_6h_025deg", "wxformer")):
         kw = workload(wl)
         with torch.device("meta"):
-            m = load_model({"model": dict(kw, type="crossformer")})
-        keys[wl] = {k: list(v.shape) for k, v in m.state_dict().items()}
-        spec = state_spec(build_geometry(**kw))
-        assert {k: list(s) for k, (s, _) in spec.items()} == keys[wl], wl
+            m = load_model({"model": dict(kw, type=variant)})
+        name = wl if variant == "crossformer" else f"{wl}:{variant}"
+        keys[name] = {k: list(v.shape) for k, v in m.state_dict().items()}
+        spec = state_spec(build_geometry(**dict(kw, variant=variant)))
+        assert {k: list(s) for k, (s, _) in spec.items()} == keys[name], name
     json.dump(keys, open(os.path.join(HERE, "state_keys.json"), "w"))
 
     # padding known answers from the reference's TensorPadding (earth + mirror), small grid

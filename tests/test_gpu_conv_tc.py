@@ -148,3 +148,23 @@ def test_pad_planes_match_fp32_pad():
     ops.pad_to_pixel_major_f16x2(x, (3, 4), (5, 2), "earth", 64, hi, lo)
     assert torch.equal(hi, ref.half())
     assert float((hi.float() + lo.float() - ref).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("cin,c,h,w,b", [(128, 64, 9, 13, 2), (256, 12, 10, 8, 1)])
+def test_subpixel_conv_pixelshuffle(cin, c, h, w, b):
+    """Conv2d(Cin -> 4C, 3x3) + PixelShuffle(2) as 4 output-parity phases with per-phase bias (wxformer decoder)."""
+    from miles_credit_b200.weights import conv_ps_weights
+
+    torch.manual_seed(c)
+    x = torch.randn(b, cin, h, w)
+    wt = torch.randn(4 * c, cin, 3, 3) / (9 * cin) ** 0.5
+    bias = torch.randn(4 * c)
+    ref = F.pixel_shuffle(F.conv2d(x.double(), wt.double(), bias.double(), padding=1), 2).float()
+    cw = conv_ps_weights(wt.to(DEV), bias.to(DEV))
+    hi, lo = planes_of(to_pm(x).to(DEV))
+    out = torch.zeros(b, 2 * h, 2 * w, c, device=DEV)
+    ops.conv_f16x2_tc(ops.make_conv_tc_desc(hi, lo, conv_tc_weights(cw), B=b, Hi=h, Wi=w, lda=cin, Ho=h, Wo=w, out=out, ldc=c))
+    assert relmax(out.cpu(), to_pm(ref)) < 3e-6
+    out32 = torch.zeros(b, 2 * h, 2 * w, c, device=DEV)
+    ops.conv_igemm_f32(ops.make_conv_desc(to_pm(x).to(DEV), cw, out32, B=b, Hi=h, Wi=w, lda=cin, Ho=h, Wo=w, ldc=c))
+    assert relmax(out32.cpu(), to_pm(ref)) < 3e-6

@@ -18,7 +18,7 @@ def relmax(a, b):
 
 
 @pytest.mark.parametrize("exact", [False, True], ids=["tensorcore", "exactfp32"])
-@pytest.mark.parametrize("case", ["unit", "unit_mirror_f2"])
+@pytest.mark.parametrize("case", ["unit", "unit_mirror_f2", "unit_wxformer"])
 def test_forward_matches_reference_golden(golden_dir, case, exact):
     fx = torch.load(os.path.join(golden_dir, f"{case}.pt"), weights_only=False)
     geo = build_geometry(**fx["kwargs"])

@@ -24,6 +24,16 @@ def test_state_dict_is_reference_compatible(golden_dir):
         model.load_state_dict(dict(sd, bogus=torch.zeros(1)), strict=True)
 
 
+def test_wxformer_variant_state_dict(golden_dir):
+    from miles_credit_b200.model import WXFormerB200
+
+    fx = torch.load(os.path.join(golden_dir, "unit_wxformer.pt"), weights_only=False)
+    kw = {k: v for k, v in fx["kwargs"].items() if k != "variant"}
+    model = WXFormerB200(**kw, upsample_with_ps=True)
+    assert {k: list(v.shape) for k, v in model.state_dict().items()} == fx["keys"]
+    assert "up_block1.sharp.weight_orig" in fx["keys"] and "layers.0.0.convs.0.1.weight_orig" in fx["keys"]
+
+
 def test_module_surface():
     kw = workload("unit")
     m = CrossFormerB200(**kw)
@@ -83,6 +93,9 @@ conf = {{"custom_models": [{os.path.join(root, "miles_credit_b200", "credit_plug
         "model": dict(workload("unit"), type="crossformer_b200")}}
 m = load_model(conf)
 assert isinstance(m, BaseModel) and type(m).__name__ == "CrossFormerB200", type(m)
+m2 = load_model({{"custom_models": conf["custom_models"], "model": dict(workload("unit"), type="wxformer_b200")}})
+ref2 = load_model({{"model": dict(workload("unit"), type="wxformer")}})
+assert {{k: tuple(v.shape) for k, v in ref2.state_dict().items()}} == {{k: tuple(v.shape) for k, v in m2.state_dict().items()}}
 ref = load_model({{"model": dict(workload("unit"), type="crossformer")}})
 assert {{k: tuple(v.shape) for k, v in ref.state_dict().items()}} == {{k: tuple(v.shape) for k, v in m.state_dict().items()}}
 m.load_state_dict(ref.state_dict(), strict=True)

@@ -10,7 +10,7 @@ from miles_credit_b200.synth import state_checksum, synthetic_input, synthetic_s
 from oracle import crossformer_oracle as oracle
 
 
-@pytest.mark.parametrize("case", ["unit", "unit_mirror_f2"])
+@pytest.mark.parametrize("case", ["unit", "unit_mirror_f2", "unit_wxformer"])
 def test_oracle_matches_reference_forward(golden_dir, case):
     fx = torch.load(os.path.join(golden_dir, f"{case}.pt"), weights_only=False)
     geo = build_geometry(**fx["kwargs"])
@@ -39,8 +39,9 @@ def test_padding_known_answers(golden_dir):
 
 def test_state_spec_matches_reference_keys(golden_dir):
     keys = json.load(open(os.path.join(golden_dir, "state_keys.json")))
-    for wl, ref in keys.items():
-        spec = state_spec(build_geometry(**workload(wl)))
+    for name, ref in keys.items():
+        wl, _, variant = name.partition(":")
+        spec = state_spec(build_geometry(**dict(workload(wl), variant=variant or "crossformer")))
         assert {k: list(s) for k, (s, _) in spec.items()} == ref
 
 

@@ -26,7 +26,7 @@ def emulated(monkeypatch):
 
 
 @pytest.mark.parametrize("tensor_cores", [False, True])
-@pytest.mark.parametrize("case", ["unit", "unit_mirror_f2"])
+@pytest.mark.parametrize("case", ["unit", "unit_mirror_f2", "unit_wxformer"])
 def test_plan_through_emulated_abi_matches_reference(golden_dir, emulated, case, tensor_cores):
     fx = torch.load(os.path.join(golden_dir, f"{case}.pt"), weights_only=False)
     geo = build_geometry(**fx["kwargs"])
@@ -44,6 +44,8 @@ def test_plan_through_emulated_abi_matches_reference(golden_dir, emulated, case,
     assert float((s0 - fx["taps"]["s0.out"]).abs().max() / fx["taps"]["s0.out"].abs().max()) < 1e-5
     assert emulated.calls.count("attention_tc" if tensor_cores else "attention") == 2 * sum(geo.depth)
     assert (emulated.calls.count("gemm_tc") == 8 * sum(geo.depth)) == tensor_cores
+    if tensor_cores and case == "unit_wxformer":  # 6 embeds + 3 x (ps, sharp, 2 convs) + 2 head convs
+        assert emulated.calls.count("conv_tc") == 6 + 12 + 2
     if tensor_cores:  # stage 1-3 cross-embed (6) + decoder (3 x 3) run as tensor-core convolutions
         assert emulated.calls.count("conv_tc") >= 15
         assert emulated.calls.count("toeplitz") == 4  # the four stage-0 cross-embed branches
