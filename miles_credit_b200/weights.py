@@ -352,7 +352,7 @@ def prepare(sd: Dict[str, torch.Tensor], geo: Geometry, cin0_pad: int) -> Prepar
         embeds_tc = [[(conv_tc_weights(c) if (s > 0 and c.n % 4 == 0 and c.t <= 64) else None) for c in brs]
                      for s, brs in enumerate(embeds)]
         head_tc = conv_tc_weights(head) if head.n % 4 == 0 else None
-        head2_tc = conv_tc_weights(head2) if (head2 is not None and head2.n % 4 == 0) else None
+        head2_tc = conv_tc_weights(head2) if (head2 is not None and head2.n % 8 == 0) else None  # its input rows are TMA rows
         st0 = geo.stages[0]
         toep = None
         if all(toeplitz_eligible(br.c_out, st0.c_in, br.kernel, br.stride) for br in st0.branches):

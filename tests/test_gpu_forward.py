@@ -99,3 +99,19 @@ def test_forward_wxformer_6h_1deg_vs_oracle(exact):
     err = relmax(y.cpu(), ref)
     print(f"wxformer_6h_1deg ({'exact fp32' if exact else 'tensor cores'}): rel-max vs oracle = {err:.3e}")
     assert err < TOL
+
+
+def test_forward_wxformer_variant_tc_head_vs_oracle():
+    """PixelShuffle decoder with a channel count that lets both up_block4 convs run on the tensor cores."""
+    kw = dict(workload("unit"), variant="wxformer", output_only_channels=8)
+    geo = build_geometry(**kw)
+    sd = synthetic_state_dict(geo, seed=12)
+    x = synthetic_input(geo, batch=2, seed=12)
+    with torch.no_grad():
+        ref = oracle.forward(x, sd, geo)
+    model = CrossFormerB200(**kw)
+    model.load_state_dict(sd, strict=True)
+    y = model.cuda().eval()(x.cuda())
+    err = relmax(y.cpu(), ref)
+    print(f"wxformer variant (tensor-core head): rel-max vs oracle = {err:.3e}")
+    assert err < TOL

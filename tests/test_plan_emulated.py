@@ -44,8 +44,8 @@ def test_plan_through_emulated_abi_matches_reference(golden_dir, emulated, case,
     assert float((s0 - fx["taps"]["s0.out"]).abs().max() / fx["taps"]["s0.out"].abs().max()) < 1e-5
     assert emulated.calls.count("attention_tc" if tensor_cores else "attention") == 2 * sum(geo.depth)
     assert (emulated.calls.count("gemm_tc") == 8 * sum(geo.depth)) == tensor_cores
-    if tensor_cores and case == "unit_wxformer":  # 6 embeds + 3 x (ps, sharp, 2 convs) + 2 head convs
-        assert emulated.calls.count("conv_tc") == 6 + 12 + 2
+    if tensor_cores and case == "unit_wxformer":  # 6 embeds + 3 x (ps, sharp, 2 convs); 12 output channels: fp32 head
+        assert emulated.calls.count("conv_tc") == 6 + 12
     if tensor_cores:  # stage 1-3 cross-embed (6) + decoder (3 x 3) run as tensor-core convolutions
         assert emulated.calls.count("conv_tc") >= 15
         assert emulated.calls.count("toeplitz") == 4  # the four stage-0 cross-embed branches
@@ -68,3 +68,22 @@ def test_plan_tensor_core_head_vs_oracle(emulated):
         ref = oracle.forward(x, sd, geo)
     assert float((y - ref).abs().max() / ref.abs().max()) < 2e-5
     assert emulated.calls.count("conv_tc") == 6 + 9 + 1
+
+
+def test_plan_wxformer_tensor_core_head_vs_oracle(emulated):
+    """wxformer variant with 16 output channels: both up_block4 convolutions run as tensor-core convs."""
+    from miles_credit_b200.geometry import workload
+    from oracle import crossformer_oracle as oracle
+
+    kw = dict(workload("unit"), variant="wxformer", output_only_channels=8, depth=[1, 1, 1, 1])
+    geo = build_geometry(**kw)
+    assert geo.output_channels == 16
+    sd = synthetic_state_dict(geo, seed=12)
+    wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
+    assert wts.head_tc is not None and wts.head2_tc is not None
+    plan = wmodel._Plan(geo, wts, 1, torch.device("cpu"), True)
+    x = synthetic_input(geo, batch=1, seed=12)
+    y = plan.run(x)
+    with torch.no_grad():
+        ref = oracle.forward(x, sd, geo)
+    assert float((y - ref).abs().max() / ref.abs().max()) < 2e-5
