@@ -327,22 +327,27 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 //      tile i overlaps the TMA loads and MMAs of tile i+1; 8 epilogue warps (two per TMEM lane quarter) -------------
 
 constexpr int P_BN = 128;
-constexpr int P_STAGES = 3;
-constexpr int P_THREADS = 64 + 256;
 constexpr int P_STAGE_BYTES = 2 * TILE_BYTES + 2 * P_BN * BLOCK_K * 2;  // 64 KB
+// Two shapes: <8 epilogue warps, 3 stages> for K >= 512 (main loop bound) and <16 epilogue warps, 2 stages> for the
+// small-K launches of stages 0-1, whose cost is the epilogue (issue-bound with 2 warps per scheduler).
 constexpr int P_STG_LD = 20;                                            // 16 columns + 4 pad per staged row
-constexpr int P_STG_BYTES = 8 * 4096;                                   // 8 epilogue warps x 4 KB (1024-byte aligned)
-constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + P_STG_BYTES + 8 * (2 * P_STAGES + 4) + 16 + 1024;
+template <int EW, int STAGES>
+constexpr int p_smem() {
+  return STAGES * P_STAGE_BYTES + EW * 4096 + 8 * (2 * STAGES + 4) + 16 + 1024;
+}
 
-template <int MODE>
-__global__ void __launch_bounds__(P_THREADS, 1)
+template <int MODE, int EW, int STAGES>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO_hi,
                      const __grid_constant__ CUtensorMap tmO_lo, const __grid_constant__ TcParams p, const int n_tiles,
                      const int m_tiles, const int total_tiles) {
   constexpr bool CONV = MODE == MODE_CONV;
-  constexpr int BN = P_BN, STAGES = P_STAGES, STAGE_BYTES = P_STAGE_BYTES, W_BYTES = P_BN * BLOCK_K * 2;
+  constexpr int BN = P_BN, STAGE_BYTES = P_STAGE_BYTES, W_BYTES = P_BN * BLOCK_K * 2;
+  constexpr int P_STG_BYTES = EW * 4096;   // one 4 KB (1024-byte aligned) staging buffer per epilogue warp
+  constexpr int CW = 128 / (EW / 4);       // columns per epilogue warp: 64 (8 warps) or 32 (16 warps)
+  constexpr int NCH = CW / 32;             // 32-column chunks per warp
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
@@ -367,7 +372,7 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);  // one arrival per epilogue warp
+      mbar_init(tempty_bar(s), EW);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -463,7 +468,7 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       }
     }
   } else {
-    // ---- 8 epilogue warps: quarter = TMEM lane quarter, half = which 64 of the 128 columns ----
+    // ---- epilogue warps: quarter = TMEM lane quarter, half = which CW-column slice of the 128 columns ----
     const int ew = warp - 2;
     const int quarter = warp & 3, half = ew >> 2;
     if constexpr (!CONV) {
@@ -478,25 +483,25 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         int n0, z, tb, oy0, ox0;
         int64_t m0;
         decode(t, n0, z, m0, tb, oy0, ox0);
-        const int nb0 = n0 + half * 64;
+        const int nb0 = n0 + half * CW;
         const int64_t m = m0 + row;
         // residual prefetch (the row's 64 columns), issued before waiting for the accumulator
-        float4 rres[16];
+        float4 rres[CW / 4];
         if (p.res) {
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
+          for (int q = 0; q < CW / 4; ++q) {
             rres[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (m < p.M && nb0 + 4 * q < p.N) rres[q] = *reinterpret_cast<const float4*>(p.res + m * p.ldr + nb0 + 4 * q);
           }
         }
         mbar_wait(tfull_bar(slot), ((uint32_t)i >> 1) & 1u);
         tc_fence_after();
-        float v[64];
+        float v[CW];
         {
-          const uint32_t tb_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 2 * BN + half * 64);
+          const uint32_t tb_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 2 * BN + half * CW);
           uint32_t r[32];
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < NCH; ++c) {
             tmem_ld32(tb_addr + (uint32_t)(c * 32), r);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(r[j]);
@@ -510,7 +515,7 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         if (lane == 0) mbar_arrive(tempty_bar(slot));  // TMEM slot free for the MMA of tile i+2
 
 #pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
+        for (int cb = 0; cb < NCH; ++cb) {
           const int nb = nb0 + cb * 32;
           if (nb >= p.N) break;  // warp-uniform
           {
@@ -575,6 +580,7 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       }
       if (lane == 0) bulk_wait0();  // all stores of this warp have landed before the CTA exits
     } else {
+    static_assert(!CONV || EW == 8, "conv epilogue is written for 8 epilogue warps");
     float* stg = staging + ew * (32 * P_STG_LD);
     const int r8 = lane >> 2, c4 = lane & 3;  // transposed pass: 8 rows x 4 float4 (16 columns) per instruction
     int i = 0;
@@ -677,7 +683,7 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         __syncwarp();
       }
     }
-    }  // CONV epilogue
+    }  // CONV epilogue (instantiated with 8 epilogue warps only)
   }
 
   tc_fence_before();
@@ -732,21 +738,23 @@ bool persistent_enabled() {
   return v == 1;
 }
 
-template <int MODE>
+template <int MODE, int EW, int STAGES>
 int launch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
                       const CUtensorMap& to, const CUtensorMap& to_hi, const CUtensorMap& to_lo, const TcParams& p,
                       int n_tiles, int m_tiles, int phases, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_persistent_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
-    if (e != cudaSuccess) WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", P_SMEM, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(tc_persistent_kernel<MODE, EW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         p_smem<EW, STAGES>());
+    if (e != cudaSuccess)
+      WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", p_smem<EW, STAGES>(), cudaGetErrorString(e));
     attr_set = true;
   }
   const int64_t total = (int64_t)n_tiles * m_tiles * phases;
   if (total > INT32_MAX) WXF_FAIL(WXF_EINVAL, "tc: too many tiles");
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  tc_persistent_kernel<MODE><<<grid, P_THREADS, P_SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, n_tiles, m_tiles,
-                                                              (int)total);
+  tc_persistent_kernel<MODE, EW, STAGES><<<grid, 64 + 32 * EW, p_smem<EW, STAGES>(), st>>>(
+      ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, n_tiles, m_tiles, (int)total);
   WXF_CHECK_LAUNCH("tc_persistent");
   return 0;
 }
@@ -811,8 +819,9 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
       if ((rc = make_map(&to_hi, d->out_hi, 2, dims, strides, box, es, 64))) return rc;
       if ((rc = make_map(&to_lo, d->out_lo, 2, dims, strides, box, es, 64))) return rc;
     }
-    return launch_persistent<MODE_GEMM>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, (d->N + BN - 1) / BN,
-                                        (int)((d->M + BLOCK_M - 1) / BLOCK_M), 1, st);
+    const int nt = (d->N + BN - 1) / BN, mt = (int)((d->M + BLOCK_M - 1) / BLOCK_M);
+    if (d->K <= 256) return launch_persistent<MODE_GEMM, 16, 2>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, nt, mt, 1, st);
+    return launch_persistent<MODE_GEMM, 8, 3>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, nt, mt, 1, st);
   }
   dim3 grid((unsigned)((d->N + BN - 1) / BN), (unsigned)((d->M + BLOCK_M - 1) / BLOCK_M), 1);
   if (BN == 256) return launch<256, 2, MODE_GEMM>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
@@ -897,8 +906,8 @@ extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
     }
   const int64_t ntiles = (int64_t)d->B * p.tiles_x * p.tiles_y;
   if (persistent)
-    return launch_persistent<MODE_CONV>(ta_hi, ta_lo, tw_hi, tw_lo, ta_hi, ta_hi, ta_hi, p, (d->N + BN - 1) / BN, (int)ntiles,
-                                        d->phases, st);
+    return launch_persistent<MODE_CONV, 8, 3>(ta_hi, ta_lo, tw_hi, tw_lo, ta_hi, ta_hi, ta_hi, p, (d->N + BN - 1) / BN,
+                                              (int)ntiles, d->phases, st);
   if (ntiles > 65535) WXF_FAIL(WXF_EINVAL, "conv_tc: too many tiles for one launch");
   dim3 grid((unsigned)((d->N + BN - 1) / BN), (unsigned)ntiles, (unsigned)d->phases);
   if (BN == 256) return launch<256, 2, MODE_CONV>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
