@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 7
+#define WXF_ABI_VERSION 8
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -219,6 +219,7 @@ typedef struct WxfToeplitzDesc {
   int32_t Ho, Wo;
   int32_t ldc, c_off;
   int32_t w_scale_log2;
+  int32_t oy_off; /* domain decomposition: local output row oy stands for global row oy + oy_off of the input image */
 } WxfToeplitzDesc;
 
 int wxf_cross_embed_toeplitz_tc(const WxfToeplitzDesc* desc, void* stream);
@@ -241,6 +242,20 @@ int wxf_groupnorm_silu(const float* x, int ldx, const float* stats, const float*
 int wxf_groupnorm_silu_f16x2(const float* x, int ldx, const float* stats, const float* gamma, const float* beta,
                              const float* res, int ldr, void* y_hi, void* y_lo, int ldh, int h_off, int B, int64_t HW,
                              int C, int G, void* stream);
+
+/*
+ * GroupNorm statistics in two halves for the lat-band domain decomposition (the reference's DomainParallelGroupNorm
+ * all-reduces (sum, sum of squares), credit/domain_parallel/layers.py:507-518): raw fp64 sums [B, G, 2] of the local
+ * band, then - after the caller's all-reduce - (mean, rstd) from the global sums.
+ */
+int wxf_groupnorm_sums(const float* x, int ldx, double* sums, void* scratch, int B, int64_t HW, int C, int G, void* stream);
+int wxf_groupnorm_stats_from_sums(const double* sums, float* stats, int B, int G, double count, float eps, void* stream);
+
+/*
+ * Row gather dst[i, 0:d] = src[idx[i], 0:d] (fp32 rows, idx int32 on the device): packs / unpacks the all-to-all buffers
+ * that move the residual stream between the lat-band layout and the attention-unit layout (multi-GPU).
+ */
+int wxf_gather_rows(const float* src, int ld_src, const int32_t* idx, float* dst, int ld_dst, int64_t n, int d, void* stream);
 
 /*
  * Un-pad + bilinear resize (align_corners = False) + pixel-major -> NCHW

@@ -964,7 +964,7 @@ extern "C" int wxf_cross_embed_toeplitz_tc(const WxfToeplitzDesc* d, void* strea
   p.a_bytes = (uint32_t)TILE_BYTES;
   for (int ky = 0; ky < d->kernel; ++ky)
     for (int r = 0; r < 2; ++r) {
-      p.taps[0][ky * 2 + r][0] = (int16_t)(ky - d->pad);
+      p.taps[0][ky * 2 + r][0] = (int16_t)(ky - d->pad + 2 * d->oy_off);
       p.taps[0][ky * 2 + r][1] = (int16_t)(r - d->pad);
     }
   const int64_t ntiles = (int64_t)d->B * p.tiles_x * p.tiles_y;

@@ -509,6 +509,94 @@ extern "C" int wxf_groupnorm_stats(const float* x, int ldx, float* stats, void* 
   return 0;
 }
 
+__global__ void gn_sums_kernel(const float2* __restrict__ part, double* __restrict__ sums, int B, int G, int nchunk) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= B * G) return;
+  const int b = i / G, g = i % G;
+  double s = 0.0, q = 0.0;
+  for (int c = lane; c < nchunk; c += 32) {
+    const float2 p = part[((int64_t)b * nchunk + c) * G + g];
+    s += (double)p.x;
+    q += (double)p.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    sums[2 * i] = s;
+    sums[2 * i + 1] = q;
+  }
+}
+
+__global__ void gn_stats_from_sums_kernel(const double* __restrict__ sums, float* __restrict__ stats, int n, double count,
+                                          float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mean = sums[2 * i] / count;
+  double var = sums[2 * i + 1] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[2 * i] = (float)mean;
+  stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+extern "C" int wxf_groupnorm_sums(const float* x, int ldx, double* sums, void* scratch, int B, int64_t HW, int C, int G,
+                                  void* stream) {
+  if (B <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G) WXF_FAIL(WXF_EINVAL, "groupnorm_sums: bad dims");
+  if (C > 1024 || !((C <= 256 && 256 % C == 0) || (C % 256 == 0)))
+    WXF_FAIL(WXF_EUNSUPPORTED, "groupnorm: C=%d must divide 256 or be a multiple of 256 (<=1024)", C);
+  const int ppb = gn_pix_per_block(HW);
+  const int nchunk = (int)((HW + ppb - 1) / ppb);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (C % 4 == 0) && (256 % (C / 4) == 0) && (ldx % 4 == 0) && wxf_aligned16(x);
+  if (vec)
+    gn_partial_vec_kernel<<<dim3(nchunk, B), 256, 0, st>>>(x, ldx, (float2*)scratch, HW, C, G, nchunk, ppb);
+  else
+    gn_partial_kernel<<<dim3(nchunk, B), 256, 0, st>>>(x, ldx, (float2*)scratch, HW, C, G, nchunk, ppb);
+  WXF_CHECK_LAUNCH("gn_partial");
+  gn_sums_kernel<<<(B * G + 3) / 4, 128, 0, st>>>((const float2*)scratch, sums, B, G, nchunk);
+  WXF_CHECK_LAUNCH("gn_sums");
+  return 0;
+}
+
+extern "C" int wxf_groupnorm_stats_from_sums(const double* sums, float* stats, int B, int G, double count, float eps,
+                                             void* stream) {
+  if (B <= 0 || G <= 0 || count <= 0) WXF_FAIL(WXF_EINVAL, "groupnorm_stats_from_sums: bad dims");
+  gn_stats_from_sums_kernel<<<(B * G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, stats, B * G, count, eps);
+  WXF_CHECK_LAUNCH("gn_stats_from_sums");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row gather (all-to-all pack / unpack of the domain decomposition)
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, int ld_src,
+                                                           const int32_t* __restrict__ idx, float* __restrict__ dst,
+                                                           int ld_dst, int64_t n, int d4) {
+  const int64_t total = n * d4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d4;
+    const int c = (int)(i - r * d4) * 4;
+    *reinterpret_cast<float4*>(dst + r * ld_dst + c) =
+        *reinterpret_cast<const float4*>(src + (int64_t)__ldg(idx + r) * ld_src + c);
+  }
+}
+
+extern "C" int wxf_gather_rows(const float* src, int ld_src, const int32_t* idx, float* dst, int ld_dst, int64_t n, int d,
+                               void* stream) {
+  if (n < 0 || d <= 0 || (d & 3) || (ld_src & 3) || (ld_dst & 3) || ld_src < d || ld_dst < d || !wxf_aligned16(src) ||
+      !wxf_aligned16(dst))
+    WXF_FAIL(WXF_EINVAL, "gather_rows: bad arguments (d, strides multiples of 4; 16-byte aligned)");
+  if (n == 0) return 0;
+  int64_t blocks = (n * (d / 4) + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, idx, dst, ld_dst, n, d / 4);
+  WXF_CHECK_LAUNCH("gather_rows");
+  return 0;
+}
+
 static int gn_silu_launch(const float* x, int ldx, const float* stats, const float* gamma, const float* beta,
                           const float* res, int ldr, float* y, void* y_hi, void* y_lo, int ldy, int B, int64_t HW,
                           int C, int G, void* stream) {

@@ -1,0 +1,369 @@
+"""Exact lat-lon domain decomposition of ONE forecast step over the GPUs of a box (torch.distributed, NCCL).
+
+The reference's ``credit/domain_parallel`` shards equal latitude bands and leaves attention "local within the shard"
+(convert.py:100-105), which changes the arithmetic of the dilated long attention (measured 1.2e-1 off its own
+single-device forward).  This decomposition is exact (same arithmetic as the single-GPU plan up to fp32
+reassociation) and uses two layouts:
+
+* **band layout** (convolutions, GroupNorm, decoder): rank r owns a contiguous band of grid rows, nested across stages
+  (band at stage s = 2x band at stage s+1), with one-row halos exchanged between neighbours
+  (the reference's halo widths: tests/test_domain_parallel.py:66-99; stage 0 reads the replicated padded input).
+* **unit layout** (the transformer stack of a stage): the windows (wy, wx) with fixed (wy mod A, wx mod B),
+  A = H/(lws*gws), B = W/(lws*gws), form a *unit*: a (lws*gws) x (lws*gws) mini-image that is closed under BOTH the
+  short windows and the dilated long groups, and inside which they are again the ordinary short / long patterns.  A rank
+  owns whole units and runs the unchanged single-GPU kernels on them as a batch: no communication inside a stage.
+
+Per step: 2 all-to-alls per stage (band <-> unit, the fp32 residual stream), 1-row halo exchanges in the decoder,
+one all-reduce of (sum, sum-of-squares) per GroupNorm, one all-gather of the decoder output.
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+from . import lib as _lib
+from . import ops
+from .geometry import Geometry
+from .model import _Plan, _round_up
+from .weights import ConvTcWeights, PreparedWeights
+
+logger = logging.getLogger(__name__)
+
+
+def _split(n: int, parts: int) -> List[int]:
+    return [(r * n) // parts for r in range(parts + 1)]
+
+
+class DomainLayout:
+    """Band boundaries and unit ownership for every stage."""
+
+    def __init__(self, geo: Geometry, world: int):
+        self.world = world
+        rb3 = _split(geo.stages[3].h, world)
+        self.rb = [[b * 2 ** (3 - s) for b in rb3] for s in range(4)]  # band row boundaries per stage
+        self.units = []
+        for st in geo.stages:
+            ws, wg = st.local_window, st.global_window
+            if st.h % (ws * wg) or st.w % (ws * wg):
+                raise NotImplementedError(
+                    f"stage {st.index}: grid {st.h}x{st.w} is not a multiple of local*global window {ws * wg}; "
+                    "the unit decomposition needs that")
+            a, b = st.h // (ws * wg), st.w // (ws * wg)
+            self.units.append(dict(a=a, b=b, hu=ws * wg, wu=ws * wg, n=a * b, ub=_split(a * b, world)))
+        if any(u["n"] < world for u in self.units):
+            raise NotImplementedError("fewer attention units than ranks")
+        if any(self.rb[3][r + 1] == self.rb[3][r] for r in range(world)):
+            raise NotImplementedError("more ranks than stage-3 grid rows")
+
+
+def _pixel_maps(st, lay: DomainLayout):
+    """Per pixel of the stage grid: (band owner, band-local index, unit owner, unit-local index)."""
+    s = st.index
+    H, W = st.h, st.w
+    ws = st.local_window
+    u = lay.units[s]
+    y = torch.arange(H)[:, None].expand(H, W)
+    x = torch.arange(W)[None, :].expand(H, W)
+    wy, s1 = y // ws, y % ws
+    wx, s2 = x // ws, x % ws
+    ua, i = wy % u["a"], wy // u["a"]
+    ub_, j = wx % u["b"], wx // u["b"]
+    uid = ua * u["b"] + ub_
+    Y, X = i * ws + s1, j * ws + s2
+    rb = torch.tensor(lay.rb[s])
+    ubnd = torch.tensor(u["ub"])
+    band_owner = torch.searchsorted(rb, y.contiguous(), right=True) - 1
+    unit_owner = torch.searchsorted(ubnd, uid.contiguous(), right=True) - 1
+    band_local = (y - rb[band_owner]) * W + x
+    unit_local = ((uid - ubnd[unit_owner]) * u["hu"] + Y) * u["wu"] + X
+    return band_owner.reshape(-1), band_local.reshape(-1), unit_owner.reshape(-1), unit_local.reshape(-1)
+
+
+class Exchange:
+    """band <-> unit re-layout of a stage's residual stream for this rank (index lists are computed once)."""
+
+    def __init__(self, st, lay: DomainLayout, rank: int, device):
+        bo, bl, uo, ul = _pixel_maps(st, lay)
+        world = lay.world
+        self.rank, self.world, self.d = rank, world, st.dim
+        send_idx, recv_idx = [], []
+        self.send_counts, self.recv_counts = [], []
+        for r in range(world):  # band side: what I send to r, ordered by r's unit-local index
+            m = (bo == rank) & (uo == r)
+            order = torch.argsort(ul[m])
+            send_idx.append(bl[m][order])
+            self.send_counts.append(int(m.sum()))
+        for q in range(world):  # unit side: what I receive from q (already in unit-local order)
+            m = (bo == q) & (uo == rank)
+            recv_idx.append(torch.sort(ul[m]).values)
+            self.recv_counts.append(int(m.sum()))
+        self.n_band = int((bo == rank).sum())
+        self.n_unit = int((uo == rank).sum())
+        cat_send = torch.cat(send_idx)
+        cat_recv = torch.cat(recv_idx)
+        inv_recv = torch.empty(self.n_unit, dtype=torch.long)
+        inv_recv[cat_recv] = torch.arange(self.n_unit)
+        inv_send = torch.empty(self.n_band, dtype=torch.long)
+        inv_send[cat_send] = torch.arange(self.n_band)
+        i32 = dict(device=device, dtype=torch.int32)
+        self.send_idx = cat_send.to(**i32)    # band-local rows in send order
+        self.recv_idx = cat_recv.to(**i32)    # unit-local rows in receive order
+        self.inv_recv = inv_recv.to(**i32)    # unit-local position -> row of the receive buffer
+        self.inv_send = inv_send.to(**i32)    # band-local position -> row of the (reverse) receive buffer
+        self.send_off = [0]
+        for c in self.send_counts:
+            self.send_off.append(self.send_off[-1] + c)
+        self.recv_off = [0]
+        for c in self.recv_counts:
+            self.recv_off.append(self.recv_off[-1] + c)
+
+    def _p2p(self, sbuf, soff, scnt, rbuf, roff, rcnt):
+        d = self.d
+        reqs = []
+        for peer in range(self.world):
+            if peer == self.rank:
+                continue
+            if rcnt[peer]:
+                reqs.append(dist.P2POp(dist.irecv, rbuf[roff[peer] * d: (roff[peer] + rcnt[peer]) * d], peer))
+            if scnt[peer]:
+                reqs.append(dist.P2POp(dist.isend, sbuf[soff[peer] * d: (soff[peer] + scnt[peer]) * d], peer))
+        if reqs:
+            for w in dist.batch_isend_irecv(reqs):
+                w.wait()
+
+    def band_to_unit(self, band, ld_band, unit, sbuf, rbuf):
+        d, me = self.d, self.rank
+        ops.gather_rows(band, ld_band, self.send_idx, sbuf, d, self.n_band, d)
+        # my own rows go straight into the receive buffer
+        n_self = self.send_counts[me]
+        if n_self:
+            ops.gather_rows(band, ld_band, self.send_idx[self.send_off[me]:], rbuf[self.recv_off[me] * d:], d, n_self, d)
+        self._p2p(sbuf, self.send_off, self.send_counts, rbuf, self.recv_off, self.recv_counts)
+        ops.gather_rows(rbuf, d, self.inv_recv, unit, d, self.n_unit, d)
+
+    def unit_to_band(self, unit, band, ld_band, sbuf, rbuf):
+        d, me = self.d, self.rank
+        ops.gather_rows(unit, d, self.recv_idx, sbuf, d, self.n_unit, d)
+        n_self = self.recv_counts[me]
+        if n_self:
+            ops.gather_rows(unit, d, self.recv_idx[self.recv_off[me]:], rbuf[self.send_off[me] * d:], d, n_self, d)
+        self._p2p(sbuf, self.recv_off, self.recv_counts, rbuf, self.send_off, self.send_counts)
+        ops.gather_rows(rbuf, d, self.inv_send, band, ld_band, self.n_band, d)
+
+
+def _halo_exchange(tensors, rows: int, rank: int, world: int):
+    """One-row halo exchange of band tensors shaped [rows + 2, W, C] (row 0 / rows+1 are the halos)."""
+    reqs = []
+    for t in tensors:
+        if rank > 0:
+            reqs.append(dist.P2POp(dist.irecv, t[0], rank - 1))
+            reqs.append(dist.P2POp(dist.isend, t[1], rank - 1))
+        if rank < world - 1:
+            reqs.append(dist.P2POp(dist.irecv, t[rows + 1], rank + 1))
+            reqs.append(dist.P2POp(dist.isend, t[rows], rank + 1))
+    if reqs:
+        for w in dist.batch_isend_irecv(reqs):
+            w.wait()
+
+
+def _shift_taps(w: ConvTcWeights, dy: int) -> ConvTcWeights:
+    """Copy of the tensor-core conv weights whose tap rows are shifted by ``dy`` (input band carries a halo row)."""
+    import copy
+    import ctypes
+
+    out = copy.copy(w)
+    flat = [int(v) for v in w.taps_host]
+    for k in range(0, len(flat), 2):
+        flat[k] += dy
+    out.taps_host = (ctypes.c_int32 * len(flat))(*flat)
+    return out
+
+
+class DomainPlan(_Plan):
+    """Launch plan of one rank.  Input: the full state (replicated); output: the full prediction on every rank."""
+
+    def __init__(self, geo: Geometry, wts: PreparedWeights, rank: int, world: int, device):  # noqa: super not called
+        if geo.variant != "crossformer":
+            raise NotImplementedError("domain decomposition is built for the `crossformer` decoder")
+        if wts.embed0_toep is None or wts.head_tc is None or any(c is None for brs in wts.embeds_tc[1:] for c in brs):
+            raise NotImplementedError("domain decomposition needs the tensor-core path (channel counts % 4 == 0)")
+        self.geo, self.batch = geo, 1
+        self.rank, self.world = rank, world
+        self.tensor_cores = True
+        self.attention_tc = True
+        self.toeplitz = True
+        self.lay = lay = DomainLayout(geo, world)
+        g = geo
+        f32 = dict(device=device, dtype=torch.float32)
+        f16 = dict(device=device, dtype=torch.float16)
+        self.ld0 = 64
+        self.xp = None
+        self.xp_planes = (torch.empty((1, g.h_pad, g.w_pad, 64), **f16), torch.empty((1, g.h_pad, g.w_pad, 64), **f16))
+        self.rows = [lay.rb[s][rank + 1] - lay.rb[s][rank] for s in range(4)]
+        self.nu = [lay.units[s]["ub"][rank + 1] - lay.units[s]["ub"][rank] for s in range(4)]
+        m_unit = [self.nu[s] * lay.units[s]["hu"] * lay.units[s]["wu"] for s in range(4)]
+        m_band = [self.rows[s] * g.stages[s].w for s in range(4)]
+        big = _round_up(max(max(m_unit[s], m_band[s]) * g.stages[s].dim for s in range(4)), 8)
+        self.ln = torch.empty(big, **f32)
+        self.scratch = torch.empty(4 * big, **f32)
+        self.ln16 = self.ln.view(torch.float16)
+        self.scratch16 = self.scratch.view(torch.float16)
+        self.sbuf = torch.empty(big, **f32)
+        self.rbuf = torch.empty(big, **f32)
+        self.xu = [torch.empty((max(self.nu[s], 1), lay.units[s]["hu"], lay.units[s]["wu"], g.stages[s].dim), **f32)
+                   for s in range(4)]
+        self.eb = [torch.empty((self.rows[s], g.stages[s].w, g.stages[s].dim), **f32) for s in range(4)]
+        # skip/concat planes in band layout with one halo row above and below (zero at the domain edges)
+        self.catp = [(torch.zeros((self.rows[s] + 2, g.stages[s].w, 2 * g.stages[s].dim), **f16),
+                      torch.zeros((self.rows[s] + 2, g.stages[s].w, 2 * g.stages[s].dim), **f16)) for s in range(3)]
+        s3 = g.stages[3]
+        self.x3p = (torch.empty((self.rows[3], s3.w, s3.dim), **f16), torch.empty((self.rows[3], s3.w, s3.dim), **f16))
+        self.dec = []
+        for k, up in enumerate(g.ups):
+            ro, wo, c = 2 * self.rows[3 - k], 2 * up.w_in, up.c_out
+            self.dec.append(dict(
+                short=torch.empty((ro, wo, c), **f32), a=torch.empty((ro, wo, c), **f32),
+                sp=(torch.zeros((ro + 2, wo, c), **f16), torch.zeros((ro + 2, wo, c), **f16)),
+                bp=(torch.zeros((ro + 2, wo, c), **f16), torch.zeros((ro + 2, wo, c), **f16))))
+        self.gn_sums = torch.empty((1, g.dim[0], 2), device=device, dtype=torch.float64)
+        self.gn_stats = torch.empty((1, g.dim[0], 2), **f32)
+        gn_bytes = max(ops.groupnorm_scratch_bytes(1, 2 * self.rows[3 - k] * 2 * up.w_in, up.c_out)
+                       for k, up in enumerate(g.ups))
+        self.gn_scratch = torch.empty(gn_bytes // 4 + 4, **f32)
+        self.y_dec = torch.empty((g.h_dec, g.w_dec, g.output_channels), **f32)  # full decoder output (all-gathered)
+        self.ex = [Exchange(g.stages[s], lay, rank, device) for s in range(4)]
+        self.steps: List[tuple] = []
+        self.bias_tiles: List[torch.Tensor] = []
+        self._build(wts)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _build(self, wts: PreparedWeights):
+        g, lay, rank, world = self.geo, self.lay, self.rank, self.world
+        add = self._add
+        for st in g.stages:
+            s, d = st.index, st.dim
+            rows, r0 = self.rows[s], lay.rb[s][rank]
+            eb = self.eb[s]
+            # ---- cross-embed in band layout: output rows [r0, r0 + rows) of the stage grid ----
+            for bi, br in enumerate(st.branches):
+                if s == 0:  # Toeplitz kernel on the replicated padded input, output-row offset r0
+                    desc = ops.make_toeplitz_desc(self.xp_planes[0], self.xp_planes[1], wts.embed0_toep[bi], eb, B=1,
+                                                  Hi=g.h_pad, Wi=g.w_pad, lda=64, Ho=rows, Wo=st.w, ldc=d,
+                                                  c_off=br.c_off, oy_off=r0)
+                    add(ops.cross_embed_toeplitz_tc, (desc,), f"embed0.k{br.kernel}",
+                        2.0 * rows * st.w * br.c_out * st.c_in * br.kernel * br.kernel)
+                else:       # input: previous stage's band planes (upper half of its concat buffer) with halo rows
+                    dp = g.stages[s - 1].dim
+                    src_hi, src_lo = self.catp[s - 1][0][..., dp:], self.catp[s - 1][1][..., dp:]
+                    self._conv_tc(src_hi, src_lo, _shift_taps(wts.embeds_tc[s][bi], 1), f"embed{s}.k{br.kernel}", B=1,
+                                  Hi=self.rows[s - 1] + 2, Wi=g.stages[s - 1].w, lda=2 * dp, Ho=rows, Wo=st.w, out=eb,
+                                  ldc=d, c_off=br.c_off)
+            # ---- band -> unit layout, transformer on the rank's units (a batch of mini-images), unit -> band ----
+            u = lay.units[s]
+            ex, xu = self.ex[s], self.xu[s]
+            add(ex.band_to_unit, (eb, d, xu, self.sbuf, self.rbuf), f"exchange.s{s}", 0, 8.0 * rows * st.w * d)
+            if self.nu[s] > 0:
+                self._transformer(wts.blocks[s], st, self.nu[s], u["hu"], u["wu"], xu, d, None)
+            add(ex.unit_to_band, (xu, eb, d, self.sbuf, self.rbuf), f"exchange.s{s}", 0, 8.0 * rows * st.w * d)
+            # ---- stage output as operand planes (band layout): skip connection + next cross-embed ----
+            m = rows * st.w
+            if s < 3:
+                hi, lo = self.catp[s]
+                add(ops.split_f16x2, (eb, d, hi[1:, :, d:], lo[1:, :, d:], 2 * d, m, d), "split", 0, 8.0 * m * d)
+            else:
+                add(ops.split_f16x2, (eb, d, self.x3p[0], self.x3p[1], d, m, d), "split", 0, 8.0 * m * d)
+            if 1 <= s + 1 <= 3 and s < 3:
+                # the next stage's k=4 branch needs one halo row of this stage's output
+                add(_halo_exchange, ((hi, lo), rows, rank, world), "halo", 0, 0)
+
+        # ---- decoder in band layout ----
+        dec_planes, dec_ld, dec_rows, dec_halo = self.x3p, g.stages[3].dim, self.rows[3], 0
+        for k, (up, uw, skip) in enumerate(zip(g.ups, wts.ups, (2, 1, 0))):
+            bufs = self.dec[k]
+            rin, ro, wo, c = self.rows[3 - k], 2 * self.rows[3 - k], 2 * up.w_in, up.c_out
+            n = ro * wo * c
+            sp_hi, sp_lo = bufs["sp"]
+            bp_hi, bp_lo = bufs["bp"]
+            in_hi, in_lo = (dec_planes[0][dec_halo:], dec_planes[1][dec_halo:]) if dec_halo else dec_planes
+            # ConvTranspose k2 s2: no halo; fp32 shortcut + planes (interior rows of the halo'd buffer)
+            self._conv_tc(in_hi, in_lo, uw.up_tc, "dec_up", B=1, Hi=rin, Wi=up.w_in, lda=dec_ld, Ho=rin, Wo=up.w_in,
+                          out=bufs["short"], ldc=c, out_hi=sp_hi[1:], out_lo=sp_lo[1:], ldh=c)
+            add(_halo_exchange, ((sp_hi, sp_lo), ro, rank, world), "halo", 0, 0)
+            self._conv_tc(sp_hi, sp_lo, _shift_taps(uw.convs_tc[0], 1), "dec_conv3x3", B=1, Hi=ro + 2, Wi=wo, lda=c,
+                          Ho=ro, Wo=wo, out=bufs["a"], ldc=c)
+            count = float(4 * up.h_in * up.w_in) * (c // up.groups)  # global pixels x channels per group
+            add(self._groupnorm, (bufs["a"], c, uw.gn_w[0], uw.gn_b[0], None, 0, bp_hi[1:], bp_lo[1:], c, 0, ro * wo, c,
+                                  up.groups, count), "groupnorm_silu", 0, 8.0 * n)
+            add(_halo_exchange, ((bp_hi, bp_lo), ro, rank, world), "halo", 0, 0)
+            self._conv_tc(bp_hi, bp_lo, _shift_taps(uw.convs_tc[1], 1), "dec_conv3x3", B=1, Hi=ro + 2, Wi=wo, lda=c,
+                          Ho=ro, Wo=wo, out=bufs["a"], ldc=c)
+            chi, clo = self.catp[skip]
+            add(self._groupnorm, (bufs["a"], c, uw.gn_w[1], uw.gn_b[1], bufs["short"], c, chi[1:], clo[1:], 2 * c, 0,
+                                  ro * wo, c, up.groups, count), "groupnorm_silu", 0, 12.0 * n)
+            dec_planes, dec_ld, dec_rows, dec_halo = self.catp[skip], 2 * c, ro, 1
+        # up_block4 (ConvT k4 s2 p1) reads one halo row of the full concat buffer
+        st0 = g.stages[0]
+        add(_halo_exchange, (self.catp[0], self.rows[0], rank, world), "halo", 0, 0)
+        y_band = self.y_dec[2 * lay.rb[0][rank]: 2 * lay.rb[0][rank + 1]]
+        self._conv_tc(self.catp[0][0], self.catp[0][1], _shift_taps(wts.head_tc, 1), "dec_head", B=1,
+                      Hi=self.rows[0] + 2, Wi=st0.w, lda=2 * st0.dim, Ho=self.rows[0], Wo=st0.w, out=y_band,
+                      ldc=g.output_channels)
+        add(self._allgather_output, (), "allgather", 0, 0)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _groupnorm(self, x, ldx, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, hw_local, C, G, count):
+        """GroupNorm + SiLU with statistics over the whole (all-rank) image: local sums, all-reduce, apply."""
+        ops.groupnorm_sums(x, ldx, self.gn_sums, self.gn_scratch, 1, hw_local, C, G)
+        dist.all_reduce(self.gn_sums)
+        ops.groupnorm_stats_from_sums(self.gn_sums, self.gn_stats, 1, G, count)
+        ops.groupnorm_apply_f16x2(x, ldx, self.gn_stats, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, 1, hw_local, C, G)
+
+    def _allgather_output(self):
+        lay, me = self.lay, self.rank
+        reqs = []
+        for peer in range(self.world):
+            if peer == me:
+                continue
+            reqs.append(dist.P2POp(dist.irecv, self.y_dec[2 * lay.rb[0][peer]: 2 * lay.rb[0][peer + 1]], peer))
+            reqs.append(dist.P2POp(dist.isend, self.y_dec[2 * lay.rb[0][me]: 2 * lay.rb[0][me + 1]], peer))
+        if reqs:
+            for w in dist.batch_isend_irecv(reqs):
+                w.wait()
+
+    def run(self, x: torch.Tensor) -> torch.Tensor:
+        g = self.geo
+        self._pad(x)
+        for fn, args, _tag, _fl, _by in self.steps:
+            fn(*args)
+        out = torch.empty((1, g.base_output_channels, g.output_frames, g.h_out, g.w_out), device=x.device,
+                          dtype=torch.float32)
+        self._unpad(out)
+        return out
+
+
+class DomainParallelForward:
+    """``y = f(x)`` of a CrossFormerB200 split over the ranks of the default process group (one process per GPU).
+
+    Every rank passes the same full input state and receives the full prediction (multi-GPU)."""
+
+    def __init__(self, model, group_rank: int = None, world: int = None):
+        self.model = model
+        self.rank = dist.get_rank() if group_rank is None else group_rank
+        self.world = dist.get_world_size() if world is None else world
+        self._plan = None
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        m = self.model
+        if x.shape[0] != 1:
+            raise ValueError("domain-parallel forward takes one state at a time (batch 1)")
+        if m._prepared is None or m._prepared_sig != m._signature():
+            m.refresh_weights()
+            self._plan = None
+        if self._plan is None:
+            self._plan = DomainPlan(m.geometry, m._prepared, self.rank, self.world, x.device)
+        return self._plan.run(x.contiguous())

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 7
+WXF_ABI_VERSION = 8
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -68,7 +68,7 @@ class WxfToeplitzDesc(Structure):
         ("ch", c_int32), ("kernel", c_int32), ("pad", c_int32),
         ("Ho", c_int32), ("Wo", c_int32),
         ("ldc", c_int32), ("c_off", c_int32),
-        ("w_scale_log2", c_int32),
+        ("w_scale_log2", c_int32), ("oy_off", c_int32),
     ]
 
 
@@ -97,6 +97,9 @@ _SIGNATURES = {
     "wxf_groupnorm_stats": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float, c_void_p]),
     "wxf_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                    c_int, c_int64, c_int, c_int, c_void_p]),
+    "wxf_groupnorm_sums": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
+    "wxf_groupnorm_stats_from_sums": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_double, c_float, c_void_p]),
+    "wxf_gather_rows": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "wxf_unpad_resize_to_nchw": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 10 + [c_void_p]),
     "wxf_copy_channels": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int64, POINTER(c_int32), POINTER(c_int32),
                                   POINTER(c_int32), c_int, c_void_p]),

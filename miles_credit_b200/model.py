@@ -187,6 +187,69 @@ class _Plan:
         m = kw["B"] * kw["Ho"] * kw["Wo"]
         self._add(ops.conv_f16x2_tc, (desc,), tag, 2.0 * m * wts.n * wts.t * wts.cin * wts.phases)
 
+    def _transformer(self, layers, st, B, h, w, xv, ld, out_planes):
+        """Launches of one Transformer stage (crossformer.py:358-365) on the residual stream ``xv`` ([B, h, w, d] view with
+        pixel stride ``ld``), in place.  ``out_planes`` = (hi, lo, stride): also emit the stage output as operand planes."""
+        g = self.geo
+        add = self._add
+        tc = self.tensor_cores
+        s, d = st.index, st.dim
+        m = B * h * w
+        scale = float(g.dim_head) ** -0.5
+        if out_planes is not None:
+            xp_hi, xp_lo, pld = out_planes
+        wts_blocks = layers
+        ln = self.ln[: m * d]
+        wide = self.scratch[: m * 4 * d]
+        # fp16 operand planes alias the same workspaces (2 planes x 2 bytes = the fp32 footprint)
+        ln_hi, ln_lo = self.ln16[: m * d], self.ln16[self.ln.numel(): self.ln.numel() + m * d]
+        hid_off = self.scratch.numel()
+        hid_hi, hid_lo = self.scratch16[: m * 4 * d], self.scratch16[hid_off: hid_off + m * 4 * d]
+        n_layers = len(wts_blocks)
+        for li, layer in enumerate(wts_blocks):
+            for half, (att, ff) in enumerate(((layer[0], layer[1]), (layer[2], layer[3]))):
+                L = att.wsz * att.wsz
+                attn_cost = (4.0 * m * L * d, 16.0 * m * d)
+                last = li == n_layers - 1 and half == 1
+                if tc:
+                    add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, att.ln_g, att.ln_b, m, d), f"layernorm.s{s}", 0,
+                        8.0 * m * d)
+                    if self.attention_tc and L <= 128:
+                        q_hi, q_lo = self.scratch16[: m * 3 * d], self.scratch16[hid_off: hid_off + m * 3 * d]
+                        self._gemm(ln_hi, ln_lo, att.qkv_tc, f"qkv.s{s}", M=m, lda=d, out_hi=q_hi, out_lo=q_lo, ldh=3 * d)
+                        tile = ops.attention_bias_tile(att.bias_t, w, att.wsz, att.kind)
+                        self.bias_tiles.append(tile)
+                        add(ops.window_attention_tc, (q_hi, q_lo, 3 * d, tile, ln_hi, ln_lo, d, B, h, w,
+                                                      d, g.dim_head, att.wsz, att.kind, scale), f"attention.s{s}",
+                            *attn_cost)
+                    else:
+                        self._gemm(ln_hi, ln_lo, att.qkv_tc, f"qkv.s{s}", M=m, lda=d, out=wide, ldc=3 * d)
+                        add(ops.window_attention_f16x2, (wide, 3 * d, att.bias_t, ln_hi, ln_lo, d, B, h, w, d,
+                                                         g.dim_head, att.wsz, att.kind, scale), f"attention.s{s}",
+                            *attn_cost)
+                    self._gemm(ln_hi, ln_lo, att.out_tc, f"out_proj.s{s}", M=m, lda=d, out=xv, ldc=ld, res=xv, ldr=ld)
+                    add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, ff.ln_g, ff.ln_b, m, d), f"layernorm.s{s}", 0,
+                        8.0 * m * d)
+                    self._gemm(ln_hi, ln_lo, ff.fc1_tc, f"ff1.s{s}", M=m, lda=d, out_hi=hid_hi, out_lo=hid_lo, ldh=4 * d,
+                               act=_lib.ACT_GELU)
+                    if last and out_planes is not None:  # the stage output also feeds the next cross-embed / the decoder
+                        self._gemm(hid_hi, hid_lo, ff.fc2_tc, f"ff2.s{s}", M=m, lda=4 * d, out=xv, ldc=ld, res=xv, ldr=ld,
+                                   out_hi=xp_hi, out_lo=xp_lo, ldh=pld)
+                    else:
+                        self._gemm(hid_hi, hid_lo, ff.fc2_tc, f"ff2.s{s}", M=m, lda=4 * d, out=xv, ldc=ld, res=xv, ldr=ld)
+                    continue
+                add(ops.layernorm, (xv, ld, ln, d, att.ln_g, att.ln_b, m, d), f"layernorm.s{s}", 0, 8.0 * m * d)
+                self._conv(ln, att.qkv, wide, tag=f"qkv.s{s}", B=B, Hi=h, Wi=w, lda=d, Ho=h, Wo=w, ldc=3 * d)
+                add(ops.window_attention_f32, (wide, 3 * d, att.bias_t, ln, d, B, h, w, d, g.dim_head,
+                                               att.wsz, att.kind, scale), f"attention.s{s}", *attn_cost)
+                self._conv(ln, att.out, xv, tag=f"out_proj.s{s}", B=B, Hi=h, Wi=w, lda=d, Ho=h, Wo=w, ldc=ld,
+                           res=xv, ldr=ld)
+                add(ops.layernorm, (xv, ld, ln, d, ff.ln_g, ff.ln_b, m, d), f"layernorm.s{s}", 0, 8.0 * m * d)
+                self._conv(ln, ff.fc1, wide, tag=f"ff1.s{s}", B=B, Hi=h, Wi=w, lda=d, Ho=h, Wo=w, ldc=4 * d,
+                           act=_lib.ACT_GELU)
+                self._conv(wide, ff.fc2, xv, tag=f"ff2.s{s}", B=B, Hi=h, Wi=w, lda=4 * d, Ho=h, Wo=w, ldc=ld,
+                           res=xv, ldr=ld)
+
     def _build(self, wts: PreparedWeights):
         g, B = self.geo, self.batch
         add = self._add
@@ -221,56 +284,7 @@ class _Plan:
                 else:
                     self._conv(src, bw, xbuf, tag=f"embed{s}.k{br.kernel}", B=B, Hi=src_h, Wi=src_w, lda=src_ld,
                                Ho=st.h, Wo=st.w, ldc=ld, c_off=xoff + br.c_off)
-            ln = self.ln[: m * d]
-            wide = self.scratch[: m * 4 * d]
-            # fp16 operand planes alias the same workspaces (2 planes x 2 bytes = the fp32 footprint)
-            ln_hi, ln_lo = self.ln16[: m * d], self.ln16[self.ln.numel(): self.ln.numel() + m * d]
-            hid_off = self.scratch.numel()
-            hid_hi, hid_lo = self.scratch16[: m * 4 * d], self.scratch16[hid_off: hid_off + m * 4 * d]
-            n_layers = len(wts.blocks[s])
-            for li, layer in enumerate(wts.blocks[s]):
-                for half, (att, ff) in enumerate(((layer[0], layer[1]), (layer[2], layer[3]))):
-                    L = att.wsz * att.wsz
-                    attn_cost = (4.0 * m * L * d, 16.0 * m * d)
-                    last = li == n_layers - 1 and half == 1
-                    if tc:
-                        add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, att.ln_g, att.ln_b, m, d), f"layernorm.s{s}", 0,
-                            8.0 * m * d)
-                        if self.attention_tc and L <= 128:
-                            q_hi, q_lo = self.scratch16[: m * 3 * d], self.scratch16[hid_off: hid_off + m * 3 * d]
-                            self._gemm(ln_hi, ln_lo, att.qkv_tc, f"qkv.s{s}", M=m, lda=d, out_hi=q_hi, out_lo=q_lo, ldh=3 * d)
-                            tile = ops.attention_bias_tile(att.bias_t, st.w, att.wsz, att.kind)
-                            self.bias_tiles.append(tile)
-                            add(ops.window_attention_tc, (q_hi, q_lo, 3 * d, tile, ln_hi, ln_lo, d, B, st.h, st.w,
-                                                          d, g.dim_head, att.wsz, att.kind, scale), f"attention.s{s}",
-                                *attn_cost)
-                        else:
-                            self._gemm(ln_hi, ln_lo, att.qkv_tc, f"qkv.s{s}", M=m, lda=d, out=wide, ldc=3 * d)
-                            add(ops.window_attention_f16x2, (wide, 3 * d, att.bias_t, ln_hi, ln_lo, d, B, st.h, st.w, d,
-                                                             g.dim_head, att.wsz, att.kind, scale), f"attention.s{s}",
-                                *attn_cost)
-                        self._gemm(ln_hi, ln_lo, att.out_tc, f"out_proj.s{s}", M=m, lda=d, out=xv, ldc=ld, res=xv, ldr=ld)
-                        add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, ff.ln_g, ff.ln_b, m, d), f"layernorm.s{s}", 0,
-                            8.0 * m * d)
-                        self._gemm(ln_hi, ln_lo, ff.fc1_tc, f"ff1.s{s}", M=m, lda=d, out_hi=hid_hi, out_lo=hid_lo, ldh=4 * d,
-                                   act=_lib.ACT_GELU)
-                        if last:  # the stage output also feeds the next cross-embed / the decoder: emit its planes
-                            self._gemm(hid_hi, hid_lo, ff.fc2_tc, f"ff2.s{s}", M=m, lda=4 * d, out=xv, ldc=ld, res=xv, ldr=ld,
-                                       out_hi=xp_hi, out_lo=xp_lo, ldh=pld)
-                        else:
-                            self._gemm(hid_hi, hid_lo, ff.fc2_tc, f"ff2.s{s}", M=m, lda=4 * d, out=xv, ldc=ld, res=xv, ldr=ld)
-                        continue
-                    add(ops.layernorm, (xv, ld, ln, d, att.ln_g, att.ln_b, m, d), f"layernorm.s{s}", 0, 8.0 * m * d)
-                    self._conv(ln, att.qkv, wide, tag=f"qkv.s{s}", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=3 * d)
-                    add(ops.window_attention_f32, (wide, 3 * d, att.bias_t, ln, d, B, st.h, st.w, d, g.dim_head,
-                                                   att.wsz, att.kind, scale), f"attention.s{s}", *attn_cost)
-                    self._conv(ln, att.out, xv, tag=f"out_proj.s{s}", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=ld,
-                               res=xv, ldr=ld)
-                    add(ops.layernorm, (xv, ld, ln, d, ff.ln_g, ff.ln_b, m, d), f"layernorm.s{s}", 0, 8.0 * m * d)
-                    self._conv(ln, ff.fc1, wide, tag=f"ff1.s{s}", B=B, Hi=st.h, Wi=st.w, lda=d, Ho=st.h, Wo=st.w, ldc=4 * d,
-                               act=_lib.ACT_GELU)
-                    self._conv(wide, ff.fc2, xv, tag=f"ff2.s{s}", B=B, Hi=st.h, Wi=st.w, lda=4 * d, Ho=st.h, Wo=st.w, ldc=ld,
-                               res=xv, ldr=ld)
+            self._transformer(wts.blocks[s], st, B, st.h, st.w, xv, ld, (xp_hi, xp_lo, pld) if tc else None)
             src, src_ld, src_h, src_w = xv, ld, st.h, st.w
             if tc:
                 src_planes = (xp_hi, xp_lo)

@@ -66,7 +66,7 @@ def pad_to_pixel_major_f16x2(x: torch.Tensor, pad_lat, pad_lon, mode: str, ld: i
 
 
 def make_toeplitz_desc(in_hi: torch.Tensor, in_lo: torch.Tensor, wts, out: torch.Tensor, *, B: int, Hi: int, Wi: int,
-                       lda: int, Ho: int, Wo: int, ldc: int, c_off: int = 0) -> WxfToeplitzDesc:
+                       lda: int, Ho: int, Wo: int, ldc: int, c_off: int = 0, oy_off: int = 0) -> WxfToeplitzDesc:
     """Descriptor of one stage-0 cross-embed branch; ``wts`` is a weights.ToeplitzWeights."""
     d = WxfToeplitzDesc()
     d.in_hi, d.in_lo = in_hi.data_ptr(), in_lo.data_ptr()
@@ -76,6 +76,7 @@ def make_toeplitz_desc(in_hi: torch.Tensor, in_lo: torch.Tensor, wts, out: torch
     d.ch, d.kernel, d.pad = wts.ch, wts.kernel, wts.pad
     d.Ho, d.Wo, d.ldc, d.c_off = Ho, Wo, ldc, c_off
     d.w_scale_log2 = wts.scale_log2
+    d.oy_off = oy_off
     return d
 
 
@@ -263,6 +264,50 @@ def groupnorm_silu(x: torch.Tensor, ldx: int, stats: torch.Tensor, scratch: torc
                               y.data_ptr(), ldy, B, HW, C, G, _stream())
     _lib.check(st, "wxf_groupnorm_silu")
     LAUNCHES += 3
+
+
+def groupnorm_sums(x: torch.Tensor, ldx: int, sums: torch.Tensor, scratch: torch.Tensor, B: int, HW: int, C: int, G: int):
+    """Local (sum, sum of squares) per (image, group) as fp64 [B, G, 2] (all-reduced by the caller)."""
+    global LAUNCHES
+    st = _lib.load().wxf_groupnorm_sums(x.data_ptr(), ldx, sums.data_ptr(), scratch.data_ptr(), B, HW, C, G, _stream())
+    _lib.check(st, "wxf_groupnorm_sums")
+    LAUNCHES += 2
+
+
+def groupnorm_stats_from_sums(sums: torch.Tensor, stats: torch.Tensor, B: int, G: int, count: float, eps: float = 1e-5):
+    global LAUNCHES
+    st = _lib.load().wxf_groupnorm_stats_from_sums(sums.data_ptr(), stats.data_ptr(), B, G, float(count), eps, _stream())
+    _lib.check(st, "wxf_groupnorm_stats_from_sums")
+    LAUNCHES += 1
+
+
+def groupnorm_apply(x, ldx, stats, gamma, beta, res, ldr, y, ldy, B, HW, C, G):
+    """normalise + affine + SiLU (+ residual) with given (mean, rstd), fp32 out."""
+    global LAUNCHES
+    st = _lib.load().wxf_groupnorm_silu(x.data_ptr(), ldx, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(res), ldr,
+                                        y.data_ptr(), ldy, B, HW, C, G, _stream())
+    _lib.check(st, "wxf_groupnorm_silu")
+    LAUNCHES += 1
+
+
+def groupnorm_apply_f16x2(x, ldx, stats, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, B, HW, C, G):
+    """normalise + affine + SiLU (+ residual) with given (mean, rstd), fp16 hi/lo planes out."""
+    global LAUNCHES
+    st = _lib.load().wxf_groupnorm_silu_f16x2(x.data_ptr(), ldx, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                              _ptr(res), ldr, y_hi.data_ptr(), y_lo.data_ptr(), ldh, h_off, B, HW, C, G,
+                                              _stream())
+    _lib.check(st, "wxf_groupnorm_silu_f16x2")
+    LAUNCHES += 1
+
+
+def gather_rows(src: torch.Tensor, ld_src: int, idx: torch.Tensor, dst: torch.Tensor, ld_dst: int, n: int, d: int):
+    """dst[i, :d] = src[idx[i], :d] (fp32 rows; idx int32)."""
+    global LAUNCHES
+    if n == 0:
+        return
+    st = _lib.load().wxf_gather_rows(src.data_ptr(), ld_src, idx.data_ptr(), dst.data_ptr(), ld_dst, n, d, _stream())
+    _lib.check(st, "wxf_gather_rows")
+    LAUNCHES += 1
 
 
 def unpad_resize_to_nchw(y: torch.Tensor, ld: int, out: torch.Tensor, B: int, C: int, Hd: int, Wd: int, top: int,

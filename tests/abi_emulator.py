@@ -33,7 +33,7 @@ class EmulatedLib:
         self.calls = []
 
     def wxf_abi_version(self):
-        return 7
+        return 8
 
     def wxf_last_error(self):
         return b"emulator"
@@ -91,7 +91,7 @@ class EmulatedLib:
         oy, mm = torch.arange(Ho) * 2, torch.arange(Mx) * 2
         for ky in range(k):
             for r in range(2):
-                iy, ix = oy + ky - p_, mm + r - p_
+                iy, ix = oy + ky - p_ + 2 * d.oy_off, mm + r - p_
                 mask = ((iy >= 0) & (iy < Hi))[:, None] & ((ix >= 0) & (ix < Wi))[None, :]
                 gh = x_hi[:, iy.clamp(0, Hi - 1)][:, :, ix.clamp(0, Wi - 1)] * mask[None, :, :, None]
                 gl = x_lo[:, iy.clamp(0, Hi - 1)][:, :, ix.clamp(0, Wi - 1)] * mask[None, :, :, None]
@@ -368,6 +368,33 @@ class EmulatedLib:
         var = (xs * xs).mean(dim=(1, 3)) - mean * mean
         st[..., 0] = mean.float()
         st[..., 1] = (1.0 / (var + eps).sqrt()).float()
+        return 0
+
+    def wxf_groupnorm_sums(self, x, ldx, sums, scratch, B, HW, C, G, stream):
+        self.calls.append("gn_sums")
+        xs = _t(_arr(x, (B * HW - 1) * ldx + C)).as_strided((B, HW, G, C // G), (HW * ldx, ldx, C // G, 1)).double()
+        out = torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(sums, ctypes.POINTER(ctypes.c_double)), shape=(B * G * 2,)))
+        out = out.view(B, G, 2)
+        out[..., 0] = xs.sum(dim=(1, 3))
+        out[..., 1] = (xs * xs).sum(dim=(1, 3))
+        return 0
+
+    def wxf_groupnorm_stats_from_sums(self, sums, stats, B, G, count, eps, stream):
+        sm = torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(sums, ctypes.POINTER(ctypes.c_double)), shape=(B * G * 2,)))
+        sm = sm.view(B, G, 2)
+        st = _t(_arr(stats, B * G * 2)).view(B, G, 2)
+        mean = sm[..., 0] / count
+        var = (sm[..., 1] / count - mean * mean).clamp_min(0)
+        st[..., 0] = mean.float()
+        st[..., 1] = (1.0 / (var + eps).sqrt()).float()
+        return 0
+
+    def wxf_gather_rows(self, src, ld_src, idx, dst, ld_dst, n, d, stream):
+        self.calls.append("gather_rows")
+        ii = _t(_iarr(idx, n)).long()
+        n_src = int(ii.max()) + 1
+        s_ = _t(_arr(src, (n_src - 1) * ld_src + d)).as_strided((n_src, d), (ld_src, 1))
+        _t(_arr(dst, (n - 1) * ld_dst + d)).as_strided((n, d), (ld_dst, 1)).copy_(s_[ii])
         return 0
 
     def wxf_groupnorm_silu(self, x, ldx, stats, gamma, beta, res, ldr, y, ldy, B, HW, C, G, stream):
