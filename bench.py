@@ -13,8 +13,10 @@ spectral-norm-converged weights (no network for ERA5 or checkpoints).
           forcing channels host->device from pinned memory and the full prediction device->host
   roofline : the dominant kernel family of the step, algorithmic FLOPs / its CUDA-event time
   cpu_baseline : the oracle (CPU restatement of the reference forward) on this box's host cores
-N > 1: the path is not sharded yet - every rank rolls out an independent forecast
-(what reference rollout_gen2.py:243-253 does with its ranks); scaling is weak, value = N*K / max-rank time.
+N > 1 (torchrun, one rank per GPU): ONE forecast decomposed over the N GPUs (miles_credit_b200/domain.py: latitude
+bands for the convolutions, attention units for the transformer stacks, NCCL P2P exchanges) - strong scaling,
+value = K / max-rank time; the line also carries ``replicas`` = N independent forecasts (what reference
+rollout_gen2.py:243-253 does with its ranks).  ``--parallel replicas`` makes that the headline instead (weak scaling).
 """
 import argparse
 import json
@@ -99,7 +101,9 @@ def dist_setup(n_gpus):
         backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
     return rank, world, local
 
 
@@ -177,6 +181,8 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-launch CUDA-event table (JSON) here")
+    ap.add_argument("--parallel", default="domain", choices=["domain", "replicas"],
+                    help="N>1: one forecast decomposed over the N GPUs (strong scaling) or N independent forecasts")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -200,8 +206,32 @@ def main():
     model = CrossFormerB200(**kw)
     model.load_state_dict(synthetic_state_dict(geo, seed=1000, sn_iters=5), strict=True)
     model = model.to(dev).eval()
+    domain = world > 1 and args.parallel == "domain"
+    replicas = None
+    if domain:
+        # secondary number first: N independent forecasts, one per GPU (what reference rollout_gen2.py:243-253 does)
+        ro = Rollout(model)
+        xr = synthetic_input(geo, batch=1, seed=1000 + rank).to(dev)
+        for _ in range(args.warmup):
+            ro.step(xr)
+        torch.cuda.synchronize()
+        barrier(world)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(args.steps):
+            ro.step(xr)
+        r1.record()
+        torch.cuda.synchronize()
+        rms = max_over_ranks(r0.elapsed_time(r1), world, dev)
+        replicas = {"value": world * args.steps / (rms / 1e3), "unit": "steps/s", "ms_per_step": rms / args.steps,
+                    "what": f"{world} independent forecasts, one per GPU, no communication"}
+        del xr
+        from miles_credit_b200.domain import convert_to_domain_parallel
+
+        convert_to_domain_parallel(model)
+    jobs = 1 if domain else world  # forecasts advanced per step by the whole job
     ro = Rollout(model)
-    x = synthetic_input(geo, batch=1, seed=1000 + rank).to(dev)
+    x = synthetic_input(geo, batch=1, seed=1000 + (0 if domain else rank)).to(dev)
     n_prog = ro.n_prog
     n_dyn = max(geo.input_only_channels // 2, 1)  # dynamic forcing (2 of the 4 input-only channels at 0.25 deg)
 
@@ -224,11 +254,11 @@ def main():
     launches = ops.LAUNCHES - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
     ms_step = ms_total / args.steps
-    value = world * args.steps / (ms_total / 1e3)
+    value = jobs * args.steps / (ms_total / 1e3)
     finite = bool(torch.isfinite(x).all().item())
 
     # ---- end to end through host buffers -----------------------------------------------------------------
-    x.copy_(synthetic_input(geo, batch=1, seed=1000 + rank).to(dev))
+    x.copy_(synthetic_input(geo, batch=1, seed=1000 + (0 if domain else rank)).to(dev))
     plane = (1, n_dyn, 1, geo.image_height, geo.image_width)
     forcing_host = [torch.randn(plane).pin_memory() for _ in range(2)]
     forcing_dev = torch.empty(plane, device=dev)
@@ -241,6 +271,8 @@ def main():
         y = ro.step(x, forcing_dev, n_dyn)
         ready = torch.cuda.Event()
         ready.record()
+        if domain and rank != 0:                                              # rank 0 hands the prediction to the host
+            return
         with torch.cuda.stream(copy_stream):                                  # D2H of the prediction, overlapped
             copy_stream.wait_event(ready)
             y_host[i & 1].copy_(y, non_blocking=True)
@@ -253,15 +285,15 @@ def main():
     barrier(world)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        if i >= 2:
+        if i >= 2 and not (domain and rank != 0):
             done[i & 1].synchronize()                                          # host buffer free again
         e2e_step(i)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev)
     barrier(world)
-    e2e_value = world * args.steps / e2e_s
-    h2d = forcing_host[0].numel() * 4
-    d2h = y_host[0].numel() * 4
+    e2e_value = jobs * args.steps / e2e_s
+    h2d = forcing_host[0].numel() * 4 * world
+    d2h = y_host[0].numel() * 4 * jobs
 
     # ---- roofline of the dominant kernel family (CUDA events around every launch of one extra step) ---------
     pk = peaks()
@@ -312,10 +344,13 @@ def main():
         fl = flops_per_forward(geo)
         line = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if domain else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "grid": f"{geo.image_height}x{geo.image_width}", "batch": 1,
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent forecasts (replicas)",
+                       "parallelism": "single GPU" if world == 1 else
+                       (f"one forecast decomposed over {world} GPUs (lat bands + attention units, NCCL P2P)" if domain
+                        else f"{world} independent forecasts (replicas)"),
                        "l2": "no flush needed: one step streams >3 GB of activations through a 126 MB L2",
                        "flops_per_step": fl["total"], "finite": finite},
             "clocks": clocks,
@@ -328,6 +363,8 @@ def main():
             "step_tflops": fl["total"] / (ms_step / 1e3) / 1e12,
             "cpu_baseline": cpu,
         }
+        if replicas is not None:
+            line["replicas"] = replicas
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

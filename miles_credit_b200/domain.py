@@ -83,12 +83,36 @@ def _pixel_maps(st, lay: DomainLayout):
     return band_owner.reshape(-1), band_local.reshape(-1), unit_owner.reshape(-1), unit_local.reshape(-1)
 
 
+class _Comm:
+    """Point-to-point plumbing inside the domain group (ranks are positions within the group)."""
+
+    def __init__(self, rank: int, world: int, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.peers = [r if group is None else dist.get_global_rank(group, r) for r in range(world)]
+
+    def recv(self, t, r):
+        return dist.P2POp(dist.irecv, t, self.peers[r], self.group)
+
+    def send(self, t, r):
+        return dist.P2POp(dist.isend, t, self.peers[r], self.group)
+
+    @staticmethod
+    def run(reqs):
+        if reqs:
+            for w in dist.batch_isend_irecv(reqs):
+                w.wait()
+
+    def all_reduce(self, t):
+        dist.all_reduce(t, group=self.group)
+
+
 class Exchange:
     """band <-> unit re-layout of a stage's residual stream for this rank (index lists are computed once)."""
 
-    def __init__(self, st, lay: DomainLayout, rank: int, device):
+    def __init__(self, st, lay: DomainLayout, comm: _Comm, device):
         bo, bl, uo, ul = _pixel_maps(st, lay)
-        world = lay.world
+        world, rank = lay.world, comm.rank
+        self.comm = comm
         self.rank, self.world, self.d = rank, world, st.dim
         send_idx, recv_idx = [], []
         self.send_counts, self.recv_counts = [], []
@@ -122,18 +146,16 @@ class Exchange:
             self.recv_off.append(self.recv_off[-1] + c)
 
     def _p2p(self, sbuf, soff, scnt, rbuf, roff, rcnt):
-        d = self.d
+        d, c = self.d, self.comm
         reqs = []
         for peer in range(self.world):
             if peer == self.rank:
                 continue
             if rcnt[peer]:
-                reqs.append(dist.P2POp(dist.irecv, rbuf[roff[peer] * d: (roff[peer] + rcnt[peer]) * d], peer))
+                reqs.append(c.recv(rbuf[roff[peer] * d: (roff[peer] + rcnt[peer]) * d], peer))
             if scnt[peer]:
-                reqs.append(dist.P2POp(dist.isend, sbuf[soff[peer] * d: (soff[peer] + scnt[peer]) * d], peer))
-        if reqs:
-            for w in dist.batch_isend_irecv(reqs):
-                w.wait()
+                reqs.append(c.send(sbuf[soff[peer] * d: (soff[peer] + scnt[peer]) * d], peer))
+        c.run(reqs)
 
     def band_to_unit(self, band, ld_band, unit, sbuf, rbuf):
         d, me = self.d, self.rank
@@ -155,19 +177,18 @@ class Exchange:
         ops.gather_rows(rbuf, d, self.inv_send, band, ld_band, self.n_band, d)
 
 
-def _halo_exchange(tensors, rows: int, rank: int, world: int):
+def _halo_exchange(tensors, rows: int, comm: _Comm):
     """One-row halo exchange of band tensors shaped [rows + 2, W, C] (row 0 / rows+1 are the halos)."""
+    rank, world = comm.rank, comm.world
     reqs = []
     for t in tensors:
         if rank > 0:
-            reqs.append(dist.P2POp(dist.irecv, t[0], rank - 1))
-            reqs.append(dist.P2POp(dist.isend, t[1], rank - 1))
+            reqs.append(comm.recv(t[0], rank - 1))
+            reqs.append(comm.send(t[1], rank - 1))
         if rank < world - 1:
-            reqs.append(dist.P2POp(dist.irecv, t[rows + 1], rank + 1))
-            reqs.append(dist.P2POp(dist.isend, t[rows], rank + 1))
-    if reqs:
-        for w in dist.batch_isend_irecv(reqs):
-            w.wait()
+            reqs.append(comm.recv(t[rows + 1], rank + 1))
+            reqs.append(comm.send(t[rows], rank + 1))
+    comm.run(reqs)
 
 
 def _shift_taps(w: ConvTcWeights, dy: int) -> ConvTcWeights:
@@ -186,13 +207,14 @@ def _shift_taps(w: ConvTcWeights, dy: int) -> ConvTcWeights:
 class DomainPlan(_Plan):
     """Launch plan of one rank.  Input: the full state (replicated); output: the full prediction on every rank."""
 
-    def __init__(self, geo: Geometry, wts: PreparedWeights, rank: int, world: int, device):  # noqa: super not called
+    def __init__(self, geo: Geometry, wts: PreparedWeights, rank: int, world: int, device, group=None):
         if geo.variant != "crossformer":
             raise NotImplementedError("domain decomposition is built for the `crossformer` decoder")
         if wts.embed0_toep is None or wts.head_tc is None or any(c is None for brs in wts.embeds_tc[1:] for c in brs):
             raise NotImplementedError("domain decomposition needs the tensor-core path (channel counts % 4 == 0)")
         self.geo, self.batch = geo, 1
         self.rank, self.world = rank, world
+        self.comm = _Comm(rank, world, group)
         self.tensor_cores = True
         self.attention_tc = True
         self.toeplitz = True
@@ -235,7 +257,7 @@ class DomainPlan(_Plan):
                        for k, up in enumerate(g.ups))
         self.gn_scratch = torch.empty(gn_bytes // 4 + 4, **f32)
         self.y_dec = torch.empty((g.h_dec, g.w_dec, g.output_channels), **f32)  # full decoder output (all-gathered)
-        self.ex = [Exchange(g.stages[s], lay, rank, device) for s in range(4)]
+        self.ex = [Exchange(g.stages[s], lay, self.comm, device) for s in range(4)]
         self.steps: List[tuple] = []
         self.bias_tiles: List[torch.Tensor] = []
         self._build(wts)
@@ -278,7 +300,7 @@ class DomainPlan(_Plan):
                 add(ops.split_f16x2, (eb, d, self.x3p[0], self.x3p[1], d, m, d), "split", 0, 8.0 * m * d)
             if 1 <= s + 1 <= 3 and s < 3:
                 # the next stage's k=4 branch needs one halo row of this stage's output
-                add(_halo_exchange, ((hi, lo), rows, rank, world), "halo", 0, 0)
+                add(_halo_exchange, ((hi, lo), rows, self.comm), "halo", 0, 0)
 
         # ---- decoder in band layout ----
         dec_planes, dec_ld, dec_rows, dec_halo = self.x3p, g.stages[3].dim, self.rows[3], 0
@@ -292,13 +314,13 @@ class DomainPlan(_Plan):
             # ConvTranspose k2 s2: no halo; fp32 shortcut + planes (interior rows of the halo'd buffer)
             self._conv_tc(in_hi, in_lo, uw.up_tc, "dec_up", B=1, Hi=rin, Wi=up.w_in, lda=dec_ld, Ho=rin, Wo=up.w_in,
                           out=bufs["short"], ldc=c, out_hi=sp_hi[1:], out_lo=sp_lo[1:], ldh=c)
-            add(_halo_exchange, ((sp_hi, sp_lo), ro, rank, world), "halo", 0, 0)
+            add(_halo_exchange, ((sp_hi, sp_lo), ro, self.comm), "halo", 0, 0)
             self._conv_tc(sp_hi, sp_lo, _shift_taps(uw.convs_tc[0], 1), "dec_conv3x3", B=1, Hi=ro + 2, Wi=wo, lda=c,
                           Ho=ro, Wo=wo, out=bufs["a"], ldc=c)
             count = float(4 * up.h_in * up.w_in) * (c // up.groups)  # global pixels x channels per group
             add(self._groupnorm, (bufs["a"], c, uw.gn_w[0], uw.gn_b[0], None, 0, bp_hi[1:], bp_lo[1:], c, 0, ro * wo, c,
                                   up.groups, count), "groupnorm_silu", 0, 8.0 * n)
-            add(_halo_exchange, ((bp_hi, bp_lo), ro, rank, world), "halo", 0, 0)
+            add(_halo_exchange, ((bp_hi, bp_lo), ro, self.comm), "halo", 0, 0)
             self._conv_tc(bp_hi, bp_lo, _shift_taps(uw.convs_tc[1], 1), "dec_conv3x3", B=1, Hi=ro + 2, Wi=wo, lda=c,
                           Ho=ro, Wo=wo, out=bufs["a"], ldc=c)
             chi, clo = self.catp[skip]
@@ -307,7 +329,7 @@ class DomainPlan(_Plan):
             dec_planes, dec_ld, dec_rows, dec_halo = self.catp[skip], 2 * c, ro, 1
         # up_block4 (ConvT k4 s2 p1) reads one halo row of the full concat buffer
         st0 = g.stages[0]
-        add(_halo_exchange, (self.catp[0], self.rows[0], rank, world), "halo", 0, 0)
+        add(_halo_exchange, (self.catp[0], self.rows[0], self.comm), "halo", 0, 0)
         y_band = self.y_dec[2 * lay.rb[0][rank]: 2 * lay.rb[0][rank + 1]]
         self._conv_tc(self.catp[0][0], self.catp[0][1], _shift_taps(wts.head_tc, 1), "dec_head", B=1,
                       Hi=self.rows[0] + 2, Wi=st0.w, lda=2 * st0.dim, Ho=self.rows[0], Wo=st0.w, out=y_band,
@@ -318,7 +340,7 @@ class DomainPlan(_Plan):
     def _groupnorm(self, x, ldx, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, hw_local, C, G, count):
         """GroupNorm + SiLU with statistics over the whole (all-rank) image: local sums, all-reduce, apply."""
         ops.groupnorm_sums(x, ldx, self.gn_sums, self.gn_scratch, 1, hw_local, C, G)
-        dist.all_reduce(self.gn_sums)
+        self.comm.all_reduce(self.gn_sums)
         ops.groupnorm_stats_from_sums(self.gn_sums, self.gn_stats, 1, G, count)
         ops.groupnorm_apply_f16x2(x, ldx, self.gn_stats, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, 1, hw_local, C, G)
 
@@ -328,11 +350,9 @@ class DomainPlan(_Plan):
         for peer in range(self.world):
             if peer == me:
                 continue
-            reqs.append(dist.P2POp(dist.irecv, self.y_dec[2 * lay.rb[0][peer]: 2 * lay.rb[0][peer + 1]], peer))
-            reqs.append(dist.P2POp(dist.isend, self.y_dec[2 * lay.rb[0][me]: 2 * lay.rb[0][me + 1]], peer))
-        if reqs:
-            for w in dist.batch_isend_irecv(reqs):
-                w.wait()
+            reqs.append(self.comm.recv(self.y_dec[2 * lay.rb[0][peer]: 2 * lay.rb[0][peer + 1]], peer))
+            reqs.append(self.comm.send(self.y_dec[2 * lay.rb[0][me]: 2 * lay.rb[0][me + 1]], peer))
+        self.comm.run(reqs)
 
     def run(self, x: torch.Tensor) -> torch.Tensor:
         g = self.geo
@@ -345,25 +365,38 @@ class DomainPlan(_Plan):
         return out
 
 
-class DomainParallelForward:
-    """``y = f(x)`` of a CrossFormerB200 split over the ranks of the default process group (one process per GPU).
+class DomainParallelManager:
+    """Process groups of the decomposition: ``domain_parallel_size`` consecutive ranks share one forecast
+    (same roles as the reference's manager, credit/domain_parallel/manager.py:22-129; no gradient groups here)."""
 
-    Every rank passes the same full input state and receives the full prediction (multi-GPU)."""
+    def __init__(self, world_size: int = None, domain_parallel_size: int = None):
+        world_size = dist.get_world_size() if world_size is None else world_size
+        domain_parallel_size = world_size if domain_parallel_size is None else domain_parallel_size
+        if world_size % domain_parallel_size:
+            raise ValueError(f"world_size ({world_size}) must be divisible by domain_parallel_size ({domain_parallel_size})")
+        self.world_size, self.domain_parallel_size = world_size, domain_parallel_size
+        self.data_parallel_size = world_size // domain_parallel_size
+        rank = dist.get_rank()
+        self.domain_rank = rank % domain_parallel_size
+        self.dp_rank = rank // domain_parallel_size
+        self.domain_group = None
+        if self.data_parallel_size > 1:
+            for i in range(self.data_parallel_size):
+                ranks = list(range(i * domain_parallel_size, (i + 1) * domain_parallel_size))
+                grp = dist.new_group(ranks)
+                if rank in ranks:
+                    self.domain_group = grp
 
-    def __init__(self, model, group_rank: int = None, world: int = None):
-        self.model = model
-        self.rank = dist.get_rank() if group_rank is None else group_rank
-        self.world = dist.get_world_size() if world is None else world
-        self._plan = None
+    @property
+    def domain_world_size(self):
+        return self.domain_parallel_size
 
-    @torch.no_grad()
-    def __call__(self, x: torch.Tensor) -> torch.Tensor:
-        m = self.model
-        if x.shape[0] != 1:
-            raise ValueError("domain-parallel forward takes one state at a time (batch 1)")
-        if m._prepared is None or m._prepared_sig != m._signature():
-            m.refresh_weights()
-            self._plan = None
-        if self._plan is None:
-            self._plan = DomainPlan(m.geometry, m._prepared, self.rank, self.world, x.device)
-        return self._plan.run(x.contiguous())
+
+def convert_to_domain_parallel(model, manager: DomainParallelManager = None):
+    """Switch a CrossFormerB200 to the decomposed forward (the call the reference makes at
+    credit/domain_parallel/convert.py:86).  Unlike the reference's sharded-tensor contract, ``model(x)`` keeps taking the
+    full state on every rank of the domain group and returns the full prediction; the decomposition is internal."""
+    manager = manager or DomainParallelManager()
+    model._domain = manager
+    model._plans = {}
+    return model

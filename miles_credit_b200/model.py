@@ -461,6 +461,7 @@ class CrossFormerB200(_Base):
         self._prepared: Optional[PreparedWeights] = None
         self._prepared_sig = None
         self._plans: Dict[tuple, _Plan] = {}
+        self._domain = None  # set by domain.convert_to_domain_parallel
 
     # -- weight folding ------------------------------------------------------------------------------
     def _signature(self):
@@ -504,7 +505,16 @@ class CrossFormerB200(_Base):
         plan = self._plans.get(key)
         if plan is None:
             with torch.cuda.device(x.device):
-                plan = self._plans[key] = _Plan(geo, self._prepared, int(x.shape[0]), x.device, not self.exact_fp32)
+                if self._domain is not None:
+                    from .domain import DomainPlan
+
+                    if x.shape[0] != 1:
+                        raise ValueError("the domain-decomposed forward takes one state at a time (batch 1)")
+                    dm = self._domain
+                    plan = DomainPlan(geo, self._prepared, dm.domain_rank, dm.domain_world_size, x.device, dm.domain_group)
+                else:
+                    plan = _Plan(geo, self._prepared, int(x.shape[0]), x.device, not self.exact_fp32)
+                self._plans[key] = plan
         with torch.cuda.device(x.device):
             return plan.run(x.contiguous())
 

@@ -1,0 +1,54 @@
+"""torchrun worker of tests/test_gpu_domain.py: decomposed forward vs the single-GPU forward on every rank."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from miles_credit_b200.domain import convert_to_domain_parallel  # noqa: E402
+from miles_credit_b200.geometry import build_geometry, workload  # noqa: E402
+from miles_credit_b200.model import CrossFormerB200  # noqa: E402
+from miles_credit_b200.synth import synthetic_input, synthetic_state_dict  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    out = {}
+    for name in sys.argv[1:]:
+        if name == "unit":
+            kw = dict(workload("unit"), output_only_channels=4)
+        elif name == "mid":  # headline windows (lws 10, gws 10/5/2/1) on a 721x640 grid, thinner and shallower
+            kw = dict(workload("wxformer_6h_025deg"), image_width=640, depth=[1, 1, 1, 1], dim=[64, 128, 256, 512])
+        else:
+            kw = workload(name)
+        geo = build_geometry(**kw)
+        model = CrossFormerB200(**kw)
+        model.load_state_dict(synthetic_state_dict(geo, seed=31), strict=True)
+        model = model.to(dev).eval()
+        x = synthetic_input(geo, batch=1, seed=31).to(dev)
+        y1 = model(x).clone()
+        convert_to_domain_parallel(model)
+        y2 = model(x).clone()
+        y3 = model(x)  # second call: buffers are reused, halo rows must still be right
+        err = float((y2 - y1).abs().max() / y1.abs().max())
+        lo, hi = y2.clone(), y2.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out[name] = {"rel_max_vs_single_gpu": err, "ranks_identical": bool(torch.equal(lo, hi)),
+                     "repeatable": bool(torch.equal(y2, y3)), "finite": bool(torch.isfinite(y2).all())}
+        del model
+        torch.cuda.empty_cache()
+    if rank == 0:
+        print("DOMAIN_RESULT " + json.dumps({"world": world, "cases": out}), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -27,14 +27,14 @@ def _kwargs():
     return dict(workload("unit"), output_only_channels=4)
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, dps):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     from abi_emulator import EmulatedLib
     from miles_credit_b200 import lib as wlib
     from miles_credit_b200 import model as wmodel
     from miles_credit_b200 import ops
-    from miles_credit_b200.domain import DomainPlan
+    from miles_credit_b200.domain import DomainParallelManager, DomainPlan
     from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
     from miles_credit_b200.weights import prepare
 
@@ -47,7 +47,8 @@ def _worker(rank, world, port, out_dir):
         geo = build_geometry(**_kwargs())
         sd = synthetic_state_dict(geo, seed=21)
         wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
-        plan = DomainPlan(geo, wts, rank, world, torch.device("cpu"))
+        dm = DomainParallelManager(world, dps)
+        plan = DomainPlan(geo, wts, dm.domain_rank, dm.domain_world_size, torch.device("cpu"), dm.domain_group)
         x = synthetic_input(geo, batch=1, seed=21)
         y = plan.run(x)
         torch.save(y, os.path.join(out_dir, f"y{rank}.pt"))
@@ -56,12 +57,12 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_domain_decomposition_matches_oracle(tmp_path, world):
+@pytest.mark.parametrize("world,dps", [(2, 2), (3, 3), (4, 2)])
+def test_domain_decomposition_matches_oracle(tmp_path, world, dps):
     from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
     from oracle import crossformer_oracle as oracle
 
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), dps), nprocs=world, join=True)
     geo = build_geometry(**_kwargs())
     sd = synthetic_state_dict(geo, seed=21)
     x = synthetic_input(geo, batch=1, seed=21)
