@@ -16,6 +16,8 @@
 //   MMA 2 : O[128 x 32] = P V, 3 passes x 8 K-steps; V is read as an MN-major B operand straight from the TMA tile;
 //           O reuses the first 32 TMEM columns of S (dead once P is written), so two CTAs of 256 columns share an SM
 //   epi   : O / rowsum -> fp16 hi/lo planes of the attention output at the token's pixel (the inverse gather)
+#include <stdlib.h>
+
 #include "wxf_tc_host.cuh"
 #include "wxf_tc_ptx.cuh"
 
@@ -50,6 +52,7 @@ struct AttnParams {
   int gpr;            // interleaved: tiles (groups of G consecutive gw) per window row
   float scale2;       // scale * log2(e): softmax runs in base 2
   int64_t nwin, ntiles;
+  int debug;          // timing experiments only (WXF_ATTN_DEBUG): 1 = no TMA loads after the first two tiles, 2 = no softmax, 4 = no stores
 };
 
 // Row r of a tile -> (window slot g, token i).  Window-major packing: rows [g*Lp, g*Lp + L); interleaved: r = i*G + g.
@@ -89,10 +92,11 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // rows the TMA boxes do not cover must be finite zeros (0 * garbage could be NaN in P V)
+  // rows the TMA boxes do not cover must be finite zeros (0 * garbage could be NaN in P V); the P columns the softmax
+  // never writes (outside every window of the row's warp) must be exact zeros
   {
     uint4* z = reinterpret_cast<uint4*>(gen);
-    for (int i = threadIdx.x; i < (6 * QKV_PLANE) / 16; i += AT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < OFF_BAR / 16; i += AT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -112,6 +116,26 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
       tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + 128u + (uint32_t)(c * 32), bb);
     }
     tc_fence_before();
+  }
+
+  // per-row constants of the softmax warps (identical for every tile of the launch): the row's window slot / token, and
+  // the warp-uniform range of 8-column groups that contain a window column of any of the warp's rows
+  const int quarter = warp & 3;
+  const int r = quarter * 32 + lane;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+  int g = 0, i = 0, ty = 0, tx = 0, g_lo = 0, g_hi = 0, c_lo = 0, c_hi = 0;
+  bool row_ok = false;
+  if (warp >= 2) {
+    row_slot(p, r, g, i);
+    row_ok = g < p.G && i < p.L;
+    ty = i / p.wsz;
+    tx = i - ty * p.wsz;
+    const int col0 = p.inter ? 0 : g * p.Lp, col1 = p.inter ? p.L * p.G : col0 + p.L;
+    g_lo = __reduce_min_sync(0xffffffffu, row_ok ? (col0 >> 3) : 16);
+    g_hi = __reduce_max_sync(0xffffffffu, row_ok ? ((col1 + 7) >> 3) : 0);
+    if (g_hi <= g_lo) g_lo = g_hi = 0;
+    c_lo = g_lo >> 2;
+    c_hi = (g_hi + 3) >> 2;
   }
 
   // persistent: each CTA (two per SM) walks tiles = (window group, head); every barrier completes once per tile, so
@@ -203,53 +227,81 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     }
   } else {
     // ---- softmax + epilogue: thread = query row ----
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;
-    int g, i;
-    row_slot(p, r, g, i);
-    const bool valid = g < nv && i < p.L;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-
     mbar_wait(bar_s, par);
     tc_fence_after();
-    // s2 = S * (scale*log2 e) + bias*log2 e (masked columns: -1e30); p = 2^(s2 - max)
-    float mx = -3.0e38f;
+    // s2 = S * (scale*log2 e) + bias*log2 e (masked columns: -1e30); p = 2^(s2 - max).  Only the 8-column groups
+    // [g_lo, g_hi) that hold a window column of one of this warp's rows are touched; everything else of P stays zero.
+    const float2 sc2 = make_float2(p.scale2, p.scale2);
+    float mx;
+    {
+      float m0 = -3.0e38f, m1 = -3.0e38f, m2 = -3.0e38f, m3 = -3.0e38f;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t rr[32], bb[32];
-      tmem_ld32(lane_base + (uint32_t)(c * 32), rr);
-      tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), bb);
+      for (int c = c_lo; c < c_hi; ++c) {
+        uint32_t rr[32], bb[32];
+        tmem_ld32_nowait(lane_base + (uint32_t)(c * 32), rr);
+        tmem_ld32_nowait(lane_base + 128u + (uint32_t)(c * 32), bb);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(rr[j]), p.scale2, __uint_as_float(bb[j])));
+        for (int q8 = 0; q8 < 4; ++q8) {
+          const int gq = c * 4 + q8;
+          if (gq >= g_lo && gq < g_hi) {  // warp-uniform
+#pragma unroll
+            for (int e = 0; e < 8; e += 4) {
+              const int j = q8 * 8 + e;
+              const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), sc2,
+                                           make_float2(__uint_as_float(bb[j]), __uint_as_float(bb[j + 1])));
+              const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(rr[j + 2]), __uint_as_float(rr[j + 3])), sc2,
+                                           make_float2(__uint_as_float(bb[j + 2]), __uint_as_float(bb[j + 3])));
+              m0 = fmaxf(m0, t0.x); m1 = fmaxf(m1, t0.y); m2 = fmaxf(m2, t1.x); m3 = fmaxf(m3, t1.y);
+            }
+          }
+        }
+      }
+      mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
     }
-    float lsum = 0.f;
+    const float2 nmx2 = make_float2(-mx, -mx);
+    float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
     uint8_t* prow_hi = gen + OFF_P + r * 128;
     uint8_t* prow_lo = prow_hi + 2 * P_ATOM;
+    // groups outside the warp's range that alias Q (P_hi columns 0..63) were overwritten by this tile's Q load
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int gq = 0; gq < 8; ++gq)
+      if (gq < g_lo || gq >= g_hi) *reinterpret_cast<uint4*>(prow_hi + ((gq ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; ++c) {
       uint32_t rr[32], bb[32];
-      tmem_ld32(lane_base + (uint32_t)(c * 32), rr);
-      tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), bb);
+      tmem_ld32_nowait(lane_base + (uint32_t)(c * 32), rr);
+      tmem_ld32_nowait(lane_base + 128u + (uint32_t)(c * 32), bb);
+      tmem_ld_wait();
 #pragma unroll
       for (int q8 = 0; q8 < 4; ++q8) {  // 8 columns = one 16-byte chunk of the swizzled row
-        __align__(16) __half2 h2[4];
-        __align__(16) __half2 l2[4];
+        const int gq = c * 4 + q8;
+        if (gq >= g_lo && gq < g_hi) {  // warp-uniform
+          __align__(16) uint32_t h2[4];
+          __align__(16) uint32_t l2[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = q8 * 8 + 2 * e;
-          const float p0 = exp2f(fmaf(__uint_as_float(rr[j]), p.scale2, __uint_as_float(bb[j])) - mx);
-          const float p1 = exp2f(fmaf(__uint_as_float(rr[j + 1]), p.scale2, __uint_as_float(bb[j + 1])) - mx);
-          lsum += p0 + p1;
-          h2[e] = __floats2half2_rn(p0, p1);
-          const float2 back = __half22float2(h2[e]);
-          l2[e] = __floats2half2_rn(p0 - back.x, p1 - back.y);
+          for (int e = 0; e < 4; ++e) {
+            const int j = q8 * 8 + 2 * e;
+            float2 t = __ffma2_rn(make_float2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), sc2,
+                                  make_float2(__uint_as_float(bb[j]), __uint_as_float(bb[j + 1])));
+            t = __fadd2_rn(t, nmx2);
+            float2 pe;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe.x) : "f"(t.x));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe.y) : "f"(t.y));
+            if (e & 1) sum_b = __fadd2_rn(sum_b, pe); else sum_a = __fadd2_rn(sum_a, pe);
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2[e]) : "f"(pe.y), "f"(pe.x));
+            const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&h2[e]));
+            const float2 dlt = __ffma2_rn(back, make_float2(-1.0f, -1.0f), pe);
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l2[e]) : "f"(dlt.y), "f"(dlt.x));
+          }
+          const int cc = (c & 1) * 4 + q8;                 // 16-byte chunk index inside the 64-column atom
+          const int off = (c >> 1) * P_ATOM + ((cc ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(prow_hi + off) = *reinterpret_cast<const uint4*>(h2);
+          *reinterpret_cast<uint4*>(prow_lo + off) = *reinterpret_cast<const uint4*>(l2);
         }
-        const int cc = (c & 1) * 4 + q8;                 // 16-byte chunk index inside the 64-column atom
-        const int off = (c >> 1) * P_ATOM + ((cc ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(prow_hi + off) = *reinterpret_cast<const uint4*>(h2);
-        *reinterpret_cast<uint4*>(prow_lo + off) = *reinterpret_cast<const uint4*>(l2);
       }
     }
+    const float lsum = (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
     fence_proxy_async();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
     tc_fence_before();
     mbar_arrive(bar_p);
@@ -260,13 +312,12 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     tmem_ld32(lane_base, oo);
     tc_fence_before();
     mbar_arrive(bar_e);  // O consumed: the next tile's QK^T may overwrite these TMEM columns
-    if (valid) {
+    if (row_ok && g < nv) {
       const int64_t w = w0 + g;
       const int per_img = p.nh * p.nw;
       const int b = (int)(w / per_img);
       const int rem = (int)(w - (int64_t)b * per_img);
       const int gh = rem / p.nw, gw = rem - gh * p.nw;
-      const int ty = i / p.wsz, tx = i - ty * p.wsz;
       int y, x;
       if (p.kind == WXF_ATTN_SHORT) {
         y = gh * p.wsz + ty;
@@ -281,10 +332,12 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
       uint4* lp = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldh + head * DH);
 #pragma unroll
       for (int c = 0; c < DH / 8; ++c) {
-        __align__(16) __half h8[8];
-        __align__(16) __half l8[8];
+        __align__(16) __half2 h8[4];
+        __align__(16) __half2 l8[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) wxf_split_f16x2(__uint_as_float(oo[8 * c + e]) * inv, h8[e], l8[e]);
+        for (int e = 0; e < 4; ++e)
+          wxf_split2_f16x2(__uint_as_float(oo[8 * c + 2 * e]) * inv, __uint_as_float(oo[8 * c + 2 * e + 1]) * inv, h8[e],
+                           l8[e]);
         hp[c] = *reinterpret_cast<const uint4*>(h8);
         lp[c] = *reinterpret_cast<const uint4*>(l8);
       }
@@ -299,6 +352,350 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+// ---- v2: one CTA per SM, two tiles in flight --------------------------------------------------------------------
+// The v1 kernel above runs load -> QK^T -> softmax -> PV -> store serially per CTA (two CTAs per SM hide part of it):
+// the profile is dominated by the softmax warps waiting for the TMA load and the two MMA round trips.  Here every
+// stage is double buffered (Q/K/V tiles and P in shared memory, S and O in TMEM) and two softmax warpgroups alternate
+// tiles, so the TMA loads run two tiles ahead, QK^T of tile i+1 is issued before PV of tile i, and one warpgroup's
+// exponentials overlap the other's waits.
+//   warp 0: TMA producer     warp 1: tcgen05.mma issuer     warps 2-5: softmax group 0     warps 6-9: softmax group 1
+constexpr int A2_THREADS = 320;
+constexpr int A2_QKV = 6 * QKV_PLANE;            // 48 KB per buffer: K hi/lo, V hi/lo, Q hi/lo
+constexpr int A2_OFF_K = 0, A2_OFF_V = 2 * QKV_PLANE, A2_OFF_Q = 4 * QKV_PLANE;
+constexpr int A2_P = 4 * P_ATOM;                 // 64 KB per buffer: P_hi (2 atoms), P_lo (2 atoms)
+constexpr int A2_OFF_P = 2 * A2_QKV;
+constexpr int A2_OFF_BAR = A2_OFF_P + 2 * A2_P;  // 224 KB
+constexpr int A2_SMEM = A2_OFF_BAR + 128 + 1024;
+constexpr uint32_t A2_COL_BIAS = 256, A2_COL_O = 384;
+
+__global__ void __launch_bounds__(A2_THREADS, 1)
+window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                            const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t bars = base + A2_OFF_BAR;
+  auto bar_qkv_full = [&](int b) { return bars + 8u * b; };
+  auto bar_qkv_empty = [&](int b) { return bars + 16u + 8u * b; };
+  auto bar_s_full = [&](int b) { return bars + 32u + 8u * b; };
+  auto bar_p_full = [&](int b) { return bars + 48u + 8u * b; };
+  auto bar_o_full = [&](int b) { return bars + 64u + 8u * b; };
+  auto bar_o_empty = [&](int b) { return bars + 80u + 8u * b; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + A2_OFF_BAR + 96);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_qkv_full(b), 1);
+      mbar_init(bar_qkv_empty(b), 1);
+      mbar_init(bar_s_full(b), 1);
+      mbar_init(bar_p_full(b), 128);
+      mbar_init(bar_o_full(b), 1);
+      mbar_init(bar_o_empty(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // operand rows the TMA boxes never cover and P columns the softmax never writes must be exact zeros
+  {
+    uint4* z = reinterpret_cast<uint4*>(gen);
+    for (int i = threadIdx.x; i < A2_OFF_BAR / 16; i += A2_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // position-bias tile (identical for every tile of the launch) -> TMEM columns [256, 384), written by group 0
+  if (warp >= 2 && warp < 6) {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t bb[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) bb[j] = __float_as_uint(__ldg(p.bias_tile + (size_t)(c * 32 + j) * ROWS + r));
+      tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + A2_COL_BIAS + (uint32_t)(c * 32), bb);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // tiles of this CTA: tile(it) = blockIdx.x + it * gridDim.x, buffer b = it & 1, k = it >> 1 = use count of buffer b
+  const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  auto tile_windows = [&](int64_t tile, int& head, int64_t& w0, int& nv) {
+    head = (int)(tile % p.heads);
+    const int64_t group = tile / p.heads;
+    if (p.inter) {  // G consecutive gw of one (b, gh) row of groups
+      const int64_t rowi = group / p.gpr;
+      const int gw0 = (int)(group - rowi * p.gpr) * p.G;
+      w0 = rowi * p.nw + gw0;
+      nv = (p.nw - gw0) < p.G ? (p.nw - gw0) : p.G;
+    } else {
+      w0 = group * p.G;
+      nv = (int)((p.nwin - w0) < p.G ? (p.nwin - w0) : p.G);
+    }
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int per_img = p.nh * p.nw;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int b = (int)(it & 1);
+        const uint32_t k = (uint32_t)(it >> 1);
+        int head, nv;
+        int64_t w0;
+        tile_windows(blockIdx.x + it * gridDim.x, head, w0, nv);
+        if (k > 0) mbar_wait(bar_qkv_empty(b), (k - 1u) & 1u);  // PV of the tile two back has read this buffer
+        const uint32_t buf = base + (uint32_t)(b * A2_QKV);
+        const uint32_t full = bar_qkv_full(b);
+        if ((p.debug & 1) && k > 0) {
+          mbar_expect_tx(full, 0u);
+          continue;
+        }
+        if (p.inter) {
+          mbar_expect_tx(full, (uint32_t)(6 * p.L * p.G * 64));
+          const int bi = (int)(w0 / per_img);
+          const int rem = (int)(w0 - (int64_t)bi * per_img);
+          const int gh = rem / p.nw, gw = rem - gh * p.nw;
+#pragma unroll
+          for (int which = 0; which < 3; ++which) {
+            const int c0 = which * p.d + head * DH;
+            const uint32_t dst = buf + (uint32_t)(which == 0 ? A2_OFF_Q : (which == 1 ? A2_OFF_K : A2_OFF_V));
+            tma_load_5d(&tm_hi, full, dst, c0, gw, 0, gh, bi * p.wsz);
+            tma_load_5d(&tm_lo, full, dst + QKV_PLANE, c0, gw, 0, gh, bi * p.wsz);
+          }
+        } else {
+          mbar_expect_tx(full, (uint32_t)(nv * 6 * p.L * 64));
+          for (int g = 0; g < nv; ++g) {
+            const int64_t w = w0 + g;
+            const int bi = (int)(w / per_img);
+            const int rem = (int)(w - (int64_t)bi * per_img);
+            const int gh = rem / p.nw, gw = rem - gh * p.nw;
+            const uint32_t row_off = (uint32_t)(g * p.Lp * 64);
+#pragma unroll
+            for (int which = 0; which < 3; ++which) {  // q, k, v
+              const int c0 = which * p.d + head * DH;
+              const uint32_t dst = buf + (uint32_t)(which == 0 ? A2_OFF_Q : (which == 1 ? A2_OFF_K : A2_OFF_V)) + row_off;
+              if (p.kind == WXF_ATTN_SHORT) {
+                tma_load_4d(&tm_hi, full, dst, c0, gw * p.wsz, gh * p.wsz, bi);
+                tma_load_4d(&tm_lo, full, dst + QKV_PLANE, c0, gw * p.wsz, gh * p.wsz, bi);
+              } else {
+                tma_load_5d(&tm_hi, full, dst, c0, gw, 0, gh, bi * p.wsz);
+                tma_load_5d(&tm_lo, full, dst + QKV_PLANE, c0, gw, 0, gh, bi * p.wsz);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // S_b = Q K^T of tile `it`; S_b is free: the P of tile it-2 was complete (bar_p_full) before PV(it-2) was issued
+      auto issue_qk = [&](int64_t it) {
+        const int b = (int)(it & 1);
+        const uint32_t k = (uint32_t)(it >> 1);
+        mbar_wait(bar_qkv_full(b), k & 1u);
+        tc_fence_after();
+        const uint32_t buf = base + (uint32_t)(b * A2_QKV);
+        const uint32_t q_hi = buf + A2_OFF_Q, q_lo = q_hi + QKV_PLANE, k_hi = buf + A2_OFF_K, k_lo = k_hi + QKV_PLANE;
+        const uint32_t d_s = tmem_base + (uint32_t)(b * 128);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {  // dh = 32 = two K=16 steps (32 bytes each inside the 64-byte row)
+          tc_mma_f16(d_s, umma_desc_sw64_kmajor(q_hi + ks * 32), umma_desc_sw64_kmajor(k_lo + ks * 32), IDESC_S, ks ? 1u : 0u);
+          tc_mma_f16(d_s, umma_desc_sw64_kmajor(q_lo + ks * 32), umma_desc_sw64_kmajor(k_hi + ks * 32), IDESC_S, 1u);
+          tc_mma_f16(d_s, umma_desc_sw64_kmajor(q_hi + ks * 32), umma_desc_sw64_kmajor(k_hi + ks * 32), IDESC_S, 1u);
+        }
+        tc_commit(bar_s_full(b));
+      };
+      auto issue_pv = [&](int64_t it) {
+        const int b = (int)(it & 1);
+        const uint32_t k = (uint32_t)(it >> 1);
+        mbar_wait(bar_p_full(b), k & 1u);                       // P_b written by softmax group b
+        if (k > 0) mbar_wait(bar_o_empty(b), (k - 1u) & 1u);    // O_b of the tile two back has been read
+        tc_fence_after();
+        const uint32_t buf = base + (uint32_t)(b * A2_QKV);
+        const uint32_t p_hi = base + (uint32_t)(A2_OFF_P + b * A2_P), p_lo = p_hi + 2 * P_ATOM;
+        const uint32_t v_hi = buf + A2_OFF_V, v_lo = v_hi + QKV_PLANE;
+        const uint32_t d_o = tmem_base + A2_COL_O + (uint32_t)(b * 32);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // 128 key rows = eight K=16 steps
+          const uint32_t pa = (uint32_t)((ks >> 2) * P_ATOM + (ks & 3) * 32);
+          const uint32_t va = (uint32_t)(ks * 16 * 64);
+          tc_mma_f16(d_o, umma_desc_sw128(p_hi + pa), umma_desc_sw64_mnmajor(v_lo + va), IDESC_O, ks ? 1u : 0u);
+          tc_mma_f16(d_o, umma_desc_sw128(p_lo + pa), umma_desc_sw64_mnmajor(v_hi + va), IDESC_O, 1u);
+          tc_mma_f16(d_o, umma_desc_sw128(p_hi + pa), umma_desc_sw64_mnmajor(v_hi + va), IDESC_O, 1u);
+        }
+        tc_commit(bar_o_full(b));
+        if (it + 2 < my_tiles) tc_commit(bar_qkv_empty(b));  // Q/K/V buffer b may be refilled (nobody waits after the last use)
+      };
+      if (my_tiles > 0) issue_qk(0);
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        if (it + 1 < my_tiles) issue_qk(it + 1);
+        issue_pv(it);
+      }
+    }
+  } else {
+    // ---- softmax + epilogue: thread = query row; group wg handles tiles it = wg, wg + 2, ... ----
+    const int wg = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    int g, i;
+    row_slot(p, r, g, i);
+    const bool row_ok = g < p.G && i < p.L;
+    const int ty = i / p.wsz, tx = i - ty * p.wsz;
+    // warp-uniform range of 8-column groups that hold a window column of any of the warp's rows
+    int g_lo, g_hi;
+    {
+      const int col0 = p.inter ? 0 : g * p.Lp, col1 = p.inter ? p.L * p.G : col0 + p.L;
+      g_lo = __reduce_min_sync(0xffffffffu, row_ok ? (col0 >> 3) : 16);
+      g_hi = __reduce_max_sync(0xffffffffu, row_ok ? ((col1 + 7) >> 3) : 0);
+      if (g_hi <= g_lo) g_lo = g_hi = 0;
+    }
+    const int c_lo = g_lo >> 2, c_hi = (g_hi + 3) >> 2;
+    const float2 sc2 = make_float2(p.scale2, p.scale2);
+    const uint32_t s_addr = tmem_base + lane_off + (uint32_t)(wg * 128);
+    const uint32_t b_addr = tmem_base + lane_off + A2_COL_BIAS;
+    const uint32_t o_addr = tmem_base + lane_off + A2_COL_O + (uint32_t)(wg * 32);
+    uint8_t* prow_hi = gen + A2_OFF_P + wg * A2_P + r * 128;
+    uint8_t* prow_lo = prow_hi + 2 * P_ATOM;
+    const int per_img = p.nh * p.nw;
+
+    for (int64_t it = wg; it < my_tiles; it += 2) {
+      const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      int head, nv;
+      int64_t w0;
+      tile_windows(blockIdx.x + it * gridDim.x, head, w0, nv);
+
+      mbar_wait(bar_s_full(wg), par);
+      tc_fence_after();
+      // s2 = S * (scale*log2 e) + bias*log2 e (masked columns: -1e30); p = 2^(s2 - max)
+      float mx;
+      const int c_end = (p.debug & 2) ? c_lo : c_hi;
+      {
+        float m0 = -3.0e38f, m1 = -3.0e38f, m2 = -3.0e38f, m3 = -3.0e38f;
+#pragma unroll 1
+        for (int c = c_lo; c < c_end; ++c) {
+          uint32_t rr[32], bb[32];
+          tmem_ld32_nowait(s_addr + (uint32_t)(c * 32), rr);
+          tmem_ld32_nowait(b_addr + (uint32_t)(c * 32), bb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            const int gq = c * 4 + q8;
+            if (gq >= g_lo && gq < g_hi) {  // warp-uniform
+#pragma unroll
+              for (int e = 0; e < 8; e += 4) {
+                const int j = q8 * 8 + e;
+                const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), sc2,
+                                             make_float2(__uint_as_float(bb[j]), __uint_as_float(bb[j + 1])));
+                const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(rr[j + 2]), __uint_as_float(rr[j + 3])), sc2,
+                                             make_float2(__uint_as_float(bb[j + 2]), __uint_as_float(bb[j + 3])));
+                m0 = fmaxf(m0, t0.x); m1 = fmaxf(m1, t0.y); m2 = fmaxf(m2, t1.x); m3 = fmaxf(m3, t1.y);
+              }
+            }
+          }
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      }
+      const float2 nmx2 = make_float2(-mx, -mx);
+      float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+#pragma unroll 1
+      for (int c = c_lo; c < c_end; ++c) {
+        uint32_t rr[32], bb[32];
+        tmem_ld32_nowait(s_addr + (uint32_t)(c * 32), rr);
+        tmem_ld32_nowait(b_addr + (uint32_t)(c * 32), bb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {  // 8 columns = one 16-byte chunk of the swizzled row
+          const int gq = c * 4 + q8;
+          if (gq >= g_lo && gq < g_hi) {  // warp-uniform
+            __align__(16) uint32_t h2[4];
+            __align__(16) uint32_t l2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = q8 * 8 + 2 * e;
+              float2 t = __ffma2_rn(make_float2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), sc2,
+                                    make_float2(__uint_as_float(bb[j]), __uint_as_float(bb[j + 1])));
+              t = __fadd2_rn(t, nmx2);
+              float2 pe;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe.x) : "f"(t.x));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe.y) : "f"(t.y));
+              if (e & 1) sum_b = __fadd2_rn(sum_b, pe); else sum_a = __fadd2_rn(sum_a, pe);
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2[e]) : "f"(pe.y), "f"(pe.x));
+              const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&h2[e]));
+              const float2 dlt = __ffma2_rn(back, make_float2(-1.0f, -1.0f), pe);
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l2[e]) : "f"(dlt.y), "f"(dlt.x));
+            }
+            const int cc = (c & 1) * 4 + q8;                 // 16-byte chunk index inside the 64-column atom
+            const int off = (c >> 1) * P_ATOM + ((cc ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(prow_hi + off) = *reinterpret_cast<const uint4*>(h2);
+            *reinterpret_cast<uint4*>(prow_lo + off) = *reinterpret_cast<const uint4*>(l2);
+          }
+        }
+      }
+      const float lsum = (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
+      fence_proxy_async();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(bar_p_full(wg));
+
+      mbar_wait(bar_o_full(wg), par);
+      tc_fence_after();
+      uint32_t oo[32];
+      tmem_ld32(o_addr, oo);
+      tc_fence_before();
+      mbar_arrive(bar_o_empty(wg));  // O_b consumed: PV of the tile two ahead may overwrite it
+      if (row_ok && g < nv && !(p.debug & 4)) {
+        const int64_t w = w0 + g;
+        const int bi = (int)(w / per_img);
+        const int rem = (int)(w - (int64_t)bi * per_img);
+        const int gh = rem / p.nw, gw = rem - gh * p.nw;
+        int y, x;
+        if (p.kind == WXF_ATTN_SHORT) {
+          y = gh * p.wsz + ty;
+          x = gw * p.wsz + tx;
+        } else {
+          y = ty * p.nh + gh;
+          x = tx * p.nw + gw;
+        }
+        const int64_t pix = ((int64_t)bi * p.H + y) * p.W + x;
+        const float inv = 1.0f / lsum;
+        uint4* hp = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldh + head * DH);
+        uint4* lp = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldh + head * DH);
+#pragma unroll
+        for (int c = 0; c < DH / 8; ++c) {
+          __align__(16) __half2 h8[4];
+          __align__(16) __half2 l8[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            wxf_split2_f16x2(__uint_as_float(oo[8 * c + 2 * e]) * inv, __uint_as_float(oo[8 * c + 2 * e + 1]) * inv, h8[e],
+                             l8[e]);
+          hp[c] = *reinterpret_cast<const uint4*>(h8);
+          lp[c] = *reinterpret_cast<const uint4*>(l8);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -386,6 +783,29 @@ extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, i
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int use_v2 = -1;
+  if (use_v2 < 0) {
+    const char* e = getenv("WXF_ATTN_V2");
+    use_v2 = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_v2) {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("WXF_ATTN_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      cudaError_t e = cudaFuncSetAttribute(window_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
+      if (e != cudaSuccess) WXF_FAIL((int)e, "attention_tc: cannot opt in to %d bytes of shared memory", A2_SMEM);
+      attr2_set = true;
+    }
+    const int64_t blocks2 = p.ntiles < (int64_t)sms ? p.ntiles : (int64_t)sms;
+    window_attention_tc2_kernel<<<(unsigned)blocks2, A2_THREADS, A2_SMEM, (cudaStream_t)stream>>>(tm_hi, tm_lo, p);
+    WXF_CHECK_LAUNCH("window_attention_tc2");
+    return 0;
+  }
   const int64_t blocks = p.ntiles < 2 * (int64_t)sms ? p.ntiles : 2 * (int64_t)sms;
   static bool attr_set = false;
   if (!attr_set) {

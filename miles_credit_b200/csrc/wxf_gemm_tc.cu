@@ -65,6 +65,7 @@ struct TcParams {
   uint32_t a_bytes;   // bytes of one A plane box
   int bias_zs;        // bias index = phase * bias_zs + n
   int step, J, ch;    // Toeplitz mode: tile step along x (128 - (J-1)), taps folded into N, channels of the branch
+  int concat;         // persistent kernel: issue A_hi [W_hi | W_lo] as one N=256 instruction
   int16_t taps[4][MAX_TAPS][2];  // [phase][tap] = (dy, dx); only [0] used when phases == 1
 };
 
@@ -349,6 +350,7 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   constexpr int CW = 128 / (EW / 4);       // columns per epilogue warp: 64 (8 warps) or 32 (16 warps)
   constexpr int NCH = CW / 32;             // 32-column chunks per warp
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -458,9 +460,17 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
             const uint64_t w_hi = umma_desc_sw128(st + 2 * TILE_BYTES + k * 32);
             const uint64_t w_lo = umma_desc_sw128(st + 2 * TILE_BYTES + W_BYTES + k * 32);
             const uint32_t acc = (ks | k) ? 1u : 0u;
-            tc_mma_f16(d_cross, a_hi, w_lo, IDESC, acc);
-            tc_mma_f16(d_cross, a_lo, w_hi, IDESC, 1u);
-            tc_mma_f16(d_main, a_hi, w_hi, IDESC, acc);
+            if (p.concat) {
+              // W_hi and W_lo tiles are adjacent in the stage: ONE N=256 instruction computes A_hi [W_hi | W_lo] into the
+              // slot's two accumulators (A_hi is read from shared memory once instead of twice), then A_lo W_hi is added
+              // to the second one.  The epilogue sums both accumulators, so which one holds "main" does not matter.
+              tc_mma_f16(d_cross, a_hi, w_hi, IDESC2, acc);
+              tc_mma_f16(d_main, a_lo, w_hi, IDESC, 1u);
+            } else {
+              tc_mma_f16(d_cross, a_hi, w_lo, IDESC, acc);
+              tc_mma_f16(d_cross, a_lo, w_hi, IDESC, 1u);
+              tc_mma_f16(d_main, a_hi, w_hi, IDESC, acc);
+            }
           }
           tc_commit(empty_bar(s));
         }
@@ -729,6 +739,15 @@ int num_sms() {
   return n;
 }
 
+bool concat_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXF_TC_CONCAT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 bool persistent_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -798,6 +817,7 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
   if ((rc = make_map_2d(&tw_hi, d->w_hi, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K, BN))) return rc;
   if ((rc = make_map_2d(&tw_lo, d->w_lo, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K, BN))) return rc;
   TcParams p{};
+  p.concat = concat_enabled() ? 1 : 0;
   p.bias = d->bias;
   p.res = d->res ? d->res + d->r_off : nullptr;
   p.out = d->out ? d->out + d->c_off : nullptr;
@@ -882,6 +902,7 @@ extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
   if ((rc = make_map_2d(&tw_lo, d->w_lo, (uint64_t)d->phases * d->N, (uint64_t)K, (uint64_t)K, BN))) return rc;
 
   TcParams p{};
+  p.concat = concat_enabled() ? 1 : 0;
   p.bias = d->bias;
   p.res = d->res ? d->res + d->r_off : nullptr;
   p.out = d->out ? d->out + d->c_off : nullptr;
@@ -947,6 +968,7 @@ extern "C" int wxf_cross_embed_toeplitz_tc(const WxfToeplitzDesc* d, void* strea
   if ((rc = make_map_2d(&tw_hi, d->w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN))) return rc;
   if ((rc = make_map_2d(&tw_lo, d->w_lo, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN))) return rc;
   TcParams p{};
+  p.concat = concat_enabled() ? 1 : 0;
   p.bias = d->bias;
   p.out = d->out + d->c_off;
   p.N = N;

@@ -260,6 +260,7 @@ class DomainPlan(_Plan):
         self.ex = [Exchange(g.stages[s], lay, self.comm, device) for s in range(4)]
         self.steps: List[tuple] = []
         self.bias_tiles: List[torch.Tensor] = []
+        self._keep: List[object] = []
         self._build(wts)
 
     # ------------------------------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@ from . import lib as _lib
 from . import ops
 from .geometry import Geometry, build_geometry, state_spec
 from .synth import synthetic_state_dict
-from .weights import ConvWeights, PreparedWeights, prepare
+from .weights import ConvWeights, GemmWeights, PreparedWeights, prepare
 
 logger = logging.getLogger(__name__)
 
@@ -166,6 +166,7 @@ class _Plan:
         self.gn_scratch = torch.empty(gn_bytes // 4 + 4, **f32)
         self.steps: List[tuple] = []
         self.bias_tiles: List[torch.Tensor] = []
+        self._keep: List[object] = []  # weight views referenced by raw pointer from the launch descriptors
         self._build(wts)
 
     # -- helpers -------------------------------------------------------------------------------
@@ -214,7 +215,17 @@ class _Plan:
                 if tc:
                     add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, att.ln_g, att.ln_b, m, d), f"layernorm.s{s}", 0,
                         8.0 * m * d)
-                    if self.attention_tc and L <= 128:
+                    if L == 1:
+                        # a one-token window: softmax over a single score is exactly 1, so the attention output is v
+                        # (crossformer.py:275-295 with i = j = 1).  Only the v rows of to_qkv are computed and the
+                        # out-projection reads them directly: no q, k, and no attention launch.
+                        vw = GemmWeights(att.qkv_tc.w_hi[2 * d: 3 * d], att.qkv_tc.w_lo[2 * d: 3 * d], None, d,
+                                         att.qkv_tc.k, att.qkv_tc.scale_log2)
+                        self._keep.append(vw)
+                        v_hi, v_lo = self.scratch16[: m * d], self.scratch16[hid_off: hid_off + m * d]
+                        self._gemm(ln_hi, ln_lo, vw, f"qkv.s{s}", M=m, lda=d, out_hi=v_hi, out_lo=v_lo, ldh=d)
+                        self._gemm(v_hi, v_lo, att.out_tc, f"out_proj.s{s}", M=m, lda=d, out=xv, ldc=ld, res=xv, ldr=ld)
+                    elif self.attention_tc and L <= 128:
                         q_hi, q_lo = self.scratch16[: m * 3 * d], self.scratch16[hid_off: hid_off + m * 3 * d]
                         self._gemm(ln_hi, ln_lo, att.qkv_tc, f"qkv.s{s}", M=m, lda=d, out_hi=q_hi, out_lo=q_lo, ldh=3 * d)
                         tile = ops.attention_bias_tile(att.bias_t, w, att.wsz, att.kind)
@@ -227,7 +238,8 @@ class _Plan:
                         add(ops.window_attention_f16x2, (wide, 3 * d, att.bias_t, ln_hi, ln_lo, d, B, h, w, d,
                                                          g.dim_head, att.wsz, att.kind, scale), f"attention.s{s}",
                             *attn_cost)
-                    self._gemm(ln_hi, ln_lo, att.out_tc, f"out_proj.s{s}", M=m, lda=d, out=xv, ldc=ld, res=xv, ldr=ld)
+                    if L != 1:
+                        self._gemm(ln_hi, ln_lo, att.out_tc, f"out_proj.s{s}", M=m, lda=d, out=xv, ldc=ld, res=xv, ldr=ld)
                     add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, ff.ln_g, ff.ln_b, m, d), f"layernorm.s{s}", 0,
                         8.0 * m * d)
                     self._gemm(ln_hi, ln_lo, ff.fc1_tc, f"ff1.s{s}", M=m, lda=d, out_hi=hid_hi, out_lo=hid_lo, ldh=4 * d,
