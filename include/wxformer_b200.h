@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 8
+#define WXF_ABI_VERSION 9
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -53,10 +53,13 @@ const char* wxf_last_error(void);
  *   xp : [B, H+pt+pb, W+pl+pr, ld] fp32, channel index c*T + t; channels [C*T, ld) are zero-filled.
  */
 int wxf_pad_to_pixel_major(const float* x, float* xp, int B, int C, int T, int H, int W,
-                           int pt, int pb, int pl, int pr, int mode, int ld, void* stream);
-/* Same pass, result written as fp16 hi/lo operand planes [B, Hp, Wp, ld] (input of the stage-0 cross-embed). */
+                           int pt, int pb, int pl, int pr, int mode, int ld, int row0, int nrows, void* stream);
+/* Same pass, result written as fp16 hi/lo operand planes [B, Hp, Wp, ld] (input of the stage-0 cross-embed).
+ * Both variants write rows [row0, row0 + nrows) of the padded image only (0, Hp = everything): a rank of the lat-band
+ * decomposition pads just the rows its stage-0 band reads (the reference pads the full grid on every rank,
+ * credit/trainers/trainer_gen2.py:211-213). */
 int wxf_pad_to_pixel_major_f16x2(const float* x, void* xp_hi, void* xp_lo, int B, int C, int T, int H, int W,
-                                 int pt, int pb, int pl, int pr, int mode, int ld, void* stream);
+                                 int pt, int pb, int pl, int pr, int mode, int ld, int row0, int nrows, void* stream);
 
 /*
  * Channel LayerNorm at every pixel (credit/models/crossformer.py:182-192):
@@ -261,10 +264,12 @@ int wxf_gather_rows(const float* src, int ld_src, const int32_t* idx, float* dst
  * Un-pad + bilinear resize (align_corners = False) + pixel-major -> NCHW
  * (TensorPadding.unpad, boundary_padding.py:35-48; F.interpolate, crossformer.py:628-635).
  *   y   : [B, Hd, Wd, ld]; the crop is rows [top, top+Hc), cols [left, left+Wc)
- *   out : [B, C, Ho, Wo] fp32 contiguous (C = base_output_channels*output_frames)
+ *   out : [B, C, Ho, Wo] fp32 contiguous (C = base_output_channels*output_frames); only output rows
+ *         [o0, o0 + n_out) are written (0, Ho = everything; a lat-band rank writes its own rows, the per-shard
+ *         un-pad of credit/parallel/domain.py:37-64)
  */
 int wxf_unpad_resize_to_nchw(const float* y, int ld, float* out, int B, int C, int Hd, int Wd, int top, int left,
-                             int Hc, int Wc, int Ho, int Wo, void* stream);
+                             int Hc, int Wc, int Ho, int Wo, int o0, int n_out, void* stream);
 
 /*
  * Autoregressive state update (update_x, credit/datasets/gen_2/channel_utils.py:253-291):

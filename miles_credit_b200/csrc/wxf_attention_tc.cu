@@ -52,7 +52,6 @@ struct AttnParams {
   int gpr;            // interleaved: tiles (groups of G consecutive gw) per window row
   float scale2;       // scale * log2(e): softmax runs in base 2
   int64_t nwin, ntiles;
-  int debug;          // timing experiments only (WXF_ATTN_DEBUG): 1 = no TMA loads after the first two tiles, 2 = no softmax, 4 = no stores
 };
 
 // Row r of a tile -> (window slot g, token i).  Window-major packing: rows [g*Lp, g*Lp + L); interleaved: r = i*G + g.
@@ -355,21 +354,89 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
   }
 }
 
-// ---- v2: one CTA per SM, two tiles in flight --------------------------------------------------------------------
-// The v1 kernel above runs load -> QK^T -> softmax -> PV -> store serially per CTA (two CTAs per SM hide part of it):
-// the profile is dominated by the softmax warps waiting for the TMA load and the two MMA round trips.  Here every
-// stage is double buffered (Q/K/V tiles and P in shared memory, S and O in TMEM) and two softmax warpgroups alternate
-// tiles, so the TMA loads run two tiles ahead, QK^T of tile i+1 is issued before PV of tile i, and one warpgroup's
-// exponentials overlap the other's waits.
+// ---- v2: one CTA per SM, decoupled load pipeline, P kept in tensor memory ---------------------------------------
+// The v1 kernel above runs load -> QK^T -> softmax -> PV -> store serially per CTA (two CTAs per SM hide part of it);
+// its profile is the softmax warps waiting for the TMA load and the MMA round trips.  Here:
+//   * Q/K/V tiles go through an A2_NST-deep shared-memory ring filled by the TMA warp, so loads run tiles ahead;
+//   * S is double buffered in TMEM and two softmax warpgroups alternate tiles (QK^T of tile i+1 is issued before PV of i);
+//   * P never touches shared memory: each softmax thread writes its row of P (fp16 hi / lo, two per 32-bit column) over
+//     its own S row with tcgen05.st, and PV reads the A operand from tensor memory;
+//   * the output row goes through a per-warp swizzled staging slab so every store instruction writes whole 64-byte runs,
+//     one tile late (four O buffers in TMEM), so a softmax group never waits for its own PV round trip.
 //   warp 0: TMA producer     warp 1: tcgen05.mma issuer     warps 2-5: softmax group 0     warps 6-9: softmax group 1
 constexpr int A2_THREADS = 320;
-constexpr int A2_QKV = 6 * QKV_PLANE;            // 48 KB per buffer: K hi/lo, V hi/lo, Q hi/lo
+constexpr int A2_NST = 3;
+constexpr int A2_QKV = 6 * QKV_PLANE;            // 48 KB per stage: K hi/lo, V hi/lo, Q hi/lo
 constexpr int A2_OFF_K = 0, A2_OFF_V = 2 * QKV_PLANE, A2_OFF_Q = 4 * QKV_PLANE;
-constexpr int A2_P = 4 * P_ATOM;                 // 64 KB per buffer: P_hi (2 atoms), P_lo (2 atoms)
-constexpr int A2_OFF_P = 2 * A2_QKV;
-constexpr int A2_OFF_BAR = A2_OFF_P + 2 * A2_P;  // 224 KB
-constexpr int A2_SMEM = A2_OFF_BAR + 128 + 1024;
+constexpr int A2_OFF_STG = A2_NST * A2_QKV;      // 8 softmax warps x 4 KB output staging
+constexpr int A2_OFF_BAR = A2_OFF_STG + 8 * 4096;
+constexpr int A2_SMEM = A2_OFF_BAR + 256 + 1024;   // 14 mbarriers + the TMEM address slot
 constexpr uint32_t A2_COL_BIAS = 256, A2_COL_O = 384;
+
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st8_nowait(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// 16 score columns [16h, 16h+16) of the row -> 8 packed fp16x2 words of P_hi and of P_lo (zeros outside [g_lo, g_hi))
+__device__ __forceinline__ void softmax_half(uint32_t s_addr, uint32_t b_addr, int h, int g_lo, int g_hi, float2 sc2,
+                                             float2 nmx2, float2& sum_a, float2& sum_b, uint32_t (&hi)[8],
+                                             uint32_t (&lo)[8]) {
+  if (h * 2 >= g_hi || h * 2 + 2 <= g_lo) {  // warp-uniform: no column of a window of this warp
+#pragma unroll
+    for (int e = 0; e < 8; ++e) hi[e] = lo[e] = 0u;
+    return;
+  }
+  uint32_t rr[16], bb[16];
+  tmem_ld16_nowait(s_addr + (uint32_t)(h * 16), rr);
+  tmem_ld16_nowait(b_addr + (uint32_t)(h * 16), bb);
+  tmem_ld_wait();
+#pragma unroll
+  for (int q8 = 0; q8 < 2; ++q8) {
+    const int gq = h * 2 + q8;
+    if (gq >= g_lo && gq < g_hi) {  // warp-uniform
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = q8 * 8 + 2 * e;
+        float2 t = __ffma2_rn(make_float2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), sc2,
+                              make_float2(__uint_as_float(bb[j]), __uint_as_float(bb[j + 1])));
+        t = __fadd2_rn(t, nmx2);
+        float2 pe;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe.x) : "f"(t.x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe.y) : "f"(t.y));
+        if (e & 1) sum_b = __fadd2_rn(sum_b, pe); else sum_a = __fadd2_rn(sum_a, pe);
+        uint32_t hw, lw;
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hw) : "f"(pe.y), "f"(pe.x));  // low half = even key
+        const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+        const float2 dlt = __ffma2_rn(back, make_float2(-1.0f, -1.0f), pe);
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lw) : "f"(dlt.y), "f"(dlt.x));
+        hi[q8 * 4 + e] = hw;
+        lo[q8 * 4 + e] = lw;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) hi[q8 * 4 + e] = lo[q8 * 4 + e] = 0u;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(A2_THREADS, 1)
 window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
@@ -379,24 +446,28 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw);
   const uint32_t bars = base + A2_OFF_BAR;
-  auto bar_qkv_full = [&](int b) { return bars + 8u * b; };
-  auto bar_qkv_empty = [&](int b) { return bars + 16u + 8u * b; };
-  auto bar_s_full = [&](int b) { return bars + 32u + 8u * b; };
-  auto bar_p_full = [&](int b) { return bars + 48u + 8u * b; };
-  auto bar_o_full = [&](int b) { return bars + 64u + 8u * b; };
-  auto bar_o_empty = [&](int b) { return bars + 80u + 8u * b; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + A2_OFF_BAR + 96);
+  auto bar_qkv_full = [&](int s) { return bars + 8u * s; };
+  auto bar_qkv_empty = [&](int s) { return bars + 8u * (A2_NST + s); };
+  auto bar_s_full = [&](int b) { return bars + 8u * (2 * A2_NST) + 8u * b; };
+  auto bar_p_full = [&](int b) { return bars + 8u * (2 * A2_NST + 2) + 8u * b; };
+  auto bar_o_full = [&](int q) { return bars + 8u * (2 * A2_NST + 4) + 8u * q; };    // q = tile & 3: four O buffers
+  auto bar_o_empty = [&](int q) { return bars + 8u * (2 * A2_NST + 8) + 8u * q; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + A2_OFF_BAR + 8 * (2 * A2_NST + 12));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    for (int s = 0; s < A2_NST; ++s) {
+      mbar_init(bar_qkv_full(s), 1);
+      mbar_init(bar_qkv_empty(s), 1);
+    }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_qkv_full(b), 1);
-      mbar_init(bar_qkv_empty(b), 1);
       mbar_init(bar_s_full(b), 1);
       mbar_init(bar_p_full(b), 128);
-      mbar_init(bar_o_full(b), 1);
-      mbar_init(bar_o_empty(b), 128);
+    }
+    for (int q = 0; q < 4; ++q) {
+      mbar_init(bar_o_full(q), 1);
+      mbar_init(bar_o_empty(q), 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -405,10 +476,10 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // operand rows the TMA boxes never cover and P columns the softmax never writes must be exact zeros
+  // operand rows the TMA boxes never cover must be finite zeros (0 * garbage could be NaN in P V)
   {
     uint4* z = reinterpret_cast<uint4*>(gen);
-    for (int i = threadIdx.x; i < A2_OFF_BAR / 16; i += A2_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < A2_OFF_STG / 16; i += A2_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -432,7 +503,7 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
   __syncthreads();
   tc_fence_after();
 
-  // tiles of this CTA: tile(it) = blockIdx.x + it * gridDim.x, buffer b = it & 1, k = it >> 1 = use count of buffer b
+  // tiles of this CTA: tile(it) = blockIdx.x + it * gridDim.x; ring stage it % A2_NST; S/P/O buffer it & 1
   const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   auto tile_windows = [&](int64_t tile, int& head, int64_t& w0, int& nv) {
@@ -453,18 +524,14 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
     if (lane == 0) {
       const int per_img = p.nh * p.nw;
       for (int64_t it = 0; it < my_tiles; ++it) {
-        const int b = (int)(it & 1);
-        const uint32_t k = (uint32_t)(it >> 1);
+        const int st = (int)(it % A2_NST);
+        const uint32_t k = (uint32_t)(it / A2_NST);
         int head, nv;
         int64_t w0;
         tile_windows(blockIdx.x + it * gridDim.x, head, w0, nv);
-        if (k > 0) mbar_wait(bar_qkv_empty(b), (k - 1u) & 1u);  // PV of the tile two back has read this buffer
-        const uint32_t buf = base + (uint32_t)(b * A2_QKV);
-        const uint32_t full = bar_qkv_full(b);
-        if ((p.debug & 1) && k > 0) {
-          mbar_expect_tx(full, 0u);
-          continue;
-        }
+        if (k > 0) mbar_wait(bar_qkv_empty(st), (k - 1u) & 1u);  // PV of the tile A2_NST back has read this stage
+        const uint32_t buf = base + (uint32_t)(st * A2_QKV);
+        const uint32_t full = bar_qkv_full(st);
         if (p.inter) {
           mbar_expect_tx(full, (uint32_t)(6 * p.L * p.G * 64));
           const int bi = (int)(w0 / per_img);
@@ -503,43 +570,45 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // S_b = Q K^T of tile `it`; S_b is free: the P of tile it-2 was complete (bar_p_full) before PV(it-2) was issued
+      // S_b = Q K^T of tile `it`.  S_b / P_b is free: tcgen05.mma instructions of one thread execute in issue order, and
+      // PV(it-2), which read P_b, was issued before this.
       auto issue_qk = [&](int64_t it) {
-        const int b = (int)(it & 1);
-        const uint32_t k = (uint32_t)(it >> 1);
-        mbar_wait(bar_qkv_full(b), k & 1u);
+        const int st = (int)(it % A2_NST);
+        const uint32_t k = (uint32_t)(it / A2_NST);
+        mbar_wait(bar_qkv_full(st), k & 1u);
         tc_fence_after();
-        const uint32_t buf = base + (uint32_t)(b * A2_QKV);
+        const uint32_t buf = base + (uint32_t)(st * A2_QKV);
         const uint32_t q_hi = buf + A2_OFF_Q, q_lo = q_hi + QKV_PLANE, k_hi = buf + A2_OFF_K, k_lo = k_hi + QKV_PLANE;
-        const uint32_t d_s = tmem_base + (uint32_t)(b * 128);
+        const uint32_t d_s = tmem_base + (uint32_t)((it & 1) * 128);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {  // dh = 32 = two K=16 steps (32 bytes each inside the 64-byte row)
           tc_mma_f16(d_s, umma_desc_sw64_kmajor(q_hi + ks * 32), umma_desc_sw64_kmajor(k_lo + ks * 32), IDESC_S, ks ? 1u : 0u);
           tc_mma_f16(d_s, umma_desc_sw64_kmajor(q_lo + ks * 32), umma_desc_sw64_kmajor(k_hi + ks * 32), IDESC_S, 1u);
           tc_mma_f16(d_s, umma_desc_sw64_kmajor(q_hi + ks * 32), umma_desc_sw64_kmajor(k_hi + ks * 32), IDESC_S, 1u);
         }
-        tc_commit(bar_s_full(b));
+        tc_commit(bar_s_full((int)(it & 1)));
       };
+      // O_b = P_b V: A = P from tensor memory (hi words in S_b columns [0, 64), lo words in [64, 128), 8 columns = 16 keys)
       auto issue_pv = [&](int64_t it) {
-        const int b = (int)(it & 1);
-        const uint32_t k = (uint32_t)(it >> 1);
-        mbar_wait(bar_p_full(b), k & 1u);                       // P_b written by softmax group b
-        if (k > 0) mbar_wait(bar_o_empty(b), (k - 1u) & 1u);    // O_b of the tile two back has been read
+        const int b = (int)(it & 1), q = (int)(it & 3);
+        const uint32_t k2 = (uint32_t)(it >> 1), k4 = (uint32_t)(it >> 2);
+        const int st = (int)(it % A2_NST);
+        mbar_wait(bar_p_full(b), k2 & 1u);                        // P_b written by softmax group b
+        if (k4 > 0) mbar_wait(bar_o_empty(q), (k4 - 1u) & 1u);    // O_q of the tile four back has been read
         tc_fence_after();
-        const uint32_t buf = base + (uint32_t)(b * A2_QKV);
-        const uint32_t p_hi = base + (uint32_t)(A2_OFF_P + b * A2_P), p_lo = p_hi + 2 * P_ATOM;
+        const uint32_t buf = base + (uint32_t)(st * A2_QKV);
         const uint32_t v_hi = buf + A2_OFF_V, v_lo = v_hi + QKV_PLANE;
-        const uint32_t d_o = tmem_base + A2_COL_O + (uint32_t)(b * 32);
+        const uint32_t p_hi = tmem_base + (uint32_t)(b * 128), p_lo = p_hi + 64u;
+        const uint32_t d_o = tmem_base + A2_COL_O + (uint32_t)(q * 32);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // 128 key rows = eight K=16 steps
-          const uint32_t pa = (uint32_t)((ks >> 2) * P_ATOM + (ks & 3) * 32);
           const uint32_t va = (uint32_t)(ks * 16 * 64);
-          tc_mma_f16(d_o, umma_desc_sw128(p_hi + pa), umma_desc_sw64_mnmajor(v_lo + va), IDESC_O, ks ? 1u : 0u);
-          tc_mma_f16(d_o, umma_desc_sw128(p_lo + pa), umma_desc_sw64_mnmajor(v_hi + va), IDESC_O, 1u);
-          tc_mma_f16(d_o, umma_desc_sw128(p_hi + pa), umma_desc_sw64_mnmajor(v_hi + va), IDESC_O, 1u);
+          tc_mma_f16_ts(d_o, p_hi + ks * 8, umma_desc_sw64_mnmajor(v_lo + va), IDESC_O, ks ? 1u : 0u);
+          tc_mma_f16_ts(d_o, p_lo + ks * 8, umma_desc_sw64_mnmajor(v_hi + va), IDESC_O, 1u);
+          tc_mma_f16_ts(d_o, p_hi + ks * 8, umma_desc_sw64_mnmajor(v_hi + va), IDESC_O, 1u);
         }
-        tc_commit(bar_o_full(b));
-        if (it + 2 < my_tiles) tc_commit(bar_qkv_empty(b));  // Q/K/V buffer b may be refilled (nobody waits after the last use)
+        tc_commit(bar_o_full(q));
+        if (it + A2_NST < my_tiles) tc_commit(bar_qkv_empty(st));  // stage may be refilled (nobody waits after the last use)
       };
       if (my_tiles > 0) issue_qk(0);
       for (int64_t it = 0; it < my_tiles; ++it) {
@@ -569,11 +638,54 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
     const float2 sc2 = make_float2(p.scale2, p.scale2);
     const uint32_t s_addr = tmem_base + lane_off + (uint32_t)(wg * 128);
     const uint32_t b_addr = tmem_base + lane_off + A2_COL_BIAS;
-    const uint32_t o_addr = tmem_base + lane_off + A2_COL_O + (uint32_t)(wg * 32);
-    uint8_t* prow_hi = gen + A2_OFF_P + wg * A2_P + r * 128;
-    uint8_t* prow_lo = prow_hi + 2 * P_ATOM;
+    uint8_t* stg = gen + A2_OFF_STG + (warp - 2) * 4096;  // this warp's 32 rows x (64 B hi | 64 B lo)
     const int per_img = p.nh * p.nw;
+    const int swz = ((lane >> 1) & 3) ^ ((lane & 1) << 2);
 
+    // Output of tile `it` (O buffer it & 3): O / rowsum -> fp16 hi/lo -> swizzled staging slab -> 64-byte runs.  It runs one
+    // iteration late (after the softmax of this group's NEXT tile), so the PV round trip is never waited for.
+    auto epilogue = [&](int64_t it, int64_t pix, float inv, int head) {
+      const int q = (int)(it & 3);
+      mbar_wait(bar_o_full(q), (uint32_t)(it >> 2) & 1u);
+      tc_fence_after();
+      uint32_t oo[32];
+      tmem_ld32(tmem_base + lane_off + A2_COL_O + (uint32_t)(q * 32), oo);
+      tc_fence_before();
+      mbar_arrive(bar_o_empty(q));  // O_q consumed: PV of the tile four ahead may overwrite it
+#pragma unroll
+      for (int c = 0; c < DH / 8; ++c) {
+        __align__(16) __half2 h8[4];
+        __align__(16) __half2 l8[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          wxf_split2_f16x2(__uint_as_float(oo[8 * c + 2 * e]) * inv, __uint_as_float(oo[8 * c + 2 * e + 1]) * inv, h8[e],
+                           l8[e]);
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ swz) << 4)) = *reinterpret_cast<const uint4*>(h8);
+        *reinterpret_cast<uint4*>(stg + lane * 128 + (((c + 4) ^ swz) << 4)) = *reinterpret_cast<const uint4*>(l8);
+      }
+      __syncwarp();
+      // 4 lanes write one row's 64 bytes: 8 rows per store instruction, hi plane then lo plane
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        const int row = ps * 8 + (lane >> 2), c = lane & 3;
+        const int64_t rp = __shfl_sync(0xffffffffu, pix, row);
+        const int rs = ((row >> 1) & 3) ^ ((row & 1) << 2);
+        const uint4 vh = *reinterpret_cast<const uint4*>(stg + row * 128 + ((c ^ rs) << 4));
+        const uint4 vl = *reinterpret_cast<const uint4*>(stg + row * 128 + (((c + 4) ^ rs) << 4));
+        if (rp >= 0) {
+          *reinterpret_cast<uint4*>(p.out_hi + rp * p.ldh + head * DH + c * 8) = vh;
+          *reinterpret_cast<uint4*>(p.out_lo + rp * p.ldh + head * DH + c * 8) = vl;
+        }
+      }
+      __syncwarp();  // the slab is rewritten by the next epilogue of this warp
+    };
+
+    // measured: the late epilogue pays for the many-window tiles of the dilated groups (L = 25: 109 -> 94 us, L = 4: 72 -> 64 us
+    // at 0.25 deg) and costs 6 % on one-window tiles (L = 100), which keep the immediate epilogue
+    const bool defer = p.L < 64;
+    int64_t pend_it = -1, pend_pix = -1;
+    float pend_inv = 0.f;
+    int pend_head = 0;
     for (int64_t it = wg; it < my_tiles; it += 2) {
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
       int head, nv;
@@ -584,11 +696,10 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
       tc_fence_after();
       // s2 = S * (scale*log2 e) + bias*log2 e (masked columns: -1e30); p = 2^(s2 - max)
       float mx;
-      const int c_end = (p.debug & 2) ? c_lo : c_hi;
       {
         float m0 = -3.0e38f, m1 = -3.0e38f, m2 = -3.0e38f, m3 = -3.0e38f;
 #pragma unroll 1
-        for (int c = c_lo; c < c_end; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           uint32_t rr[32], bb[32];
           tmem_ld32_nowait(s_addr + (uint32_t)(c * 32), rr);
           tmem_ld32_nowait(b_addr + (uint32_t)(c * 32), bb);
@@ -611,54 +722,47 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
         }
         mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
+      // P over S, in place.  16-column halves h = 0..7: hi words -> columns [8h, 8h+8) (already consumed), lo words ->
+      // [64+8h, 64+8h+8) = S half 4 + h/2: the lo words of halves 0-3 wait in registers until halves 4 and 5 were read
       const float2 nmx2 = make_float2(-mx, -mx);
       float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
-#pragma unroll 1
-      for (int c = c_lo; c < c_end; ++c) {
-        uint32_t rr[32], bb[32];
-        tmem_ld32_nowait(s_addr + (uint32_t)(c * 32), rr);
-        tmem_ld32_nowait(b_addr + (uint32_t)(c * 32), bb);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q8 = 0; q8 < 4; ++q8) {  // 8 columns = one 16-byte chunk of the swizzled row
-          const int gq = c * 4 + q8;
-          if (gq >= g_lo && gq < g_hi) {  // warp-uniform
-            __align__(16) uint32_t h2[4];
-            __align__(16) uint32_t l2[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = q8 * 8 + 2 * e;
-              float2 t = __ffma2_rn(make_float2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), sc2,
-                                    make_float2(__uint_as_float(bb[j]), __uint_as_float(bb[j + 1])));
-              t = __fadd2_rn(t, nmx2);
-              float2 pe;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe.x) : "f"(t.x));
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe.y) : "f"(t.y));
-              if (e & 1) sum_b = __fadd2_rn(sum_b, pe); else sum_a = __fadd2_rn(sum_a, pe);
-              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2[e]) : "f"(pe.y), "f"(pe.x));
-              const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&h2[e]));
-              const float2 dlt = __ffma2_rn(back, make_float2(-1.0f, -1.0f), pe);
-              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l2[e]) : "f"(dlt.y), "f"(dlt.x));
-            }
-            const int cc = (c & 1) * 4 + q8;                 // 16-byte chunk index inside the 64-column atom
-            const int off = (c >> 1) * P_ATOM + ((cc ^ (r & 7)) << 4);
-            *reinterpret_cast<uint4*>(prow_hi + off) = *reinterpret_cast<const uint4*>(h2);
-            *reinterpret_cast<uint4*>(prow_lo + off) = *reinterpret_cast<const uint4*>(l2);
-          }
-        }
+      {
+        uint32_t hi[8], lo[8], d0[8], d1[8], d2[8], d3[8];
+        softmax_half(s_addr, b_addr, 0, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, d0);
+        tmem_st8_nowait(s_addr + 0u, hi);
+        softmax_half(s_addr, b_addr, 1, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, d1);
+        tmem_st8_nowait(s_addr + 8u, hi);
+        softmax_half(s_addr, b_addr, 2, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, d2);
+        tmem_st8_nowait(s_addr + 16u, hi);
+        softmax_half(s_addr, b_addr, 3, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, d3);
+        tmem_st8_nowait(s_addr + 24u, hi);
+        softmax_half(s_addr, b_addr, 7, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, lo);   // halves 7, 6, 5, 4: every lo
+        tmem_st8_nowait(s_addr + 56u, hi);                                             // target is already consumed
+        tmem_st8_nowait(s_addr + 120u, lo);
+        softmax_half(s_addr, b_addr, 6, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, lo);
+        tmem_st8_nowait(s_addr + 48u, hi);
+        tmem_st8_nowait(s_addr + 112u, lo);
+        softmax_half(s_addr, b_addr, 5, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, lo);
+        tmem_st8_nowait(s_addr + 40u, hi);
+        tmem_st8_nowait(s_addr + 104u, lo);
+        softmax_half(s_addr, b_addr, 4, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, lo);
+        tmem_st8_nowait(s_addr + 32u, hi);
+        tmem_st8_nowait(s_addr + 96u, lo);
+        tmem_st8_nowait(s_addr + 64u, d0);   // halves 4 and 5 (columns 64..95) have been read
+        tmem_st8_nowait(s_addr + 72u, d1);
+        tmem_st8_nowait(s_addr + 80u, d2);
+        tmem_st8_nowait(s_addr + 88u, d3);
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       const float lsum = (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
-      fence_proxy_async();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(bar_p_full(wg));
 
-      mbar_wait(bar_o_full(wg), par);
-      tc_fence_after();
-      uint32_t oo[32];
-      tmem_ld32(o_addr, oo);
-      tc_fence_before();
-      mbar_arrive(bar_o_empty(wg));  // O_b consumed: PV of the tile two ahead may overwrite it
-      if (row_ok && g < nv && !(p.debug & 4)) {
+      if (defer && pend_it >= 0) epilogue(pend_it, pend_pix, pend_inv, pend_head);  // the previous tile of this group
+
+      // this row's output pixel
+      int64_t pix = -1;
+      if (row_ok && g < nv) {
         const int64_t w = w0 + g;
         const int bi = (int)(w / per_img);
         const int rem = (int)(w - (int64_t)bi * per_img);
@@ -671,23 +775,15 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
           y = ty * p.nh + gh;
           x = tx * p.nw + gw;
         }
-        const int64_t pix = ((int64_t)bi * p.H + y) * p.W + x;
-        const float inv = 1.0f / lsum;
-        uint4* hp = reinterpret_cast<uint4*>(p.out_hi + pix * p.ldh + head * DH);
-        uint4* lp = reinterpret_cast<uint4*>(p.out_lo + pix * p.ldh + head * DH);
-#pragma unroll
-        for (int c = 0; c < DH / 8; ++c) {
-          __align__(16) __half2 h8[4];
-          __align__(16) __half2 l8[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            wxf_split2_f16x2(__uint_as_float(oo[8 * c + 2 * e]) * inv, __uint_as_float(oo[8 * c + 2 * e + 1]) * inv, h8[e],
-                             l8[e]);
-          hp[c] = *reinterpret_cast<const uint4*>(h8);
-          lp[c] = *reinterpret_cast<const uint4*>(l8);
-        }
+        pix = ((int64_t)bi * p.H + y) * p.W + x;
+      }
+      if (defer) {
+        pend_it = it; pend_pix = pix; pend_inv = 1.0f / lsum; pend_head = head;
+      } else {
+        epilogue(it, pix, 1.0f / lsum, head);
       }
     }
+    if (pend_it >= 0) epilogue(pend_it, pend_pix, pend_inv, pend_head);
   }
 
   tc_fence_before();
@@ -789,12 +885,6 @@ extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, i
     use_v2 = (e && e[0] == '0') ? 0 : 1;
   }
   if (use_v2) {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("WXF_ATTN_DEBUG");
-      dbg = e ? atoi(e) : 0;
-    }
-    p.debug = dbg;
     static bool attr2_set = false;
     if (!attr2_set) {
       cudaError_t e = cudaFuncSetAttribute(window_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);

@@ -17,11 +17,11 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256) pad_to_pixel_major_kernel(const float* __restrict__ x, float* __restrict__ xp,
                                                                   __half* __restrict__ xp_hi, __half* __restrict__ xp_lo,
                                                                   int CT, int H, int W, int pt, int pl, int mode,
-                                                                  int ld, int Hp, int Wp, int cgroups) {
+                                                                  int ld, int Hp, int Wp, int cgroups, int row0) {
   __shared__ float tile[32][33];  // [channel][column]
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int b = blockIdx.z / cgroups, cg = blockIdx.z % cgroups;
-  const int r = blockIdx.y;
+  const int r = row0 + blockIdx.y;
   const int c0 = blockIdx.x * 32;
 
   int sr;
@@ -79,8 +79,86 @@ __global__ void __launch_bounds__(256) pad_to_pixel_major_kernel(const float* __
   }
 }
 
+// Same index map, one CTA = one padded row x 64 columns x a block of 64 channels: the column loop reads whole 128-byte
+// runs of the NCHW rows, the transposed write stores 16 bytes per thread (8 fp16 of a plane / 4 fp32), i.e. whole
+// 128-byte pixel rows.  Needs ld % 8 == 0 (otherwise the scalar kernel above runs).
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) pad_rows_vec_kernel(const float* __restrict__ x, float* __restrict__ xp,
+                                                            __half* __restrict__ xp_hi, __half* __restrict__ xp_lo,
+                                                            int CT, int H, int W, int pt, int pl, int mode, int ld,
+                                                            int Hp, int Wp, int cblocks, int row0) {
+  __shared__ float tile[64][65];  // [channel][column]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z / cblocks, cb = blockIdx.z % cblocks;
+  const int r = row0 + blockIdx.y;
+  const int c0 = blockIdx.x * 64;
+  const int ch0 = cb * 64;
+  const int nch = min(64, ld - ch0);
+
+  int sr;
+  bool roll = false;
+  if (mode == WXF_PAD_EARTH) {
+    if (r < pt) {
+      sr = pt - 1 - r;
+      roll = true;
+    } else if (r < pt + H) {
+      sr = r - pt;
+    } else {
+      sr = H - 1 - (r - pt - H);
+      roll = true;
+    }
+  } else {
+    sr = r - pt;
+    if (sr < 0) sr = -sr;
+    if (sr >= H) sr = 2 * (H - 1) - sr;
+  }
+  int sc[2];
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const int col = c0 + hf * 32 + lane;
+    sc[hf] = -1;
+    if (col < Wp) {
+      int j = (col - pl) % W;
+      if (j < 0) j += W;
+      if (roll) {
+        j -= W / 2;
+        if (j < 0) j += W;
+      }
+      sc[hf] = j;
+    }
+  }
+  for (int i = warp; i < nch; i += 8) {
+    const int ch = ch0 + i;
+    const float* row = x + ((size_t)(b * CT + ch) * H + sr) * W;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) tile[i][hf * 32 + lane] = (ch < CT && sc[hf] >= 0) ? __ldg(row + sc[hf]) : 0.f;
+  }
+  __syncthreads();
+  const int ngrp = nch >> 3;  // groups of 8 channels
+  for (int idx = tid; idx < 64 * ngrp; idx += 256) {
+    const int cg = idx % ngrp, colx = idx / ngrp;
+    const int cw = c0 + colx;
+    if (cw >= Wp) continue;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = tile[cg * 8 + e][colx];
+    const size_t o = ((size_t)(b * Hp + r) * Wp + cw) * ld + ch0 + cg * 8;
+    if constexpr (SPLIT) {
+      __align__(16) __half2 h8[4];
+      __align__(16) __half2 l8[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wxf_split2_f16x2(v[2 * e], v[2 * e + 1], h8[e], l8[e]);
+      *reinterpret_cast<uint4*>(xp_hi + o) = *reinterpret_cast<const uint4*>(h8);
+      *reinterpret_cast<uint4*>(xp_lo + o) = *reinterpret_cast<const uint4*>(l8);
+    } else {
+      *reinterpret_cast<float4*>(xp + o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(xp + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
 static int pad_launch(const float* x, float* xp, void* xp_hi, void* xp_lo, int B, int C, int T, int H, int W, int pt,
-                      int pb, int pl, int pr, int mode, int ld, void* stream) {
+                      int pb, int pl, int pr, int mode, int ld, int row0, int nrows, void* stream) {
   if (B <= 0 || C <= 0 || T <= 0 || H <= 0 || W <= 0 || pt < 0 || pb < 0 || pl < 0 || pr < 0)
     WXF_FAIL(WXF_EINVAL, "pad: bad dims");
   if (ld < C * T) WXF_FAIL(WXF_EINVAL, "pad: ld %d < C*T %d", ld, C * T);
@@ -88,30 +166,47 @@ static int pad_launch(const float* x, float* xp, void* xp_hi, void* xp_lo, int B
   if (mode == WXF_PAD_EARTH && (pt > H || pb > H)) WXF_FAIL(WXF_EINVAL, "pad: earth pad_lat larger than H");
   if (mode == WXF_PAD_MIRROR && (pt >= H || pb >= H)) WXF_FAIL(WXF_EINVAL, "pad: mirror pad_lat must be < H");
   const int Hp = H + pt + pb, Wp = W + pl + pr;
-  const int cgroups = (ld + 31) / 32;
-  if (Hp > 65535 || (int64_t)B * cgroups > 65535) WXF_FAIL(WXF_EINVAL, "pad: grid too large");
-  dim3 grid((Wp + 31) / 32, Hp, B * cgroups), block(32, 8);
+  if (row0 < 0 || nrows < 0 || row0 + nrows > Hp) WXF_FAIL(WXF_EINVAL, "pad: rows [%d, %d) outside [0, %d)", row0, row0 + nrows, Hp);
+  if (nrows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (ld % 8 == 0) && wxf_aligned16(xp_hi ? xp_hi : (void*)xp) && (!xp_lo || wxf_aligned16(xp_lo));
+  if (vec) {
+    const int cblocks = (ld + 63) / 64;
+    if (nrows > 65535 || (int64_t)B * cblocks > 65535) WXF_FAIL(WXF_EINVAL, "pad: grid too large");
+    dim3 grid((Wp + 63) / 64, nrows, B * cblocks);
+    if (xp_hi)
+      pad_rows_vec_kernel<true><<<grid, 256, 0, st>>>(x, nullptr, (__half*)xp_hi, (__half*)xp_lo, C * T, H, W, pt, pl, mode,
+                                                      ld, Hp, Wp, cblocks, row0);
+    else
+      pad_rows_vec_kernel<false><<<grid, 256, 0, st>>>(x, xp, nullptr, nullptr, C * T, H, W, pt, pl, mode, ld, Hp, Wp,
+                                                       cblocks, row0);
+    WXF_CHECK_LAUNCH("pad_to_pixel_major");
+    return 0;
+  }
+  const int cgroups = (ld + 31) / 32;
+  if (nrows > 65535 || (int64_t)B * cgroups > 65535) WXF_FAIL(WXF_EINVAL, "pad: grid too large");
+  dim3 grid((Wp + 31) / 32, nrows, B * cgroups), block(32, 8);
   if (xp_hi)
     pad_to_pixel_major_kernel<true><<<grid, block, 0, st>>>(x, nullptr, (__half*)xp_hi, (__half*)xp_lo, C * T, H, W, pt,
-                                                            pl, mode, ld, Hp, Wp, cgroups);
+                                                            pl, mode, ld, Hp, Wp, cgroups, row0);
   else
     pad_to_pixel_major_kernel<false><<<grid, block, 0, st>>>(x, xp, nullptr, nullptr, C * T, H, W, pt, pl, mode, ld, Hp,
-                                                             Wp, cgroups);
+                                                             Wp, cgroups, row0);
   WXF_CHECK_LAUNCH("pad_to_pixel_major");
   return 0;
 }
 
 extern "C" int wxf_pad_to_pixel_major(const float* x, float* xp, int B, int C, int T, int H, int W, int pt, int pb,
-                                      int pl, int pr, int mode, int ld, void* stream) {
+                                      int pl, int pr, int mode, int ld, int row0, int nrows, void* stream) {
   if (!xp) WXF_FAIL(WXF_EINVAL, "pad: null output");
-  return pad_launch(x, xp, nullptr, nullptr, B, C, T, H, W, pt, pb, pl, pr, mode, ld, stream);
+  return pad_launch(x, xp, nullptr, nullptr, B, C, T, H, W, pt, pb, pl, pr, mode, ld, row0, nrows, stream);
 }
 
 extern "C" int wxf_pad_to_pixel_major_f16x2(const float* x, void* xp_hi, void* xp_lo, int B, int C, int T, int H, int W,
-                                            int pt, int pb, int pl, int pr, int mode, int ld, void* stream) {
+                                            int pt, int pb, int pl, int pr, int mode, int ld, int row0, int nrows,
+                                            void* stream) {
   if (!xp_hi || !xp_lo) WXF_FAIL(WXF_EINVAL, "pad: null output planes");
-  return pad_launch(x, nullptr, xp_hi, xp_lo, B, C, T, H, W, pt, pb, pl, pr, mode, ld, stream);
+  return pad_launch(x, nullptr, xp_hi, xp_lo, B, C, T, H, W, pt, pb, pl, pr, mode, ld, row0, nrows, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -665,11 +760,11 @@ __device__ __forceinline__ void bilin_axis(int dst, float scale, int n_in, int& 
 
 __global__ void __launch_bounds__(256) unpad_resize_kernel(const float* __restrict__ y, int ld, float* __restrict__ out,
                                                             int C, int Hd, int Wd, int top, int left, int Hc, int Wc,
-                                                            int Ho, int Wo, float sh, float sw, int cgroups) {
+                                                            int Ho, int Wo, float sh, float sw, int cgroups, int o0) {
   __shared__ float tile[32][33];  // [channel][column]
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int b = blockIdx.z / cgroups, cg = blockIdx.z % cgroups;
-  const int h = blockIdx.y, w0 = blockIdx.x * 32;
+  const int h = o0 + blockIdx.y, w0 = blockIdx.x * 32;
   int y0, y1;
   float ly0, ly1;
   bilin_axis(h, sh, Hc, y0, y1, ly0, ly1);
@@ -699,17 +794,87 @@ __global__ void __launch_bounds__(256) unpad_resize_kernel(const float* __restri
   }
 }
 
+// One CTA = one output row x 64 columns x a block of 64 channels: each thread interpolates 4 channels of a pixel from
+// float4 loads (whole 128/256-byte pixel rows), the transposed write stores float4 runs along W.
+__global__ void __launch_bounds__(256) unpad_resize_vec_kernel(const float* __restrict__ y, int ld, float* __restrict__ out,
+                                                                int C, int Hd, int Wd, int top, int left, int Hc, int Wc,
+                                                                int Ho, int Wo, float sh, float sw, int cblocks, int o0) {
+  __shared__ float tile[64][65];  // [channel][column]
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z / cblocks, cb = blockIdx.z % cblocks;
+  const int h = o0 + blockIdx.y, w0 = blockIdx.x * 64;
+  const int ch0 = cb * 64;
+  const int nch = min(64, C - ch0);  // multiple of 4 (checked by the launcher)
+  int y0, y1;
+  float ly0, ly1;
+  bilin_axis(h, sh, Hc, y0, y1, ly0, ly1);
+  const int nq = nch >> 2;
+  const float* base0 = y + ((size_t)(b * Hd + top + y0) * Wd + left) * ld + ch0;
+  const float* base1 = y + ((size_t)(b * Hd + top + y1) * Wd + left) * ld + ch0;
+  for (int idx = tid; idx < 64 * nq; idx += 256) {
+    const int q = idx % nq, colx = idx / nq;
+    const int w = w0 + colx;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (w < Wo) {
+      int x0, x1;
+      float lx0, lx1;
+      bilin_axis(w, sw, Wc, x0, x1, lx0, lx1);
+      const float4 v00 = *reinterpret_cast<const float4*>(base0 + (size_t)x0 * ld + 4 * q);
+      const float4 v10 = *reinterpret_cast<const float4*>(base1 + (size_t)x0 * ld + 4 * q);
+      float4 v01 = v00, v11 = v10;
+      if (x1 != x0) {
+        v01 = *reinterpret_cast<const float4*>(base0 + (size_t)x1 * ld + 4 * q);
+        v11 = *reinterpret_cast<const float4*>(base1 + (size_t)x1 * ld + 4 * q);
+      }
+      v.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+      v.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+      v.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+      v.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+    }
+    tile[4 * q][colx] = v.x;
+    tile[4 * q + 1][colx] = v.y;
+    tile[4 * q + 2][colx] = v.z;
+    tile[4 * q + 3][colx] = v.w;
+  }
+  __syncthreads();
+  if ((Wo & 3) == 0) {
+    for (int idx = tid; idx < nch * 16; idx += 256) {
+      const int w4 = idx & 15, c = idx >> 4;
+      const int w = w0 + 4 * w4;
+      if (w < Wo)
+        *reinterpret_cast<float4*>(out + ((size_t)(b * C + ch0 + c) * Ho + h) * Wo + w) =
+            make_float4(tile[c][4 * w4], tile[c][4 * w4 + 1], tile[c][4 * w4 + 2], tile[c][4 * w4 + 3]);
+    }
+  } else {
+    for (int idx = tid; idx < nch * 64; idx += 256) {
+      const int wx = idx & 63, c = idx >> 6;
+      if (w0 + wx < Wo) out[((size_t)(b * C + ch0 + c) * Ho + h) * Wo + w0 + wx] = tile[c][wx];
+    }
+  }
+}
+
 extern "C" int wxf_unpad_resize_to_nchw(const float* y, int ld, float* out, int B, int C, int Hd, int Wd, int top,
-                                        int left, int Hc, int Wc, int Ho, int Wo, void* stream) {
+                                        int left, int Hc, int Wc, int Ho, int Wo, int o0, int n_out, void* stream) {
   if (B <= 0 || C <= 0 || Hc <= 0 || Wc <= 0 || Ho <= 0 || Wo <= 0 || top < 0 || left < 0 || top + Hc > Hd ||
       left + Wc > Wd || ld < C)
     WXF_FAIL(WXF_EINVAL, "unpad_resize: bad dims");
-  const int cgroups = (C + 31) / 32;
-  if (Ho > 65535 || (int64_t)B * cgroups > 65535) WXF_FAIL(WXF_EINVAL, "unpad_resize: grid too large");
+  if (o0 < 0 || n_out < 0 || o0 + n_out > Ho) WXF_FAIL(WXF_EINVAL, "unpad_resize: rows [%d, %d) outside [0, %d)", o0, o0 + n_out, Ho);
+  if (n_out == 0) return 0;
   const float sh = (float)Hc / (float)Ho, sw = (float)Wc / (float)Wo;
-  dim3 grid((Wo + 31) / 32, Ho, B * cgroups), block(32, 8);
+  if ((C & 3) == 0 && (ld & 3) == 0 && wxf_aligned16(y) && wxf_aligned16(out)) {
+    const int cblocks = (C + 63) / 64;
+    if (n_out > 65535 || (int64_t)B * cblocks > 65535) WXF_FAIL(WXF_EINVAL, "unpad_resize: grid too large");
+    dim3 grid((Wo + 63) / 64, n_out, B * cblocks);
+    unpad_resize_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, ld, out, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, sh,
+                                                                    sw, cblocks, o0);
+    WXF_CHECK_LAUNCH("unpad_resize");
+    return 0;
+  }
+  const int cgroups = (C + 31) / 32;
+  if (n_out > 65535 || (int64_t)B * cgroups > 65535) WXF_FAIL(WXF_EINVAL, "unpad_resize: grid too large");
+  dim3 grid((Wo + 31) / 32, n_out, B * cgroups), block(32, 8);
   unpad_resize_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(y, ld, out, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, sh,
-                                                                 sw, cgroups);
+                                                                 sw, cgroups, o0);
   WXF_CHECK_LAUNCH("unpad_resize");
   return 0;
 }

@@ -14,7 +14,10 @@ reassociation) and uses two layouts:
   owns whole units and runs the unchanged single-GPU kernels on them as a batch: no communication inside a stage.
 
 Per step: 2 all-to-alls per stage (band <-> unit, the fp32 residual stream), 1-row halo exchanges in the decoder,
-one all-reduce of (sum, sum-of-squares) per GroupNorm, one all-gather of the decoder output.
+one all-reduce of (sum, sum-of-squares) per GroupNorm.  Boundary padding and un-pad + resize are sharded too: a rank pads
+only the rows its stage-0 band reads and writes only its own rows of the prediction.  ``model(x)`` all-gathers those rows
+(full prediction on every rank, the reference contract); the rollout (rollout.py) keeps the state sharded between steps
+and exchanges only the halo rows the next step's padding needs.
 """
 
 from __future__ import annotations
@@ -105,6 +108,9 @@ class _Comm:
     def all_reduce(self, t):
         dist.all_reduce(t, group=self.group)
 
+    def all_to_all(self, out, inp, out_splits, in_splits):
+        dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=self.group)
+
 
 class Exchange:
     """band <-> unit re-layout of a stage's residual stream for this rank (index lists are computed once)."""
@@ -145,35 +151,18 @@ class Exchange:
         for c in self.recv_counts:
             self.recv_off.append(self.recv_off[-1] + c)
 
-    def _p2p(self, sbuf, soff, scnt, rbuf, roff, rcnt):
-        d, c = self.d, self.comm
-        reqs = []
-        for peer in range(self.world):
-            if peer == self.rank:
-                continue
-            if rcnt[peer]:
-                reqs.append(c.recv(rbuf[roff[peer] * d: (roff[peer] + rcnt[peer]) * d], peer))
-            if scnt[peer]:
-                reqs.append(c.send(sbuf[soff[peer] * d: (soff[peer] + scnt[peer]) * d], peer))
-        c.run(reqs)
-
     def band_to_unit(self, band, ld_band, unit, sbuf, rbuf):
-        d, me = self.d, self.rank
+        d = self.d
         ops.gather_rows(band, ld_band, self.send_idx, sbuf, d, self.n_band, d)
-        # my own rows go straight into the receive buffer
-        n_self = self.send_counts[me]
-        if n_self:
-            ops.gather_rows(band, ld_band, self.send_idx[self.send_off[me]:], rbuf[self.recv_off[me] * d:], d, n_self, d)
-        self._p2p(sbuf, self.send_off, self.send_counts, rbuf, self.recv_off, self.recv_counts)
+        self.comm.all_to_all(rbuf[: self.n_unit * d], sbuf[: self.n_band * d], [c * d for c in self.recv_counts],
+                             [c * d for c in self.send_counts])
         ops.gather_rows(rbuf, d, self.inv_recv, unit, d, self.n_unit, d)
 
     def unit_to_band(self, unit, band, ld_band, sbuf, rbuf):
-        d, me = self.d, self.rank
+        d = self.d
         ops.gather_rows(unit, d, self.recv_idx, sbuf, d, self.n_unit, d)
-        n_self = self.recv_counts[me]
-        if n_self:
-            ops.gather_rows(unit, d, self.recv_idx[self.recv_off[me]:], rbuf[self.send_off[me] * d:], d, n_self, d)
-        self._p2p(sbuf, self.recv_off, self.recv_counts, rbuf, self.send_off, self.send_counts)
+        self.comm.all_to_all(rbuf[: self.n_band * d], sbuf[: self.n_unit * d], [c * d for c in self.send_counts],
+                             [c * d for c in self.recv_counts])
         ops.gather_rows(rbuf, d, self.inv_send, band, ld_band, self.n_band, d)
 
 
@@ -261,6 +250,7 @@ class DomainPlan(_Plan):
         self.steps: List[tuple] = []
         self.bias_tiles: List[torch.Tensor] = []
         self._keep: List[object] = []
+        self._row_ranges()
         self._build(wts)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -335,7 +325,7 @@ class DomainPlan(_Plan):
         self._conv_tc(self.catp[0][0], self.catp[0][1], _shift_taps(wts.head_tc, 1), "dec_head", B=1,
                       Hi=self.rows[0] + 2, Wi=st0.w, lda=2 * st0.dim, Ho=self.rows[0], Wo=st0.w, out=y_band,
                       ldc=g.output_channels)
-        add(self._allgather_output, (), "allgather", 0, 0)
+        add(self._ydec_halo, (), "halo", 0, 0)
 
     # ------------------------------------------------------------------------------------------------------------
     def _groupnorm(self, x, ldx, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, hw_local, C, G, count):
@@ -345,24 +335,124 @@ class DomainPlan(_Plan):
         ops.groupnorm_stats_from_sums(self.gn_sums, self.gn_stats, 1, G, count)
         ops.groupnorm_apply_f16x2(x, ldx, self.gn_stats, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, 1, hw_local, C, G)
 
-    def _allgather_output(self):
-        lay, me = self.lay, self.rank
+    def _row_ranges(self):
+        """Host-side bookkeeping of the sharded boundary passes (all ranks compute all ranks' ranges).
+
+        pad_rows[r]  : padded-input rows rank r's stage-0 band reads (cross-embed kernel k, stride s, padding (k-s)//2)
+        out_rows[r]  : output rows rank r writes = rows whose upper bilinear source row lies in r's band of the decoder
+        src_rows[r]  : rows of the UNPADDED state that pad_rows[r] maps to (earth / mirror index map)
+        """
+        g, lay, world = self.geo, self.lay, self.world
+        st0 = g.stages[0]
+        kmax = max(br.kernel for br in st0.branches)
+        stride = st0.branches[0].stride
+        p = (kmax - stride) // 2
+        pt, pb = g.padding.pad_lat if g.padding.activate else (0, 0)
+        H = g.image_height
+        self.pad_rows, self.out_rows, self.src_rows = [], [], []
+        # bilinear source rows, the kernel's arithmetic: src = fma(scale, dst + 0.5, -0.5) in fp32, clamped at 0
+        scale = float(torch.tensor(g.h_crop, dtype=torch.float32) / torch.tensor(g.h_out, dtype=torch.float32))
+        o = torch.arange(g.h_out, dtype=torch.float64)
+        src = (scale * (o + 0.5) - 0.5).float().clamp_min(0)
+        y0 = src.floor().long().clamp_max(g.h_crop - 1)
+        y1 = (y0 + 1).clamp_max(g.h_crop - 1)
+        top = pt
+        for r in range(world):
+            r0, r1 = lay.rb[0][r], lay.rb[0][r + 1]
+            a, b = max(0, stride * r0 - p), min(g.h_pad, stride * (r1 - 1) - p + kmax)
+            self.pad_rows.append((a, b))
+            rows = torch.arange(a, b)
+            if g.padding.activate and g.padding.mode == "earth":
+                sr = torch.where(rows < pt, pt - 1 - rows, torch.where(rows < pt + H, rows - pt, H - 1 - (rows - pt - H)))
+            elif g.padding.activate:
+                sr = (rows - pt).abs()
+                sr = torch.where(sr >= H, 2 * (H - 1) - sr, sr)
+            else:
+                sr = rows
+            self.src_rows.append((int(sr.min()), int(sr.max()) + 1))
+            d_lo, d_hi = 2 * r0, 2 * r1  # band of the decoder output (up_block4 doubles the stage-0 grid)
+            own = ((y0 + top) >= d_lo) & ((y0 + top) < d_hi)
+            idx = own.nonzero().flatten()
+            if idx.numel() == 0:
+                self.out_rows.append((0, 0))
+                continue
+            o_lo, o_hi = int(idx[0]), int(idx[-1]) + 1
+            if o_hi - o_lo != idx.numel() or int((y1 + top)[o_lo:o_hi].max()) > d_hi or int((y0 + top)[o_lo:o_hi].min()) < d_lo - 1:
+                raise NotImplementedError("bilinear resize reaches beyond one halo row of the decoder band")
+            self.out_rows.append((o_lo, o_hi))
+        covered = sum(b - a for a, b in self.out_rows)
+        if covered != g.h_out:
+            raise NotImplementedError("output rows are not partitioned by the decoder bands")
+
+    def _pad(self, x):
+        g = self.geo
+        lat, lon, mode = ((g.padding.pad_lat, g.padding.pad_lon, g.padding.mode) if g.padding.activate
+                          else ((0, 0), (0, 0), "earth"))
+        a, b = self.pad_rows[self.rank]
+        ops.pad_to_pixel_major_f16x2(x, lat, lon, mode, 64, self.xp_planes[0], self.xp_planes[1], rows=(a, b - a))
+
+    def _ydec_halo(self):
+        """First / last row of the rank's decoder band -> the neighbours' full-size buffers (bilinear resize halo)."""
+        lay, me, c = self.lay, self.rank, self.comm
+        d_lo, d_hi = 2 * lay.rb[0][me], 2 * lay.rb[0][me + 1]
         reqs = []
+        if me > 0:
+            reqs.append(c.recv(self.y_dec[d_lo - 1], me - 1))
+            reqs.append(c.send(self.y_dec[d_lo], me - 1))
+        if me < self.world - 1:
+            reqs.append(c.recv(self.y_dec[d_hi], me + 1))
+            reqs.append(c.send(self.y_dec[d_hi - 1], me + 1))
+        c.run(reqs)
+
+    def _unpad(self, out):
+        g = self.geo
+        pt, pl = (g.padding.pad_lat[0], g.padding.pad_lon[0]) if g.padding.activate else (0, 0)
+        o_lo, o_hi = self.out_rows[self.rank]
+        ops.unpad_resize_to_nchw(self.y_dec, g.output_channels, out, 1, g.output_channels, g.h_dec, g.w_dec, pt, pl,
+                                 g.h_crop, g.w_crop, g.h_out, g.w_out, rows=(o_lo, o_hi - o_lo))
+
+    def exchange_rows(self, t: torch.Tensor, n_ch: int, need):
+        """Make rows ``need[r]`` of ``t[0, :n_ch, 0]`` ([B=1, C, 1, H, W]) valid on every rank r, given that each rank holds
+        its own ``out_rows`` (point-to-point, compact [n_ch, rows, W] messages)."""
+        me, c = self.rank, self.comm
+        view = t[0, :n_ch, 0]
+        recvs, reqs = [], []
         for peer in range(self.world):
             if peer == me:
                 continue
-            reqs.append(self.comm.recv(self.y_dec[2 * lay.rb[0][peer]: 2 * lay.rb[0][peer + 1]], peer))
-            reqs.append(self.comm.send(self.y_dec[2 * lay.rb[0][me]: 2 * lay.rb[0][me + 1]], peer))
-        self.comm.run(reqs)
+            po_lo, po_hi = self.out_rows[peer]
+            mo_lo, mo_hi = self.out_rows[me]
+            a, b = max(need[me][0], po_lo), min(need[me][1], po_hi)      # rows I need that the peer owns
+            if b > a:
+                buf = torch.empty((n_ch, b - a, view.shape[-1]), device=t.device, dtype=t.dtype)
+                recvs.append((buf, a, b))
+                reqs.append(c.recv(buf, peer))
+            a, b = max(need[peer][0], mo_lo), min(need[peer][1], mo_hi)  # rows the peer needs that I own
+            if b > a:
+                reqs.append(c.send(view[:, a:b].contiguous(), peer))
+        c.run(reqs)
+        for buf, a, b in recvs:
+            view[:, a:b].copy_(buf)
 
-    def run(self, x: torch.Tensor) -> torch.Tensor:
+    def run_band(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """One forward on this rank's share: reads rows ``src_rows[rank]`` of ``x`` (full-size tensor, other rows are not
+        touched) and writes rows ``out_rows[rank]`` of the full-size prediction tensor."""
         g = self.geo
         self._pad(x)
         for fn, args, _tag, _fl, _by in self.steps:
             fn(*args)
-        out = torch.empty((1, g.base_output_channels, g.output_frames, g.h_out, g.w_out), device=x.device,
-                          dtype=torch.float32)
+        if out is None:
+            out = torch.empty((1, g.base_output_channels, g.output_frames, g.h_out, g.w_out), device=x.device,
+                              dtype=torch.float32)
         self._unpad(out)
+        return out
+
+    def run(self, x: torch.Tensor) -> torch.Tensor:
+        """Full state in, full prediction out on every rank (what ``model(x)`` returns)."""
+        g = self.geo
+        out = self.run_band(x)
+        flat = out.view(1, g.output_channels, 1, g.h_out, g.w_out)  # [C, T] -> C*T: rows are exchanged for every frame
+        self.exchange_rows(flat, g.output_channels, [(0, g.h_out)] * self.world)
         return out
 
 

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 8
+WXF_ABI_VERSION = 9
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -75,8 +75,8 @@ class WxfToeplitzDesc(Structure):
 _SIGNATURES = {
     "wxf_abi_version": (c_int, []),
     "wxf_last_error": (c_char_p, []),
-    "wxf_pad_to_pixel_major": (c_int, [c_void_p, c_void_p] + [c_int] * 11 + [c_void_p]),
-    "wxf_pad_to_pixel_major_f16x2": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 11 + [c_void_p]),
+    "wxf_pad_to_pixel_major": (c_int, [c_void_p, c_void_p] + [c_int] * 13 + [c_void_p]),
+    "wxf_pad_to_pixel_major_f16x2": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 13 + [c_void_p]),
     "wxf_cross_embed_toeplitz_tc": (c_int, [POINTER(WxfToeplitzDesc), c_void_p]),
     "wxf_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
     "wxf_layernorm_f16x2": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float,
@@ -100,7 +100,7 @@ _SIGNATURES = {
     "wxf_groupnorm_sums": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
     "wxf_groupnorm_stats_from_sums": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_double, c_float, c_void_p]),
     "wxf_gather_rows": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
-    "wxf_unpad_resize_to_nchw": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 10 + [c_void_p]),
+    "wxf_unpad_resize_to_nchw": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 12 + [c_void_p]),
     "wxf_copy_channels": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int64, POINTER(c_int32), POINTER(c_int32),
                                   POINTER(c_int32), c_int, c_void_p]),
 }

@@ -500,8 +500,8 @@ class CrossFormerB200(_Base):
         return out
 
     # -- forward ---------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def _plan_for(self, x: torch.Tensor):
+        """Validated input + the launch plan for its batch size / device (built on first use)."""
         if self.training:
             raise NotImplementedError("CrossFormerB200 implements the eval-mode forecast forward only: call .eval()")
         geo = self.geometry
@@ -527,8 +527,13 @@ class CrossFormerB200(_Base):
                 else:
                     plan = _Plan(geo, self._prepared, int(x.shape[0]), x.device, not self.exact_fp32)
                 self._plans[key] = plan
+        return x.contiguous(), plan
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x, plan = self._plan_for(x)
         with torch.cuda.device(x.device):
-            return plan.run(x.contiguous())
+            return plan.run(x)
 
 
 class WXFormerB200(CrossFormerB200):

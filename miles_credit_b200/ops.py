@@ -34,8 +34,10 @@ def _req(t: torch.Tensor, name: str, dtype=torch.float32):
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
 
 
-def pad_to_pixel_major(x: torch.Tensor, pad_lat, pad_lon, mode: str, ld: int, out: Optional[torch.Tensor] = None):
-    """[B, C, T, H, W] -> padded pixel-major [B, Hp, Wp, ld] (channel c*T + t)."""
+def pad_to_pixel_major(x: torch.Tensor, pad_lat, pad_lon, mode: str, ld: int, out: Optional[torch.Tensor] = None,
+                       rows=None):
+    """[B, C, T, H, W] -> padded pixel-major [B, Hp, Wp, ld] (channel c*T + t); ``rows`` = (first, count) of the padded
+    rows to write (default: all)."""
     global LAUNCHES
     _req(x, "x")
     x = x.contiguous()
@@ -44,23 +46,26 @@ def pad_to_pixel_major(x: torch.Tensor, pad_lat, pad_lon, mode: str, ld: int, ou
     if out is None:
         out = torch.empty((b, hp, wp, ld), device=x.device, dtype=torch.float32)
     m = _lib.PAD_EARTH if mode == "earth" else _lib.PAD_MIRROR
+    r0, nr = rows if rows is not None else (0, hp)
     st = _lib.load().wxf_pad_to_pixel_major(x.data_ptr(), out.data_ptr(), b, c, t, h, w, pad_lat[0], pad_lat[1],
-                                            pad_lon[0], pad_lon[1], m, ld, _stream())
+                                            pad_lon[0], pad_lon[1], m, ld, r0, nr, _stream())
     _lib.check(st, "wxf_pad_to_pixel_major")
     LAUNCHES += 1
     return out
 
 
 def pad_to_pixel_major_f16x2(x: torch.Tensor, pad_lat, pad_lon, mode: str, ld: int, out_hi: torch.Tensor,
-                             out_lo: torch.Tensor):
-    """[B, C, T, H, W] fp32 -> padded pixel-major fp16 hi/lo planes [B, Hp, Wp, ld]."""
+                             out_lo: torch.Tensor, rows=None):
+    """[B, C, T, H, W] fp32 -> padded pixel-major fp16 hi/lo planes [B, Hp, Wp, ld]; ``rows`` = (first, count) of the
+    padded rows to write (default: all)."""
     global LAUNCHES
     _req(x, "x")
     x = x.contiguous()
     b, c, t, h, w = x.shape
     m = _lib.PAD_EARTH if mode == "earth" else _lib.PAD_MIRROR
+    r0, nr = rows if rows is not None else (0, h + pad_lat[0] + pad_lat[1])
     st = _lib.load().wxf_pad_to_pixel_major_f16x2(x.data_ptr(), out_hi.data_ptr(), out_lo.data_ptr(), b, c, t, h, w,
-                                                  pad_lat[0], pad_lat[1], pad_lon[0], pad_lon[1], m, ld, _stream())
+                                                  pad_lat[0], pad_lat[1], pad_lon[0], pad_lon[1], m, ld, r0, nr, _stream())
     _lib.check(st, "wxf_pad_to_pixel_major_f16x2")
     LAUNCHES += 1
 
@@ -311,10 +316,12 @@ def gather_rows(src: torch.Tensor, ld_src: int, idx: torch.Tensor, dst: torch.Te
 
 
 def unpad_resize_to_nchw(y: torch.Tensor, ld: int, out: torch.Tensor, B: int, C: int, Hd: int, Wd: int, top: int,
-                         left: int, Hc: int, Wc: int, Ho: int, Wo: int):
+                         left: int, Hc: int, Wc: int, Ho: int, Wo: int, rows=None):
+    """``rows`` = (first, count) of the output rows to write (default: all)."""
     global LAUNCHES
+    o0, n_out = rows if rows is not None else (0, Ho)
     st = _lib.load().wxf_unpad_resize_to_nchw(y.data_ptr(), ld, out.data_ptr(), B, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo,
-                                              _stream())
+                                              o0, n_out, _stream())
     _lib.check(st, "wxf_unpad_resize_to_nchw")
     LAUNCHES += 1
 

@@ -33,18 +33,19 @@ class EmulatedLib:
         self.calls = []
 
     def wxf_abi_version(self):
-        return 8
+        return 9
 
     def wxf_last_error(self):
         return b"emulator"
 
-    def wxf_pad_to_pixel_major(self, x, xp, B, C, T, H, W, pt, pb, pl, pr, mode, ld, stream):
+    def wxf_pad_to_pixel_major(self, x, xp, B, C, T, H, W, pt, pb, pl, pr, mode, ld, row0, nrows, stream):
         self.calls.append("pad")
         xs = _t(_arr(x, B * C * T * H * W)).view(B, C * T, H, W)
         Hp, Wp = H + pt + pb, W + pl + pr
+        assert 0 <= row0 and row0 + nrows <= Hp
         out = _t(_arr(xp, B * Hp * Wp * ld)).view(B, Hp, Wp, ld)
-        out.zero_()
-        for r in range(Hp):
+        out[:, row0: row0 + nrows].zero_()
+        for r in range(row0, row0 + nrows):
             roll = False
             if mode == 0:
                 if r < pt:
@@ -63,13 +64,15 @@ class EmulatedLib:
             out[:, r, :, : C * T] = xs[:, :, sr, :][:, :, j].permute(0, 2, 1)
         return 0
 
-    def wxf_pad_to_pixel_major_f16x2(self, x, xp_hi, xp_lo, B, C, T, H, W, pt, pb, pl, pr, mode, ld, stream):
+    def wxf_pad_to_pixel_major_f16x2(self, x, xp_hi, xp_lo, B, C, T, H, W, pt, pb, pl, pr, mode, ld, row0, nrows,
+                                     stream):
         Hp, Wp = H + pt + pb, W + pl + pr
         tmp = np.zeros(B * Hp * Wp * ld, dtype=np.float32)
-        self.wxf_pad_to_pixel_major(x, tmp.ctypes.data, B, C, T, H, W, pt, pb, pl, pr, mode, ld, stream)
+        self.wxf_pad_to_pixel_major(x, tmp.ctypes.data, B, C, T, H, W, pt, pb, pl, pr, mode, ld, row0, nrows, stream)
         hi, lo = self._split(torch.from_numpy(tmp))
-        self._harr(xp_hi, tmp.size).copy_(hi)
-        self._harr(xp_lo, tmp.size).copy_(lo)
+        sel = slice(row0, row0 + nrows)  # only the requested rows are written
+        self._harr(xp_hi, tmp.size).view(B, Hp, Wp, ld)[:, sel].copy_(hi.view(B, Hp, Wp, ld)[:, sel])
+        self._harr(xp_lo, tmp.size).view(B, Hp, Wp, ld)[:, sel].copy_(lo.view(B, Hp, Wp, ld)[:, sel])
         return 0
 
     def wxf_cross_embed_toeplitz_tc(self, dref, stream):
@@ -410,7 +413,7 @@ class EmulatedLib:
         _t(_arr(y, (B * HW - 1) * ldy + C)).as_strided((B, HW, C), (HW * ldy, ldy, 1)).copy_(v)
         return 0
 
-    def wxf_unpad_resize_to_nchw(self, y, ld, outp, B, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, stream):
+    def wxf_unpad_resize_to_nchw(self, y, ld, outp, B, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, o0, n_out, stream):
         self.calls.append("unpad_resize")
         ys = _t(_arr(y, (B * Hd * Wd - 1) * ld + C)).as_strided((B, Hd, Wd, C), (Hd * Wd * ld, Wd * ld, ld, 1))
         crop = ys[:, top: top + Hc, left: left + Wc].permute(0, 3, 1, 2)
@@ -429,7 +432,8 @@ class EmulatedLib:
         x0, x1, lx0, lx1 = axis(Wc, Wo)
         top_ = crop[:, :, y0][..., x0] * lx0 + crop[:, :, y0][..., x1] * lx1
         bot_ = crop[:, :, y1][..., x0] * lx0 + crop[:, :, y1][..., x1] * lx1
-        out.copy_(top_ * ly0[:, None] + bot_ * ly1[:, None])
+        assert 0 <= o0 and o0 + n_out <= Ho
+        out[:, :, o0: o0 + n_out].copy_((top_ * ly0[:, None] + bot_ * ly1[:, None])[:, :, o0: o0 + n_out])
         return 0
 
     def wxf_copy_channels(self, dst, dst_C, src, src_C, B, plane, d0, s0, ln, n, stream):

@@ -43,6 +43,24 @@ def main():
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         out[name] = {"rel_max_vs_single_gpu": err, "ranks_identical": bool(torch.equal(lo, hi)),
                      "repeatable": bool(torch.equal(y2, y3)), "finite": bool(torch.isfinite(y2).all())}
+        # sharded rollout (state kept sharded, halo rows only) vs the full-state rollout of the same decomposed model
+        from miles_credit_b200.rollout import Rollout
+
+        geo_ = model.geometry
+        n_prog = geo_.channels * geo_.levels + geo_.surface_channels
+        xs, xf = x.clone(), x.clone()
+        ro = Rollout(model)
+        for _ in range(3):
+            ys = ro.step(xs)
+            yf = model(xf)
+            xf[:, :n_prog] = yf[:, :n_prog]
+        a, b = ro.own_rows(xs)
+        e_own = (ys[..., a:b, :] - yf[..., a:b, :]).abs().max() if b > a else torch.zeros((), device=dev)
+        full = ro.gather(ys.clone())
+        e_full = (full - yf).abs().max()
+        e = torch.stack([e_own, e_full]) / yf.abs().max()
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        out[name]["sharded_rollout_rel_max"] = float(e.max())
         del model
         torch.cuda.empty_cache()
     if rank == 0:

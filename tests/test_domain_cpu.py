@@ -77,6 +77,92 @@ def test_domain_decomposition_matches_oracle(tmp_path, world, dps):
         assert torch.equal(y, ys[0])
 
 
+class _FakeModel:
+    """What rollout.Rollout needs from CrossFormerB200, with the plan built on CPU memory (emulated ABI)."""
+
+    def __init__(self, geo, plan, manager):
+        self.geometry, self._domain, self._plans = geo, manager, {0: plan}
+
+    def _plan_for(self, x):
+        return x, self._plans[0]
+
+
+def _rollout_worker(rank, world, port, out_dir, steps):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from abi_emulator import EmulatedLib
+    from miles_credit_b200 import lib as wlib
+    from miles_credit_b200 import model as wmodel
+    from miles_credit_b200 import ops
+    from miles_credit_b200.domain import DomainParallelManager, DomainPlan
+    from miles_credit_b200.rollout import Rollout
+    from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
+    from miles_credit_b200.weights import prepare
+
+    torch.set_num_threads(2)
+    wlib._lib = EmulatedLib()
+    ops._stream = lambda: 0
+    ops._req = lambda *a, **k: None
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        geo = build_geometry(**_kwargs())
+        sd = synthetic_state_dict(geo, seed=21)
+        wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
+        dm = DomainParallelManager(world, world)
+        plan = DomainPlan(geo, wts, dm.domain_rank, dm.domain_world_size, torch.device("cpu"), dm.domain_group)
+        ro = Rollout(_FakeModel(geo, plan, dm))
+        assert ro.sharded
+        x = synthetic_input(geo, batch=1, seed=21)
+        for _ in range(steps):
+            y = ro.step(x)
+        o_lo, o_hi = ro.own_rows(x)
+        torch.save({"rows": (o_lo, o_hi), "y": y[..., o_lo:o_hi, :].clone(), "src": plan.src_rows[rank],
+                    "x": x[..., plan.src_rows[rank][0]: plan.src_rows[rank][1], :].clone()},
+                   os.path.join(out_dir, f"r{rank}.pt"))
+        full = ro.gather(y.clone())
+        torch.save(full, os.path.join(out_dir, f"full{rank}.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_rollout_matches_oracle_rollout(tmp_path, world):
+    """Two steps with the state kept sharded (halo rows only) == two oracle steps on the full state."""
+    from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
+    from oracle import crossformer_oracle as oracle
+
+    steps = 2
+    mp.spawn(_rollout_worker, args=(world, _free_port(), str(tmp_path), steps), nprocs=world, join=True)
+    geo = build_geometry(**_kwargs())
+    sd = synthetic_state_dict(geo, seed=21)
+    x = synthetic_input(geo, batch=1, seed=21)
+    n_prog = geo.channels * geo.levels + geo.surface_channels
+    with torch.no_grad():
+        for _ in range(steps):
+            y = oracle.forward(x, sd, geo)
+            x = x.clone()
+            x[:, :n_prog] = y[:, :n_prog]  # update_x (datasets/gen_2/channel_utils.py:253-291)
+    got = torch.zeros_like(y)
+    covered = 0
+    for r in range(world):
+        d = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        a, b = d["rows"]
+        got[..., a:b, :] = d["y"]
+        covered += b - a
+        sa, sb = d["src"]
+        assert sa <= a and b <= sb  # a rank keeps at least its own rows of the state current
+        ex = float((d["x"] - x[..., sa:sb, :]).abs().max() / x.abs().max())
+        assert ex < 5e-5, (r, ex)
+    assert covered == geo.h_out
+    err = float((got - y).abs().max() / y.abs().max())
+    print("sharded rollout rel-max", err)
+    assert err < 5e-5, err
+    for r in range(world):
+        full = torch.load(os.path.join(tmp_path, f"full{r}.pt"))
+        assert torch.equal(full, got)
+
+
 @pytest.mark.parametrize("name,world", [("unit", 2), ("unit", 3), ("wxformer_6h_025deg", 2), ("wxformer_6h_025deg", 8)])
 def test_layout_partitions(name, world):
     from miles_credit_b200.domain import DomainLayout, _pixel_maps
