@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--profile-out", default=None, help="write the per-launch CUDA-event table (JSON) here")
     ap.add_argument("--parallel", default="domain", choices=["domain", "replicas"],
                     help="N>1: one forecast decomposed over the N GPUs (strong scaling) or N independent forecasts")
+    ap.add_argument("--graph", type=int, default=1,
+                    help="1: Rollout.step replays one CUDA graph per step (kernels + NCCL exchanges); 0: eager launches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -230,8 +232,16 @@ def main():
 
         convert_to_domain_parallel(model)
     jobs = 1 if domain else world  # forecasts advanced per step by the whole job
-    ro = Rollout(model)
     x = synthetic_input(geo, batch=1, seed=1000 + (0 if domain else rank)).to(dev)
+    ro = Rollout(model, graph=bool(args.graph))
+    graph_note = "cuda graph replay" if args.graph else "eager launches"
+    if args.graph:
+        try:
+            ro.step(x)
+        except Exception as exc:  # capture refused (driver / NCCL): measure the eager path and say so
+            print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); eager launches", file=sys.stderr)
+            ro = Rollout(model, graph=False)
+            graph_note = "eager launches (graph capture failed)"
     n_prog = ro.n_prog
     n_dyn = max(geo.input_only_channels // 2, 1)  # dynamic forcing (2 of the 4 input-only channels at 0.25 deg)
 
@@ -264,20 +274,27 @@ def main():
     forcing_dev = torch.empty(plane, device=dev)
     o_lo, o_hi = ro.own_rows(x)  # decomposed forecast: every rank hands ITS rows of the prediction to the host
     y_host = [torch.empty((1, *geo.out_shape[:-2], o_hi - o_lo, geo.out_shape[-1])).pin_memory() for _ in range(2)]
+    y_snap = ([torch.empty(y_host[0].shape, device=dev) for _ in range(2)] if (ro.graph or ro.sharded) and o_hi > o_lo
+              else None)
     copy_stream = torch.cuda.Stream(device=dev)
     done = [torch.cuda.Event(), torch.cuda.Event()]
 
     def e2e_step(i):
         forcing_dev.copy_(forcing_host[i & 1], non_blocking=True)           # H2D of this step's forcing channels
         y = ro.step(x, forcing_dev, n_dyn)
-        ready = torch.cuda.Event()
-        ready.record()
         if o_hi == o_lo:
             return
+        if y_snap is not None:  # the rollout reuses its prediction buffer: copy this rank's rows aside (device, ~0.1 ms)
+            y_snap[i & 1].copy_(y[..., o_lo:o_hi, :])
+            src = y_snap[i & 1]
+        else:
+            src = y[..., o_lo:o_hi, :]
+        ready = torch.cuda.Event()
+        ready.record()
         with torch.cuda.stream(copy_stream):                                  # D2H of the prediction, overlapped
             copy_stream.wait_event(ready)
-            y_host[i & 1].copy_(y[..., o_lo:o_hi, :], non_blocking=True)
-            y.record_stream(copy_stream)
+            y_host[i & 1].copy_(src, non_blocking=True)
+            src.record_stream(copy_stream)
             done[i & 1].record(copy_stream)
 
     for i in range(2):
@@ -354,7 +371,7 @@ def main():
                         "rows; the state stays sharded between steps)" if domain
                         else f"{world} independent forecasts (replicas)"),
                        "l2": "no flush needed: one step streams >3 GB of activations through a 126 MB L2",
-                       "flops_per_step": fl["total"], "finite": finite},
+                       "flops_per_step": fl["total"], "finite": finite, "launch": graph_note},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "rollout via Rollout.step: forcing channels H2D from pinned memory, prediction D2H to pinned "
@@ -369,9 +386,12 @@ def main():
             line["replicas"] = replicas
         print(json.dumps(line), flush=True)
     if world > 1:
-        import torch.distributed as dist
-
-        dist.destroy_process_group()
+        # Captured graphs hold NCCL work: tearing the communicator down under them deadlocks (seen on 2 GPUs), so the ranks
+        # meet at a barrier, flush and leave without running the NCCL destructors.
+        barrier(world)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -397,13 +397,14 @@ class _Plan:
         ops.unpad_resize_to_nchw(self.y_dec, g.output_channels, out, B, g.output_channels, g.h_dec, g.w_dec, pt, pl,
                                  g.h_crop, g.w_crop, g.h_out, g.w_out)
 
-    def run(self, x: torch.Tensor) -> torch.Tensor:
+    def run(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         g, B = self.geo, self.batch
         self._pad(x)
         for fn, args, _tag, _fl, _by in self.steps:
             fn(*args)
-        out = torch.empty((B, g.base_output_channels, g.output_frames, g.h_out, g.w_out), device=x.device,
-                          dtype=torch.float32)
+        if out is None:
+            out = torch.empty((B, g.base_output_channels, g.output_frames, g.h_out, g.w_out), device=x.device,
+                              dtype=torch.float32)
         self._unpad(out)
         return out
 

@@ -82,6 +82,29 @@ def test_rollout_two_steps_vs_oracle():
     assert relmax(xs.cpu(), xo) < TOL
 
 
+def test_rollout_cuda_graph_replay_equals_eager_launches():
+    """Rollout(graph=True) captures one step (kernels + state update) and replays it: same bits as eager launches."""
+    kw = workload("unit")
+    geo = build_geometry(**kw)
+    sd = synthetic_state_dict(geo, seed=5)
+    model = CrossFormerB200(**kw)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    from miles_credit_b200.rollout import Rollout
+
+    x0 = synthetic_input(geo, batch=1, seed=5).cuda()
+    n_dyn = max(geo.input_only_channels // 2, 1)
+    frc = torch.randn(1, n_dyn, 1, geo.image_height, geo.image_width, device="cuda")
+    xe, xg = x0.clone(), x0.clone()
+    eager, graph = Rollout(model), Rollout(model, graph=True)
+    for _ in range(3):
+        ye = eager.step(xe, frc, n_dyn)
+        yg = graph.step(xg, frc, n_dyn)
+        assert torch.equal(ye, yg)
+    assert torch.equal(xe, xg)
+    assert graph.launches_per_replay > 0
+
+
 @pytest.mark.parametrize("exact", [False, True], ids=["tensorcore", "exactfp32"])
 def test_forward_wxformer_6h_1deg_vs_oracle(exact):
     """BASELINE config[1]: the 0.25-degree architecture (dims 128..1024, depth 2/2/8/2, lws 10) on the 181x360 grid."""

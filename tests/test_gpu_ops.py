@@ -42,6 +42,34 @@ def test_pad_bit_exact(mode, lat, lon):
     assert torch.count_nonzero(out[..., c * t:]) == 0
 
 
+@pytest.mark.parametrize("mode,lat,lon,ld,ct", [("earth", (3, 4), (5, 2), 16, (5, 2)), ("mirror", (2, 3), (4, 4), 8, (3, 2)),
+                                                ("earth", (9, 9), (70, 61), 72, (35, 2)), ("earth", (4, 4), (0, 0), 64, (60, 1))])
+def test_pad_vectorised_path_and_row_range(mode, lat, lon, ld, ct):
+    """ld % 8 == 0 takes the 64x64-tile kernel (16-byte stores); a row range writes exactly those padded rows."""
+    torch.manual_seed(4)
+    c, t = ct
+    x = torch.randn(2, c, t, 11, 40)
+    ref = oracle.pad_field(x, mode, lat, lon)
+    b, _, _, hp, wp = ref.shape
+    ref_pm = ref.reshape(b, c * t, hp, wp).permute(0, 2, 3, 1)
+    out = ops.pad_to_pixel_major(x.to(DEV), lat, lon, mode, ld).cpu()
+    assert torch.equal(out[..., : c * t], ref_pm)
+    assert torch.count_nonzero(out[..., c * t:]) == 0
+    # fp16 hi/lo planes of the same pass, rows [r0, r0 + n) only
+    r0, n = 2, hp - 5
+    hi = torch.full((b, hp, wp, ld), 7.0, device=DEV, dtype=torch.float16)
+    lo = torch.full((b, hp, wp, ld), 7.0, device=DEV, dtype=torch.float16)
+    ops.pad_to_pixel_major_f16x2(x.to(DEV), lat, lon, mode, ld, hi, lo, rows=(r0, n))
+    got = (hi.float() + lo.float()).cpu()
+    assert torch.all(got[:, :r0] == 14.0) and torch.all(got[:, r0 + n:] == 14.0)      # untouched rows
+    err = (got[:, r0: r0 + n, :, : c * t] - ref_pm[:, r0: r0 + n]).abs().max() / ref_pm.abs().max()
+    assert float(err) < 2e-6                                                          # 22 significant bits
+    assert torch.count_nonzero(got[:, r0: r0 + n, :, c * t:]) == 0
+    part = torch.full((b, hp, wp, ld), -3.0, device=DEV)
+    ops.pad_to_pixel_major(x.to(DEV), lat, lon, mode, ld, out=part, rows=(r0, n))
+    assert torch.equal(part[:, r0: r0 + n].cpu(), out[:, r0: r0 + n]) and torch.all(part[:, :r0] == -3.0)
+
+
 def test_pad_golden_reference_vectors(golden_dir):
     fx = torch.load(os.path.join(golden_dir, "padding.pt"), weights_only=False)
     x = fx["x"]
@@ -206,6 +234,23 @@ def test_unpad_resize(hd, wd, top, left, hc, wc, ho, wo, c):
     out = torch.empty(b, c, ho, wo, device=DEV)
     ops.unpad_resize_to_nchw(ypm.to(DEV), ld, out, b, c, hd, wd, top, left, hc, wc, ho, wo)
     assert torch.allclose(out.cpu(), ref, atol=2e-6)
+
+
+def test_unpad_resize_row_range():
+    """Only output rows [o0, o0 + n) are written (a lat-band rank writes its own rows of the prediction)."""
+    torch.manual_seed(5)
+    b, c, hd, wd, top, left, hc, wc, ho, wo = 1, 64, 30, 50, 5, 6, 20, 36, 21, 36
+    y = torch.randn(b, c, hd, wd)
+    ref = oracle.bilinear_resize(y[..., top: top + hc, left: left + wc], ho, wo)
+    ypm = to_pm(y).contiguous().to(DEV)
+    full = torch.empty(b, c, ho, wo, device=DEV)
+    ops.unpad_resize_to_nchw(ypm, c, full, b, c, hd, wd, top, left, hc, wc, ho, wo)
+    assert torch.allclose(full.cpu(), ref, atol=2e-6)
+    part = torch.full((b, c, ho, wo), 9.0, device=DEV)
+    ops.unpad_resize_to_nchw(ypm, c, part, b, c, hd, wd, top, left, hc, wc, ho, wo, rows=(4, 9))
+    assert torch.equal(part[:, :, 4:13], full[:, :, 4:13])
+    assert torch.all(part[:, :, :4] == 9.0) and torch.all(part[:, :, 13:] == 9.0)
+    ops.unpad_resize_to_nchw(ypm, c, part, b, c, hd, wd, top, left, hc, wc, ho, wo, rows=(0, 0))  # empty band: no-op
 
 
 def test_copy_channels():
