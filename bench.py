@@ -188,10 +188,10 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
-    rank, world, local = dist_setup(args.gpus)
-    if args.impl == "reference":
-        run_reference(args, rank, world)
+    if args.impl == "reference":  # CPU arm: rank 0 alone works, no process group (the other ranks exit 0 at once)
+        run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return
+    rank, world, local = dist_setup(args.gpus)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
@@ -332,6 +332,10 @@ def main():
         achieved = tf["flops"] / (tf["ms"] / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": pk["bf16_tflops_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+                "traffic_note": "per-launch DRAM bytes are in profiles/r1_ncu_full_stage0_v26_raw.csv (stage-0 launches: "
+                                "ff1 173 MB read + 612 MB written vs 819 MB algorithmic)",
+                "executed": {"what": "f16x2 scheme: 3 fp16 tensor-core passes per algorithmic product",
+                             "tflops": 3.0 * achieved, "frac": 3.0 * achieved / pk["bf16_tflops_sustained"]},
                 "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
                 "launches_per_step": tf["launches"], "ms_per_launch": tf["ms"] / tf["launches"],
                 "share_of_step": tf["ms"] / tot_ms}
