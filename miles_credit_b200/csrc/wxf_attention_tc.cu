@@ -455,6 +455,7 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + A2_OFF_BAR + 8 * (2 * A2_NST + 12));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  wxf_pdl_trigger();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < A2_NST; ++s) {
@@ -486,6 +487,7 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  wxf_pdl_wait();  // barrier init, TMEM allocation and the shared-memory zero fill overlap the previous kernel's tail
 
   // position-bias tile (identical for every tile of the launch) -> TMEM columns [256, 384), written by group 0
   if (warp >= 2 && warp < 6) {
@@ -892,7 +894,7 @@ extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, i
       attr2_set = true;
     }
     const int64_t blocks2 = p.ntiles < (int64_t)sms ? p.ntiles : (int64_t)sms;
-    window_attention_tc2_kernel<<<(unsigned)blocks2, A2_THREADS, A2_SMEM, (cudaStream_t)stream>>>(tm_hi, tm_lo, p);
+    wxf_launch(window_attention_tc2_kernel, dim3((unsigned)blocks2), dim3(A2_THREADS), A2_SMEM, (cudaStream_t)stream, tm_hi, tm_lo, p);
     WXF_CHECK_LAUNCH("window_attention_tc2");
     return 0;
   }

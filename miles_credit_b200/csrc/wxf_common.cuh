@@ -24,6 +24,35 @@ extern thread_local char wxf_err_buf[512];
     }                                                                                              \
   } while (0)
 
+// ---- programmatic dependent launch (WXF_PDL=1; round-2 candidate, off by default) --------------------------------------
+// With the attribute, kernel N+1 may be scheduled while kernel N drains: its prologue (barrier init, TMEM allocation,
+// index math) overlaps N's tail, and griddepcontrol.wait holds it before the first access to memory N produced.  Every
+// kernel triggers its dependents at entry and waits before touching global memory; without the launch attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void wxf_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void wxf_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool wxf_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void wxf_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  if (wxf_pdl_enabled()) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+  } else {
+    kernel<<<grid, block, smem, st>>>(args...);
+  }
+}
+
 __host__ __device__ static inline bool wxf_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __device__ __forceinline__ float wxf_warp_sum(float v) {

@@ -113,6 +113,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     m0 = (int64_t)blockIdx.y * BLOCK_M;
   }
 
+  wxf_pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -130,6 +131,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  wxf_pdl_wait();  // everything above overlaps the previous kernel's tail (programmatic dependent launch)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -367,6 +369,7 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = p.num_ksteps;
 
+  wxf_pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -387,6 +390,7 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  wxf_pdl_wait();  // everything above overlaps the previous kernel's tail (programmatic dependent launch)
 
   // tile t -> (n tile, m tile, phase); n fastest so CTAs running concurrently share the A tile in L2
   auto decode = [&](int t, int& n0, int& z, int64_t& m0, int& tb, int& oy0, int& ox0) {
@@ -705,6 +709,255 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   }
 }
 
+// ---- small-K GEMM (K <= 128: to_qkv / to_out / FF fc1 of stage 0) with the weight tile RESIDENT in shared memory ------
+// One TMA tile load takes ~2500 cycles (profiles/r1_tma_microbench.txt) and a K = 128 tile is only 2 K-steps = 1536 cycles
+// of MMA: with the 2-stage ring of the generic kernel every tile exposes the full load latency (ff1 at stage 0: 8000
+// cycles per tile).  Here the grid is a multiple of the number of N tiles, so a CTA keeps ONE N tile for its whole life:
+// W (hi|lo per K-step, 64 KB) is loaded once, and the ring streams only A (32 KB per K-step, 3 stages = 1.5 tiles ahead).
+// Same MMA issue, TMEM double buffering and 16-warp TMA-store epilogue as tc_persistent_kernel<GEMM, 16, 2>.
+constexpr int RW_STA = 3;                                  // A stages (hi + lo planes of one K-step: 32 KB)
+constexpr int RW_EW = 16;
+constexpr int RW_A_BYTES = 2 * TILE_BYTES;
+constexpr int RW_W_BYTES = 2 * P_BN * BLOCK_K * 2;         // W_hi | W_lo of one K-step: 32 KB
+constexpr int RW_SMEM = 2 * RW_W_BYTES + RW_STA * RW_A_BYTES + RW_EW * 4096 + 8 * (2 * RW_STA + 5) + 16 + 1024;
+
+__global__ void __launch_bounds__(64 + 32 * RW_EW, 1)
+tc_resident_w_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO_hi,
+                     const __grid_constant__ CUtensorMap tmO_lo, const __grid_constant__ TcParams p, const int n_tiles,
+                     const int m_tiles, const int total_tiles) {
+  constexpr bool CONV = false;
+  constexpr int EW = RW_EW, STAGES = RW_STA, BN = P_BN, W_BYTES = P_BN * BLOCK_K * 2;
+  constexpr int CW = 128 / (EW / 4);
+  constexpr int NCH = CW / 32;
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  constexpr int OFF_A = 2 * RW_W_BYTES;                    // [W k-step 0 | W k-step 1 | A ring | staging | barriers]
+  constexpr int OFF_STG = OFF_A + STAGES * RW_A_BYTES;
+  constexpr int OFF_BARS = OFF_STG + EW * 4096;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  float* staging = reinterpret_cast<float*>(gen + OFF_STG);
+  const uint32_t bar_base = base + OFF_BARS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + OFF_BARS + 8 * (2 * STAGES + 5));
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t w_bar = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = p.num_ksteps;  // 1 or 2
+
+  wxf_pdl_trigger();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), EW);
+    }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  wxf_pdl_wait();  // everything above overlaps the previous kernel's tail (programmatic dependent launch)
+
+  // gridDim.x is a multiple of n_tiles: t % n_tiles == blockIdx.x % n_tiles for every tile of this CTA
+  auto decode = [&](int t, int& n0, int& z, int64_t& m0, int& tb, int& oy0, int& ox0) {
+    n0 = (t % n_tiles) * BN;
+    m0 = (int64_t)(t / n_tiles) * BLOCK_M;
+    z = 0; tb = 0; oy0 = 0; ox0 = 0;
+  };
+  (void)m_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int n0 = (int)(blockIdx.x % n_tiles) * BN;
+      mbar_expect_tx(w_bar, (uint32_t)(num_k * RW_W_BYTES));
+      for (int ks = 0; ks < num_k; ++ks) {
+        tma_load_2d(&tmW_hi, w_bar, base + ks * RW_W_BYTES, ks * BLOCK_K, n0);
+        tma_load_2d(&tmW_lo, w_bar, base + ks * RW_W_BYTES + W_BYTES, ks * BLOCK_K, n0);
+      }
+      uint32_t g = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * BLOCK_M;
+        for (int ks = 0; ks < num_k; ++ks, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (g / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t st = base + OFF_A + s * RW_A_BYTES;
+          mbar_expect_tx(full_bar(s), (uint32_t)RW_A_BYTES);
+          tma_load_2d(&tmA_hi, full_bar(s), st, ks * BLOCK_K, m0);
+          tma_load_2d(&tmA_lo, full_bar(s), st + TILE_BYTES, ks * BLOCK_K, m0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(w_bar, 0);
+      uint32_t g = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        const int slot = i & 1;
+        mbar_wait(tempty_bar(slot), (((uint32_t)i >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(slot * 2 * BN), d1 = d0 + BN;
+        for (int ks = 0; ks < num_k; ++ks, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (g / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = base + OFF_A + s * RW_A_BYTES, sw = base + ks * RW_W_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t a_hi = umma_desc_sw128(sa + k * 32);
+            const uint64_t a_lo = umma_desc_sw128(sa + TILE_BYTES + k * 32);
+            const uint64_t w_hi = umma_desc_sw128(sw + k * 32);
+            const uint32_t acc = (ks | k) ? 1u : 0u;
+            tc_mma_f16(d0, a_hi, w_hi, IDESC2, acc);  // A_hi [W_hi | W_lo] -> both accumulators of the slot
+            tc_mma_f16(d1, a_lo, w_hi, IDESC, 1u);    // + A_lo W_hi
+          }
+          tc_commit(empty_bar(s));
+        }
+        tc_commit(tfull_bar(slot));
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quarter = warp & 3, half = ew >> 2;
+      // GEMM mode: lane = output row.  Accumulator row -> registers -> scale/bias/GELU/residual -> 32-column chunks
+      // staged in swizzled shared memory -> TMA store (fp32 tile and/or fp16 hi/lo plane tiles).
+      uint8_t* stg_b = reinterpret_cast<uint8_t*>(staging) + ew * 4096;
+      const uint32_t stg_a = base + OFF_STG + ew * 4096;
+      const int row = quarter * 32 + lane;
+      int i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        const int slot = i & 1;
+        int n0, z, tb, oy0, ox0;
+        int64_t m0;
+        decode(t, n0, z, m0, tb, oy0, ox0);
+        const int nb0 = n0 + half * CW;
+        const int64_t m = m0 + row;
+        // residual prefetch (the row's 64 columns), issued before waiting for the accumulator
+        float4 rres[CW / 4];
+        if (p.res) {
+#pragma unroll
+          for (int q = 0; q < CW / 4; ++q) {
+            rres[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < p.M && nb0 + 4 * q < p.N) rres[q] = *reinterpret_cast<const float4*>(p.res + m * p.ldr + nb0 + 4 * q);
+          }
+        }
+        mbar_wait(tfull_bar(slot), ((uint32_t)i >> 1) & 1u);
+        tc_fence_after();
+        float v[CW];
+        {
+          const uint32_t tb_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 2 * BN + half * CW);
+          uint32_t r[32];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            tmem_ld32(tb_addr + (uint32_t)(c * 32), r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(r[j]);
+            tmem_ld32(tb_addr + (uint32_t)(BN + c * 32), r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[c * 32 + j] += __uint_as_float(r[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(slot));  // TMEM slot free for the MMA of tile i+2
+
+#pragma unroll
+        for (int cb = 0; cb < NCH; ++cb) {
+          const int nb = nb0 + cb * 32;
+          if (nb >= p.N) break;  // warp-uniform
+          {
+            const float2 sc = make_float2(p.w_scale, p.w_scale);
+            float2* v2 = reinterpret_cast<float2*>(v + cb * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {  // packed fp32 math (FFMA2): scale + bias, GELU, residual
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias && nb + 4 * q < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 4 * q));
+              float2 a0 = __ffma2_rn(v2[2 * q], sc, make_float2(b4.x, b4.y));
+              float2 a1 = __ffma2_rn(v2[2 * q + 1], sc, make_float2(b4.z, b4.w));
+              if (p.act == WXF_ACT_GELU_ERF) {
+                a0 = wxf_gelu_erf2(a0);
+                a1 = wxf_gelu_erf2(a1);
+              }
+              if (p.res) {
+                const float4 rr = rres[cb * 8 + q];
+                a0 = __fadd2_rn(a0, make_float2(rr.x, rr.y));
+                a1 = __fadd2_rn(a1, make_float2(rr.z, rr.w));
+              }
+              v2[2 * q] = a0;
+              v2[2 * q + 1] = a1;
+            }
+          }
+          if (p.out) {
+            if (lane == 0) bulk_wait_read0();  // previous TMA store has finished reading the staging buffer
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)  // fp32 row of 128 B, SWIZZLE_128B: 16-byte chunk ^= row % 8
+              *reinterpret_cast<float4*>(stg_b + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                  make_float4(v[cb * 32 + 4 * q], v[cb * 32 + 4 * q + 1], v[cb * 32 + 4 * q + 2], v[cb * 32 + 4 * q + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmO, stg_a, nb, (int)(m0 + quarter * 32));
+              bulk_commit();
+            }
+          }
+          if (p.out_hi) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // fp16 rows of 64 B, SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
+              __align__(16) __half2 h8[4];
+              __align__(16) __half2 l8[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                wxf_split2_f16x2(v[cb * 32 + 8 * q + 2 * e], v[cb * 32 + 8 * q + 2 * e + 1], h8[e], l8[e]);
+              const int off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
+              *reinterpret_cast<uint4*>(stg_b + off) = *reinterpret_cast<const uint4*>(h8);
+              *reinterpret_cast<uint4*>(stg_b + 2048 + off) = *reinterpret_cast<const uint4*>(l8);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmO_hi, stg_a, nb, (int)(m0 + quarter * 32));
+              tma_store_2d(&tmO_lo, stg_a + 2048, nb, (int)(m0 + quarter * 32));
+              bulk_commit();
+            }
+          }
+        }
+      }
+      if (lane == 0) bulk_wait0();  // all stores of this warp have landed before the CTA exits
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ---- host side: TMA descriptors -----------------------------------------------------------------------------
 
 template <int BN, int STAGES>
@@ -723,7 +976,7 @@ int launch(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap
     if (e != cudaSuccess) WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", SMEM, cudaGetErrorString(e));
     attr_set = true;
   }
-  tc_contract_kernel<BN, STAGES, MODE><<<grid, NUM_THREADS, SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
+  wxf_launch(tc_contract_kernel<BN, STAGES, MODE>, grid, dim3(NUM_THREADS), SMEM, st, ta_hi, ta_lo, tw_hi, tw_lo, p);
   WXF_CHECK_LAUNCH("tc_contract");
   return 0;
 }
@@ -744,6 +997,15 @@ bool concat_enabled() {
   if (v < 0) {
     const char* e = getenv("WXF_TC_CONCAT");
     v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+bool resident_w_enabled() {  // WXF_GEMM_RESIDENT_W=1: K <= 128 GEMMs keep their weight tile in shared memory (round-2 candidate)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXF_GEMM_RESIDENT_W");
+    v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
 }
@@ -772,8 +1034,8 @@ int launch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const 
   const int64_t total = (int64_t)n_tiles * m_tiles * phases;
   if (total > INT32_MAX) WXF_FAIL(WXF_EINVAL, "tc: too many tiles");
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  tc_persistent_kernel<MODE, EW, STAGES><<<grid, 64 + 32 * EW, p_smem<EW, STAGES>(), st>>>(
-      ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, n_tiles, m_tiles, (int)total);
+  wxf_launch(tc_persistent_kernel<MODE, EW, STAGES>, dim3(grid), dim3(64 + 32 * EW), p_smem<EW, STAGES>(), st, ta_hi, ta_lo,
+             tw_hi, tw_lo, to, to_hi, to_lo, p, n_tiles, m_tiles, (int)total);
   WXF_CHECK_LAUNCH("tc_persistent");
   return 0;
 }
@@ -840,6 +1102,21 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
       if ((rc = make_map(&to_lo, d->out_lo, 2, dims, strides, box, es, 64))) return rc;
     }
     const int nt = (d->N + BN - 1) / BN, mt = (int)((d->M + BLOCK_M - 1) / BLOCK_M);
+    if (d->K <= 128 && nt <= num_sms() && resident_w_enabled()) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_resident_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM);
+        if (e != cudaSuccess) WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", RW_SMEM, cudaGetErrorString(e));
+        attr_set = true;
+      }
+      const int64_t total = (int64_t)nt * mt;
+      int64_t grid = (num_sms() / nt) * nt;   // a multiple of the N-tile count: every CTA keeps one N tile
+      if (grid > total) grid = total;         // total is a multiple of nt as well
+      wxf_launch(tc_resident_w_kernel, dim3((unsigned)grid), dim3(64 + 32 * RW_EW), RW_SMEM, st, ta_hi, ta_lo, tw_hi, tw_lo, to,
+                 to_hi, to_lo, p, nt, mt, (int)total);
+      WXF_CHECK_LAUNCH("tc_resident_w");
+      return 0;
+    }
     if (d->K <= 256) return launch_persistent<MODE_GEMM, 16, 2>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, nt, mt, 1, st);
     return launch_persistent<MODE_GEMM, 8, 3>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, nt, mt, 1, st);
   }

@@ -1,9 +1,20 @@
 // HBM-bound passes of the forecast step: boundary pad (+NCHW->pixel-major), channel LayerNorm,
 // GroupNorm+SiLU, un-pad + bilinear resize (+pixel-major->NCHW), rollout channel copy.
 // Each is one coalesced read and one coalesced write of its tensor; see DESIGN.md for the byte counts.
+#include <stdlib.h>
+
 #include "wxf_common.cuh"
 
 thread_local char wxf_err_buf[512] = "";
+
+bool wxf_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXF_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 extern "C" int wxf_abi_version(void) { return WXF_ABI_VERSION; }
 extern "C" const char* wxf_last_error(void) { return wxf_err_buf; }
@@ -87,6 +98,8 @@ __global__ void __launch_bounds__(256) pad_rows_vec_kernel(const float* __restri
                                                             __half* __restrict__ xp_hi, __half* __restrict__ xp_lo,
                                                             int CT, int H, int W, int pt, int pl, int mode, int ld,
                                                             int Hp, int Wp, int cblocks, int row0) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
   __shared__ float tile[64][65];  // [channel][column]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z / cblocks, cb = blockIdx.z % cblocks;
@@ -175,10 +188,10 @@ static int pad_launch(const float* x, float* xp, void* xp_hi, void* xp_lo, int B
     if (nrows > 65535 || (int64_t)B * cblocks > 65535) WXF_FAIL(WXF_EINVAL, "pad: grid too large");
     dim3 grid((Wp + 63) / 64, nrows, B * cblocks);
     if (xp_hi)
-      pad_rows_vec_kernel<true><<<grid, 256, 0, st>>>(x, nullptr, (__half*)xp_hi, (__half*)xp_lo, C * T, H, W, pt, pl, mode,
+      wxf_launch(pad_rows_vec_kernel<true>, dim3(grid), dim3(256), 0, st, x, nullptr, (__half*)xp_hi, (__half*)xp_lo, C * T, H, W, pt, pl, mode,
                                                       ld, Hp, Wp, cblocks, row0);
     else
-      pad_rows_vec_kernel<false><<<grid, 256, 0, st>>>(x, xp, nullptr, nullptr, C * T, H, W, pt, pl, mode, ld, Hp, Wp,
+      wxf_launch(pad_rows_vec_kernel<false>, dim3(grid), dim3(256), 0, st, x, xp, nullptr, nullptr, C * T, H, W, pt, pl, mode, ld, Hp, Wp,
                                                        cblocks, row0);
     WXF_CHECK_LAUNCH("pad_to_pixel_major");
     return 0;
@@ -217,6 +230,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                          int ldy, __half* __restrict__ y_hi, __half* __restrict__ y_lo,
                                                          const float* __restrict__ g, const float* __restrict__ bta,
                                                          int64_t M, int d, float eps) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -262,6 +277,8 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
                                                              int ldy, __half* __restrict__ y_hi, __half* __restrict__ y_lo,
                                                              const float* __restrict__ g, const float* __restrict__ bta,
                                                              int64_t M, float eps) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
   constexpr int d = NV4 * 128;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -321,7 +338,7 @@ static int layernorm_launch(const float* x, int ldx, float* y, int ldy, void* y_
   if (vec) {
 #define LN_VEC(NV4)                                                                                                   \
   if (d == NV4 * 128) {                                                                                               \
-    layernorm_vec_kernel<NV4, SPLIT><<<blocks, 256, 0, st>>>(x, ldx, y, ldy, (__half*)y_hi, (__half*)y_lo, g, b, M, eps); \
+    wxf_launch(layernorm_vec_kernel<NV4, SPLIT>, dim3(blocks), dim3(256), 0, st, x, ldx, y, ldy, (__half*)y_hi, (__half*)y_lo, g, b, M, eps); \
     WXF_CHECK_LAUNCH("layernorm");                                                                                    \
     return 0;                                                                                                         \
   }
@@ -330,7 +347,7 @@ static int layernorm_launch(const float* x, int ldx, float* y, int ldy, void* y_
   }
 #define LN_CASE(NV)                                                                                         \
   if (nv <= NV) {                                                                                           \
-    layernorm_kernel<NV, SPLIT><<<blocks, 256, 0, st>>>(x, ldx, y, ldy, (__half*)y_hi, (__half*)y_lo, g, b, M, d, eps); \
+    wxf_launch(layernorm_kernel<NV, SPLIT>, dim3(blocks), dim3(256), 0, st, x, ldx, y, ldy, (__half*)y_hi, (__half*)y_lo, g, b, M, d, eps); \
     WXF_CHECK_LAUNCH("layernorm");                                                                          \
     return 0;                                                                                               \
   }
@@ -352,6 +369,8 @@ extern "C" int wxf_layernorm_f16x2(const float* x, int ldx, void* y_hi, void* y_
 
 __global__ void __launch_bounds__(256) split_f16x2_kernel(const float* __restrict__ x, int ldx, __half* __restrict__ hi,
                                                            __half* __restrict__ lo, int ldh, int64_t M, int d) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
   const int64_t total = M * d;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / d;
@@ -367,7 +386,7 @@ extern "C" int wxf_split_f16x2(const float* x, int ldx, void* hi, void* lo, int 
   if (M <= 0 || d <= 0 || ldx < d || ldh < d || !hi || !lo) WXF_FAIL(WXF_EINVAL, "split_f16x2: bad args");
   int64_t blocks = (M * d + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  split_f16x2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, (__half*)hi, (__half*)lo, ldh, M, d);
+  wxf_launch(split_f16x2_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, ldx, (__half*)hi, (__half*)lo, ldh, M, d);
   WXF_CHECK_LAUNCH("split_f16x2");
   return 0;
 }
@@ -388,6 +407,8 @@ static inline int gn_pix_per_block(int64_t HW) {
 // partial (sum, sumsq) per group for a chunk of pixels; C % 4 == 0 and C/4 divides 256: float4 loads
 __global__ void __launch_bounds__(256) gn_partial_vec_kernel(const float* __restrict__ x, int ldx, float2* __restrict__ part,
                                                               int64_t HW, int C, int G, int nchunk, int ppb) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
   __shared__ float4 rs[256], rq[256];
   const int tid = threadIdx.x;
   const int TC = C >> 2;          // float4 columns
@@ -474,6 +495,8 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict
 // one warp per (image, group): lanes stride over the chunk partials, fp64 combine
 __global__ void gn_finalize_kernel(const float2* __restrict__ part, float* __restrict__ stats, int B, int G, int nchunk,
                                    double count, float eps) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= B * G) return;
@@ -534,6 +557,8 @@ __global__ void __launch_bounds__(256) gn_silu_vec_kernel(const float* __restric
                                                            int ldr, float* __restrict__ y, __half* __restrict__ y_hi,
                                                            __half* __restrict__ y_lo, int ldy, int64_t HW, int C, int cpg,
                                                            int G) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
   __shared__ __align__(16) float sa[1024], sb[1024];
   const int b = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += 256) {
@@ -594,17 +619,19 @@ extern "C" int wxf_groupnorm_stats(const float* x, int ldx, float* stats, void* 
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (C % 4 == 0) && (256 % (C / 4) == 0) && (ldx % 4 == 0) && wxf_aligned16(x);
   if (vec)
-    gn_partial_vec_kernel<<<dim3(nchunk, B), 256, 0, st>>>(x, ldx, (float2*)scratch, HW, C, G, nchunk, ppb);
+    wxf_launch(gn_partial_vec_kernel, dim3(nchunk, B), dim3(256), 0, st, x, ldx, (float2*)scratch, HW, C, G, nchunk, ppb);
   else
     gn_partial_kernel<<<dim3(nchunk, B), 256, 0, st>>>(x, ldx, (float2*)scratch, HW, C, G, nchunk, ppb);
   WXF_CHECK_LAUNCH("gn_partial");
-  gn_finalize_kernel<<<(B * G + 3) / 4, 128, 0, st>>>((const float2*)scratch, stats, B, G, nchunk,
+  wxf_launch(gn_finalize_kernel, dim3((B * G + 3) / 4), dim3(128), 0, st, (const float2*)scratch, stats, B, G, nchunk,
                                                           (double)HW * (double)(C / G), eps);
   WXF_CHECK_LAUNCH("gn_finalize");
   return 0;
 }
 
 __global__ void gn_sums_kernel(const float2* __restrict__ part, double* __restrict__ sums, int B, int G, int nchunk) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= B * G) return;
@@ -628,6 +655,8 @@ __global__ void gn_sums_kernel(const float2* __restrict__ part, double* __restri
 
 __global__ void gn_stats_from_sums_kernel(const double* __restrict__ sums, float* __restrict__ stats, int n, double count,
                                           float eps) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double mean = sums[2 * i] / count;
@@ -647,11 +676,11 @@ extern "C" int wxf_groupnorm_sums(const float* x, int ldx, double* sums, void* s
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (C % 4 == 0) && (256 % (C / 4) == 0) && (ldx % 4 == 0) && wxf_aligned16(x);
   if (vec)
-    gn_partial_vec_kernel<<<dim3(nchunk, B), 256, 0, st>>>(x, ldx, (float2*)scratch, HW, C, G, nchunk, ppb);
+    wxf_launch(gn_partial_vec_kernel, dim3(nchunk, B), dim3(256), 0, st, x, ldx, (float2*)scratch, HW, C, G, nchunk, ppb);
   else
     gn_partial_kernel<<<dim3(nchunk, B), 256, 0, st>>>(x, ldx, (float2*)scratch, HW, C, G, nchunk, ppb);
   WXF_CHECK_LAUNCH("gn_partial");
-  gn_sums_kernel<<<(B * G + 3) / 4, 128, 0, st>>>((const float2*)scratch, sums, B, G, nchunk);
+  wxf_launch(gn_sums_kernel, dim3((B * G + 3) / 4), dim3(128), 0, st, (const float2*)scratch, sums, B, G, nchunk);
   WXF_CHECK_LAUNCH("gn_sums");
   return 0;
 }
@@ -659,7 +688,7 @@ extern "C" int wxf_groupnorm_sums(const float* x, int ldx, double* sums, void* s
 extern "C" int wxf_groupnorm_stats_from_sums(const double* sums, float* stats, int B, int G, double count, float eps,
                                              void* stream) {
   if (B <= 0 || G <= 0 || count <= 0) WXF_FAIL(WXF_EINVAL, "groupnorm_stats_from_sums: bad dims");
-  gn_stats_from_sums_kernel<<<(B * G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, stats, B * G, count, eps);
+  wxf_launch(gn_stats_from_sums_kernel, dim3((B * G + 127) / 128), dim3(128), 0, (cudaStream_t)stream, sums, stats, B * G, count, eps);
   WXF_CHECK_LAUNCH("gn_stats_from_sums");
   return 0;
 }
@@ -670,6 +699,8 @@ extern "C" int wxf_groupnorm_stats_from_sums(const double* sums, float* stats, i
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, int ld_src,
                                                            const int32_t* __restrict__ idx, float* __restrict__ dst,
                                                            int ld_dst, int64_t n, int d4) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
   const int64_t total = n * d4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / d4;
@@ -687,7 +718,7 @@ extern "C" int wxf_gather_rows(const float* src, int ld_src, const int32_t* idx,
   if (n == 0) return 0;
   int64_t blocks = (n * (d / 4) + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, idx, dst, ld_dst, n, d / 4);
+  wxf_launch(gather_rows_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, src, ld_src, idx, dst, ld_dst, n, d / 4);
   WXF_CHECK_LAUNCH("gather_rows");
   return 0;
 }
@@ -706,10 +737,10 @@ static int gn_silu_launch(const float* x, int ldx, const float* stats, const flo
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)B);
     if (y_hi)
-      gn_silu_vec_kernel<true><<<grid, 256, 0, st>>>(x, ldx, stats, gamma, beta, res, ldr, nullptr, (__half*)y_hi,
+      wxf_launch(gn_silu_vec_kernel<true>, dim3(grid), dim3(256), 0, st, x, ldx, stats, gamma, beta, res, ldr, nullptr, (__half*)y_hi,
                                                      (__half*)y_lo, ldy, HW, C, C / G, G);
     else
-      gn_silu_vec_kernel<false><<<grid, 256, 0, st>>>(x, ldx, stats, gamma, beta, res, ldr, y, nullptr, nullptr, ldy, HW,
+      wxf_launch(gn_silu_vec_kernel<false>, dim3(grid), dim3(256), 0, st, x, ldx, stats, gamma, beta, res, ldr, y, nullptr, nullptr, ldy, HW,
                                                       C, C / G, G);
     WXF_CHECK_LAUNCH("gn_silu");
     return 0;
@@ -799,6 +830,8 @@ __global__ void __launch_bounds__(256) unpad_resize_kernel(const float* __restri
 __global__ void __launch_bounds__(256) unpad_resize_vec_kernel(const float* __restrict__ y, int ld, float* __restrict__ out,
                                                                 int C, int Hd, int Wd, int top, int left, int Hc, int Wc,
                                                                 int Ho, int Wo, float sh, float sw, int cblocks, int o0) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
   __shared__ float tile[64][65];  // [channel][column]
   const int tid = threadIdx.x;
   const int b = blockIdx.z / cblocks, cb = blockIdx.z % cblocks;
@@ -865,7 +898,7 @@ extern "C" int wxf_unpad_resize_to_nchw(const float* y, int ld, float* out, int 
     const int cblocks = (C + 63) / 64;
     if (n_out > 65535 || (int64_t)B * cblocks > 65535) WXF_FAIL(WXF_EINVAL, "unpad_resize: grid too large");
     dim3 grid((Wo + 63) / 64, n_out, B * cblocks);
-    unpad_resize_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, ld, out, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, sh,
+    wxf_launch(unpad_resize_vec_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, y, ld, out, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, sh,
                                                                     sw, cblocks, o0);
     WXF_CHECK_LAUNCH("unpad_resize");
     return 0;
@@ -889,6 +922,8 @@ struct CopyGroups {
 __global__ void __launch_bounds__(256) copy_channels_kernel(float* __restrict__ dst, int dst_C,
                                                              const float* __restrict__ src, int src_C, int64_t plane,
                                                              CopyGroups gr, int B) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
   const int g = blockIdx.y / B, b = blockIdx.y % B;
   const int64_t n = (int64_t)gr.len[g] * plane;
   float* d = dst + ((int64_t)b * dst_C + gr.dst_c0[g]) * plane;
@@ -917,7 +952,7 @@ extern "C" int wxf_copy_channels(float* dst, int dst_C, const float* src, int sr
     gr.len[g] = len[g];
   }
   dim3 grid(148 * 4, n_groups * B);
-  copy_channels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dst, dst_C, src, src_C, plane, gr, B);
+  wxf_launch(copy_channels_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dst, dst_C, src, src_C, plane, gr, B);
   WXF_CHECK_LAUNCH("copy_channels");
   return 0;
 }

@@ -23,7 +23,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _kwargs():
+def _kwargs(name="unit"):
+    if name == "unit8":
+        # 128x64 padded grid, windows 2 / (4, 2, 1, 1): 32, 32, 32, 8 attention units and 8 stage-3 rows, so 8 ranks get
+        # one unit and one row each at the coarsest stage; the 16-row input halos span more than one neighbour
+        return dict(workload("unit"), image_height=101, image_width=48, levels=2, depth=[1, 1, 1, 1],
+                    global_window_size=[4, 2, 1, 1], local_window_size=2, output_only_channels=2,
+                    padding_conf=dict(activate=True, mode="earth", pad_lat=[13, 14], pad_lon=[8, 8]))
     return dict(workload("unit"), output_only_channels=4)
 
 
@@ -87,7 +93,7 @@ class _FakeModel:
         return x, self._plans[0]
 
 
-def _rollout_worker(rank, world, port, out_dir, steps):
+def _rollout_worker(rank, world, port, out_dir, steps, name="unit"):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     from abi_emulator import EmulatedLib
@@ -105,7 +111,7 @@ def _rollout_worker(rank, world, port, out_dir, steps):
     ops._req = lambda *a, **k: None
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        geo = build_geometry(**_kwargs())
+        geo = build_geometry(**_kwargs(name))
         sd = synthetic_state_dict(geo, seed=21)
         wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
         dm = DomainParallelManager(world, world)
@@ -126,15 +132,15 @@ def _rollout_worker(rank, world, port, out_dir, steps):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_rollout_matches_oracle_rollout(tmp_path, world):
+@pytest.mark.parametrize("world,name", [(2, "unit"), (3, "unit"), (8, "unit8")])
+def test_sharded_rollout_matches_oracle_rollout(tmp_path, world, name):
     """Two steps with the state kept sharded (halo rows only) == two oracle steps on the full state."""
     from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
     from oracle import crossformer_oracle as oracle
 
     steps = 2
-    mp.spawn(_rollout_worker, args=(world, _free_port(), str(tmp_path), steps), nprocs=world, join=True)
-    geo = build_geometry(**_kwargs())
+    mp.spawn(_rollout_worker, args=(world, _free_port(), str(tmp_path), steps, name), nprocs=world, join=True)
+    geo = build_geometry(**_kwargs(name))
     sd = synthetic_state_dict(geo, seed=21)
     x = synthetic_input(geo, batch=1, seed=21)
     n_prog = geo.channels * geo.levels + geo.surface_channels
