@@ -197,3 +197,43 @@ def test_layout_partitions(name, world):
         for key in (short_key, long_key):
             first = torch.zeros(int(key.max()) + 1, dtype=gid.dtype).scatter_(0, key, gid)
             assert torch.equal(first[key], gid)
+
+class _NoComm:
+    """DomainPlan._row_ranges needs geometry, layout and world only."""
+
+
+@pytest.mark.parametrize("name,world", [("unit", 2), ("unit", 3), ("wxformer_6h_025deg", 2), ("wxformer_6h_025deg", 4),
+                                        ("wxformer_6h_025deg", 8)])
+def test_sharded_boundary_row_ranges(name, world):
+    """Host bookkeeping of the sharded pad / un-pad: every rank pads the rows its stage-0 band reads, the output rows are a
+    partition, a rank's bilinear resize stays within one halo row of its decoder band, and the state rows a rank keeps
+    current contain the rows it writes (so update_x never reads a stale row)."""
+    from miles_credit_b200.domain import DomainLayout, DomainPlan
+
+    geo = build_geometry(**workload(name))
+    plan = DomainPlan.__new__(DomainPlan)
+    plan.geo, plan.world, plan.lay = geo, world, DomainLayout(geo, world)
+    plan._row_ranges()
+    st0 = geo.stages[0]
+    kmax = max(br.kernel for br in st0.branches)
+    p = (kmax - 2) // 2
+    prev_hi = 0
+    for r in range(world):
+        r0, r1 = plan.lay.rb[0][r], plan.lay.rb[0][r + 1]
+        a, b = plan.pad_rows[r]
+        for oy in (r0, r1 - 1):  # first and last output row of the band: every tap row inside the image is padded
+            lo, hi = 2 * oy - p, 2 * oy - p + kmax
+            assert a <= max(lo, 0) and min(hi, geo.h_pad) <= b
+        o_lo, o_hi = plan.out_rows[r]
+        if o_hi > o_lo:
+            assert o_lo == prev_hi
+            prev_hi = o_hi
+            s_lo, s_hi = plan.src_rows[r]
+            assert s_lo <= o_lo and o_hi <= s_hi
+    assert prev_hi == geo.h_out
+    if name == "wxformer_6h_025deg" and world == 8:
+        # 0.25 deg on 8 GPUs: 48-56 stage-0 rows per rank; at most 17 halo rows of state per side and neighbour
+        for r in range(world):
+            o_lo, o_hi = plan.out_rows[r]
+            s_lo, s_hi = plan.src_rows[r]
+            assert o_lo - s_lo <= 17 and s_hi - o_hi <= 17
