@@ -91,3 +91,36 @@ def test_plan_wxformer_tensor_core_head_vs_oracle(emulated):
     with torch.no_grad():
         ref = oracle.forward(x, sd, geo)
     assert float((y - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("variant", ["batch2", "no_padding", "no_interp", "mirror_batch2_frames2"])
+def test_plan_edge_configurations_vs_oracle(emulated, variant):
+    """Host logic on configurations the golden fixtures do not cover: batch > 1, padding switched off
+    (crossformer.py:598-599 skipped), interpolation switched off (:631-632: the output keeps the cropped size)."""
+    from miles_credit_b200.geometry import workload
+    from oracle import crossformer_oracle as oracle
+
+    kw = dict(workload("unit"), depth=[1, 1, 1, 1], output_only_channels=4)
+    batch = 1
+    if variant == "batch2":
+        batch = 2
+    elif variant == "no_padding":  # 96 x 144 is what the padded unit grid is: windows still divide every stage
+        kw.update(image_height=96, image_width=144, padding_conf=dict(activate=False))
+    elif variant == "no_interp":
+        kw.update(interp=False)
+    elif variant == "mirror_batch2_frames2":
+        kw.update(frames=2, padding_conf=dict(activate=True, mode="mirror", pad_lat=[25, 26], pad_lon=[24, 24]),
+                  image_height=45)
+        batch = 2
+    geo = build_geometry(**kw)
+    sd = synthetic_state_dict(geo, seed=13)
+    wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
+    plan = wmodel._Plan(geo, wts, batch, torch.device("cpu"), True)
+    x = synthetic_input(geo, batch=batch, seed=13)
+    y = plan.run(x)
+    with torch.no_grad():
+        ref = oracle.forward(x, sd, geo)
+    assert y.shape == ref.shape, (y.shape, ref.shape)
+    err = float((y - ref).abs().max() / ref.abs().max())
+    print(variant, tuple(y.shape), "rel-max", err)
+    assert err < 2e-5, err
