@@ -142,7 +142,7 @@ def cpu_forward_seconds(name, steps, warmup, threads):
             x = oracle.rollout_update(x, y, geo)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return times, geo
+    return times, geo, y
 
 
 def run_reference(args, rank, world):
@@ -154,7 +154,7 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     full = build_geometry(**workload(WORKLOAD))
     # bounded sample: the same architecture on a 1-degree grid (320x480 padded); cost is linear in pixels
-    times, geo = cpu_forward_seconds("wxformer_6h_1deg", args.steps, min(args.warmup, 1), cores)
+    times, geo, _ = cpu_forward_seconds("wxformer_6h_1deg", args.steps, min(args.warmup, 1), cores)
     scale = (geo.h_pad * geo.w_pad) / float(full.h_pad * full.w_pad)
     sec = sum(times) / len(times)
     value = scale / sec
@@ -356,11 +356,20 @@ def main():
 
     # ---- CPU baseline (oracle on the host cores; one full-size step) ---------------------------------------
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        times, _ = cpu_forward_seconds(args.workload, 1, 0, cores)
+        times, _, y_cpu = cpu_forward_seconds(args.workload, 1, 0, cores)
         cpu = {"value": 1.0 / times[0], "unit": "steps/s", "cores": cores, "kind": "port",
                "sample": f"1 forward+update step of {args.workload} (full 721x1440 grid), {times[0]:.1f} s, no warm-up"}
+        # the oracle's step started from the same seeded state and weights: full-size parity of the first forward
+        try:
+            y_gpu = model(synthetic_input(geo, batch=1, seed=1000).to(dev)).cpu()
+            parity = {"rel_max_vs_oracle": float((y_gpu - y_cpu).abs().max() / y_cpu.abs().max()), "tolerance": 1e-4,
+                      "what": f"first forward of {args.workload} (full grid), CUDA path vs CPU oracle, same seeded "
+                              "state and weights"}
+        except Exception as exc:  # never lose the bench line over the extra check
+            parity = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         fl = flops_per_forward(geo)
@@ -385,6 +394,7 @@ def main():
             "kernel_families": families,
             "step_tflops": fl["total"] / (ms_step / 1e3) / 1e12,
             "cpu_baseline": cpu,
+            "parity": parity,
         }
         if replicas is not None:
             line["replicas"] = replicas
