@@ -2,6 +2,10 @@
 // Reference arithmetic: credit/models/crossformer.py:261-296, 301-314 (window / dilated token gather, q*scale,
 // QK^T + dynamic position bias, softmax, PV, inverse gather).
 //
+// Two kernels share the tile layout below.  window_attention_tc2_kernel (further down; the default) pipelines tiles:
+// one CTA per SM, a 3-stage TMA ring, S double buffered in TMEM, P kept in tensor memory, two softmax warpgroups.
+// window_attention_tc_kernel (first, WXF_ATTN_V2=0) is the serial-per-tile version it replaced, kept for A/B.
+//
 // One CTA = one (window group, head) tile of up to 128 query rows: G = 128 / Lp windows of the same head are packed
 // block-diagonally (Lp = L rounded up to 2 so every TMA box lands 128-byte aligned).  All operands are f16x2 planes:
 //   TMA   : per window 6 boxes (Q, K, V) x (hi, lo) of the qkv planes [B, H, W, 3d]; short windows are a 4-D box
