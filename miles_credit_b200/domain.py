@@ -206,6 +206,7 @@ class DomainPlan(_Plan):
         self.comm = _Comm(rank, world, group)
         self.tensor_cores = True
         self.attention_tc = True
+        self.ff_fused = False
         self.toeplitz = True
         self.lay = lay = DomainLayout(geo, world)
         g = geo
