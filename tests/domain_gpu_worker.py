@@ -61,10 +61,28 @@ def main():
         e = torch.stack([e_own, e_full]) / yf.abs().max()
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
         out[name]["sharded_rollout_rel_max"] = float(e.max())
+        # the same sharded rollout replayed as ONE CUDA graph per step (kernels + NCCL exchanges captured together)
+        out[name]["graph_replay_max_abs_diff"] = 0.0
+        if world > 1:  # (a one-rank group has nothing to exchange; the 1-GPU graph test is tests/test_gpu_forward.py)
+            xg = x.clone()
+            rg = Rollout(model, graph=True)
+            for _ in range(3):
+                yg = rg.step(xg)
+            a, b = rg.own_rows(xg)
+            eg = (yg[..., a:b, :] - ys[..., a:b, :]).abs().max() if b > a else torch.zeros((), device=dev)
+            sa, sb = next(iter(model._plans.values())).src_rows[rank]
+            eg = torch.stack([eg, (xg[..., sa:sb, :] - xs[..., sa:sb, :]).abs().max()])
+            dist.all_reduce(eg, op=dist.ReduceOp.MAX)
+            out[name]["graph_replay_max_abs_diff"] = float(eg.max())
         del model
         torch.cuda.empty_cache()
     if rank == 0:
         print("DOMAIN_RESULT " + json.dumps({"world": world, "cases": out}), flush=True)
+    if world > 1:
+        # captured graphs hold NCCL work: tearing the communicator down under them deadlocks (seen in bench.py on 2 GPUs)
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
     dist.destroy_process_group()
 
 

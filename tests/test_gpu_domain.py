@@ -75,3 +75,4 @@ def test_domain_decomposition_on_n_gpus(n):
         assert r["finite"] and r["repeatable"] and r["ranks_identical"], (name, r)
         assert r["rel_max_vs_single_gpu"] < 1e-5, (name, r)
         assert r["sharded_rollout_rel_max"] < 1e-5, (name, r)  # 3 steps, state sharded between them
+        assert r["graph_replay_max_abs_diff"] == 0.0, (name, r)  # graph replay (kernels + NCCL) == eager launches
