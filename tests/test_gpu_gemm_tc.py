@@ -135,3 +135,27 @@ def test_ff_fused_matches_two_gemms(m):
     e_pl = float(((o_hi.float() + o_lo.float()) - out).abs().max() / out.abs().max())
     print(f"ff_fused M={m}: vs fp64 {e_ref:.3e}, vs two GEMMs {e_two:.3e}, planes {e_pl:.3e}")
     assert e_ref < 5e-6 and e_two < 2e-6 and e_pl < 2e-6
+
+
+@pytest.mark.skipif(__import__("os").environ.get("WXF_GEMM_CLUSTER") != "1",
+                    reason="round-2 candidate: the 2-CTA multicast GEMM has not run on hardware yet (set WXF_GEMM_CLUSTER=1)")
+@pytest.mark.parametrize("m,n,k", [(3000, 512, 512), (20000, 2048, 512), (700, 256, 2048), (129, 1536, 512)])
+def test_gemm_cluster_multicast(m, n, k):
+    """K >= 512 with an even number of N tiles takes tc_cluster2_kernel: fp32 + residual and plane outputs vs fp64."""
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k)
+    w, b = torch.randn(n, k) / k**0.5, torch.randn(n) * 0.1
+    res = torch.randn(m, n)
+    ref = a.double() @ w.double().t() + b.double()
+    a_hi, a_lo = planes(a.to(DEV))
+    gw = gemm_weights(w.to(DEV), b.to(DEV))
+    out = res.to(DEV).clone()
+    ops.gemm_f16x2_tc(ops.make_gemm_desc(a_hi, a_lo, gw, M=m, lda=k, out=out, ldc=n, res=out, ldr=n))
+    o_hi = torch.zeros(m, n, device=DEV, dtype=torch.float16)
+    o_lo = torch.zeros_like(o_hi)
+    ops.gemm_f16x2_tc(ops.make_gemm_desc(a_hi, a_lo, gw, M=m, lda=k, out_hi=o_hi, out_lo=o_lo, ldh=n))
+    torch.cuda.synchronize()
+    e1 = float((out.cpu().double() - (ref + res.double())).abs().max() / ref.abs().max())
+    e2 = float(((o_hi.float() + o_lo.float()).cpu().double() - ref).abs().max() / ref.abs().max())
+    print(f"gemm cluster {m}x{n}x{k}: fp32+res {e1:.3e}, planes {e2:.3e}")
+    assert e1 < 8e-6 and e2 < 8e-6
