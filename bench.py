@@ -313,6 +313,21 @@ def main():
     h2d = forcing_host[0].numel() * 4 * world
     d2h = 4 * jobs * int(torch.tensor(geo.out_shape).prod())  # the ranks' row bands add up to the full prediction
 
+    # ---- decomposed forecast: the graph-replayed step (kernels + NCCL exchanges) must equal eager launches --------
+    graph_check = None
+    if domain and ro.graph:
+        try:
+            x0 = synthetic_input(geo, batch=1, seed=1000).to(dev)
+            xa, xb = x0.clone(), x0.clone()
+            ya = Rollout(model, graph=False).step(xa).clone()
+            yb = ro.step(xb)  # captured again for this state buffer
+            ga, gb = ro.own_rows(xb)
+            diff = (ya[..., ga:gb, :] - yb[..., ga:gb, :]).abs().max() if gb > ga else torch.zeros((), device=dev)
+            graph_check = {"max_abs_diff_graph_vs_eager": max_over_ranks(float(diff), world, dev),
+                           "what": "one sharded step from the seeded state, this rank's rows, max over ranks"}
+        except Exception as exc:
+            graph_check = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- roofline of the dominant kernel family (CUDA events around every launch of one extra step) ---------
     pk = peaks()
     plan = next(iter(model._plans.values()))
@@ -398,6 +413,8 @@ def main():
         }
         if replicas is not None:
             line["replicas"] = replicas
+        if graph_check is not None:
+            line["graph_check"] = graph_check
         print(json.dumps(line), flush=True)
     if world > 1:
         # Captured graphs hold NCCL work: tearing the communicator down under them deadlocks (seen on 2 GPUs), so the ranks
