@@ -207,6 +207,7 @@ class DomainPlan(_Plan):
         self.tensor_cores = True
         self.attention_tc = True
         self.ff_fused = False
+        self.attn_simt_small = False
         self.toeplitz = True
         self.lay = lay = DomainLayout(geo, world)
         g = geo

@@ -132,6 +132,7 @@ class _Plan:
         self.tensor_cores = tensor_cores
         self.attention_tc = tensor_cores and os.environ.get("WXF_ATTN_TC", "1") != "0"
         self.ff_fused = tensor_cores and os.environ.get("WXF_FF_FUSED", "0") == "1"
+        self.attn_simt_small = tensor_cores and os.environ.get("WXF_ATTN_SIMT_SMALL", "0") == "1"
         f32 = dict(device=device, dtype=torch.float32)
         f16 = dict(device=device, dtype=torch.float16)
         B = batch
@@ -226,6 +227,14 @@ class _Plan:
                         v_hi, v_lo = self.scratch16[: m * d], self.scratch16[hid_off: hid_off + m * d]
                         self._gemm(ln_hi, ln_lo, vw, f"qkv.s{s}", M=m, lda=d, out_hi=v_hi, out_lo=v_lo, ldh=d)
                         self._gemm(v_hi, v_lo, att.out_tc, f"out_proj.s{s}", M=m, lda=d, out=xv, ldc=ld, res=xv, ldr=ld)
+                    elif self.attn_simt_small and att.kind == _lib.ATTN_LONG and L <= 8:
+                        # round-2 candidate (WXF_ATTN_SIMT_SMALL=1): dilated groups of <= 8 tokens (stage 2: L = 4) fill 3 %
+                        # of a 128x128 tensor-core tile; the CUDA-core kernel (one thread per query) only has to stream
+                        # the tensor.  Both kernels are validated; which is faster at L = 4 is not measured yet.
+                        self._gemm(ln_hi, ln_lo, att.qkv_tc, f"qkv.s{s}", M=m, lda=d, out=wide, ldc=3 * d)
+                        add(ops.window_attention_f16x2, (wide, 3 * d, att.bias_t, ln_hi, ln_lo, d, B, h, w, d,
+                                                         g.dim_head, att.wsz, att.kind, scale), f"attention.s{s}",
+                            *attn_cost)
                     elif self.attention_tc and L <= 128:
                         q_hi, q_lo = self.scratch16[: m * 3 * d], self.scratch16[hid_off: hid_off + m * 3 * d]
                         self._gemm(ln_hi, ln_lo, att.qkv_tc, f"qkv.s{s}", M=m, lda=d, out_hi=q_hi, out_lo=q_lo, ldh=3 * d)

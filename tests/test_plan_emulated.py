@@ -144,3 +144,25 @@ def test_plan_with_fused_feedforward_vs_oracle(emulated, monkeypatch):
     assert float((y - ref).abs().max() / ref.abs().max()) < 2e-5
     assert emulated.calls.count("ff_fused") == 2 * geo.depth[2]
     assert emulated.calls.count("gemm_tc") == 8 * sum(geo.depth) - 2 * emulated.calls.count("ff_fused")
+
+
+def test_plan_with_simt_small_window_attention_vs_oracle(emulated, monkeypatch):
+    """WXF_ATTN_SIMT_SMALL=1 (round-2 candidate): dilated groups of <= 8 tokens go through the CUDA-core attention kernel
+    (fp32 qkv in, planes out); everything else stays on the tensor-core kernel."""
+    from miles_credit_b200.geometry import workload
+    from oracle import crossformer_oracle as oracle
+
+    monkeypatch.setenv("WXF_ATTN_SIMT_SMALL", "1")
+    kw = dict(workload("unit"), output_only_channels=4)  # global windows 8, 4, 2, 1: stage 2 has L = 4
+    geo = build_geometry(**kw)
+    sd = synthetic_state_dict(geo, seed=15)
+    wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
+    plan = wmodel._Plan(geo, wts, 1, torch.device("cpu"), True)
+    x = synthetic_input(geo, batch=1, seed=15)
+    y = plan.run(x)
+    with torch.no_grad():
+        ref = oracle.forward(x, sd, geo)
+    assert float((y - ref).abs().max() / ref.abs().max()) < 2e-5
+    n_small = sum(dep for dep, st in zip(geo.depth, geo.stages) if 1 < st.global_window ** 2 <= 8)
+    assert n_small == geo.depth[2]
+    assert emulated.calls.count("attention") == n_small  # the f16x2 entry point logs through the fp32 emulation
