@@ -166,3 +166,43 @@ def test_plan_with_simt_small_window_attention_vs_oracle(emulated, monkeypatch):
     n_small = sum(dep for dep, st in zip(geo.depth, geo.stages) if 1 < st.global_window ** 2 <= 8)
     assert n_small == geo.depth[2]
     assert emulated.calls.count("attention") == n_small  # the f16x2 entry point logs through the fp32 emulation
+
+
+def test_rollout_state_update_with_forcing_vs_oracle(emulated):
+    """rollout.Rollout (non-decomposed): y = model(x); prognostic channels of x come from y, the first n_dynamic input-only
+    channels from the forcing tensor, the rest is carried (update_x, datasets/gen_2/channel_utils.py:253-291)."""
+    from miles_credit_b200.geometry import workload
+    from miles_credit_b200.rollout import Rollout
+    from oracle import crossformer_oracle as oracle
+
+    kw = dict(workload("unit"), depth=[1, 1, 1, 1], output_only_channels=4)
+    geo = build_geometry(**kw)
+    sd = synthetic_state_dict(geo, seed=16)
+    wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
+    plan = wmodel._Plan(geo, wts, 1, torch.device("cpu"), True)
+
+    class _Model:  # what Rollout needs from CrossFormerB200 when it is not decomposed
+        geometry = geo
+        _domain = None
+
+        def __call__(self, x):
+            return plan.run(x)
+
+    ro = Rollout(_Model())
+    n_prog = geo.channels * geo.levels + geo.surface_channels
+    assert ro.n_prog == n_prog and not ro.sharded and ro.own_rows(None) == (0, geo.h_out)
+    x = synthetic_input(geo, batch=1, seed=16)
+    xo = x.clone()
+    n_dyn = 1
+    for step in range(2):
+        frc = torch.randn(1, n_dyn, 1, geo.image_height, geo.image_width)
+        y = ro.step(x, frc, n_dyn)
+        with torch.no_grad():
+            yo = oracle.forward(xo, sd, geo)
+        assert float((y - yo).abs().max() / yo.abs().max()) < 5e-5
+        nxt = xo.clone()
+        nxt[:, :n_prog] = yo[:, :n_prog]
+        nxt[:, n_prog: n_prog + n_dyn] = frc
+        xo = nxt
+        assert float((x - xo).abs().max() / xo.abs().max()) < 5e-5
+        assert torch.equal(x[:, n_prog + n_dyn:], xo[:, n_prog + n_dyn:])  # static channels carried bit for bit
