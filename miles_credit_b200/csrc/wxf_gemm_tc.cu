@@ -1116,13 +1116,23 @@ tc_cluster2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         decode(t, n0, z, m0, tb, oy0, ox0);
         const int nb0 = n0 + half * CW;
         const int64_t m = m0 + row;
-        // residual prefetch (the row's 64 columns), issued before waiting for the accumulator
+        // Residual prefetch, issued before waiting for the accumulator.  COALESCED (this kernel only): a load instruction of
+        // the generic kernel has every lane on its own row (32 lines, 32 LSU wavefronts per instruction, 4096 per tile - the
+        // to_out launches wait on it: long_scoreboard 11.5 per issue in ncu).  Here 8 lanes read one row's 128 bytes, 4 rows
+        // per instruction: rres[cb*8 + it] = chunk cb, row it*4 + lane/8, columns 4*(lane%8)..+3; the chunk is transposed
+        // through the warp's staging slab right before it is added.
         float4 rres[CW / 4];
+        const int rrow = lane >> 3, rc4 = lane & 7;
         if (p.res) {
 #pragma unroll
-          for (int q = 0; q < CW / 4; ++q) {
-            rres[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < p.M && nb0 + 4 * q < p.N) rres[q] = *reinterpret_cast<const float4*>(p.res + m * p.ldr + nb0 + 4 * q);
+          for (int cb = 0; cb < NCH; ++cb) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int64_t mr = m0 + quarter * 32 + it * 4 + rrow;
+              const int nc = nb0 + cb * 32 + 4 * rc4;
+              rres[cb * 8 + it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (mr < p.M && nc < p.N) rres[cb * 8 + it] = *reinterpret_cast<const float4*>(p.res + mr * p.ldr + nc);
+            }
           }
         }
         mbar_wait(tfull_bar(slot), ((uint32_t)i >> 1) & 1u);
@@ -1149,6 +1159,16 @@ tc_cluster2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         for (int cb = 0; cb < NCH; ++cb) {
           const int nb = nb0 + cb * 32;
           if (nb >= p.N) break;  // warp-uniform
+          if (p.res) {  // residual chunk: coalesced registers -> swizzled slab -> each lane reads its own row below
+            if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the slab
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + rrow;
+              *reinterpret_cast<float4*>(stg_b + r * 128 + ((rc4 ^ (r & 7)) << 4)) = rres[cb * 8 + it];
+            }
+            __syncwarp();
+          }
           {
             const float2 sc = make_float2(p.w_scale, p.w_scale);
             float2* v2 = reinterpret_cast<float2*>(v + cb * 32);
@@ -1163,7 +1183,7 @@ tc_cluster2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 a1 = wxf_gelu_erf2(a1);
               }
               if (p.res) {
-                const float4 rr = rres[cb * 8 + q];
+                const float4 rr = *reinterpret_cast<const float4*>(stg_b + lane * 128 + ((q ^ (lane & 7)) << 4));  // own row
                 a0 = __fadd2_rn(a0, make_float2(rr.x, rr.y));
                 a1 = __fadd2_rn(a1, make_float2(rr.z, rr.w));
               }
@@ -1173,7 +1193,7 @@ tc_cluster2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           }
           if (p.out) {
             if (lane == 0) bulk_wait_read0();  // previous TMA store has finished reading the staging buffer
-            __syncwarp();
+            __syncwarp();                      // (also: every lane has read its residual row out of the slab)
 #pragma unroll
             for (int q = 0; q < 8; ++q)  // fp32 row of 128 B, SWIZZLE_128B: 16-byte chunk ^= row % 8
               *reinterpret_cast<float4*>(stg_b + lane * 128 + ((q ^ (lane & 7)) << 4)) =
