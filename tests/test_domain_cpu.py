@@ -30,6 +30,9 @@ def _kwargs(name="unit"):
         return dict(workload("unit"), image_height=101, image_width=48, levels=2, depth=[1, 1, 1, 1],
                     global_window_size=[4, 2, 1, 1], local_window_size=2, output_only_channels=2,
                     padding_conf=dict(activate=True, mode="earth", pad_lat=[13, 14], pad_lon=[8, 8]))
+    if name == "unit_mirror":  # reflect-in-latitude padding: the rows a rank's padding pass reads fold back at the poles
+        return dict(workload("unit"), output_only_channels=4,
+                    padding_conf=dict(activate=True, mode="mirror", pad_lat=[25, 26], pad_lon=[24, 24]))
     return dict(workload("unit"), output_only_channels=4)
 
 
@@ -132,7 +135,7 @@ def _rollout_worker(rank, world, port, out_dir, steps, name="unit"):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,name", [(2, "unit"), (3, "unit"), (8, "unit8")])
+@pytest.mark.parametrize("world,name", [(2, "unit"), (3, "unit"), (8, "unit8"), (3, "unit_mirror")])
 def test_sharded_rollout_matches_oracle_rollout(tmp_path, world, name):
     """Two steps with the state kept sharded (halo rows only) == two oracle steps on the full state."""
     from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
