@@ -197,10 +197,11 @@ class DomainPlan(_Plan):
     """Launch plan of one rank.  Input: the full state (replicated); output: the full prediction on every rank."""
 
     def __init__(self, geo: Geometry, wts: PreparedWeights, rank: int, world: int, device, group=None):
-        if geo.variant != "crossformer":
-            raise NotImplementedError("domain decomposition is built for the `crossformer` decoder")
+        self.wx = geo.variant == "wxformer"
         if wts.embed0_toep is None or wts.head_tc is None or any(c is None for brs in wts.embeds_tc[1:] for c in brs):
             raise NotImplementedError("domain decomposition needs the tensor-core path (channel counts % 4 == 0)")
+        if self.wx and (wts.head2_tc is None or any(u.sharp_tc is None for u in wts.ups)):
+            raise NotImplementedError("domain decomposition of the wxformer variant needs output channels % 8 == 0")
         self.geo, self.batch = geo, 1
         self.rank, self.world = rank, world
         self.comm = _Comm(rank, world, group)
@@ -234,7 +235,8 @@ class DomainPlan(_Plan):
         self.catp = [(torch.zeros((self.rows[s] + 2, g.stages[s].w, 2 * g.stages[s].dim), **f16),
                       torch.zeros((self.rows[s] + 2, g.stages[s].w, 2 * g.stages[s].dim), **f16)) for s in range(3)]
         s3 = g.stages[3]
-        self.x3p = (torch.empty((self.rows[3], s3.w, s3.dim), **f16), torch.empty((self.rows[3], s3.w, s3.dim), **f16))
+        # stage-3 output planes; the wxformer decoder's first conv3x3 reads one halo row of them
+        self.x3p = (torch.zeros((self.rows[3] + 2, s3.w, s3.dim), **f16), torch.zeros((self.rows[3] + 2, s3.w, s3.dim), **f16))
         self.dec = []
         for k, up in enumerate(g.ups):
             ro, wo, c = 2 * self.rows[3 - k], 2 * up.w_in, up.c_out
@@ -242,6 +244,13 @@ class DomainPlan(_Plan):
                 short=torch.empty((ro, wo, c), **f32), a=torch.empty((ro, wo, c), **f32),
                 sp=(torch.zeros((ro + 2, wo, c), **f16), torch.zeros((ro + 2, wo, c), **f16)),
                 bp=(torch.zeros((ro + 2, wo, c), **f16), torch.zeros((ro + 2, wo, c), **f16))))
+            if self.wx:  # PixelShuffle output u (fp32 + planes with halo rows): input of the `sharp` convolution
+                self.dec[-1].update(u=torch.empty((ro, wo, c), **f32),
+                                    up=(torch.zeros((ro + 2, wo, c), **f16), torch.zeros((ro + 2, wo, c), **f16)))
+        if self.wx:  # up_block4 = conv3x3 -> PixelShuffle -> conv3x3: the shuffled tensor, band rows + halo
+            rv = 2 * self.rows[0]
+            self.vp = (torch.zeros((rv + 2, g.w_dec, g.output_channels), **f16),
+                       torch.zeros((rv + 2, g.w_dec, g.output_channels), **f16))
         self.gn_sums = torch.empty((1, g.dim[0], 2), device=device, dtype=torch.float64)
         self.gn_stats = torch.empty((1, g.dim[0], 2), **f32)
         gn_bytes = max(ops.groupnorm_scratch_bytes(1, 2 * self.rows[3 - k] * 2 * up.w_in, up.c_out)
@@ -290,13 +299,15 @@ class DomainPlan(_Plan):
                 hi, lo = self.catp[s]
                 add(ops.split_f16x2, (eb, d, hi[1:, :, d:], lo[1:, :, d:], 2 * d, m, d), "split", 0, 8.0 * m * d)
             else:
-                add(ops.split_f16x2, (eb, d, self.x3p[0], self.x3p[1], d, m, d), "split", 0, 8.0 * m * d)
+                add(ops.split_f16x2, (eb, d, self.x3p[0][1:], self.x3p[1][1:], d, m, d), "split", 0, 8.0 * m * d)
+                if self.wx:
+                    add(_halo_exchange, (self.x3p, rows, self.comm), "halo", 0, 0)
             if 1 <= s + 1 <= 3 and s < 3:
                 # the next stage's k=4 branch needs one halo row of this stage's output
                 add(_halo_exchange, ((hi, lo), rows, self.comm), "halo", 0, 0)
 
         # ---- decoder in band layout ----
-        dec_planes, dec_ld, dec_rows, dec_halo = self.x3p, g.stages[3].dim, self.rows[3], 0
+        dec_planes, dec_ld, dec_rows, dec_halo = self.x3p, g.stages[3].dim, self.rows[3], 1
         for k, (up, uw, skip) in enumerate(zip(g.ups, wts.ups, (2, 1, 0))):
             bufs = self.dec[k]
             rin, ro, wo, c = self.rows[3 - k], 2 * self.rows[3 - k], 2 * up.w_in, up.c_out
@@ -304,9 +315,22 @@ class DomainPlan(_Plan):
             sp_hi, sp_lo = bufs["sp"]
             bp_hi, bp_lo = bufs["bp"]
             in_hi, in_lo = (dec_planes[0][dec_halo:], dec_planes[1][dec_halo:]) if dec_halo else dec_planes
-            # ConvTranspose k2 s2: no halo; fp32 shortcut + planes (interior rows of the halo'd buffer)
-            self._conv_tc(in_hi, in_lo, uw.up_tc, "dec_up", B=1, Hi=rin, Wi=up.w_in, lda=dec_ld, Ho=rin, Wo=up.w_in,
-                          out=bufs["short"], ldc=c, out_hi=sp_hi[1:], out_lo=sp_lo[1:], ldh=c)
+            if self.wx:
+                # UpBlockPS (wxformer/crossformer.py:137-162): conv3x3 C -> 4 C_out as four sub-pixel phases (one halo row of
+                # the low-resolution input, exchanged for the skip half by the stage and here for the decoder half), then
+                # x = u + sharp(u) with a halo row of u
+                if k > 0:
+                    add(_halo_exchange, (dec_planes, rin, self.comm), "halo", 0, 0)
+                u_hi, u_lo = bufs["up"]
+                self._conv_tc(dec_planes[0], dec_planes[1], _shift_taps(uw.up_tc, 1), "dec_up", B=1, Hi=rin + 2, Wi=up.w_in,
+                              lda=dec_ld, Ho=rin, Wo=up.w_in, out=bufs["u"], ldc=c, out_hi=u_hi[1:], out_lo=u_lo[1:], ldh=c)
+                add(_halo_exchange, ((u_hi, u_lo), ro, self.comm), "halo", 0, 0)
+                self._conv_tc(u_hi, u_lo, _shift_taps(uw.sharp_tc, 1), "dec_conv3x3", B=1, Hi=ro + 2, Wi=wo, lda=c, Ho=ro,
+                              Wo=wo, out=bufs["short"], ldc=c, res=bufs["u"], ldr=c, out_hi=sp_hi[1:], out_lo=sp_lo[1:], ldh=c)
+            else:
+                # ConvTranspose k2 s2: no halo; fp32 shortcut + planes (interior rows of the halo'd buffer)
+                self._conv_tc(in_hi, in_lo, uw.up_tc, "dec_up", B=1, Hi=rin, Wi=up.w_in, lda=dec_ld, Ho=rin, Wo=up.w_in,
+                              out=bufs["short"], ldc=c, out_hi=sp_hi[1:], out_lo=sp_lo[1:], ldh=c)
             add(_halo_exchange, ((sp_hi, sp_lo), ro, self.comm), "halo", 0, 0)
             self._conv_tc(sp_hi, sp_lo, _shift_taps(uw.convs_tc[0], 1), "dec_conv3x3", B=1, Hi=ro + 2, Wi=wo, lda=c,
                           Ho=ro, Wo=wo, out=bufs["a"], ldc=c)
@@ -324,9 +348,20 @@ class DomainPlan(_Plan):
         st0 = g.stages[0]
         add(_halo_exchange, (self.catp[0], self.rows[0], self.comm), "halo", 0, 0)
         y_band = self.y_dec[2 * lay.rb[0][rank]: 2 * lay.rb[0][rank + 1]]
-        self._conv_tc(self.catp[0][0], self.catp[0][1], _shift_taps(wts.head_tc, 1), "dec_head", B=1,
-                      Hi=self.rows[0] + 2, Wi=st0.w, lda=2 * st0.dim, Ho=self.rows[0], Wo=st0.w, out=y_band,
-                      ldc=g.output_channels)
+        if self.wx:
+            # up_block4 of the wxformer variant (wxformer/crossformer.py:813-830): conv3x3 -> PixelShuffle -> conv3x3
+            co = g.output_channels
+            rv = 2 * self.rows[0]
+            self._conv_tc(self.catp[0][0], self.catp[0][1], _shift_taps(wts.head_tc, 1), "dec_head", B=1,
+                          Hi=self.rows[0] + 2, Wi=st0.w, lda=2 * st0.dim, Ho=self.rows[0], Wo=st0.w, out_hi=self.vp[0][1:],
+                          out_lo=self.vp[1][1:], ldh=co)
+            add(_halo_exchange, (self.vp, rv, self.comm), "halo", 0, 0)
+            self._conv_tc(self.vp[0], self.vp[1], _shift_taps(wts.head2_tc, 1), "dec_head", B=1, Hi=rv + 2, Wi=g.w_dec, lda=co,
+                          Ho=rv, Wo=g.w_dec, out=y_band, ldc=co)
+        else:
+            self._conv_tc(self.catp[0][0], self.catp[0][1], _shift_taps(wts.head_tc, 1), "dec_head", B=1,
+                          Hi=self.rows[0] + 2, Wi=st0.w, lda=2 * st0.dim, Ho=self.rows[0], Wo=st0.w, out=y_band,
+                          ldc=g.output_channels)
         add(self._ydec_halo, (), "halo", 0, 0)
 
     # ------------------------------------------------------------------------------------------------------------

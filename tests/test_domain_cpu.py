@@ -30,13 +30,15 @@ def _kwargs(name="unit"):
         return dict(workload("unit"), image_height=101, image_width=48, levels=2, depth=[1, 1, 1, 1],
                     global_window_size=[4, 2, 1, 1], local_window_size=2, output_only_channels=2,
                     padding_conf=dict(activate=True, mode="earth", pad_lat=[13, 14], pad_lon=[8, 8]))
+    if name == "unit_wx":  # PixelShuffle decoder (registry keys wxformer / wxformer_base), 16 output channels
+        return dict(workload("unit"), variant="wxformer", output_only_channels=8, depth=[1, 1, 1, 1])
     if name == "unit_mirror":  # reflect-in-latitude padding: the rows a rank's padding pass reads fold back at the poles
         return dict(workload("unit"), output_only_channels=4,
                     padding_conf=dict(activate=True, mode="mirror", pad_lat=[25, 26], pad_lon=[24, 24]))
     return dict(workload("unit"), output_only_channels=4)
 
 
-def _worker(rank, world, port, out_dir, dps):
+def _worker(rank, world, port, out_dir, dps, name="unit"):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     from abi_emulator import EmulatedLib
@@ -53,7 +55,7 @@ def _worker(rank, world, port, out_dir, dps):
     ops._req = lambda *a, **k: None
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        geo = build_geometry(**_kwargs())
+        geo = build_geometry(**_kwargs(name))
         sd = synthetic_state_dict(geo, seed=21)
         wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
         dm = DomainParallelManager(world, dps)
@@ -66,13 +68,13 @@ def _worker(rank, world, port, out_dir, dps):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,dps", [(2, 2), (3, 3), (4, 2)])
-def test_domain_decomposition_matches_oracle(tmp_path, world, dps):
+@pytest.mark.parametrize("world,dps,name", [(2, 2, "unit"), (3, 3, "unit"), (4, 2, "unit"), (3, 3, "unit_wx")])
+def test_domain_decomposition_matches_oracle(tmp_path, world, dps, name):
     from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
     from oracle import crossformer_oracle as oracle
 
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), dps), nprocs=world, join=True)
-    geo = build_geometry(**_kwargs())
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), dps, name), nprocs=world, join=True)
+    geo = build_geometry(**_kwargs(name))
     sd = synthetic_state_dict(geo, seed=21)
     x = synthetic_input(geo, batch=1, seed=21)
     with torch.no_grad():
