@@ -235,8 +235,10 @@ class DomainPlan(_Plan):
         self.catp = [(torch.zeros((self.rows[s] + 2, g.stages[s].w, 2 * g.stages[s].dim), **f16),
                       torch.zeros((self.rows[s] + 2, g.stages[s].w, 2 * g.stages[s].dim), **f16)) for s in range(3)]
         s3 = g.stages[3]
-        # stage-3 output planes; the wxformer decoder's first conv3x3 reads one halo row of them
-        self.x3p = (torch.zeros((self.rows[3] + 2, s3.w, s3.dim), **f16), torch.zeros((self.rows[3] + 2, s3.w, s3.dim), **f16))
+        # stage-3 output planes; only the wxformer decoder's first conv3x3 reads a halo row of them
+        h3 = self.halo3 = 1 if self.wx else 0
+        self.x3p = (torch.zeros((self.rows[3] + 2 * h3, s3.w, s3.dim), **f16),
+                    torch.zeros((self.rows[3] + 2 * h3, s3.w, s3.dim), **f16))
         self.dec = []
         for k, up in enumerate(g.ups):
             ro, wo, c = 2 * self.rows[3 - k], 2 * up.w_in, up.c_out
@@ -299,7 +301,8 @@ class DomainPlan(_Plan):
                 hi, lo = self.catp[s]
                 add(ops.split_f16x2, (eb, d, hi[1:, :, d:], lo[1:, :, d:], 2 * d, m, d), "split", 0, 8.0 * m * d)
             else:
-                add(ops.split_f16x2, (eb, d, self.x3p[0][1:], self.x3p[1][1:], d, m, d), "split", 0, 8.0 * m * d)
+                add(ops.split_f16x2, (eb, d, self.x3p[0][self.halo3:], self.x3p[1][self.halo3:], d, m, d), "split", 0,
+                    8.0 * m * d)
                 if self.wx:
                     add(_halo_exchange, (self.x3p, rows, self.comm), "halo", 0, 0)
             if 1 <= s + 1 <= 3 and s < 3:
@@ -307,7 +310,7 @@ class DomainPlan(_Plan):
                 add(_halo_exchange, ((hi, lo), rows, self.comm), "halo", 0, 0)
 
         # ---- decoder in band layout ----
-        dec_planes, dec_ld, dec_rows, dec_halo = self.x3p, g.stages[3].dim, self.rows[3], 1
+        dec_planes, dec_ld, dec_rows, dec_halo = self.x3p, g.stages[3].dim, self.rows[3], self.halo3
         for k, (up, uw, skip) in enumerate(zip(g.ups, wts.ups, (2, 1, 0))):
             bufs = self.dec[k]
             rin, ro, wo, c = self.rows[3 - k], 2 * self.rows[3 - k], 2 * up.w_in, up.c_out
