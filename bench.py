@@ -2,7 +2,8 @@
 """Forecast-step benchmark (driver contract: one JSON line on stdout from rank 0).
 
     python bench.py --gpus N --steps K --warmup W            # B200 arm (hand-written sm_100a kernels)
-    python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU forward of the oracle port
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the UNMODIFIED reference forward on the
+                                                             # host cores (oracle/_ref; oracle port if not staged)
 
 Metric (BASELINE.json): forecast steps/sec of WXFormer-6h at 0.25 deg (721x1440).  One step = one
 ``y = model(x)`` forward plus the autoregressive state update (update_x); synthetic N(0,1) state, synthetic
@@ -12,7 +13,11 @@ spectral-norm-converged weights (no network for ERA5 or checkpoints).
   e2e   : the same rollout driven through the public API with HOST buffers: every step copies that step's
           forcing channels host->device from pinned memory and the full prediction device->host
   roofline : the dominant kernel family of the step, algorithmic FLOPs / its CUDA-event time
-  cpu_baseline : the oracle (CPU restatement of the reference forward) on this box's host cores
+  cpu_baseline : the unmodified reference module (oracle/_ref, staged by oracle/make_ref.py; kind "reference") or, if it
+          is not staged, the oracle restatement (kind "port") on this box's host cores, one full-size step
+  gpu_eager_baseline : the same unmodified reference module run eagerly on cuda:0 with TF32 off (credit/seed.py:7-25) -
+          the real competitor; also gives full-size parity of the CUDA path vs the reference on GPU
+  parity : full-grid rel-max of the CUDA path vs the reference / the oracle, at every N (N > 1: the decomposed forward)
 N > 1 (torchrun, one rank per GPU): ONE forecast decomposed over the N GPUs (miles_credit_b200/domain.py: latitude
 bands for the convolutions, attention units for the transformer stacks, NCCL P2P exchanges) - strong scaling,
 value = K / max-rank time; the line also carries ``replicas`` = N independent forecasts (what reference
@@ -124,52 +129,124 @@ def max_over_ranks(val, world, device):
     return float(t.item())
 
 
-def cpu_forward_seconds(name, steps, warmup, threads):
-    """Time the oracle forward (the reference arithmetic on CPU) for a named workload."""
+def _cpu_forward(name):
+    """(forward(x) -> y, kind, geo) of the CPU baseline for a named workload: the UNMODIFIED reference module when
+    oracle/_ref is staged (kind "reference"), else the oracle restatement (kind "port")."""
     from miles_credit_b200.geometry import build_geometry, workload
-    from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
+    from miles_credit_b200.synth import synthetic_state_dict
+    from oracle import ref_loader
+
+    kw = workload(name)
+    geo = build_geometry(**kw)
+    sd = synthetic_state_dict(geo, seed=1000, sn_iters=5)
+    if ref_loader.available() and os.environ.get("WXF_BENCH_CPU_PORT", "0") != "1":
+        model = ref_loader.reference_model(kw, sd, kw.get("variant", "crossformer"))
+        return (lambda x: model(x)), "reference", geo
     from oracle import crossformer_oracle as oracle
 
+    return (lambda x: oracle.forward(x, sd, geo)), "port", geo
+
+
+def cpu_forward_seconds(name, steps, warmup, threads, budget_s=None):
+    """Time ``steps`` forward + state-update steps of the CPU baseline for a named workload (full grid, nothing scaled).
+    ``budget_s``: stop early once the timed steps exceed it (the line then reports the number of steps really timed)."""
+    from miles_credit_b200.synth import synthetic_input
+
     torch.set_num_threads(threads)
-    geo = build_geometry(**workload(name))
-    sd = synthetic_state_dict(geo, seed=1000, sn_iters=5)
+    fwd, kind, geo = _cpu_forward(name)
+    n_prog = geo.channels * geo.levels + geo.surface_channels
     x = synthetic_input(geo, batch=1, seed=1000)
-    times = []
+    times, y0 = [], None
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            y = oracle.forward(x, sd, geo)
-            x = oracle.rollout_update(x, y, geo)
+            y = fwd(x)
+            nxt = x.clone()  # update_x (datasets/gen_2/channel_utils.py:253-291): clone, overwrite the prognostic channels
+            nxt[:, :n_prog, -1] = y[:, :n_prog, 0]
+            x = nxt
+            if y0 is None:
+                y0 = y
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return times, geo, y
+                if budget_s is not None and sum(times) > budget_s:
+                    break
+    return times, geo, y0, kind
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the reference's CPU forward (oracle port; the Python reference cannot travel to this box)."""
+    """Reference arm: the reference's own CPU forward of the STATED config (full 721x1440 grid, every step a real step)."""
     if rank != 0:
         return
-    from miles_credit_b200.geometry import build_geometry, workload
-
     cores = os.cpu_count() or 1
-    full = build_geometry(**workload(WORKLOAD))
-    # bounded sample: the same architecture on a 1-degree grid (320x480 padded); cost is linear in pixels
-    times, geo, _ = cpu_forward_seconds("wxformer_6h_1deg", args.steps, min(args.warmup, 1), cores)
-    scale = (geo.h_pad * geo.w_pad) / float(full.h_pad * full.w_pad)
+    warm = min(args.warmup, 1)
+    times, geo, _, kind = cpu_forward_seconds(args.workload, args.steps, warm, cores, budget_s=300.0)
     sec = sum(times) / len(times)
-    value = scale / sec
+    value = 1.0 / sec
+    what = ("the UNMODIFIED reference module (credit.models.load_model, staged under oracle/_ref)" if kind == "reference"
+            else "the oracle restatement of the reference forward (oracle/_ref not staged)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "steps": len(times), "warmup": warm, "ms_per_step": 1e3 * sec, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "grid": "721x1440", "batch": 1},
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} forward+update steps of the same architecture on a 181x360 grid "
-                                   f"({geo.h_pad}x{geo.w_pad} padded), {sec:.2f} s each, scaled by the pixel ratio "
-                                   f"{scale:.4f} to 801x1600"},
+        "config": {"workload": args.workload, "grid": f"{geo.image_height}x{geo.image_width}", "batch": 1},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": kind,
+                         "sample": f"{len(times)} forward+update steps of {args.workload} on the full "
+                                   f"{geo.image_height}x{geo.image_width} grid ({geo.h_pad}x{geo.w_pad} padded), "
+                                   f"{sec:.2f} s each after {warm} warm-up step, {what}, torch CPU fp32, {cores} threads"},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_baseline(name, dev, steps=5, warmup=2):
+    """The UNMODIFIED reference module, eager PyTorch on the same GPU, exact fp32 (TF32 off, deterministic cuDNN: the
+    operating conditions of the reference's rollout apps, credit/seed.py:7-25).  Returns (record, first prediction)."""
+    from miles_credit_b200.geometry import build_geometry, workload
+    from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        return {"unavailable": "oracle/_ref not staged"}, None
+    ref_loader.seed_policy()
+    kw = workload(name)
+    geo = build_geometry(**kw)
+    sd = synthetic_state_dict(geo, seed=1000, sn_iters=5)
+    model = ref_loader.reference_model(kw, sd, kw.get("variant", "crossformer")).to(dev)
+    n_prog = geo.channels * geo.levels + geo.surface_channels
+    x = synthetic_input(geo, batch=1, seed=1000).to(dev)
+    y0 = None
+    torch.cuda.reset_peak_memory_stats(dev)
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            if i == warmup:
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            y = model(x)
+            if y0 is None:
+                y0 = y.clone()
+            nxt = x.clone()
+            nxt[:, :n_prog, -1] = y[:, :n_prog, 0]
+            x = nxt
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    rec = {"value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30,
+           "what": "unmodified reference nn.Module (oracle/_ref) in eval()/no_grad, eager PyTorch on cuda:0, fp32 with TF32 off "
+                   "and deterministic cuDNN (credit/seed.py:7-25), forward + update_x clone, CUDA events"}
+    del model
+    torch.cuda.empty_cache()
+    return rec, y0
+
+
+def family_traffic():
+    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) by kernel family, from the committed ncu
+    capture of one forecast step (profiles/traffic_by_family.json, written by tools/ncu_traffic.py)."""
+    p = os.path.join(ROOT, "profiles", "traffic_by_family.json")
+    if os.path.isfile(p):
+        return json.load(open(p))
+    return {}
 
 
 def main():
@@ -343,12 +420,13 @@ def main():
     tot_ms = sum(f["ms"] for f in fam.values())
     top = max(fam, key=lambda k: fam[k]["ms"])
     tf = fam[top]
+    traffic = family_traffic().get(top, {})
     if tf["flops"] > 0:
         achieved = tf["flops"] / (tf["ms"] / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": pk["bf16_tflops_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
-                "traffic_note": "per-launch DRAM bytes are in profiles/r1_ncu_full_stage0_v26_raw.csv (stage-0 launches: "
-                                "ff1 173 MB read + 612 MB written vs 819 MB algorithmic)",
+                "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic.get("bytes_per_launch"),
+                "traffic_note": traffic.get("note", "no ncu DRAM capture committed for this family"),
+                "algorithmic_flops_per_launch": tf["flops"] / tf["launches"],
                 "executed": {"what": "f16x2 scheme: 3 fp16 tensor-core passes per algorithmic product",
                              "tflops": 3.0 * achieved, "frac": 3.0 * achieved / pk["bf16_tflops_sustained"]},
                 "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
@@ -357,7 +435,9 @@ def main():
     else:
         achieved = tf["bytes"] / (tf["ms"] / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic.get("bytes_per_launch"),
+                "traffic_note": traffic.get("note", "no ncu DRAM capture committed for this family"),
+                "algorithmic_bytes_per_launch": tf["bytes"] / tf["launches"], "peak_source": pk["source"],
                 "launches_per_step": tf["launches"], "ms_per_launch": tf["ms"] / tf["launches"],
                 "share_of_step": tf["ms"] / tot_ms}
     families = {k: {"ms": round(v["ms"], 4), "share": round(v["ms"] / tot_ms, 4),
@@ -369,22 +449,40 @@ def main():
         json.dump({"families": families, "launches": [[t, ms, fl, by] for t, ms, fl, by in recs]},
                   open(args.profile_out, "w"), indent=1)
 
-    # ---- CPU baseline (oracle on the host cores; one full-size step) ---------------------------------------
+    # ---- CPU baseline (the reference on the host cores; one full-size step) + full-size parity at every N ------------
     cpu = None
     parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        times, _, y_cpu = cpu_forward_seconds(args.workload, 1, 0, cores)
-        cpu = {"value": 1.0 / times[0], "unit": "steps/s", "cores": cores, "kind": "port",
-               "sample": f"1 forward+update step of {args.workload} (full 721x1440 grid), {times[0]:.1f} s, no warm-up"}
-        # the oracle's step started from the same seeded state and weights: full-size parity of the first forward
-        try:
-            y_gpu = model(synthetic_input(geo, batch=1, seed=1000).to(dev)).cpu()
-            parity = {"rel_max_vs_oracle": float((y_gpu - y_cpu).abs().max() / y_cpu.abs().max()), "tolerance": 1e-4,
-                      "what": f"first forward of {args.workload} (full grid), CUDA path vs CPU oracle, same seeded "
-                              "state and weights"}
-        except Exception as exc:  # never lose the bench line over the extra check
-            parity = {"error": f"{type(exc).__name__}: {exc}"}
+    eager = None
+    if not args.no_cpu_baseline:
+        # every rank runs the forward of the seeded state (collective when decomposed); rank 0 owns the comparison
+        y_gpu = model(synthetic_input(geo, batch=1, seed=1000).to(dev)).cpu()
+        if rank == 0:
+            try:
+                cores = os.cpu_count() or 1
+                times, _, y_cpu, kind = cpu_forward_seconds(args.workload, 1, 0, cores)
+                cpu = {"value": 1.0 / times[0], "unit": "steps/s", "cores": cores, "kind": kind,
+                       "sample": f"1 forward+update step of {args.workload} (full {geo.image_height}x{geo.image_width} grid), "
+                                 f"{times[0]:.1f} s, no warm-up, " + ("unmodified reference module (oracle/_ref)"
+                                                                       if kind == "reference" else "oracle restatement")}
+                key = "rel_max_vs_reference" if kind == "reference" else "rel_max_vs_oracle"
+                parity = {key: float((y_gpu - y_cpu).abs().max() / y_cpu.abs().max()), "tolerance": 1e-4, "n_gpus": world,
+                          "what": f"first forward of {args.workload} (full grid) from the seeded state and weights: CUDA path "
+                                  + (f"decomposed over {world} GPUs" if domain else "on one GPU")
+                                  + (" vs the UNMODIFIED reference forward on the CPU" if kind == "reference"
+                                     else " vs the CPU oracle")}
+                if world == 1:
+                    try:
+                        eager, y_eager = gpu_eager_baseline(args.workload, dev)
+                        if y_eager is not None:
+                            ye = y_eager.cpu()
+                            parity["rel_max_vs_reference_on_gpu"] = float((y_gpu - ye).abs().max() / ye.abs().max())
+                            parity["reference_gpu_vs_cpu_rel_max"] = float((ye - y_cpu).abs().max() / y_cpu.abs().max())
+                            eager["speedup_of_this_path"] = value / eager["value"]
+                    except Exception as exc:  # never lose the bench line over the extra leg
+                        eager = {"error": f"{type(exc).__name__}: {exc}"}
+            except Exception as exc:  # a failed baseline leg must not hang the other ranks at the barrier
+                parity = {"error": f"{type(exc).__name__}: {exc}"}
+        barrier(world)
 
     if rank == 0:
         fl = flops_per_forward(geo)
@@ -409,6 +507,7 @@ def main():
             "kernel_families": families,
             "step_tflops": fl["total"] / (ms_step / 1e3) / 1e12,
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager,
             "parity": parity,
         }
         if replicas is not None:

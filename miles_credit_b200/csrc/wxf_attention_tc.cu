@@ -891,7 +891,8 @@ extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, i
     use_v2 = (e && e[0] == '0') ? 0 : 1;
   }
   if (use_v2) {
-    static bool attr2_set = false;
+    static WxfPerDevice<bool> attr2_set_pd;
+    bool& attr2_set = attr2_set_pd.get();  // function attributes are per device
     if (!attr2_set) {
       cudaError_t e = cudaFuncSetAttribute(window_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
       if (e != cudaSuccess) WXF_FAIL((int)e, "attention_tc: cannot opt in to %d bytes of shared memory", A2_SMEM);
@@ -903,7 +904,8 @@ extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, i
     return 0;
   }
   const int64_t blocks = p.ntiles < 2 * (int64_t)sms ? p.ntiles : 2 * (int64_t)sms;
-  static bool attr_set = false;
+  static WxfPerDevice<bool> attr_set_pd;
+  bool& attr_set = attr_set_pd.get();  // function attributes are per device
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e != cudaSuccess) WXF_FAIL((int)e, "attention_tc: cannot opt in to %d bytes of shared memory", AT_SMEM);

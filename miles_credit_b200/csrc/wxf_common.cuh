@@ -7,6 +7,18 @@
 
 #include "wxformer_b200.h"
 
+// One value per CUDA device of the process (function attributes, SM counts and occupancy limits are per device; a
+// process-wide `static` would skip the opt-in on the second GPU of a multi-device process).
+template <typename T>
+struct WxfPerDevice {
+  T v[64] = {};
+  T& get() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return v[dev & 63];
+  }
+};
+
 extern thread_local char wxf_err_buf[512];
 
 #define WXF_FAIL(code, ...)                                  \

@@ -357,7 +357,8 @@ extern "C" int wxf_ff_fused_f16x2_tc(const WxfFfDesc* d, void* stream) {
   p.s2 = ldexpf(1.0f, -d->w2_scale_log2);
   p.has_out = d->out ? 1 : 0;
   p.has_planes = d->out_hi ? 1 : 0;
-  static bool attr_set = false;
+  static WxfPerDevice<bool> attr_set_pd;
+  bool& attr_set = attr_set_pd.get();  // function attributes are per device
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(ff_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM);
     if (e != cudaSuccess) WXF_FAIL((int)e, "ff_fused: cannot opt in to %d bytes of shared memory: %s", FF_SMEM, cudaGetErrorString(e));

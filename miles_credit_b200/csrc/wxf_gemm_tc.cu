@@ -1253,7 +1253,8 @@ template <int BN, int STAGES, int MODE>
 int launch(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
            const TcParams& p, dim3 grid, cudaStream_t st) {
   constexpr int SMEM = smem_bytes<BN, STAGES>();
-  static bool attr_set = false;
+  static WxfPerDevice<bool> attr_set_pd;
+  bool& attr_set = attr_set_pd.get();  // function attributes are per device
   if (!attr_set) {
     cudaError_t e =
         cudaFuncSetAttribute(tc_contract_kernel<BN, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -1266,7 +1267,8 @@ int launch(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap
 }
 
 int num_sms() {
-  static int n = 0;
+  static WxfPerDevice<int> n_pd;
+  int& n = n_pd.get();
   if (!n) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1316,7 +1318,8 @@ template <int MODE, int EW, int STAGES>
 int launch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
                       const CUtensorMap& to, const CUtensorMap& to_hi, const CUtensorMap& to_lo, const TcParams& p,
                       int n_tiles, int m_tiles, int phases, cudaStream_t st) {
-  static bool attr_set = false;
+  static WxfPerDevice<bool> attr_set_pd;
+  bool& attr_set = attr_set_pd.get();  // function attributes are per device
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_persistent_kernel<MODE, EW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          p_smem<EW, STAGES>());
@@ -1396,7 +1399,8 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
     }
     const int nt = (d->N + BN - 1) / BN, mt = (int)((d->M + BLOCK_M - 1) / BLOCK_M);
     if (d->K <= 128 && nt <= num_sms() && resident_w_enabled()) {
-      static bool attr_set = false;
+      static WxfPerDevice<bool> attr_set_pd;
+  bool& attr_set = attr_set_pd.get();  // function attributes are per device
       if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_resident_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM);
         if (e != cudaSuccess) WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", RW_SMEM, cudaGetErrorString(e));
@@ -1412,7 +1416,8 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
     }
     if (d->K >= 512 && (nt % 2) == 0 && cluster_enabled()) {
       constexpr int SMEM = p_smem<CL_EW, CL_STAGES>();
-      static bool attr_set = false;
+      static WxfPerDevice<bool> attr_set_pd;
+  bool& attr_set = attr_set_pd.get();  // function attributes are per device
       if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_cluster2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", SMEM, cudaGetErrorString(e));
@@ -1431,7 +1436,8 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      static int max_clusters = 0;
+      static WxfPerDevice<int> max_clusters_pd;
+      int& max_clusters = max_clusters_pd.get();
       if (!max_clusters) {
         cfg.gridDim = dim3(2 * (num_sms() / 2));
         if (cudaOccupancyMaxActiveClusters(&max_clusters, tc_cluster2_kernel, &cfg) != cudaSuccess || max_clusters <= 0)

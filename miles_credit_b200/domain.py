@@ -46,6 +46,15 @@ class DomainLayout:
 
     def __init__(self, geo: Geometry, world: int):
         self.world = world
+        # the band plan exchanges ONE halo row for the stage 1-3 cross-embeds and builds nested bands from stride 2
+        for st in geo.stages:
+            for br in st.branches:
+                if br.stride != 2:
+                    raise NotImplementedError(f"stage {st.index}: cross-embed stride {br.stride}; the band layout needs 2")
+                if st.index > 0 and (br.kernel - br.stride) // 2 > 1:
+                    raise NotImplementedError(
+                        f"stage {st.index}: cross-embed kernel {br.kernel} needs a {(br.kernel - br.stride) // 2}-row halo; "
+                        "the decomposed plan exchanges one row for stages 1-3")
         rb3 = _split(geo.stages[3].h, world)
         self.rb = [[b * 2 ** (3 - s) for b in rb3] for s in range(4)]  # band row boundaries per stage
         self.units = []

@@ -393,6 +393,30 @@ def flops_per_forward(geo: Geometry) -> Dict[str, float]:
 # named workloads (BASELINE.json configs -> constructor kwargs)
 
 
+def check_kernel_limits(geo: "Geometry") -> List[str]:
+    """Limits of the sm_100a kernels, checked at construction instead of at the first forward.  Raises for geometries no
+    kernel covers; returns warnings for geometries that run on a slower path."""
+    notes = []
+    if geo.dim_head != 32:
+        raise NotImplementedError(f"dim_head={geo.dim_head}: the window-attention kernels are built for dim_head = 32 "
+                                  "(every CREDIT WXFormer/CrossFormer config)")
+    for st in geo.stages:
+        for wsz, kind in ((st.local_window, "local"), (st.global_window, "global")):
+            if wsz * wsz > 128:
+                raise NotImplementedError(f"stage {st.index}: {kind} window {wsz}x{wsz} = {wsz * wsz} tokens; the attention "
+                                          "kernels hold at most 128 tokens per window")
+        if st.dim % 8:
+            raise NotImplementedError(f"dim[{st.index}]={st.dim} must be a multiple of 8 (16-byte operand rows)")
+    st0 = geo.stages[0]
+    if st0.c_in > 64:
+        notes.append(f"{st0.c_in} input channels > 64: the stage-0 cross-embed runs on the exact-fp32 CUDA-core kernel "
+                     "(much slower than the Toeplitz tensor-core kernel) and the domain decomposition is unavailable")
+    if geo.output_channels % 4:
+        notes.append(f"{geo.output_channels} output channels (not a multiple of 4): the decoder head runs on the exact-fp32 "
+                     "CUDA-core kernel")
+    return notes
+
+
 def workload(name: str) -> dict:
     """Constructor kwargs of the named BASELINE.json configs."""
     wx6h = dict(

@@ -142,7 +142,10 @@ def load(path: str = LIB_PATH):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    # signatures of symbols added by later ABI revisions are attached where they are declared
+    got = int(lib.wxf_abi_version())
+    if got != WXF_ABI_VERSION:  # a stale .so would be called with mismatched descriptor layouts
+        raise RuntimeError(f"{path} has ABI version {got}, this package needs {WXF_ABI_VERSION}: rebuild it "
+                           "(python -c 'import __graft_entry__ as g; g.build()')")
     _lib = lib
     return lib
 

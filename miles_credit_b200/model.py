@@ -25,7 +25,7 @@ from torch import nn
 
 from . import lib as _lib
 from . import ops
-from .geometry import Geometry, build_geometry, state_spec
+from .geometry import Geometry, build_geometry, check_kernel_limits, state_spec
 from .synth import synthetic_state_dict
 from .weights import ConvWeights, GemmWeights, PreparedWeights, prepare
 
@@ -59,16 +59,22 @@ except Exception:  # noqa: BLE001 - CREDIT (or one of its heavy deps) absent: lo
         @classmethod
         def load_model_name(cls, conf, model_name):
             conf = copy.deepcopy(conf)
-            return cls._from_checkpoint(conf, os.path.join(os.path.expandvars(conf["save_loc"]), model_name))
+            # base_model.py:94-117: an FSDP checkpoint IS the state dict, every other mode wraps it in "model_state_dict"
+            fsdp = conf.get("trainer", {}).get("mode") == "fsdp"
+            return cls._from_checkpoint(conf, os.path.join(os.path.expandvars(conf["save_loc"]), model_name),
+                                        bare=fsdp, named=True)
 
         @classmethod
-        def _from_checkpoint(cls, conf, ckpt):
+        def _from_checkpoint(cls, conf, ckpt, bare=None, named=False):
             if not os.path.isfile(ckpt):
-                raise ValueError("No saved checkpoint exists. You must train a model first. Exiting.")
+                raise ValueError((f"No saved checkpoint {ckpt} exists." if named else "No saved checkpoint exists.")
+                                 + " You must train a model first. Exiting.")
             checkpoint = torch.load(ckpt, map_location="cpu" if not torch.cuda.is_available() else None)
             conf["model"].pop("type", None)
             model = cls(**conf["model"])
-            sd = checkpoint["model_state_dict"] if "model_state_dict" in checkpoint else checkpoint
+            if bare is None:
+                bare = "model_state_dict" not in checkpoint
+            sd = checkpoint if bare else checkpoint["model_state_dict"]
             msg = model.load_state_dict(sd, strict=False)
             if msg.unexpected_keys:  # models/checkpoint.py:25-31: unexpected keys raise, missing keys warn
                 raise RuntimeError(str(msg))
@@ -113,6 +119,23 @@ def _round_up(v: int, m: int) -> int:
     return (v + m - 1) // m * m
 
 
+def _to_device(obj, dev):
+    """Recursively move the tensors of the prepared-weight dataclasses to ``dev`` (plain H2D copies, no kernels)."""
+    import dataclasses
+
+    if isinstance(obj, torch.Tensor):
+        return obj.to(dev)
+    if dataclasses.is_dataclass(obj) and not isinstance(obj, type):
+        for f in dataclasses.fields(obj):
+            setattr(obj, f.name, _to_device(getattr(obj, f.name), dev))
+        return obj
+    if isinstance(obj, list):
+        return [_to_device(o, dev) for o in obj]
+    if isinstance(obj, tuple):
+        return tuple(_to_device(o, dev) for o in obj)
+    return obj
+
+
 class _Plan:
     """Workspace + ordered kernel launches of one forward for a fixed batch size.
 
@@ -150,7 +173,7 @@ class _Plan:
         big = _round_up(big, 8)
         self.ln = torch.empty(big, **f32)
         y_elems = B * g.h_dec * g.w_dec * g.output_channels
-        self.scratch = torch.empty(_round_up(max(4 * big, 2 * big + y_elems, 2 * y_elems), 8), **f32)
+        self.scratch = torch.empty(_round_up(max(4 * big, 2 * big + y_elems, 2 * y_elems + 8), 8), **f32)
         self.ln16 = self.ln.view(torch.float16)            # [hi plane | lo plane], each ln.numel() halves
         self.scratch16 = self.scratch.view(torch.float16)  # [hi plane | lo plane], each scratch.numel() halves
         # residual streams: stages 0..2 live in the upper half of their skip-concat buffer
@@ -324,7 +347,13 @@ class _Plan:
         wx = g.variant == "wxformer"
         st0 = g.stages[0]
         big2 = 2 * (B * st0.h * st0.w * st0.dim)
-        self.y_dec = self.scratch[big2: big2 + B * g.h_dec * g.w_dec * g.output_channels]
+        y_elems = B * g.h_dec * g.w_dec * g.output_channels
+        if wx:
+            # up_block4 of the wxformer variant stages its PixelShuffle output (y_elems values, fp32 or hi/lo planes) at
+            # scratch[0:y_elems] and the next conv3x3 reads it with a halo while writing y_dec: keep y_dec behind it
+            # (output_channels > dim[0]/2 in every shipped wxformer config)
+            big2 = max(big2, _round_up(y_elems, 8))
+        self.y_dec = self.scratch[big2: big2 + y_elems]
         head_tc = tc and wts.head_tc is not None and (not wx or wts.head2_tc is not None)
         dec_in, dec_ld = self.x3, g.stages[3].dim
         dec_planes = self.x3p if tc else None
@@ -455,10 +484,12 @@ class CrossFormerB200(_Base):
 
     VARIANT = "crossformer"
 
-    def __init__(self, **kwargs):
+    def __init__(self, init_weights: Optional[bool] = None, **kwargs):
         super().__init__()
         kwargs.setdefault("variant", self.VARIANT)
         self.geometry = geo = build_geometry(**kwargs)
+        for note in check_kernel_limits(geo):
+            logger.warning(note)
         # attributes CREDIT reads off the model
         self.image_height, self.image_width = geo.image_height, geo.image_width
         self.patch_height = self.patch_width = 1
@@ -474,8 +505,13 @@ class CrossFormerB200(_Base):
         self.upsample_v_conv = False
         if self.use_padding:
             self.padding_opt = PaddingView(geo)
-        # parameters: same dotted names as the reference module tree
-        init = synthetic_state_dict(geo, seed=int(torch.initial_seed() % (2**31)), sn_iters=5)
+        # parameters: same dotted names as the reference module tree.  The reference's constructor leaves a randomly
+        # initialised model; here that initialisation (synthetic weights with power-iterated spectral-norm vectors, 124 M
+        # parameters at 0.25 deg) is LAZY: it runs at the first forward / state_dict() unless a checkpoint has been loaded by
+        # then, which is what BaseModel.load_model does right after construction (base_model.py:72-85).
+        self._init_seed = int(torch.initial_seed() % (2**31))
+        self._lazy_init = not bool(init_weights) if init_weights is not None else True
+        init = None if self._lazy_init else synthetic_state_dict(geo, seed=self._init_seed, sn_iters=5)
         for key, (shape, role) in state_spec(geo).items():
             parts = key.split(".")
             mod = self
@@ -483,16 +519,39 @@ class CrossFormerB200(_Base):
                 if p not in mod._modules:
                     mod.add_module(p, _Holder())
                 mod = mod._modules[p]
+            val = torch.empty(tuple(shape), dtype=torch.float32) if init is None else init[key]
             if role in ("u", "v"):
-                mod.register_buffer(parts[-1], init[key])
+                mod.register_buffer(parts[-1], val)
             else:
-                mod.register_parameter(parts[-1], nn.Parameter(init[key], requires_grad=False))
+                mod.register_parameter(parts[-1], nn.Parameter(val, requires_grad=False))
+        self.register_load_state_dict_post_hook(CrossFormerB200._loaded_hook)
         # exact-fp32 CUDA-core contractions instead of the f16x2 tensor-core GEMMs (validation aid, ~5x slower)
         self.exact_fp32 = os.environ.get("WXF_EXACT_FP32", "0") == "1"
         self._prepared: Optional[PreparedWeights] = None
         self._prepared_sig = None
         self._plans: Dict[tuple, _Plan] = {}
         self._domain = None  # set by domain.convert_to_domain_parallel
+
+    # -- lazy initialisation ---------------------------------------------------------------------------
+    @staticmethod
+    def _loaded_hook(module, incompatible):
+        if not incompatible.missing_keys:
+            module._lazy_init = False
+
+    def _materialise(self):
+        """Give a model that never received a checkpoint its synthetic initial weights (what the eager constructor did)."""
+        if not self._lazy_init:
+            return
+        self._lazy_init = False
+        init = synthetic_state_dict(self.geometry, seed=self._init_seed, sn_iters=5)
+        with torch.no_grad():
+            own = nn.Module.state_dict(self)
+            for k, v in init.items():
+                own[k].copy_(v)
+
+    def state_dict(self, *args, **kwargs):
+        self._materialise()
+        return super().state_dict(*args, **kwargs)
 
     # -- weight folding ------------------------------------------------------------------------------
     def _signature(self):
@@ -504,18 +563,26 @@ class CrossFormerB200(_Base):
 
     def refresh_weights(self):
         """Re-fold spectral norm / position bias and re-lay weights (automatic when parameters change)."""
-        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        self._materialise()
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("CrossFormerB200 parameters must live on a CUDA device (call .cuda()/.to('cuda'))")
-        self._prepared = prepare(sd, self.geometry, _round_up(self.geometry.input_channels, 4))
+        # The fold (spectral norm, position-bias MLPs, plane split) runs ONCE per load, on the host: a few seconds of CPU
+        # work instead of ~1000 small ATen launches, the result is bit-identical on every rank, and the only kernels this
+        # module ever launches on the GPU are its own (WXF_FOLD_DEVICE=cuda folds on the device instead).
+        on_host = os.environ.get("WXF_FOLD_DEVICE", "cpu") != "cuda"
+        sd = {k: (v.detach().cpu() if on_host else v.detach()) for k, v in self.state_dict().items()}
+        prepared = prepare(sd, self.geometry, _round_up(self.geometry.input_channels, 4))
+        self._prepared = _to_device(prepared, dev) if on_host else prepared
         self._prepared_sig = self._signature()
         self._plans.clear()
+        self._weights_version = getattr(self, "_weights_version", 0) + 1  # captured CUDA graphs key on this (rollout.py)
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         self._prepared = None
         self._plans = {}
+        self._weights_version = getattr(self, "_weights_version", 0) + 1
         return out
 
     # -- forward ---------------------------------------------------------------------------------------
@@ -561,6 +628,33 @@ class WXFormerB200(CrossFormerB200):
     (``upsample_with_ps`` accepted and ignored, :669-673)."""
 
     VARIANT = "wxformer"
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.register_load_state_dict_pre_hook(WXFormerB200._legacy_keys_pre_hook)
+
+    @staticmethod
+    def _legacy_keys_pre_hook(module, state_dict, prefix, *args):
+        """Checkpoints written before the ZeroPad2d wrap keep the cross-embed convs at ``convs.<i>.<suffix>``; the
+        reference renames them to ``convs.<i>.1.<suffix>`` in a load_state_dict pre-hook and refuses checkpoints of the
+        removed ConvTranspose2d decoder (wxformer/crossformer.py:239-310).  Same behaviour here."""
+        import re
+
+        if f"{prefix}up_block4.weight" in state_dict or f"{prefix}up_block4.weight_orig" in state_dict:
+            raise RuntimeError("this checkpoint holds the ConvTranspose2d decoder (upsample_with_ps=False), which the "
+                               "wxformer class no longer has: load it with type 'crossformer' / CrossFormerB200")
+        pat = re.compile(r"^(layers\.\d+\.0\.convs\.\d+)\.(?!\d+\.)(.+)$")
+        renamed = 0
+        for key in [k for k in state_dict if k.startswith(prefix)]:
+            m = pat.match(key[len(prefix):])
+            if m is None:
+                continue
+            new = f"{prefix}{m.group(1)}.1.{m.group(2)}"
+            if new not in state_dict:
+                state_dict[new] = state_dict.pop(key)
+                renamed += 1
+        if renamed:
+            logger.warning("Legacy CrossEmbedLayer checkpoint: remapped %d conv key(s) (convs.<i>.X -> convs.<i>.1.X)", renamed)
 
 
 def register_with_credit(key: str = "crossformer_b200", message: Optional[str] = None):

@@ -41,6 +41,7 @@ class Rollout:
         self._y = None  # sharded / graph mode: the full-size prediction buffer is reused
         self.graph = graph
         self._graphs = {}
+        self._graphs_version = None
         self.launches_per_replay = 0
 
     @property
@@ -69,6 +70,13 @@ class Rollout:
         """
         if not self.graph:
             return self._step(x, forcing, n_dynamic)
+        # captured graphs hold raw pointers into the plan workspaces and the prepared weights: a weight change
+        # (load_state_dict, .to(), refresh_weights) bumps the model's version and drops every graph captured before it
+        self.model._plan_for(x)
+        ver = getattr(self.model, "_weights_version", 0)
+        if ver != self._graphs_version:
+            self._graphs.clear()
+            self._graphs_version = ver
         key = (x.data_ptr(), tuple(x.shape), None if forcing is None else forcing.data_ptr(), n_dynamic)
         entry = self._graphs.get(key)
         if entry is None:
@@ -96,7 +104,8 @@ class Rollout:
                     y = plan.run(xc, self._y)
             else:
                 y = self.model(x)
-            ops.copy_channels(x, y, [(0, 0, self.n_prog)])
+            with torch.cuda.device(x.device):
+                ops.copy_channels(x, y, [(0, 0, self.n_prog)])
         else:
             xc, plan = self.model._plan_for(x)
             if xc.data_ptr() != x.data_ptr():
@@ -111,5 +120,6 @@ class Rollout:
             x[:, : self.n_prog, :, a:b].copy_(y[:, : self.n_prog, :, a:b])
         if forcing is not None:
             n_dyn = forcing.shape[1] if n_dynamic is None else n_dynamic
-            ops.copy_channels(x, forcing, [(self.n_prog, 0, n_dyn)])
+            with (torch.cuda.device(x.device) if x.is_cuda else contextlib.nullcontext()):
+                ops.copy_channels(x, forcing, [(self.n_prog, 0, n_dyn)])
         return y

@@ -1,0 +1,68 @@
+"""TEST INFRASTRUCTURE — import the UNMODIFIED reference forward (``oracle/_ref``, staged by ``oracle/make_ref.py``).
+
+Used by ``tests/``, ``__graft_entry__`` and ``bench.py``'s baseline legs (``--impl reference``, ``cpu_baseline``,
+``gpu_eager_baseline``) only; the product (``miles_credit_b200``) never imports this module.
+"""
+import os
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED = os.path.join(HERE, "_ref")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(STAGED, "credit", "models", "crossformer.py"))
+
+
+def _install_stub():
+    """``credit/models/crossformer.py:10`` imports ``credit.postblock.gen1`` (-> xarray, absent here); the class is only
+    instantiated under ``post_conf.activate`` (crossformer.py:580-586), which the hot-path configs switch off."""
+    if "credit.postblock.gen1" in sys.modules:
+        return
+    from torch import nn
+
+    stub = types.ModuleType("credit.postblock.gen1")
+
+    class PostBlock(nn.Module):  # never instantiated (post_conf.activate=False)
+        def __init__(self, *a, **k):
+            super().__init__()
+            raise RuntimeError("credit.postblock.gen1 is stubbed: post_conf.activate must be False")
+
+    stub.PostBlock = PostBlock
+    sys.modules["credit.postblock.gen1"] = stub
+
+
+def load_reference(root: str = None):
+    """Returns the reference's own ``credit.models.load_model`` (credit/models/__init__.py:301-387)."""
+    root = root or STAGED
+    if not os.path.isdir(os.path.join(root, "credit")):
+        raise FileNotFoundError(f"{root}: the reference is not staged (run oracle/make_ref.py in the build container)")
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    _install_stub()
+    from credit.models import load_model  # type: ignore
+
+    return load_model
+
+
+def reference_model(kwargs: dict, state_dict: dict, variant: str = "crossformer"):
+    """The reference ``nn.Module`` for our constructor kwargs with ``state_dict`` loaded ``strict=True``, in ``eval()``."""
+    import copy
+
+    load_model = load_reference()
+    conf = copy.deepcopy({k: v for k, v in kwargs.items() if k != "variant"})
+    conf["type"] = variant
+    model = load_model({"model": conf})
+    model.load_state_dict(state_dict, strict=True)
+    return model.eval()
+
+
+def seed_policy():
+    """The operating conditions of the reference's rollout apps (credit/seed.py:7-25): exact fp32, deterministic."""
+    import torch
+
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False

@@ -32,6 +32,15 @@ class EmulatedLib:
     def __init__(self):
         self.calls = []
 
+    @staticmethod
+    def _no_overlap(what, reads, writes):
+        """A contraction reads a halo of its input while other CTAs write the output: on the GPU an input byte range that
+        overlaps an output byte range is a cross-CTA race (the emulator accumulates out of place and would hide it)."""
+        for rn, r0, r1 in reads:
+            for wn, w0, w1 in writes:
+                if r0 and w0 and r0 < w1 and w0 < r1:
+                    raise AssertionError(f"{what}: input {rn} [{r0:#x}, {r1:#x}) overlaps output {wn} [{w0:#x}, {w1:#x})")
+
     def wxf_abi_version(self):
         return 10
 
@@ -216,6 +225,12 @@ class EmulatedLib:
         w_lo = self._harr(d.w_lo, P * N * T * cp).view(P, N, T, cp)[..., :Cin].double()
         taps = _t(_iarr(d.taps, P * T * 2)).view(P, T, 2)
         Hout, Wout = Ho * osc, Wo * osc
+        n_o = lambda ld, off: ((B * Hout - 1) * Wout + Wout - 1) * ld + off + N  # noqa: E731
+        self._no_overlap("conv_tc", [("in_hi", d.in_hi or 0, (d.in_hi or 0) + 2 * n_in),
+                                     ("in_lo", d.in_lo or 0, (d.in_lo or 0) + 2 * n_in)],
+                         [("out", (d.out or 0) and d.out + 4 * d.c_off, (d.out or 0) + 4 * n_o(d.ldc, d.c_off)),
+                          ("out_hi", (d.out_hi or 0) and d.out_hi + 2 * d.h_off, (d.out_hi or 0) + 2 * n_o(d.ldh, d.h_off)),
+                          ("out_lo", (d.out_lo or 0) and d.out_lo + 2 * d.h_off, (d.out_lo or 0) + 2 * n_o(d.ldh, d.h_off))])
 
         def view(ptr, ld, off, harr=False):
             n_el = ((B * Hout - 1) * Wout + Wout - 1) * ld + off + N
@@ -326,6 +341,8 @@ class EmulatedLib:
         taps = _t(_iarr(d.taps, P * T * 2)).view(P, T, 2)
         Hout, Wout = Ho * osc, Wo * osc
         n_out = ((B * Hout - 1) * Wout + Wout - 1) * d.ldc + d.c_off + N
+        if T > 1:  # a 1x1 convolution reads only the pixel it writes
+            self._no_overlap("conv", [("in", d.inp, d.inp + 4 * n_in)], [("out", d.out + 4 * d.c_off, d.out + 4 * n_out)])
         out = _t(_arr(d.out, n_out)).as_strided((B, Hout, Wout, N), (Hout * Wout * d.ldc, Wout * d.ldc, d.ldc, 1),
                                                 d.c_off)
         res = None

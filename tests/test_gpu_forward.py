@@ -138,3 +138,57 @@ def test_forward_wxformer_variant_tc_head_vs_oracle():
     err = relmax(y.cpu(), ref)
     print(f"wxformer variant (tensor-core head): rel-max vs oracle = {err:.3e}")
     assert err < TOL
+
+
+@pytest.mark.parametrize("out_only", [16, 15], ids=["tc_head_24ch", "fp32_head_23ch"])
+def test_forward_wxformer_variant_wide_output_vs_oracle(out_only):
+    """output_channels > dim[0]/2, as in every shipped `type: wxformer` config (71 vs 128, 84 vs 32): up_block4's
+    PixelShuffle output and the decoder output used to share scratch (a cross-CTA read/write race on the GPU)."""
+    kw = dict(workload("unit"), variant="wxformer", output_only_channels=out_only)
+    geo = build_geometry(**kw)
+    assert geo.output_channels > geo.dim[0] // 2
+    sd = synthetic_state_dict(geo, seed=15)
+    x = synthetic_input(geo, batch=2, seed=15)
+    with torch.no_grad():
+        ref = oracle.forward(x, sd, geo)
+    model = CrossFormerB200(**kw)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    y = model(x.cuda())
+    err = relmax(y.cpu(), ref)
+    print(f"wxformer variant, {geo.output_channels} output channels: rel-max vs oracle = {err:.3e}")
+    assert err < TOL
+    assert torch.equal(y, model(x.cuda()))  # a race would also show as run-to-run differences
+
+
+def test_forward_full_grid_025deg_vs_reference():
+    """BASELINE config[2] at FULL size: WXFormer-6h on the 721x1440 grid, CUDA path vs the UNMODIFIED reference module
+    (oracle/_ref; the oracle restatement when the reference is not staged).  ~15-40 s of host time for the reference."""
+    from oracle import ref_loader
+
+    kw = workload("wxformer_6h_025deg")
+    geo = build_geometry(**kw)
+    sd = synthetic_state_dict(geo, seed=1000, sn_iters=5)
+    x = synthetic_input(geo, batch=1, seed=1000)
+    torch.set_num_threads(os.cpu_count() or 8)
+    with torch.no_grad():
+        if ref_loader.available():
+            ref, who = ref_loader.reference_model(kw, sd)(x), "unmodified reference"
+        else:
+            ref, who = oracle.forward(x, sd, geo), "oracle"
+    model = CrossFormerB200(**kw)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    y = model(x.cuda())
+    assert y.shape == (1, 64, 1, 721, 1440)
+    err = relmax(y.cpu(), ref)
+    print(f"wxformer_6h_025deg full grid: rel-max vs {who} = {err:.3e}")
+    assert err < TOL
+    # size-independent properties at full size: bit-determinism, and batch independence (a batch of two states gives the
+    # two single-state predictions up to the reduction order of the GroupNorm statistics: no cross-sample leakage through
+    # the window packing)
+    assert torch.equal(y, model(x.cuda()))
+    x2 = torch.cat([x, torch.flip(x, dims=[-1])]).cuda()
+    y2 = model(x2)
+    assert relmax(y2[:1], y) < 1e-6
+    assert relmax(y2[1:], model(x2[1:].contiguous())) < 1e-6

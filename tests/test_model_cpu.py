@@ -103,3 +103,89 @@ print("ok")
 """
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_lazy_initialisation_and_checkpoint_load(tmp_path):
+    """Constructing the module costs no weight synthesis: the synthetic initial weights appear at the first state_dict() /
+    forward unless a checkpoint arrives first (what BaseModel.load_model does, base_model.py:72-85)."""
+    kw = workload("unit")
+    torch.manual_seed(7)
+    a = CrossFormerB200(**kw)
+    assert a._lazy_init
+    sd_a = a.state_dict()          # materialises
+    assert not a._lazy_init and all(torch.isfinite(v).all() for v in sd_a.values())
+    torch.manual_seed(7)
+    b = CrossFormerB200(**kw, init_weights=True)   # eager: same weights for the same torch seed
+    assert not b._lazy_init and all(torch.equal(sd_a[k], v) for k, v in b.state_dict().items())
+    c = CrossFormerB200(**kw)
+    sd = synthetic_state_dict(build_geometry(**kw), seed=3)
+    c.load_state_dict(sd, strict=True)
+    assert not c._lazy_init and torch.equal(c.state_dict()["up_block4.weight_orig"], sd["up_block4.weight_orig"])
+    # partial checkpoint: the missing tensors still get their initial values at first use
+    d = CrossFormerB200(**kw)
+    part = {k: v for k, v in sd.items() if not k.startswith("up_block4")}
+    msg = d.load_state_dict(part, strict=False)
+    assert msg.missing_keys and d._lazy_init
+    # save_model / load_model round trip through the BaseModel classmethods
+    conf = {"save_loc": str(tmp_path), "model": dict(kw, type="crossformer_b200"), "trainer": {"mode": "none"}}
+    c.save_model(conf)
+    e = CrossFormerB200.load_model(conf)
+    assert torch.equal(e.state_dict()["layers.2.1.layers.1.0.to_qkv.weight_orig"], sd["layers.2.1.layers.1.0.to_qkv.weight_orig"])
+    f = CrossFormerB200.load_model_name(conf, "checkpoint.pt")
+    assert torch.equal(f.state_dict()["up_block1.b.1.weight"], sd["up_block1.b.1.weight"])
+    with pytest.raises(ValueError):
+        CrossFormerB200.load_model_name(conf, "nope.pt")
+    bad = dict(sd, bogus=torch.zeros(1))
+    torch.save({"model_state_dict": bad}, os.path.join(str(tmp_path), "checkpoint.pt"))
+    with pytest.raises(RuntimeError):  # models/checkpoint.py:25-31: unexpected keys raise
+        CrossFormerB200.load_model(conf)
+
+
+def test_wxformer_legacy_checkpoint_keys_are_migrated():
+    """Reference behaviour (wxformer/crossformer.py:239-310, tests/test_legacy_checkpoint_compat.py:62-106): cross-embed
+    conv keys of pre-ZeroPad2d checkpoints are renamed on load; a ConvTranspose2d-decoder checkpoint is refused."""
+    from miles_credit_b200.model import WXFormerB200
+
+    kw = dict(workload("unit"), depth=[1, 1, 1, 1])
+    geo = build_geometry(**dict(kw, variant="wxformer"))
+    sd = synthetic_state_dict(geo, seed=5)
+    legacy = {}
+    for k, v in sd.items():
+        parts = k.split(".")
+        if len(parts) > 5 and parts[0] == "layers" and parts[2] == "0" and parts[3] == "convs" and parts[5] == "1":
+            k = ".".join(parts[:5] + parts[6:])
+        legacy[k] = v
+    assert "layers.0.0.convs.2.weight_orig" in legacy and "layers.0.0.convs.2.1.weight_orig" not in legacy
+    m = WXFormerB200(**kw)
+    msg = m.load_state_dict(legacy, strict=True)
+    assert not msg.missing_keys and not msg.unexpected_keys
+    assert torch.equal(m.state_dict()["layers.0.0.convs.2.1.weight_orig"], sd["layers.0.0.convs.2.1.weight_orig"])
+    m.load_state_dict(sd, strict=True)  # idempotent on the current layout
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(dict(sd, **{"up_block4.weight": torch.zeros(1)}), strict=False)
+
+
+def test_kernel_limits_are_checked_at_construction():
+    kw = workload("unit")
+    with pytest.raises(NotImplementedError):
+        CrossFormerB200(**dict(kw, dim_head=16))
+    with pytest.raises(NotImplementedError):  # 12 x 12 = 144 tokens per local window
+        CrossFormerB200(**dict(kw, local_window_size=12, image_height=192, image_width=192,
+                               padding_conf=dict(activate=False)))
+
+
+def test_stale_library_is_refused(monkeypatch, tmp_path):
+    if not os.path.isfile(wlib.LIB_PATH):
+        pytest.skip("library not built")
+    monkeypatch.setattr(wlib, "_lib", None)
+    monkeypatch.setattr(wlib, "WXF_ABI_VERSION", wlib.WXF_ABI_VERSION + 1)
+    with pytest.raises(RuntimeError, match="ABI version"):
+        wlib.load()
+
+
+def test_domain_layout_rejects_wide_stage_halos():
+    from miles_credit_b200.domain import DomainLayout
+
+    kw = dict(workload("unit"), cross_embed_kernel_sizes=[[4, 8, 16, 32], [2, 4, 8], [2, 4], [2, 4]])
+    with pytest.raises(NotImplementedError, match="halo"):
+        DomainLayout(build_geometry(**kw), 2)

@@ -93,6 +93,29 @@ def test_plan_wxformer_tensor_core_head_vs_oracle(emulated):
     assert float((y - ref).abs().max() / ref.abs().max()) < 2e-5
 
 
+@pytest.mark.parametrize("out_only", [16, 15])
+def test_plan_wxformer_wide_output_head_does_not_alias(emulated, out_only):
+    """wxformer variant with output_channels > dim[0]/2 (every shipped `type: wxformer` config: 71 vs 128, 84 vs 32):
+    up_block4's PixelShuffle output and the decoder output must not share scratch (the second conv3x3 reads a halo of
+    the first while other CTAs write the second).  The emulator asserts disjoint byte ranges; 24 channels = tensor-core
+    head, 23 = fp32 head."""
+    from miles_credit_b200.geometry import workload
+    from oracle import crossformer_oracle as oracle
+
+    kw = dict(workload("unit"), variant="wxformer", output_only_channels=out_only, depth=[1, 1, 1, 1])
+    geo = build_geometry(**kw)
+    assert geo.output_channels > geo.dim[0] // 2
+    sd = synthetic_state_dict(geo, seed=15)
+    wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
+    assert (wts.head2_tc is not None) == (geo.output_channels % 8 == 0)
+    plan = wmodel._Plan(geo, wts, 1, torch.device("cpu"), True)
+    x = synthetic_input(geo, batch=1, seed=15)
+    y = plan.run(x)
+    with torch.no_grad():
+        ref = oracle.forward(x, sd, geo)
+    assert float((y - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
 @pytest.mark.parametrize("variant", ["batch2", "no_padding", "no_interp", "mirror_batch2_frames2"])
 def test_plan_edge_configurations_vs_oracle(emulated, variant):
     """Host logic on configurations the golden fixtures do not cover: batch > 1, padding switched off
