@@ -42,6 +42,70 @@ WORKLOAD = "wxformer_6h_025deg"
 TENSOR_FAMILIES = ("qkv", "out_proj", "ff1", "ff2", "embed", "dec_up", "dec_conv3x3", "dec_head", "attention")
 
 
+class Arm:
+    """Everything model-specific the bench needs for a named workload (WXFormer / CrossFormer or FuXi)."""
+
+    def __init__(self, name):
+        self.name = name
+        if name.startswith("fuxi"):
+            from miles_credit_b200 import fuxi as F
+
+            self.kw = F.fuxi_workload(name)
+            self.geo = geo = F.build_fuxi_geometry(**self.kw)
+            self.cls, self.variant = F.FuxiB200, "fuxi"
+            self.state_dict = lambda: F.synthetic_fuxi_state_dict(geo, seed=1000, sn_iters=5)
+            self.input = lambda seed=1000: F.synthetic_fuxi_input(geo, batch=1, seed=seed)
+            self.flops = F.fuxi_flops_per_forward(geo)["total"]
+            self.label = "FuXi-6h"
+            self.can_decompose = False
+        else:
+            from miles_credit_b200.geometry import build_geometry, flops_per_forward, workload
+            from miles_credit_b200.model import CrossFormerB200, WXFormerB200
+            from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
+
+            self.kw = workload(name)
+            self.geo = geo = build_geometry(**self.kw)
+            self.variant = self.kw.get("variant", "crossformer")
+            self.cls = WXFormerB200 if self.variant == "wxformer" else CrossFormerB200
+            self.state_dict = lambda: synthetic_state_dict(geo, seed=1000, sn_iters=5)
+            self.input = lambda seed=1000: synthetic_input(geo, batch=1, seed=seed)
+            self.flops = flops_per_forward(geo)["total"]
+            self.label = "WXFormer-6h"
+            self.can_decompose = True
+        g = self.geo
+        self.n_prog = g.channels * g.levels + g.surface_channels
+        self.metric = (f"forecast steps/sec at 0.25deg {g.image_height}x{g.image_width} ({self.label} forward + state update)"
+                       if (g.image_height, g.image_width) == (721, 1440) else
+                       f"forecast steps/sec on the {g.image_height}x{g.image_width} grid ({self.label} forward + state update)")
+
+    def update(self, x, y):
+        """update_x / history slide on the host tensors of the CPU and eager-GPU baselines."""
+        nxt = x.clone()
+        if nxt.shape[2] > 1:
+            nxt[:, :, :-1] = x[:, :, 1:]
+        nxt[:, : self.n_prog, -1] = y[:, : self.n_prog, 0]
+        return nxt
+
+    def cpu_forward(self):
+        """(forward(x) -> y, kind): the UNMODIFIED reference module when oracle/_ref is staged (kind "reference"; for FuXi
+        its third-party Swin-V2 stage is the restatement of oracle/swin_v2.py, timm being absent), else the oracle."""
+        from oracle import ref_loader
+
+        sd = self.state_dict()
+        if ref_loader.available(self.variant) and os.environ.get("WXF_BENCH_CPU_PORT", "0") != "1":
+            model = ref_loader.reference_model(self.kw, sd, self.variant)
+            return (lambda x: model(x)), "reference", model
+        if self.variant == "fuxi":
+            from oracle import fuxi_oracle
+
+            spec = fuxi_oracle.FuxiSpec.from_kwargs(**self.kw)
+            return (lambda x: fuxi_oracle.forward(x, sd, spec)), "port", None
+        from oracle import crossformer_oracle as oracle
+
+        geo = self.geo
+        return (lambda x: oracle.forward(x, sd, geo)), "port", None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -129,48 +193,26 @@ def max_over_ranks(val, world, device):
     return float(t.item())
 
 
-def _cpu_forward(name):
-    """(forward(x) -> y, kind, geo) of the CPU baseline for a named workload: the UNMODIFIED reference module when
-    oracle/_ref is staged (kind "reference"), else the oracle restatement (kind "port")."""
-    from miles_credit_b200.geometry import build_geometry, workload
-    from miles_credit_b200.synth import synthetic_state_dict
-    from oracle import ref_loader
-
-    kw = workload(name)
-    geo = build_geometry(**kw)
-    sd = synthetic_state_dict(geo, seed=1000, sn_iters=5)
-    if ref_loader.available() and os.environ.get("WXF_BENCH_CPU_PORT", "0") != "1":
-        model = ref_loader.reference_model(kw, sd, kw.get("variant", "crossformer"))
-        return (lambda x: model(x)), "reference", geo
-    from oracle import crossformer_oracle as oracle
-
-    return (lambda x: oracle.forward(x, sd, geo)), "port", geo
-
-
 def cpu_forward_seconds(name, steps, warmup, threads, budget_s=None):
     """Time ``steps`` forward + state-update steps of the CPU baseline for a named workload (full grid, nothing scaled).
     ``budget_s``: stop early once the timed steps exceed it (the line then reports the number of steps really timed)."""
-    from miles_credit_b200.synth import synthetic_input
-
     torch.set_num_threads(threads)
-    fwd, kind, geo = _cpu_forward(name)
-    n_prog = geo.channels * geo.levels + geo.surface_channels
-    x = synthetic_input(geo, batch=1, seed=1000)
+    arm = Arm(name)
+    fwd, kind, _ = arm.cpu_forward()
+    x = arm.input(1000)
     times, y0 = [], None
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
             y = fwd(x)
-            nxt = x.clone()  # update_x (datasets/gen_2/channel_utils.py:253-291): clone, overwrite the prognostic channels
-            nxt[:, :n_prog, -1] = y[:, :n_prog, 0]
-            x = nxt
+            x = arm.update(x, y)  # update_x (datasets/gen_2/channel_utils.py:253-291): clone, overwrite the prognostic channels
             if y0 is None:
                 y0 = y
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
                 if budget_s is not None and sum(times) > budget_s:
                     break
-    return times, geo, y0, kind
+    return times, arm, y0, kind
 
 
 def run_reference(args, rank, world):
@@ -179,13 +221,14 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     warm = min(args.warmup, 1)
-    times, geo, _, kind = cpu_forward_seconds(args.workload, args.steps, warm, cores, budget_s=300.0)
+    times, arm, _, kind = cpu_forward_seconds(args.workload, args.steps, warm, cores, budget_s=300.0)
+    geo = arm.geo
     sec = sum(times) / len(times)
     value = 1.0 / sec
     what = ("the UNMODIFIED reference module (credit.models.load_model, staged under oracle/_ref)" if kind == "reference"
             else "the oracle restatement of the reference forward (oracle/_ref not staged)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": arm.metric, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": warm, "ms_per_step": 1e3 * sec, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "grid": f"{geo.image_height}x{geo.image_width}", "batch": 1},
@@ -201,19 +244,14 @@ def run_reference(args, rank, world):
 def gpu_eager_baseline(name, dev, steps=5, warmup=2):
     """The UNMODIFIED reference module, eager PyTorch on the same GPU, exact fp32 (TF32 off, deterministic cuDNN: the
     operating conditions of the reference's rollout apps, credit/seed.py:7-25).  Returns (record, first prediction)."""
-    from miles_credit_b200.geometry import build_geometry, workload
-    from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
     from oracle import ref_loader
 
-    if not ref_loader.available():
+    arm = Arm(name)
+    if not ref_loader.available(arm.variant):
         return {"unavailable": "oracle/_ref not staged"}, None
     ref_loader.seed_policy()
-    kw = workload(name)
-    geo = build_geometry(**kw)
-    sd = synthetic_state_dict(geo, seed=1000, sn_iters=5)
-    model = ref_loader.reference_model(kw, sd, kw.get("variant", "crossformer")).to(dev)
-    n_prog = geo.channels * geo.levels + geo.surface_channels
-    x = synthetic_input(geo, batch=1, seed=1000).to(dev)
+    model = ref_loader.reference_model(arm.kw, arm.state_dict(), arm.variant).to(dev)
+    x = arm.input(1000).to(dev)
     y0 = None
     torch.cuda.reset_peak_memory_stats(dev)
     with torch.no_grad():
@@ -225,9 +263,7 @@ def gpu_eager_baseline(name, dev, steps=5, warmup=2):
             y = model(x)
             if y0 is None:
                 y0 = y.clone()
-            nxt = x.clone()
-            nxt[:, :n_prog, -1] = y[:, :n_prog, 0]
-            x = nxt
+            x = arm.update(x, y)
         e1.record()
         torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / steps
@@ -240,12 +276,14 @@ def gpu_eager_baseline(name, dev, steps=5, warmup=2):
     return rec, y0
 
 
-def family_traffic():
+def family_traffic(workload):
     """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) by kernel family, from the committed ncu
-    capture of one forecast step (profiles/traffic_by_family.json, written by tools/ncu_traffic.py)."""
-    p = os.path.join(ROOT, "profiles", "traffic_by_family.json")
-    if os.path.isfile(p):
-        return json.load(open(p))
+    capture of one forecast step of this workload (profiles/traffic_by_family[.<workload>].json, tools/ncu_traffic.py)."""
+    names = [f"traffic_by_family.{workload}.json"] + (["traffic_by_family.json"] if workload == WORKLOAD else [])
+    for n in names:
+        p = os.path.join(ROOT, "profiles", n)
+        if os.path.isfile(p):
+            return json.load(open(p))
     return {}
 
 
@@ -273,19 +311,20 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     from miles_credit_b200 import ops
-    from miles_credit_b200.geometry import build_geometry, flops_per_forward, workload
-    from miles_credit_b200.model import CrossFormerB200
     from miles_credit_b200.rollout import Rollout
-    from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
 
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    kw = workload(args.workload)
-    geo = build_geometry(**kw)
-    model = CrossFormerB200(**kw)
-    model.load_state_dict(synthetic_state_dict(geo, seed=1000, sn_iters=5), strict=True)
+    arm = Arm(args.workload)
+    kw, geo = arm.kw, arm.geo
+
+    def synthetic_input(_geo, batch=1, seed=1000):
+        return arm.input(seed)
+
+    model = arm.cls(**kw)
+    model.load_state_dict(arm.state_dict(), strict=True)
     model = model.to(dev).eval()
-    domain = world > 1 and args.parallel == "domain"
+    domain = world > 1 and args.parallel == "domain" and arm.can_decompose
     replicas = None
     if domain:
         # secondary number first: N independent forecasts, one per GPU (what reference rollout_gen2.py:243-253 does)
@@ -346,7 +385,7 @@ def main():
 
     # ---- end to end through host buffers -----------------------------------------------------------------
     x.copy_(synthetic_input(geo, batch=1, seed=1000 + (0 if domain else rank)).to(dev))
-    plane = (1, n_dyn, 1, geo.image_height, geo.image_width)
+    plane = (1, n_dyn, 1, geo.image_height, geo.image_width)  # one new time step of the dynamic forcing
     forcing_host = [torch.randn(plane).pin_memory() for _ in range(2)]
     forcing_dev = torch.empty(plane, device=dev)
     o_lo, o_hi = ro.own_rows(x)  # decomposed forecast: every rank hands ITS rows of the prediction to the host
@@ -420,7 +459,7 @@ def main():
     tot_ms = sum(f["ms"] for f in fam.values())
     top = max(fam, key=lambda k: fam[k]["ms"])
     tf = fam[top]
-    traffic = family_traffic().get(top, {})
+    traffic = family_traffic(args.workload).get(top, {})
     if tf["flops"] > 0:
         achieved = tf["flops"] / (tf["ms"] / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": pk["bf16_tflops_sustained"],
@@ -485,9 +524,9 @@ def main():
         barrier(world)
 
     if rank == 0:
-        fl = flops_per_forward(geo)
+        fl = {"total": arm.flops}
         line = {
-            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "metric": arm.metric, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if domain else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",

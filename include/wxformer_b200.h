@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 10
+#define WXF_ABI_VERSION 11
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -206,7 +206,9 @@ int wxf_ff_fused_f16x2_tc(const WxfFfDesc* desc, void* stream);
  *   taps         : HOST pointer, [phases, T, 2] = (dy, dx) with padding already subtracted, T <= 64
  *   epilogue     : v = acc*2^-w_scale_log2 + bias[n]; act; + res[pixel*ldr + r_off + n];
  *                  out[pixel*ldc + c_off + n] (fp32, optional), out_hi/lo[pixel*ldh + h_off + n] (optional)
- * N % 4 == 0, lda % 8 == 0, cin_pad % 64 == 0 (weights zero-padded per tap), stride in {1, 2}.
+ * N % 4 == 0, lda % 8 == 0, cin_pad % 64 == 0 (weights zero-padded per tap), stride in {1, 2, 4} (4: the patch
+ * embedding of FuXi's CubeEmbedding, Conv3d kernel = stride = (T, 4, 4) with the frames folded into the channels,
+ * credit/models/fuxi.py:107).
  */
 typedef struct WxfConvTcDesc {
   const void* in_hi;
@@ -308,6 +310,70 @@ int wxf_unpad_resize_to_nchw(const float* y, int ld, float* out, int B, int C, i
  */
 int wxf_copy_channels(float* dst, int dst_C, const float* src, int src_C, int B, int64_t plane,
                       const int32_t* dst_c0, const int32_t* src_c0, const int32_t* len, int n_groups, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * FuXi forecast step (credit/models/fuxi.py:454-506).  Its contractions run on the entry points above: CubeEmbedding
+ * (fuxi.py:82-143) = wxf_conv_f16x2_tc with a 4x4 stride-4 kernel on the frame-folded padded input + wxf_layernorm;
+ * DownBlock / UpBlock (fuxi.py:146-201) = wxf_conv_f16x2_tc + wxf_groupnorm_*; the Linear layers of the Swin-V2 stage
+ * (timm SwinTransformerV2Stage, fuxi.py:250-260) and the dense head (fuxi.py:420, 484) = wxf_gemm_f16x2_tc.
+ * The four entry points below are what FuXi needs on top.
+ */
+
+/*
+ * Res-post-norm of a Swin-V2 block (timm SwinTransformerV2Block.forward: x = x + norm1(attn(x)); x = x + norm2(mlp(x))):
+ *   o = res[m, :] + LayerNorm(x[m, :]) * g + b   (biased variance, eps inside the root, nn.LayerNorm)
+ * written as fp32 (out, optional, may alias res) and / or fp16 hi/lo operand planes (out_hi/out_lo, optional).
+ */
+int wxf_layernorm_residual(const float* x, int ldx, const float* res, int ldr, float* out, int ldo, void* out_hi,
+                           void* out_lo, int ldh, const float* g, const float* b, int64_t M, int d, float eps, void* stream);
+
+/*
+ * Swin-V2 window attention core (timm WindowAttention.forward + the shift / mask logic of SwinTransformerV2Block) for all
+ * windows and heads of one block, exact fp32:
+ *   qkv  : [B, H, W, ldq] fp32 (output of the qkv Linear incl. q_bias / v_bias), q = [0,d), k = [d,2d), v = [2d,3d),
+ *          head h = channels h*dh .. h*dh+dh-1, dh = d / heads
+ *   window (wy, wx), token (ty, tx) = source pixel ((wy*ws_h + ty + shift_h) mod H, (wx*ws_w + tx + shift_w) mod W)
+ *          [torch.roll(x, (-shift_h, -shift_w)) then window_partition]; the output row returns to the same pixel
+ *   S[i][j] = <q_i / max(|q_i|, 1e-12), k_j / max(|k_j|, 1e-12)> * logit_scale[h] + bias[h][i][j]
+ *             + (region(i) != region(j) ? -100 : 0),   P = softmax_j(S),   out_i = sum_j P[i][j] v_j
+ *   region = the 3 x 3 partition of the rolled image by the slices (0, -ws), (-ws, -shift), (-shift, end) per axis
+ *            (only for a non-zero shift on that axis)
+ *   bias        : [heads, L, L] fp32 = 16 * sigmoid(cpb_mlp(log-spaced relative coordinates)), L = ws_h*ws_w <= 64
+ *   logit_scale : [heads] fp32 = exp(min(logit_scale, ln 100))
+ *   output: fp16 hi/lo planes [B*H*W, ldh] (input of the proj GEMM) or fp32 [B*H*W, ldh] (exactly one of the two).
+ */
+int wxf_swin_window_attention(const float* qkv, int ldq, const float* bias, const float* logit_scale, void* out_hi,
+                              void* out_lo, float* out_f32, int ldh, int B, int H, int W, int d, int heads, int ws_h,
+                              int ws_w, int shift_h, int shift_w, void* stream);
+
+/*
+ * Row gather with zero fill: dst[i, 0:d] = idx[i] >= 0 ? src[idx[i], 0:d] : 0, written as fp32 (dst, optional) and / or
+ * fp16 hi/lo planes at column offset h_off (optional).  ZeroPad2d to a window multiple and its crop (fuxi.py:67-79,
+ * 281-283, 288-289) and the channel concat with the shortcut (fuxi.py:292) are index lists for this pass.
+ */
+int wxf_gather_rows_ex(const float* src, int ld_src, const int32_t* idx, float* dst, int ld_dst, void* hi, void* lo, int ldh,
+                       int h_off, int64_t n, int d, void* stream);
+
+/*
+ * Dense-head output -> prediction (fuxi.py:484-498): y is token-major [B, Lat, Lon, ph*pw*cp] where pixel (py, px) of a
+ * patch owns the columns (py*pw + px)*cp + c, c < C <= cp (the head's weight rows re-ordered and padded at load);
+ * un-patchify, crop rows [top, top+Hc) x cols [left, left+Wc), bilinear resize (align_corners = False) to Ho x Wo,
+ * write NCHW [B, C, Ho, Wo]; only output rows [o0, o0 + n_out).
+ */
+int wxf_unpatchify_unpad_resize_to_nchw(const float* y, float* out, int B, int C, int cp, int Lat, int Lon, int ph, int pw,
+                                        int top, int left, int Hc, int Wc, int Ho, int Wo, int o0, int n_out, void* stream);
+
+/*
+ * Autoregressive state update with a history window of T input frames (the gen2 rollout's slide,
+ * credit/trainers/rollout_utils.py:288-311: drop the oldest time step, append the newest; the newest step is update_x,
+ * credit/datasets/gen_2/channel_utils.py:253-291), in place on x [B, C, T, plane]:
+ *   t < T-1 : x[b, c, t] = x[b, c, t+1]
+ *   t = T-1 : c < n_prog: y[b, c, 0] (y is [B, Cy, Ty, plane]);  n_prog <= c < n_prog + n_dyn: forcing[b, c - n_prog]
+ *             (forcing [B, n_dyn, plane], NULL = carried);  other channels (static) carried.
+ * T = 1 is the plain update_x.
+ */
+int wxf_history_update(float* x, const float* y, const float* forcing, int B, int C, int T, int n_prog, int n_dyn, int Cy,
+                       int Ty, int64_t plane, void* stream);
 
 #ifdef __cplusplus
 }

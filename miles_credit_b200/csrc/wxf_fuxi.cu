@@ -320,7 +320,43 @@ __global__ void __launch_bounds__(256) unpatchify_resize_kernel(const float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Autoregressive state update with a history window (trainers/rollout_utils.py:288-311: drop the oldest time step,
+// append the newest; update_x, datasets/gen_2/channel_utils.py:253-291, for the newest step).  x: [B, C, T, plane].
+// One thread owns a pixel of one (b, c) and walks t upwards, so the in-place shift never reads a value it has written.
+__global__ void __launch_bounds__(256) history_update_kernel(float* __restrict__ x, const float* __restrict__ y,
+                                                             const float* __restrict__ frc, int C, int T, int n_prog,
+                                                             int n_dyn, int Cy, int Ty, int64_t plane, int64_t total) {
+  wxf_pdl_trigger();
+  wxf_pdl_wait();
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = e % plane;
+    const int64_t bc = e / plane;
+    const int c = (int)(bc % C);
+    const int64_t b = bc / C;
+    float* xc = x + (bc * T) * plane + p;
+    for (int t = 0; t + 1 < T; ++t) xc[(int64_t)t * plane] = xc[(int64_t)(t + 1) * plane];
+    if (c < n_prog)
+      xc[(int64_t)(T - 1) * plane] = y[((b * Cy + c) * Ty) * plane + p];
+    else if (frc && c < n_prog + n_dyn)
+      xc[(int64_t)(T - 1) * plane] = frc[(b * n_dyn + (c - n_prog)) * plane + p];
+  }
+}
+
 }  // namespace
+
+extern "C" int wxf_history_update(float* x, const float* y, const float* forcing, int B, int C, int T, int n_prog, int n_dyn,
+                                  int Cy, int Ty, int64_t plane, void* stream) {
+  if (!x || !y || B <= 0 || C <= 0 || T <= 0 || n_prog < 0 || n_dyn < 0 || n_prog + n_dyn > C || n_prog > Cy || Ty <= 0 ||
+      plane <= 0)
+    WXF_FAIL(WXF_EINVAL, "history_update: bad dims");
+  const int64_t total = (int64_t)B * C * plane;
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  wxf_launch(history_update_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, y, forcing, C, T, n_prog, n_dyn, Cy, Ty,
+             plane, total);
+  WXF_CHECK_LAUNCH("history_update");
+  return 0;
+}
 
 extern "C" int wxf_layernorm_residual(const float* x, int ldx, const float* res, int ldr, float* out, int ldo, void* out_hi,
                                       void* out_lo, int ldh, const float* g, const float* b, int64_t M, int d, float eps,

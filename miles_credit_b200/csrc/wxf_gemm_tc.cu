@@ -1469,7 +1469,7 @@ extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
       d->lda < d->Cin)
     WXF_FAIL(WXF_EINVAL, "conv_tc: bad dims");
   if (d->T > MAX_TAPS) WXF_FAIL(WXF_EUNSUPPORTED, "conv_tc: %d taps > %d", d->T, MAX_TAPS);
-  if (d->stride != 1 && d->stride != 2) WXF_FAIL(WXF_EUNSUPPORTED, "conv_tc: stride must be 1 or 2");
+  if (d->stride != 1 && d->stride != 2 && d->stride != 4) WXF_FAIL(WXF_EUNSUPPORTED, "conv_tc: stride must be 1, 2 or 4");
   if (d->phases != 1 && d->phases != 4) WXF_FAIL(WXF_EINVAL, "conv_tc: phases must be 1 or 4");
   if ((d->phases == 4) != (d->out_scale == 2) || (d->phases == 1 && d->out_scale != 1))
     WXF_FAIL(WXF_EINVAL, "conv_tc: phases/out_scale mismatch");

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 10
+WXF_ABI_VERSION = 11
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -113,6 +113,14 @@ _SIGNATURES = {
     "wxf_groupnorm_stats_from_sums": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_double, c_float, c_void_p]),
     "wxf_gather_rows": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "wxf_unpad_resize_to_nchw": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 12 + [c_void_p]),
+    "wxf_layernorm_residual": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                       c_void_p, c_int64, c_int, c_float, c_void_p]),
+    "wxf_swin_window_attention": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]
+                                  + [c_int] * 9 + [c_void_p]),
+    "wxf_gather_rows_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int64,
+                                   c_int, c_void_p]),
+    "wxf_unpatchify_unpad_resize_to_nchw": (c_int, [c_void_p, c_void_p] + [c_int] * 15 + [c_void_p]),
+    "wxf_history_update": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_int64, c_void_p]),
     "wxf_copy_channels": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int64, POINTER(c_int32), POINTER(c_int32),
                                   POINTER(c_int32), c_int, c_void_p]),
 }

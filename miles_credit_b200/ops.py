@@ -367,3 +367,68 @@ def copy_channels(dst: torch.Tensor, src: torch.Tensor, groups):
     st = _lib.load().wxf_copy_channels(dst.data_ptr(), dc, src.data_ptr(), sc, B, plane, d0, s0, ln, n, _stream())
     _lib.check(st, "wxf_copy_channels")
     LAUNCHES += 1
+
+
+# ---- FuXi (credit/models/fuxi.py): the entry points on top of the shared contraction / normalisation kernels ----------
+
+def layernorm_residual(x: torch.Tensor, ldx: int, res: Optional[torch.Tensor], ldr: int, out: Optional[torch.Tensor], ldo: int,
+                       out_hi: Optional[torch.Tensor], out_lo: Optional[torch.Tensor], ldh: int, g: torch.Tensor,
+                       b: torch.Tensor, m: int, d: int, eps: float = 1e-5):
+    """o = res + LayerNorm(x) * g + b, as fp32 and / or fp16 hi/lo planes (res-post-norm of a Swin-V2 block)."""
+    global LAUNCHES
+    st = _lib.load().wxf_layernorm_residual(x.data_ptr(), ldx, _ptr(res), ldr, _ptr(out), ldo, _ptr(out_hi), _ptr(out_lo), ldh,
+                                            g.data_ptr(), b.data_ptr(), m, d, eps, _stream())
+    _lib.check(st, "wxf_layernorm_residual")
+    LAUNCHES += 1
+
+
+def swin_window_attention(qkv: torch.Tensor, ldq: int, bias: torch.Tensor, logit_scale: torch.Tensor, out_hi, out_lo, out_f32,
+                          ldh: int, B: int, H: int, W: int, d: int, heads: int, ws, shift):
+    """Swin-V2 scaled-cosine window attention of one block (cyclic shift, per-head bias and scale, -100 shift masks)."""
+    global LAUNCHES
+    st = _lib.load().wxf_swin_window_attention(qkv.data_ptr(), ldq, bias.data_ptr(), logit_scale.data_ptr(), _ptr(out_hi),
+                                               _ptr(out_lo), _ptr(out_f32), ldh, B, H, W, d, heads, ws[0], ws[1], shift[0],
+                                               shift[1], _stream())
+    _lib.check(st, "wxf_swin_window_attention")
+    LAUNCHES += 1
+
+
+def gather_rows_ex(src: torch.Tensor, ld_src: int, idx: torch.Tensor, dst: Optional[torch.Tensor], ld_dst: int, hi, lo, ldh: int,
+                   h_off: int, n: int, d: int):
+    """dst[i, :d] = src[idx[i], :d] or 0 where idx[i] < 0; fp32 and / or fp16 hi/lo planes at column offset h_off."""
+    global LAUNCHES
+    if n == 0:
+        return
+    st = _lib.load().wxf_gather_rows_ex(src.data_ptr(), ld_src, idx.data_ptr(), _ptr(dst), ld_dst, _ptr(hi), _ptr(lo), ldh,
+                                        h_off, n, d, _stream())
+    _lib.check(st, "wxf_gather_rows_ex")
+    LAUNCHES += 1
+
+
+def unpatchify_unpad_resize_to_nchw(y: torch.Tensor, out: torch.Tensor, B: int, C: int, cp: int, Lat: int, Lon: int, ph: int,
+                                    pw: int, top: int, left: int, Hc: int, Wc: int, Ho: int, Wo: int, rows=None):
+    """Token-major dense-head output -> un-patchify, crop, bilinear resize, NCHW (fuxi.py:484-498)."""
+    global LAUNCHES
+    o0, n_out = rows if rows is not None else (0, Ho)
+    st = _lib.load().wxf_unpatchify_unpad_resize_to_nchw(y.data_ptr(), out.data_ptr(), B, C, cp, Lat, Lon, ph, pw, top, left, Hc,
+                                                         Wc, Ho, Wo, o0, n_out, _stream())
+    _lib.check(st, "wxf_unpatchify_unpad_resize_to_nchw")
+    LAUNCHES += 1
+
+
+def history_update(x: torch.Tensor, y: torch.Tensor, forcing: Optional[torch.Tensor], n_prog: int, n_dyn: int):
+    """In-place rollout update of x [B, C, T, H, W] with a history window: slide the frames, newest frame from the prediction
+    y [B, Cy, Ty, H, W] (prognostic channels) and ``forcing`` [B, n_dyn, 1, H, W] (None = carried)."""
+    global LAUNCHES
+    _req(x, "x")
+    _req(y, "y")
+    if not (x.is_contiguous() and y.is_contiguous() and (forcing is None or forcing.is_contiguous())):
+        raise ValueError("history_update needs contiguous tensors")
+    B, C, T = x.shape[:3]
+    plane = x.shape[3] * x.shape[4]
+    if y.shape[0] != B or y.shape[3] * y.shape[4] != plane:
+        raise ValueError("history_update: prediction / state shape mismatch")
+    st = _lib.load().wxf_history_update(x.data_ptr(), y.data_ptr(), _ptr(forcing), B, C, T, n_prog, n_dyn, y.shape[1],
+                                        y.shape[2], plane, _stream())
+    _lib.check(st, "wxf_history_update")
+    LAUNCHES += 1

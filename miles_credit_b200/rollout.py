@@ -3,7 +3,9 @@
 Mirrors the reference's flat rollout loop (applications/rollout_to_netcdf.py:269-310): ``y = model(x)``,
 then ``x <- update_x(x, forcing, y)`` (datasets/gen_2/channel_utils.py:253-291): prognostic channels come
 from the prediction, dynamic-forcing channels from the data stream, static channels are carried.
-Only single-frame inputs (history_len == 1) are supported, like ``build_channel_layout`` (channel_utils.py:205-211).
+With ``frames > 1`` (FuXi: two input states; CrossFormer configs with a history window) the input slides like the gen2
+rollout does (trainers/rollout_utils.py:288-311: drop the oldest time step, append the newest), in one in-place kernel
+(``wxf_history_update``); the flat reference loop refuses that case (``build_channel_layout``, channel_utils.py:205-211).
 """
 
 from __future__ import annotations
@@ -33,8 +35,9 @@ class Rollout:
         step on 8 GPUs, where the average kernel lasts ~15 us).  The returned prediction is then a buffer owned by the
         rollout that the next step overwrites."""
         geo = model.geometry
-        if geo.frames != 1 or geo.output_frames != 1:
-            raise ValueError("rollout state update needs frames == output_frames == 1 (reference: history_len == 1)")
+        if getattr(geo, "output_frames", 1) != 1:
+            raise ValueError("rollout state update needs output_frames == 1 (one new state per step)")
+        self.frames = geo.frames
         self.model = model
         self.n_prog = geo.channels * geo.levels + geo.surface_channels
         self.n_forced = geo.input_only_channels
@@ -104,9 +107,17 @@ class Rollout:
                     y = plan.run(xc, self._y)
             else:
                 y = self.model(x)
-            with torch.cuda.device(x.device):
+            dev_ctx = torch.cuda.device(x.device) if x.is_cuda else contextlib.nullcontext()
+            if self.frames > 1:  # history window: slide the frames, newest from the prediction (+ forcing), one kernel
+                n_dyn = 0 if forcing is None else (forcing.shape[1] if n_dynamic is None else n_dynamic)
+                with dev_ctx:
+                    ops.history_update(x, y, forcing, self.n_prog, n_dyn)
+                return y
+            with dev_ctx:
                 ops.copy_channels(x, y, [(0, 0, self.n_prog)])
         else:
+            if self.frames > 1:
+                raise NotImplementedError("the sharded rollout keeps a single-frame state (frames == 1)")
             xc, plan = self.model._plan_for(x)
             if xc.data_ptr() != x.data_ptr():
                 raise ValueError("sharded rollout updates the state in place: pass a contiguous fp32 tensor")

@@ -45,7 +45,12 @@ def power_iterate(w_mat: torch.Tensor, g: torch.Generator, iters: int = 30, eps:
 
 
 def synthetic_state_dict(geo: Geometry, seed: int = 1000, sn_iters: int = 30) -> "OrderedDict[str, torch.Tensor]":
-    spec = state_spec(geo)
+    return synthesize(state_spec(geo), seed, sn_iters)
+
+
+def synthesize(spec, seed: int = 1000, sn_iters: int = 30) -> "OrderedDict[str, torch.Tensor]":
+    """Deterministic weights for a ``key -> (shape, role)`` table (roles: ``weight:<sn dim>``, ``u``, ``v``, ``bias``,
+    ``gain``, ``shift``, ``const:<value>``)."""
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     keys = list(spec.keys())
     for idx, key in enumerate(keys):
@@ -75,6 +80,8 @@ def synthetic_state_dict(geo: Geometry, seed: int = 1000, sn_iters: int = 30) ->
             sd[key] = 1.0 + 0.1 * torch.randn(shape, generator=g)
         elif role == "shift":
             sd[key] = 0.1 * torch.randn(shape, generator=g)
+        elif role.startswith("const:"):
+            sd[key] = torch.full(shape, float(role.split(":")[1]))
         else:
             raise AssertionError(role)
     return OrderedDict((k, sd[k]) for k in keys)

@@ -52,6 +52,16 @@ def stage(verbose=True):
         with torch.no_grad():
             m.train()
             m(torch.randn(1, 10, 1, 45, 96))
+    # FuXi (credit/models/fuxi.py) with the Swin-V2 stand-in registered as timm (oracle/swin_v2.py)
+    import swin_v2  # noqa: E402
+
+    swin_v2.install_timm_stub()
+    fx = dict(image_height=32, image_width=96, patch_height=4, patch_width=4, frames=2, frame_patch_size=2, levels=2, channels=2,
+              surface_channels=1, input_only_channels=0, output_only_channels=0, dim=32, num_groups=8, num_heads=4, depth=2,
+              window_size=5, use_spectral_norm=True, interp=True, padding_conf=dict(activate=False), post_conf={"activate": False})
+    m = load_model({"model": dict(fx, type="fuxi")}).cpu()
+    with torch.no_grad():
+        m(torch.randn(1, 5, 2, 32, 96))
     import credit.boundary_padding  # noqa: F401,E402
     import credit.seed  # noqa: F401,E402
 

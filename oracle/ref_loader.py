@@ -11,8 +11,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 STAGED = os.path.join(HERE, "_ref")
 
 
-def available() -> bool:
-    return os.path.isfile(os.path.join(STAGED, "credit", "models", "crossformer.py"))
+def available(variant: str = "crossformer") -> bool:
+    name = {"fuxi": "fuxi.py", "wxformer": os.path.join("wxformer", "crossformer.py")}.get(variant, "crossformer.py")
+    return os.path.isfile(os.path.join(STAGED, "credit", "models", name))
 
 
 def _install_stub():
@@ -50,10 +51,18 @@ def reference_model(kwargs: dict, state_dict: dict, variant: str = "crossformer"
     """The reference ``nn.Module`` for our constructor kwargs with ``state_dict`` loaded ``strict=True``, in ``eval()``."""
     import copy
 
+    if variant == "fuxi":
+        # credit/models/fuxi.py:4-5 imports timm's SwinTransformerV2Stage; timm is in neither the reference tree nor this
+        # image: the restatement of oracle/swin_v2.py stands in (parity of that stage: unpinned, SURVEY.md section 8c)
+        from oracle import swin_v2
+
+        swin_v2.install_timm_stub()
     load_model = load_reference()
     conf = copy.deepcopy({k: v for k, v in kwargs.items() if k != "variant"})
     conf["type"] = variant
     model = load_model({"model": conf})
+    if variant == "fuxi":
+        model = model.cpu()  # Fuxi.__init__ moves itself to cuda when one is visible (fuxi.py:433-435); callers place it
     model.load_state_dict(state_dict, strict=True)
     return model.eval()
 

@@ -42,7 +42,7 @@ class EmulatedLib:
                     raise AssertionError(f"{what}: input {rn} [{r0:#x}, {r1:#x}) overlaps output {wn} [{w0:#x}, {w1:#x})")
 
     def wxf_abi_version(self):
-        return 10
+        return 11
 
     def wxf_last_error(self):
         return b"emulator"
@@ -486,4 +486,100 @@ class EmulatedLib:
         ss = _t(_arr(src, B * src_C * plane)).view(B, src_C, plane)
         for g in range(n):
             dd[:, d0[g]: d0[g] + ln[g]] = ss[:, s0[g]: s0[g] + ln[g]]
+        return 0
+
+    # ---- FuXi entry points (documented semantics of include/wxformer_b200.h) ------------------------------------------
+
+    def wxf_layernorm_residual(self, x, ldx, res, ldr, out, ldo, out_hi, out_lo, ldh, g, b, M, d, eps, stream):
+        self.calls.append("layernorm_residual")
+        xs = _t(_arr(x, (M - 1) * ldx + d)).as_strided((M, d), (ldx, 1))
+        gg, bb = _t(_arr(g, d)), _t(_arr(b, d))
+        mean = xs.mean(1, keepdim=True)
+        var = ((xs - mean) ** 2).mean(1, keepdim=True)
+        v = (xs - mean) / (var + eps).sqrt() * gg + bb
+        if res:
+            v = v + _t(_arr(res, (M - 1) * ldr + d)).as_strided((M, d), (ldr, 1))
+        if out:
+            _t(_arr(out, (M - 1) * ldo + d)).as_strided((M, d), (ldo, 1)).copy_(v)
+        if out_hi:
+            hi, lo = self._split(v)
+            self._harr(out_hi, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(hi)
+            self._harr(out_lo, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(lo)
+        return 0
+
+    def wxf_swin_window_attention(self, qkv, ldq, bias, logit_scale, out_hi, out_lo, out_f32, ldh, B, H, W, d, heads, ws_h,
+                                  ws_w, shift_h, shift_w, stream):
+        self.calls.append("swin_attention")
+        dh, L = d // heads, ws_h * ws_w
+        q3 = _t(_arr(qkv, (B * H * W - 1) * ldq + 3 * d)).as_strided((B, H, W, 3 * d), (H * W * ldq, W * ldq, ldq, 1))
+        bs = _t(_arr(bias, heads * L * L)).view(heads, L, L)
+        sc = _t(_arr(logit_scale, heads))
+        rolled = torch.roll(q3, shifts=(-shift_h, -shift_w), dims=(1, 2))
+        nwy, nwx = H // ws_h, W // ws_w
+        win = rolled.view(B, nwy, ws_h, nwx, ws_w, 3, heads, dh).permute(5, 0, 1, 3, 6, 2, 4, 7).reshape(3, B, nwy, nwx, heads, L, dh)
+        q, k, v = win[0].double(), win[1].double(), win[2].double()
+        qn = q / q.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        kn = k / k.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        s = (qn @ kn.transpose(-1, -2)) * sc.view(1, 1, 1, heads, 1, 1).double() + bs.view(1, 1, 1, heads, L, L).double()
+
+        def region(n, ws, sh):
+            r = torch.zeros(n, dtype=torch.long)
+            if sh > 0:
+                r[n - ws: n - sh] = 1
+                r[n - sh:] = 2
+            return r
+
+        ry, rx = region(H, ws_h, shift_h), region(W, ws_w, shift_w)
+        rid = (3 * ry[:, None] + rx[None, :]).view(nwy, ws_h, nwx, ws_w).permute(0, 2, 1, 3).reshape(nwy, nwx, L)
+        mask = torch.where(rid[..., :, None] != rid[..., None, :], -100.0, 0.0).double()
+        s = s + mask.view(1, nwy, nwx, 1, L, L)
+        o = (torch.softmax(s, dim=-1) @ v).float()                                   # [B, nwy, nwx, heads, L, dh]
+        o = o.view(B, nwy, nwx, heads, ws_h, ws_w, dh).permute(0, 1, 4, 2, 5, 3, 6).reshape(B, H, W, d)
+        o = torch.roll(o, shifts=(shift_h, shift_w), dims=(1, 2)).reshape(B * H * W, d)
+        M = B * H * W
+        if out_f32:
+            _t(_arr(out_f32, (M - 1) * ldh + d)).as_strided((M, d), (ldh, 1)).copy_(o)
+        else:
+            hi, lo = self._split(o)
+            self._harr(out_hi, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(hi)
+            self._harr(out_lo, (M - 1) * ldh + d).as_strided((M, d), (ldh, 1)).copy_(lo)
+        return 0
+
+    def wxf_gather_rows_ex(self, src, ld_src, idx, dst, ld_dst, hi_p, lo_p, ldh, h_off, n, d, stream):
+        self.calls.append("gather_rows_ex")
+        ii = _t(_iarr(idx, n)).long()
+        n_src = int(ii.max()) + 1
+        s_ = _t(_arr(src, (n_src - 1) * ld_src + d)).as_strided((n_src, d), (ld_src, 1))
+        v = torch.where((ii >= 0)[:, None], s_[ii.clamp_min(0)], torch.zeros(()))
+        if dst:
+            _t(_arr(dst, (n - 1) * ld_dst + d)).as_strided((n, d), (ld_dst, 1)).copy_(v)
+        if hi_p:
+            hi, lo = self._split(v)
+            self._harr(hi_p, (n - 1) * ldh + h_off + d).as_strided((n, d), (ldh, 1), h_off).copy_(hi)
+            self._harr(lo_p, (n - 1) * ldh + h_off + d).as_strided((n, d), (ldh, 1), h_off).copy_(lo)
+        return 0
+
+    def wxf_unpatchify_unpad_resize_to_nchw(self, y, outp, B, C, cp, Lat, Lon, ph, pw, top, left, Hc, Wc, Ho, Wo, o0, n_out,
+                                            stream):
+        self.calls.append("unpatchify_resize")
+        ys = _t(_arr(y, B * Lat * Lon * ph * pw * cp)).view(B, Lat, Lon, ph, pw, cp)[..., :C]
+        img = ys.permute(0, 1, 3, 2, 4, 5).reshape(B, Lat * ph, Lon * pw, C).contiguous()
+        # the rest is wxf_unpad_resize_to_nchw on a pixel-major image with ld = C
+        keep = self.calls
+        self.calls = []
+        rc = self.wxf_unpad_resize_to_nchw(img.data_ptr(), C, outp, B, C, Lat * ph, Lon * pw, top, left, Hc, Wc, Ho, Wo, o0,
+                                           n_out, stream)
+        self.calls = keep
+        return rc
+
+    def wxf_history_update(self, x, y, forcing, B, C, T, n_prog, n_dyn, Cy, Ty, plane, stream):
+        self.calls.append("history_update")
+        xs = _t(_arr(x, B * C * T * plane)).view(B, C, T, plane)
+        ys = _t(_arr(y, B * Cy * Ty * plane)).view(B, Cy, Ty, plane)
+        new = xs.clone()
+        new[:, :, : T - 1] = xs[:, :, 1:]
+        new[:, :n_prog, T - 1] = ys[:, :n_prog, 0]
+        if forcing:
+            new[:, n_prog: n_prog + n_dyn, T - 1] = _t(_arr(forcing, B * n_dyn * plane)).view(B, n_dyn, plane)
+        xs.copy_(new)
         return 0

@@ -54,3 +54,23 @@ print('BITEXACT', bool(torch.equal(y, fx['y'])), float((y - fx['y']).abs().max()
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "BITEXACT True" in res.stdout, res.stdout
+
+
+@pytest.mark.skipif(not ref_loader.available("fuxi"), reason="oracle/_ref not staged (run oracle/make_ref.py)")
+def test_staged_fuxi_reference_reproduces_golden_bit_exact(golden_dir):
+    """credit/models/fuxi.py from oracle/_ref (with the Swin-V2 stand-in registered as timm, as when the golden was made)."""
+    code = f"""
+import sys, torch
+sys.path.insert(0, {ROOT!r})
+from oracle import ref_loader
+fx = torch.load({os.path.join(golden_dir, 'unit_fuxi.pt')!r}, weights_only=False)
+m = ref_loader.reference_model(fx['kwargs'], fx['state_dict'], 'fuxi')
+import credit.models.fuxi as f
+assert f.__file__.startswith({ref_loader.STAGED!r}), f.__file__
+with torch.no_grad():
+    y = m(fx['x'])
+print('BITEXACT', bool(torch.equal(y, fx['y'])), float((y - fx['y']).abs().max()))
+"""
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "BITEXACT True" in res.stdout, res.stdout
