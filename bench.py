@@ -250,7 +250,7 @@ def gpu_eager_baseline(name, dev, steps=5, warmup=2):
     if not ref_loader.available(arm.variant):
         return {"unavailable": "oracle/_ref not staged"}, None
     ref_loader.seed_policy()
-    model = ref_loader.reference_model(arm.kw, arm.state_dict(), arm.variant).to(dev)
+    model = ref_loader.move(ref_loader.reference_model(arm.kw, arm.state_dict(), arm.variant), dev)
     x = arm.input(1000).to(dev)
     y0 = None
     torch.cuda.reset_peak_memory_stats(dev)

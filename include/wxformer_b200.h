@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 11
+#define WXF_ABI_VERSION 12
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -374,6 +374,35 @@ int wxf_unpatchify_unpad_resize_to_nchw(const float* y, float* out, int B, int C
  */
 int wxf_history_update(float* x, const float* y, const float* forcing, int B, int C, int T, int n_prog, int n_dyn, int Cy,
                        int Ty, int64_t plane, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Exchanges of the lat-lon domain decomposition over NVLink peer memory (csrc/wxf_peer.cu): what the reference does with
+ * batch_isend_irecv per convolution (credit/domain_parallel/halo_exchange.py:56-67) and two all-reduces per GroupNorm
+ * (credit/domain_parallel/layers.py:507-518) becomes stores into the consumer's memory plus an arrival counter.
+ *
+ * wxf_peer_alloc / _free      : one arena per rank (cudaMalloc, zero-filled)
+ * wxf_peer_export / _open / _close : 64-byte cudaIpc handle of an arena; peers map it (lazy peer access)
+ * wxf_peer_epoch_advance      : *epoch += 1 on the stream (once per forward)
+ * wxf_peer_put                : copy nseg <= 8 segments (16-byte multiples) to peer (or local) addresses, then add 1 to
+ *                               nsig <= 16 counters with system-scope release.  done_counter: a zeroed uint32 of this rank
+ * wxf_peer_scatter_rows       : row i: src[src_idx[i], 0:d] -> dst_base[dst_rank[i]] + dst_idx[i]*ld_dst, then add 1 to
+ *                               signals[r] for every rank r (world <= 8): the band <-> attention-unit re-layout
+ * wxf_peer_wait               : block the stream until every counter >= *epoch (acquire; traps after ~seconds)
+ * wxf_sum_rank_slots          : sums[i] = sum_r slots[r*n + i] in rank order (GroupNorm sums, bit-identical on all ranks)
+ */
+int wxf_peer_alloc(void** ptr, int64_t bytes);
+int wxf_peer_free(void* ptr);
+int wxf_peer_export(const void* ptr, void* handle64);
+int wxf_peer_open(const void* handle64, void** ptr);
+int wxf_peer_close(void* ptr);
+int wxf_peer_epoch_advance(void* epoch, void* stream);
+int wxf_peer_put(const void* const* src, void* const* dst, const int64_t* bytes, int nseg, void* const* signals, int nsig,
+                 void* done_counter, void* stream);
+int wxf_peer_scatter_rows(const float* src, int ld_src, const int32_t* src_idx, const int32_t* dst_rank, const int32_t* dst_idx,
+                          void* const* dst_base, void* const* signals, int world, int ld_dst, int64_t n, int d,
+                          void* done_counter, void* stream);
+int wxf_peer_wait(void* const* signals, int nsig, const void* epoch, void* stream);
+int wxf_sum_rank_slots(const double* slots, double* sums, int world, int n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -293,11 +293,11 @@ __global__ void __launch_bounds__(256) unpatchify_resize_kernel(const float* __r
   bilin_axis_f(h, sh, Hc, y0, y1, ly0, ly1);
   const int ch = cg * 32 + tx;
   const int64_t tok = (int64_t)ph * pw * cp;
-  auto at = [&](int Y, int X) -> const float* {
-    Y += top;
-    X += left;
-    return y + (((int64_t)b * Lat + Y / ph) * Lon + X / pw) * tok + ((Y % ph) * pw + X % pw) * cp + ch;
-  };
+  // row part of the source address once per CTA, column part once per (thread, column); zero-weight taps are not loaded
+  // (W is not resized in the forecast configs, so half of the four taps usually drop out)
+  const int Y0 = y0 + top, Y1 = y1 + top;
+  const float* row0 = y + ((int64_t)b * Lat + Y0 / ph) * Lon * tok + (int64_t)(Y0 % ph) * pw * cp + ch;
+  const float* row1 = y + ((int64_t)b * Lat + Y1 / ph) * Lon * tok + (int64_t)(Y1 % ph) * pw * cp + ch;
 #pragma unroll
   for (int i = ty; i < 32; i += 8) {
     const int w = w0 + i;
@@ -306,8 +306,15 @@ __global__ void __launch_bounds__(256) unpatchify_resize_kernel(const float* __r
       int x0, x1;
       float lx0, lx1;
       bilin_axis_f(w, sw, Wc, x0, x1, lx0, lx1);
-      const float v00 = *at(y0, x0), v01 = *at(y0, x1), v10 = *at(y1, x0), v11 = *at(y1, x1);
-      v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+      const int X0 = x0 + left, X1 = x1 + left;
+      const int64_t c0 = (int64_t)(X0 / pw) * tok + (X0 % pw) * cp;
+      float top_v = lx0 * row0[c0], bot_v = (ly1 != 0.f) ? lx0 * row1[c0] : 0.f;
+      if (lx1 != 0.f) {
+        const int64_t c1 = (int64_t)(X1 / pw) * tok + (X1 % pw) * cp;
+        top_v += lx1 * row0[c1];
+        if (ly1 != 0.f) bot_v += lx1 * row1[c1];
+      }
+      v = ly0 * top_v + ly1 * bot_v;
     }
     tile[tx][i] = v;
   }

@@ -23,6 +23,7 @@ and exchanges only the halo rows the next step's padding needs.
 from __future__ import annotations
 
 import logging
+import os
 from typing import List
 
 import torch
@@ -159,6 +160,10 @@ class Exchange:
         self.recv_off = [0]
         for c in self.recv_counts:
             self.recv_off.append(self.recv_off[-1] + c)
+        # peer-memory path: every row is stored straight into its owner's buffer (no pack / unpack)
+        mb, mu = bo == rank, uo == rank
+        self.b2u = tuple(t[mb].contiguous().to(**i32) for t in (bl, uo, ul))   # my band rows -> (unit owner, unit-local row)
+        self.u2b = tuple(t[mu].contiguous().to(**i32) for t in (ul, bo, bl))   # my unit rows -> (band owner, band-local row)
 
     def band_to_unit(self, band, ld_band, unit, sbuf, rbuf):
         d = self.d
@@ -166,6 +171,16 @@ class Exchange:
         self.comm.all_to_all(rbuf[: self.n_unit * d], sbuf[: self.n_band * d], [c * d for c in self.recv_counts],
                              [c * d for c in self.send_counts])
         ops.gather_rows(rbuf, d, self.inv_recv, unit, d, self.n_unit, d)
+
+    def band_to_unit_peer(self, band, ld_band, peer, xu_off, site):
+        src_idx, dst_rank, dst_idx = self.b2u
+        peer.scatter_rows(band, ld_band, src_idx, dst_rank, dst_idx, xu_off, self.d, self.n_band, self.d, site)
+        peer.wait_all(site)
+
+    def unit_to_band_peer(self, unit, peer, eb_off, ld_band, site):
+        src_idx, dst_rank, dst_idx = self.u2b
+        peer.scatter_rows(unit, self.d, src_idx, dst_rank, dst_idx, eb_off, ld_band, self.n_unit, self.d, site)
+        peer.wait_all(site)
 
     def unit_to_band(self, unit, band, ld_band, sbuf, rbuf):
         d = self.d
@@ -226,8 +241,11 @@ class DomainPlan(_Plan):
         self.ld0 = 64
         self.xp = None
         self.xp_planes = (torch.empty((1, g.h_pad, g.w_pad, 64), **f16), torch.empty((1, g.h_pad, g.w_pad, 64), **f16))
-        self.rows = [lay.rb[s][rank + 1] - lay.rb[s][rank] for s in range(4)]
-        self.nu = [lay.units[s]["ub"][rank + 1] - lay.units[s]["ub"][rank] for s in range(4)]
+        rows_of = lambda r: [lay.rb[s][r + 1] - lay.rb[s][r] for s in range(4)]  # noqa: E731
+        nu_of = lambda r: [lay.units[s]["ub"][r + 1] - lay.units[s]["ub"][r] for s in range(4)]  # noqa: E731
+        self.rows_all = [rows_of(r) for r in range(world)]
+        self.rows = self.rows_all[rank]
+        self.nu = nu_of(rank)
         m_unit = [self.nu[s] * lay.units[s]["hu"] * lay.units[s]["wu"] for s in range(4)]
         m_band = [self.rows[s] * g.stages[s].w for s in range(4)]
         big = _round_up(max(max(m_unit[s], m_band[s]) * g.stages[s].dim for s in range(4)), 8)
@@ -237,37 +255,81 @@ class DomainPlan(_Plan):
         self.scratch16 = self.scratch.view(torch.float16)
         self.sbuf = torch.empty(big, **f32)
         self.rbuf = torch.empty(big, **f32)
-        self.xu = [torch.empty((max(self.nu[s], 1), lay.units[s]["hu"], lay.units[s]["wu"], g.stages[s].dim), **f32)
-                   for s in range(4)]
-        self.eb = [torch.empty((self.rows[s], g.stages[s].w, g.stages[s].dim), **f32) for s in range(4)]
-        # skip/concat planes in band layout with one halo row above and below (zero at the domain edges)
-        self.catp = [(torch.zeros((self.rows[s] + 2, g.stages[s].w, 2 * g.stages[s].dim), **f16),
-                      torch.zeros((self.rows[s] + 2, g.stages[s].w, 2 * g.stages[s].dim), **f16)) for s in range(3)]
-        s3 = g.stages[3]
-        # stage-3 output planes; only the wxformer decoder's first conv3x3 reads a halo row of them
         h3 = self.halo3 = 1 if self.wx else 0
-        self.x3p = (torch.zeros((self.rows[3] + 2 * h3, s3.w, s3.dim), **f16),
-                    torch.zeros((self.rows[3] + 2 * h3, s3.w, s3.dim), **f16))
+
+        # ---- buffers other ranks write into (halo rows, re-layout targets, GroupNorm sums): peer arena or plain tensors ----
+        def shapes(r):
+            rows, nu = rows_of(r), nu_of(r)
+            sh = {}
+            for s in range(4):
+                st = g.stages[s]
+                sh[f"xu{s}"] = ((max(nu[s], 1), lay.units[s]["hu"], lay.units[s]["wu"], st.dim), torch.float32)
+                sh[f"eb{s}"] = ((rows[s], st.w, st.dim), torch.float32)
+                if s < 3:
+                    for pl in ("hi", "lo"):
+                        sh[f"catp{s}.{pl}"] = ((rows[s] + 2, st.w, 2 * st.dim), torch.float16)
+            s3 = g.stages[3]
+            for pl in ("hi", "lo"):
+                sh[f"x3p.{pl}"] = ((rows[3] + 2 * h3, s3.w, s3.dim), torch.float16)
+            for k, up in enumerate(g.ups):
+                ro, wo, c = 2 * rows[3 - k], 2 * up.w_in, up.c_out
+                for nm in (("sp", "bp", "up") if self.wx else ("sp", "bp")):
+                    for pl in ("hi", "lo"):
+                        sh[f"dec{k}.{nm}.{pl}"] = ((ro + 2, wo, c), torch.float16)
+            if self.wx:
+                for pl in ("hi", "lo"):
+                    sh[f"vp.{pl}"] = ((2 * rows[0] + 2, g.w_dec, g.output_channels), torch.float16)
+            sh["y_dec"] = ((g.h_dec, g.w_dec, g.output_channels), torch.float32)
+            for i in range(2 * len(g.ups)):
+                sh[f"gn_slots{i}"] = ((world, g.dim[0] * 2), torch.float64)
+            return sh
+
+        own = shapes(rank)
+        numel = lambda shp: int(torch.Size(shp).numel())  # noqa: E731
+        self.peer = None
+        self._off = {}
+        mode = os.environ.get("WXF_DOMAIN_COMM", "peer")
+        if world > 1 and torch.device(device).type == "cuda" and mode == "peer":
+            from .peer import PeerComm, _ITEMSIZE
+
+            every = self._every = [shapes(r) for r in range(world)]
+            biggest = {k: max((every[r][k][0] for r in range(world)), key=numel) for k in own}
+            total = sum((numel(biggest[k]) * _ITEMSIZE[own[k][1]] + 255) // 256 * 256 + 256 for k in own) + 64 * 256
+            self.peer = PeerComm(rank, world, group, total, device)
+        buf = {}
+        for k, (shp, dt) in own.items():
+            if self.peer is not None:
+                buf[k], self._off[k] = self.peer.buffer(biggest[k], shp, dt)
+            else:
+                buf[k] = torch.zeros(shp, device=device, dtype=dt)
+        self._buf = buf
+        self.xu = [buf[f"xu{s}"] for s in range(4)]
+        self.eb = [buf[f"eb{s}"] for s in range(4)]
+        # skip/concat planes in band layout with one halo row above and below (zero at the domain edges)
+        self.catp = [(buf[f"catp{s}.hi"], buf[f"catp{s}.lo"]) for s in range(3)]
+        # stage-3 output planes; only the wxformer decoder's first conv3x3 reads a halo row of them
+        self.x3p = (buf["x3p.hi"], buf["x3p.lo"])
         self.dec = []
         for k, up in enumerate(g.ups):
             ro, wo, c = 2 * self.rows[3 - k], 2 * up.w_in, up.c_out
             self.dec.append(dict(
                 short=torch.empty((ro, wo, c), **f32), a=torch.empty((ro, wo, c), **f32),
-                sp=(torch.zeros((ro + 2, wo, c), **f16), torch.zeros((ro + 2, wo, c), **f16)),
-                bp=(torch.zeros((ro + 2, wo, c), **f16), torch.zeros((ro + 2, wo, c), **f16))))
+                sp=(buf[f"dec{k}.sp.hi"], buf[f"dec{k}.sp.lo"]), bp=(buf[f"dec{k}.bp.hi"], buf[f"dec{k}.bp.lo"])))
             if self.wx:  # PixelShuffle output u (fp32 + planes with halo rows): input of the `sharp` convolution
-                self.dec[-1].update(u=torch.empty((ro, wo, c), **f32),
-                                    up=(torch.zeros((ro + 2, wo, c), **f16), torch.zeros((ro + 2, wo, c), **f16)))
+                self.dec[-1].update(u=torch.empty((ro, wo, c), **f32), up=(buf[f"dec{k}.up.hi"], buf[f"dec{k}.up.lo"]))
         if self.wx:  # up_block4 = conv3x3 -> PixelShuffle -> conv3x3: the shuffled tensor, band rows + halo
-            rv = 2 * self.rows[0]
-            self.vp = (torch.zeros((rv + 2, g.w_dec, g.output_channels), **f16),
-                       torch.zeros((rv + 2, g.w_dec, g.output_channels), **f16))
+            self.vp = (buf["vp.hi"], buf["vp.lo"])
         self.gn_sums = torch.empty((1, g.dim[0], 2), device=device, dtype=torch.float64)
         self.gn_stats = torch.empty((1, g.dim[0], 2), **f32)
         gn_bytes = max(ops.groupnorm_scratch_bytes(1, 2 * self.rows[3 - k] * 2 * up.w_in, up.c_out)
                        for k, up in enumerate(g.ups))
         self.gn_scratch = torch.empty(gn_bytes // 4 + 4, **f32)
-        self.y_dec = torch.empty((g.h_dec, g.w_dec, g.output_channels), **f32)  # full decoder output (all-gathered)
+        self.y_dec = buf["y_dec"]  # full decoder output (own band rows + one halo row from each neighbour)
+        self._gn_calls = 0
+        self._halo_names = {}
+        for k in own:
+            if k.endswith(".hi"):
+                self._halo_names[buf[k].data_ptr()] = k[:-3]
         self.ex = [Exchange(g.stages[s], lay, self.comm, device) for s in range(4)]
         self.steps: List[tuple] = []
         self.bias_tiles: List[torch.Tensor] = []
@@ -300,10 +362,18 @@ class DomainPlan(_Plan):
             # ---- band -> unit layout, transformer on the rank's units (a batch of mini-images), unit -> band ----
             u = lay.units[s]
             ex, xu = self.ex[s], self.xu[s]
-            add(ex.band_to_unit, (eb, d, xu, self.sbuf, self.rbuf), f"exchange.s{s}", 0, 8.0 * rows * st.w * d)
+            if self.peer is not None:
+                add(ex.band_to_unit_peer, (eb, d, self.peer, self._off[f"xu{s}"], self.peer.site()), f"exchange.s{s}", 0,
+                    8.0 * rows * st.w * d)
+            else:
+                add(ex.band_to_unit, (eb, d, xu, self.sbuf, self.rbuf), f"exchange.s{s}", 0, 8.0 * rows * st.w * d)
             if self.nu[s] > 0:
                 self._transformer(wts.blocks[s], st, self.nu[s], u["hu"], u["wu"], xu, d, None)
-            add(ex.unit_to_band, (xu, eb, d, self.sbuf, self.rbuf), f"exchange.s{s}", 0, 8.0 * rows * st.w * d)
+            if self.peer is not None:
+                add(ex.unit_to_band_peer, (xu, self.peer, self._off[f"eb{s}"], d, self.peer.site()), f"exchange.s{s}", 0,
+                    8.0 * rows * st.w * d)
+            else:
+                add(ex.unit_to_band, (xu, eb, d, self.sbuf, self.rbuf), f"exchange.s{s}", 0, 8.0 * rows * st.w * d)
             # ---- stage output as operand planes (band layout): skip connection + next cross-embed ----
             m = rows * st.w
             if s < 3:
@@ -313,10 +383,10 @@ class DomainPlan(_Plan):
                 add(ops.split_f16x2, (eb, d, self.x3p[0][self.halo3:], self.x3p[1][self.halo3:], d, m, d), "split", 0,
                     8.0 * m * d)
                 if self.wx:
-                    add(_halo_exchange, (self.x3p, rows, self.comm), "halo", 0, 0)
+                    self._add_halo(self.x3p, rows)
             if 1 <= s + 1 <= 3 and s < 3:
                 # the next stage's k=4 branch needs one halo row of this stage's output
-                add(_halo_exchange, ((hi, lo), rows, self.comm), "halo", 0, 0)
+                self._add_halo((hi, lo), rows)
 
         # ---- decoder in band layout ----
         dec_planes, dec_ld, dec_rows, dec_halo = self.x3p, g.stages[3].dim, self.rows[3], self.halo3
@@ -332,33 +402,33 @@ class DomainPlan(_Plan):
                 # the low-resolution input, exchanged for the skip half by the stage and here for the decoder half), then
                 # x = u + sharp(u) with a halo row of u
                 if k > 0:
-                    add(_halo_exchange, (dec_planes, rin, self.comm), "halo", 0, 0)
+                    self._add_halo(dec_planes, rin)
                 u_hi, u_lo = bufs["up"]
                 self._conv_tc(dec_planes[0], dec_planes[1], _shift_taps(uw.up_tc, 1), "dec_up", B=1, Hi=rin + 2, Wi=up.w_in,
                               lda=dec_ld, Ho=rin, Wo=up.w_in, out=bufs["u"], ldc=c, out_hi=u_hi[1:], out_lo=u_lo[1:], ldh=c)
-                add(_halo_exchange, ((u_hi, u_lo), ro, self.comm), "halo", 0, 0)
+                self._add_halo((u_hi, u_lo), ro)
                 self._conv_tc(u_hi, u_lo, _shift_taps(uw.sharp_tc, 1), "dec_conv3x3", B=1, Hi=ro + 2, Wi=wo, lda=c, Ho=ro,
                               Wo=wo, out=bufs["short"], ldc=c, res=bufs["u"], ldr=c, out_hi=sp_hi[1:], out_lo=sp_lo[1:], ldh=c)
             else:
                 # ConvTranspose k2 s2: no halo; fp32 shortcut + planes (interior rows of the halo'd buffer)
                 self._conv_tc(in_hi, in_lo, uw.up_tc, "dec_up", B=1, Hi=rin, Wi=up.w_in, lda=dec_ld, Ho=rin, Wo=up.w_in,
                               out=bufs["short"], ldc=c, out_hi=sp_hi[1:], out_lo=sp_lo[1:], ldh=c)
-            add(_halo_exchange, ((sp_hi, sp_lo), ro, self.comm), "halo", 0, 0)
+            self._add_halo((sp_hi, sp_lo), ro)
             self._conv_tc(sp_hi, sp_lo, _shift_taps(uw.convs_tc[0], 1), "dec_conv3x3", B=1, Hi=ro + 2, Wi=wo, lda=c,
                           Ho=ro, Wo=wo, out=bufs["a"], ldc=c)
             count = float(4 * up.h_in * up.w_in) * (c // up.groups)  # global pixels x channels per group
             add(self._groupnorm, (bufs["a"], c, uw.gn_w[0], uw.gn_b[0], None, 0, bp_hi[1:], bp_lo[1:], c, 0, ro * wo, c,
-                                  up.groups, count), "groupnorm_silu", 0, 8.0 * n)
-            add(_halo_exchange, ((bp_hi, bp_lo), ro, self.comm), "halo", 0, 0)
+                                  up.groups, count, self._gn_site()), "groupnorm_silu", 0, 8.0 * n)
+            self._add_halo((bp_hi, bp_lo), ro)
             self._conv_tc(bp_hi, bp_lo, _shift_taps(uw.convs_tc[1], 1), "dec_conv3x3", B=1, Hi=ro + 2, Wi=wo, lda=c,
                           Ho=ro, Wo=wo, out=bufs["a"], ldc=c)
             chi, clo = self.catp[skip]
             add(self._groupnorm, (bufs["a"], c, uw.gn_w[1], uw.gn_b[1], bufs["short"], c, chi[1:], clo[1:], 2 * c, 0,
-                                  ro * wo, c, up.groups, count), "groupnorm_silu", 0, 12.0 * n)
+                                  ro * wo, c, up.groups, count, self._gn_site()), "groupnorm_silu", 0, 12.0 * n)
             dec_planes, dec_ld, dec_rows, dec_halo = self.catp[skip], 2 * c, ro, 1
         # up_block4 (ConvT k4 s2 p1) reads one halo row of the full concat buffer
         st0 = g.stages[0]
-        add(_halo_exchange, (self.catp[0], self.rows[0], self.comm), "halo", 0, 0)
+        self._add_halo(self.catp[0], self.rows[0])
         y_band = self.y_dec[2 * lay.rb[0][rank]: 2 * lay.rb[0][rank + 1]]
         if self.wx:
             # up_block4 of the wxformer variant (wxformer/crossformer.py:813-830): conv3x3 -> PixelShuffle -> conv3x3
@@ -367,20 +437,87 @@ class DomainPlan(_Plan):
             self._conv_tc(self.catp[0][0], self.catp[0][1], _shift_taps(wts.head_tc, 1), "dec_head", B=1,
                           Hi=self.rows[0] + 2, Wi=st0.w, lda=2 * st0.dim, Ho=self.rows[0], Wo=st0.w, out_hi=self.vp[0][1:],
                           out_lo=self.vp[1][1:], ldh=co)
-            add(_halo_exchange, (self.vp, rv, self.comm), "halo", 0, 0)
+            self._add_halo(self.vp, rv)
             self._conv_tc(self.vp[0], self.vp[1], _shift_taps(wts.head2_tc, 1), "dec_head", B=1, Hi=rv + 2, Wi=g.w_dec, lda=co,
                           Ho=rv, Wo=g.w_dec, out=y_band, ldc=co)
         else:
             self._conv_tc(self.catp[0][0], self.catp[0][1], _shift_taps(wts.head_tc, 1), "dec_head", B=1,
                           Hi=self.rows[0] + 2, Wi=st0.w, lda=2 * st0.dim, Ho=self.rows[0], Wo=st0.w, out=y_band,
                           ldc=g.output_channels)
-        add(self._ydec_halo, (), "halo", 0, 0)
+        if self.peer is not None:
+            # first / last row of the rank's decoder band -> the neighbours' buffers (bilinear resize halo)
+            P, me, off = self.peer, self.rank, self._off["y_dec"]
+            rb = g.w_dec * g.output_channels * 4
+            d_lo, d_hi = 2 * lay.rb[0][me], 2 * lay.rb[0][me + 1]
+            site = P.site()
+            segs, sigs, waits = [], [], []
+            if me > 0:
+                segs.append((self.y_dec.data_ptr() + d_lo * rb, P.arena.base[me - 1] + off + d_lo * rb, rb))
+                sigs.append(P.sig(me - 1, site, 1))
+                waits.append(P.sig(me, site, 0))
+            if me < world - 1:
+                segs.append((self.y_dec.data_ptr() + (d_hi - 1) * rb, P.arena.base[me + 1] + off + (d_hi - 1) * rb, rb))
+                sigs.append(P.sig(me + 1, site, 0))
+                waits.append(P.sig(me, site, 1))
+            add(self._peer_halo, (segs, sigs, waits), "halo", 0, 0)
+        else:
+            add(self._ydec_halo, (), "halo", 0, 0)
 
     # ------------------------------------------------------------------------------------------------------------
-    def _groupnorm(self, x, ldx, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, hw_local, C, G, count):
+    def _add_halo(self, tensors, rows):
+        """One-row halo exchange of a band tensor pair [rows + 2, W, C] with the two neighbours (NCCL send / recv, or stores
+        into the neighbours' arenas + arrival counters)."""
+        if self.peer is None:
+            self._add(_halo_exchange, (tensors, rows, self.comm), "halo", 0, 0)
+            return
+        P, me, world = self.peer, self.rank, self.world
+        name = self._halo_names[tensors[0].data_ptr()]
+        site = P.site()
+        segs, sigs, waits = [], [], []
+        for pl, t in zip(("hi", "lo"), tensors):
+            key = f"{name}.{pl}"
+            off = self._off[key]
+            rb = t[0].numel() * t.element_size()
+            if me > 0:      # my first interior row -> the bottom halo row of the rank above
+                rows_prev = self._every[me - 1][key][0][0] - 2
+                segs.append((t.data_ptr() + rb, P.arena.base[me - 1] + off + (rows_prev + 1) * rb, rb))
+            if me < world - 1:  # my last interior row -> the top halo row of the rank below
+                segs.append((t.data_ptr() + rows * rb, P.arena.base[me + 1] + off, rb))
+        if me > 0:
+            sigs.append(P.sig(me - 1, site, 1))
+            waits.append(P.sig(me, site, 0))
+        if me < world - 1:
+            sigs.append(P.sig(me + 1, site, 0))
+            waits.append(P.sig(me, site, 1))
+        self._add(self._peer_halo, (segs, sigs, waits), "halo", 0, 0)
+
+    def _peer_halo(self, segs, sigs, waits):
+        self.peer.put(segs, sigs)
+        self.peer.wait(waits)
+
+    def _gn_site(self):
+        """Arrival counters + per-rank slots of one GroupNorm call (its own block: a fast rank may already be at the next
+        GroupNorm while a rank two bands away still reads this one's sums)."""
+        if self.peer is None:
+            return None
+        i = self._gn_calls
+        self._gn_calls += 1
+        return (self.peer.site(), self._buf[f"gn_slots{i}"], self._off[f"gn_slots{i}"])
+
+    def _groupnorm(self, x, ldx, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, hw_local, C, G, count, site=None):
         """GroupNorm + SiLU with statistics over the whole (all-rank) image: local sums, all-reduce, apply."""
         ops.groupnorm_sums(x, ldx, self.gn_sums, self.gn_scratch, 1, hw_local, C, G)
-        self.comm.all_reduce(self.gn_sums)
+        if site is not None:
+            P, (sg, slots, off) = self.peer, site
+            nb = G * 2 * 8
+            segs = [(self.gn_sums.data_ptr(), P.arena.base[r] + off + self.rank * slots.shape[1] * 8, nb) for r in range(self.world)]
+            P.put(segs, [P.sig(r, sg, self.rank) for r in range(self.world)])
+            P.wait_all(sg)
+            # every rank adds the slots in rank order: bit-identical statistics everywhere
+            assert slots.shape[1] == 2 * G
+            P.sum_slots(slots, self.gn_sums, 2 * G)
+        else:
+            self.comm.all_reduce(self.gn_sums)
         ops.groupnorm_stats_from_sums(self.gn_sums, self.gn_stats, 1, G, count)
         ops.groupnorm_apply_f16x2(x, ldx, self.gn_stats, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, 1, hw_local, C, G)
 
@@ -437,6 +574,8 @@ class DomainPlan(_Plan):
         g = self.geo
         lat, lon, mode = ((g.padding.pad_lat, g.padding.pad_lon, g.padding.mode) if g.padding.activate
                           else ((0, 0), (0, 0), "earth"))
+        if self.peer is not None:
+            self.peer.advance()  # one step number per forward: arrival counters are compared with it
         a, b = self.pad_rows[self.rank]
         ops.pad_to_pixel_major_f16x2(x, lat, lon, mode, 64, self.xp_planes[0], self.xp_planes[1], rows=(a, b - a))
 

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 11
+WXF_ABI_VERSION = 12
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -120,6 +120,18 @@ _SIGNATURES = {
     "wxf_gather_rows_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int64,
                                    c_int, c_void_p]),
     "wxf_unpatchify_unpad_resize_to_nchw": (c_int, [c_void_p, c_void_p] + [c_int] * 15 + [c_void_p]),
+    "wxf_peer_alloc": (c_int, [POINTER(c_void_p), c_int64]),
+    "wxf_peer_free": (c_int, [c_void_p]),
+    "wxf_peer_export": (c_int, [c_void_p, c_void_p]),
+    "wxf_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "wxf_peer_close": (c_int, [c_void_p]),
+    "wxf_peer_epoch_advance": (c_int, [c_void_p, c_void_p]),
+    "wxf_peer_put": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int, POINTER(c_void_p), c_int, c_void_p,
+                             c_void_p]),
+    "wxf_peer_scatter_rows": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int,
+                                      c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "wxf_peer_wait": (c_int, [POINTER(c_void_p), c_int, c_void_p, c_void_p]),
+    "wxf_sum_rank_slots": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "wxf_history_update": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_int64, c_void_p]),
     "wxf_copy_channels": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int64, POINTER(c_int32), POINTER(c_int32),
                                   POINTER(c_int32), c_int, c_void_p]),

@@ -62,9 +62,26 @@ def reference_model(kwargs: dict, state_dict: dict, variant: str = "crossformer"
     conf["type"] = variant
     model = load_model({"model": conf})
     if variant == "fuxi":
-        model = model.cpu()  # Fuxi.__init__ moves itself to cuda when one is visible (fuxi.py:433-435); callers place it
+        model = move(model, "cpu")  # Fuxi.__init__ moves itself to cuda when one is visible (fuxi.py:433-435); callers place it
     model.load_state_dict(state_dict, strict=True)
     return model.eval()
+
+
+def move(model, device):
+    """``model.to(device)`` that keeps the old-style spectral-norm alias intact.
+
+    ``torch.nn.utils.spectral_norm`` leaves ``module.weight`` behind as a PLAIN attribute aliasing ``weight_orig``'s storage
+    (so a checkpoint loaded in place shows through it); the forward pre-hook overwrites it on every module call.  timm's
+    Swin-V2 attention never calls its ``qkv`` module (``F.linear(x, self.qkv.weight, ...)``), so for that layer the alias IS
+    the weight in use (oracle/swin_v2.py).  ``nn.Module.to`` re-creates parameter storage but not plain attributes: after a
+    device move the alias would point at the old device and the construction-time values.  In the reference's own flow the
+    model is built on its final device and checkpoints load in place (credit/models/base_model.py:72-85), so the alias always
+    holds there; this helper restores exactly that state after moving."""
+    model = model.to(device)
+    for m in model.modules():
+        if "weight_orig" in getattr(m, "_parameters", {}) and "weight" in m.__dict__:
+            m.__dict__["weight"] = m._parameters["weight_orig"].data
+    return model
 
 
 def seed_policy():

@@ -42,7 +42,7 @@ class EmulatedLib:
                     raise AssertionError(f"{what}: input {rn} [{r0:#x}, {r1:#x}) overlaps output {wn} [{w0:#x}, {w1:#x})")
 
     def wxf_abi_version(self):
-        return 11
+        return 12
 
     def wxf_last_error(self):
         return b"emulator"
