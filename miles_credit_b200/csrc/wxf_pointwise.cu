@@ -93,11 +93,21 @@ __global__ void __launch_bounds__(256) pad_to_pixel_major_kernel(const float* __
 // Same index map, one CTA = one padded row x 64 columns x a block of 64 channels: the column loop reads whole 128-byte
 // runs of the NCHW rows, the transposed write stores 16 bytes per thread (8 fp16 of a plane / 4 fp32), i.e. whole
 // 128-byte pixel rows.  Needs ld % 8 == 0 (otherwise the scalar kernel above runs).
-template <bool SPLIT>
+// PRE: the per-step pre-blocks fused in: the source is not one tensor but a table of per-channel planes
+// (ConcatToTensor, credit/preblock/concat.py:101-207: torch.cat of the sorted variables along the channel axis) and
+// every value is z-scored on the way, (x - mean[c]) / max(std[c], 1e-12) (ERA5Normalizer, credit/preblock/norm.py:80-98).
+struct PadPre {
+  const float* const* chan;  // [B * C] device pointers to [T, H, W] planes (variable-major; nullptr: read x)
+  const float* mean;         // [C] (0 for pass-through variables)
+  const float* stdv;         // [C] (1 for pass-through variables)
+  int T;
+};
+
+template <bool SPLIT, bool PRE = false>
 __global__ void __launch_bounds__(256) pad_rows_vec_kernel(const float* __restrict__ x, float* __restrict__ xp,
                                                             __half* __restrict__ xp_hi, __half* __restrict__ xp_lo,
                                                             int CT, int H, int W, int pt, int pl, int mode, int ld,
-                                                            int Hp, int Wp, int cblocks, int row0) {
+                                                            int Hp, int Wp, int cblocks, int row0, PadPre pre = PadPre{}) {
   wxf_pdl_trigger();
   wxf_pdl_wait();
   __shared__ float tile[64][65];  // [channel][column]
@@ -142,9 +152,18 @@ __global__ void __launch_bounds__(256) pad_rows_vec_kernel(const float* __restri
   }
   for (int i = warp; i < nch; i += 8) {
     const int ch = ch0 + i;
-    const float* row = x + ((size_t)(b * CT + ch) * H + sr) * W;
+    if constexpr (PRE) {
+      const int c = ch / pre.T, t = ch - c * pre.T;
+      const bool ok = ch < CT;
+      const float* row = ok ? pre.chan[(size_t)b * (CT / pre.T) + c] + ((size_t)t * H + sr) * W : nullptr;
+      const float m = ok ? __ldg(pre.mean + c) : 0.f, sd = ok ? fmaxf(__ldg(pre.stdv + c), 1e-12f) : 1.f;
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) tile[i][hf * 32 + lane] = (ch < CT && sc[hf] >= 0) ? __ldg(row + sc[hf]) : 0.f;
+      for (int hf = 0; hf < 2; ++hf) tile[i][hf * 32 + lane] = (ok && sc[hf] >= 0) ? (__ldg(row + sc[hf]) - m) / sd : 0.f;
+    } else {
+      const float* row = x + ((size_t)(b * CT + ch) * H + sr) * W;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) tile[i][hf * 32 + lane] = (ch < CT && sc[hf] >= 0) ? __ldg(row + sc[hf]) : 0.f;
+    }
   }
   __syncthreads();
   const int ngrp = nch >> 3;  // groups of 8 channels
@@ -206,6 +225,37 @@ static int pad_launch(const float* x, float* xp, void* xp_hi, void* xp_lo, int B
     pad_to_pixel_major_kernel<false><<<grid, block, 0, st>>>(x, xp, nullptr, nullptr, C * T, H, W, pt, pl, mode, ld, Hp,
                                                              Wp, cgroups, row0);
   WXF_CHECK_LAUNCH("pad_to_pixel_major");
+  return 0;
+}
+
+// Pre-blocks + padding in one pass: per-variable planes in, z-scored padded pixel-major planes out (f2).
+extern "C" int wxf_preblock_pad_to_pixel_major(const void* const* chan_planes, const float* mean, const float* stdv, float* xp,
+                                               void* xp_hi, void* xp_lo, int B, int C, int T, int H, int W, int pt, int pb,
+                                               int pl, int pr, int mode, int ld, int row0, int nrows, void* stream) {
+  if (!chan_planes || !mean || !stdv) WXF_FAIL(WXF_EINVAL, "preblock_pad: null table");
+  if ((xp_hi == nullptr) != (xp_lo == nullptr) || (!xp && !xp_hi) || (xp && xp_hi))
+    WXF_FAIL(WXF_EINVAL, "preblock_pad: give either the fp32 output or the plane pair");
+  if (B <= 0 || C <= 0 || T <= 0 || H <= 0 || W <= 0 || pt < 0 || pb < 0 || pl < 0 || pr < 0) WXF_FAIL(WXF_EINVAL, "preblock_pad: bad dims");
+  if (ld < C * T || (ld & 7)) WXF_FAIL(WXF_EINVAL, "preblock_pad: ld %d must be a multiple of 8 and >= C*T %d", ld, C * T);
+  if (mode != WXF_PAD_EARTH && mode != WXF_PAD_MIRROR) WXF_FAIL(WXF_EINVAL, "preblock_pad: bad mode %d", mode);
+  if (mode == WXF_PAD_EARTH && (pt > H || pb > H)) WXF_FAIL(WXF_EINVAL, "preblock_pad: earth pad_lat larger than H");
+  if (mode == WXF_PAD_MIRROR && (pt >= H || pb >= H)) WXF_FAIL(WXF_EINVAL, "preblock_pad: mirror pad_lat must be < H");
+  const int Hp = H + pt + pb, Wp = W + pl + pr;
+  if (row0 < 0 || nrows < 0 || row0 + nrows > Hp) WXF_FAIL(WXF_EINVAL, "preblock_pad: rows outside the padded image");
+  if (nrows == 0) return 0;
+  if (!wxf_aligned16(xp_hi ? xp_hi : (void*)xp) || (xp_lo && !wxf_aligned16(xp_lo))) WXF_FAIL(WXF_EALIGN, "preblock_pad: output alignment");
+  const int cblocks = (ld + 63) / 64;
+  if (nrows > 65535 || (int64_t)B * cblocks > 65535) WXF_FAIL(WXF_EINVAL, "preblock_pad: grid too large");
+  PadPre pre{reinterpret_cast<const float* const*>(chan_planes), mean, stdv, T};
+  dim3 grid((Wp + 63) / 64, nrows, B * cblocks);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (xp_hi)
+    wxf_launch(pad_rows_vec_kernel<true, true>, dim3(grid), dim3(256), 0, st, (const float*)nullptr, (float*)nullptr, (__half*)xp_hi,
+               (__half*)xp_lo, C * T, H, W, pt, pl, mode, ld, Hp, Wp, cblocks, row0, pre);
+  else
+    wxf_launch(pad_rows_vec_kernel<false, true>, dim3(grid), dim3(256), 0, st, (const float*)nullptr, xp, (__half*)nullptr,
+               (__half*)nullptr, C * T, H, W, pt, pl, mode, ld, Hp, Wp, cblocks, row0, pre);
+  WXF_CHECK_LAUNCH("preblock_pad_to_pixel_major");
   return 0;
 }
 
