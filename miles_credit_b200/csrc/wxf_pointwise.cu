@@ -107,7 +107,7 @@ template <bool SPLIT, bool PRE = false>
 __global__ void __launch_bounds__(256) pad_rows_vec_kernel(const float* __restrict__ x, float* __restrict__ xp,
                                                             __half* __restrict__ xp_hi, __half* __restrict__ xp_lo,
                                                             int CT, int H, int W, int pt, int pl, int mode, int ld,
-                                                            int Hp, int Wp, int cblocks, int row0, PadPre pre = PadPre{}) {
+                                                            int Hp, int Wp, int cblocks, int row0, PadPre pre) {
   wxf_pdl_trigger();
   wxf_pdl_wait();
   __shared__ float tile[64][65];  // [channel][column]
@@ -208,10 +208,10 @@ static int pad_launch(const float* x, float* xp, void* xp_hi, void* xp_lo, int B
     dim3 grid((Wp + 63) / 64, nrows, B * cblocks);
     if (xp_hi)
       wxf_launch(pad_rows_vec_kernel<true>, dim3(grid), dim3(256), 0, st, x, nullptr, (__half*)xp_hi, (__half*)xp_lo, C * T, H, W, pt, pl, mode,
-                                                      ld, Hp, Wp, cblocks, row0);
+                                                      ld, Hp, Wp, cblocks, row0, PadPre{});
     else
       wxf_launch(pad_rows_vec_kernel<false>, dim3(grid), dim3(256), 0, st, x, xp, nullptr, nullptr, C * T, H, W, pt, pl, mode, ld, Hp, Wp,
-                                                       cblocks, row0);
+                                                       cblocks, row0, PadPre{});
     WXF_CHECK_LAUNCH("pad_to_pixel_major");
     return 0;
   }
