@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 12
+#define WXF_ABI_VERSION 13
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -60,6 +60,18 @@ int wxf_pad_to_pixel_major(const float* x, float* xp, int B, int C, int T, int H
  * credit/trainers/trainer_gen2.py:211-213). */
 int wxf_pad_to_pixel_major_f16x2(const float* x, void* xp_hi, void* xp_lo, int B, int C, int T, int H, int W,
                                  int pt, int pb, int pl, int pr, int mode, int ld, int row0, int nrows, void* stream);
+
+/*
+ * The per-step pre-blocks fused into the padding pass: instead of one [B, C, T, H, W] tensor the source is a
+ * device table of per-channel planes, chan_planes[b*C + c] -> [T, H, W] fp32 (the variables in ConcatToTensor's sorted
+ * order, credit/preblock/concat.py:101-207: the torch.cat along the channel axis never materialises), and every value is
+ * z-scored on the way, (x - mean[c]) / max(std[c], 1e-12) (ERA5Normalizer._normalize_tensor, credit/preblock/norm.py:80-98;
+ * pass-through variables carry mean 0 / std 1).  Output exactly as wxf_pad_to_pixel_major (xp) or its _f16x2 variant
+ * (xp_hi / xp_lo); give one of the two.  ld % 8 == 0.
+ */
+int wxf_preblock_pad_to_pixel_major(const void* const* chan_planes, const float* mean, const float* stdv, float* xp,
+                                    void* xp_hi, void* xp_lo, int B, int C, int T, int H, int W, int pt, int pb, int pl,
+                                    int pr, int mode, int ld, int row0, int nrows, void* stream);
 
 /*
  * Channel LayerNorm at every pixel (credit/models/crossformer.py:182-192):
@@ -302,6 +314,31 @@ int wxf_gather_rows(const float* src, int ld_src, const int32_t* idx, float* dst
  */
 int wxf_unpad_resize_to_nchw(const float* y, int ld, float* out, int B, int C, int Hd, int Wd, int top, int left,
                              int Hc, int Wc, int Ho, int Wo, int o0, int n_out, void* stream);
+
+/*
+ * The same pass with the per-step post-blocks fused into its epilogue, per output channel c:
+ *   v = v * scale[c] + shift[c]      inverse scaling (y * std + mean, applications/rollout_to_netcdf.py:287; the gen2
+ *                                    bridgescaler inverse transform), two roundings like torch
+ *   v = min(max(v, clamp_lo[c]), clamp_hi[c])   TracerFixer (credit/postblock/conservation.py:88-115); -inf / +inf = no clamp
+ */
+int wxf_unpad_resize_post_to_nchw(const float* y, int ld, float* out, int B, int C, int Hd, int Wd, int top, int left,
+                                  int Hc, int Wc, int Ho, int Wo, int o0, int n_out, const float* scale, const float* shift,
+                                  const float* clamp_lo, const float* clamp_hi, void* stream);
+
+/*
+ * GlobalMassFixer (credit/postblock/conservation.py:118-176; hybrid-sigma grid, midpoint quantities): the two global sums
+ *   sums[b, 0] = sum_p area[p] * sum_l da[l] * (1 - q[b, l, p])
+ *   sums[b, 1] = sum_p area[p] * sp[b, p] * sum_l db[l] * (1 - q[b, l, p])
+ * over the pixels p in [p0, p0 + np) (a latitude band of a decomposed forecast; the caller adds the bands).  q is addressed
+ * as q[b*q_bstride + l*q_lstride + p], sp as sp[b*sp_bstride + p] (channel views of an NCHW state).  Column sums in fp32 in
+ * level order, pixel sums in fp64 (deterministic two-level reduction).  scratch: wxf_dry_mass_scratch_bytes(B), zeroed once.
+ * wxf_scale_planes: x[b, 0:n] *= ratio[b] (the corrected surface pressure).
+ */
+int64_t wxf_dry_mass_scratch_bytes(int B);
+int wxf_dry_mass_sums(const float* q, int64_t q_bstride, int64_t q_lstride, const float* sp, int64_t sp_bstride,
+                      const float* area, const float* da, const float* db, int B, int L, int64_t p0, int64_t np, double* sums,
+                      void* scratch, void* stream);
+int wxf_scale_planes(float* x, int64_t bstride, int64_t n, const float* ratio, int B, void* stream);
 
 /*
  * Autoregressive state update (update_x, credit/datasets/gen_2/channel_utils.py:253-291):

@@ -839,9 +839,25 @@ __device__ __forceinline__ void bilin_axis(int dst, float scale, int n_in, int& 
   l0 = 1.f - l1;
 }
 
+// POST: the per-step post-blocks fused into the epilogue: inverse scaling v * scale[c] + shift[c] (two
+// roundings, like torch's y * std + mean, applications/rollout_to_netcdf.py:287) then the TracerFixer clamps
+// (credit/postblock/conservation.py:88-115) max(v, lo[c]), min(v, hi[c]).
+struct UnpadPost {
+  const float* scale;
+  const float* shift;
+  const float* lo;
+  const float* hi;
+};
+__device__ __forceinline__ float unpad_post(float v, const UnpadPost& p, int c) {
+  v = __fadd_rn(__fmul_rn(v, __ldg(p.scale + c)), __ldg(p.shift + c));
+  return fminf(fmaxf(v, __ldg(p.lo + c)), __ldg(p.hi + c));
+}
+
+template <bool POST>
 __global__ void __launch_bounds__(256) unpad_resize_kernel(const float* __restrict__ y, int ld, float* __restrict__ out,
                                                             int C, int Hd, int Wd, int top, int left, int Hc, int Wc,
-                                                            int Ho, int Wo, float sh, float sw, int cgroups, int o0) {
+                                                            int Ho, int Wo, float sh, float sw, int cgroups, int o0,
+                                                            UnpadPost post) {
   __shared__ float tile[32][33];  // [channel][column]
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int b = blockIdx.z / cgroups, cg = blockIdx.z % cgroups;
@@ -863,6 +879,7 @@ __global__ void __launch_bounds__(256) unpad_resize_kernel(const float* __restri
       const float v00 = r0[(size_t)x0 * ld], v01 = r0[(size_t)x1 * ld];
       const float v10 = r1[(size_t)x0 * ld], v11 = r1[(size_t)x1 * ld];
       v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+      if constexpr (POST) v = unpad_post(v, post, ch);
     }
     tile[tx][i] = v;
   }
@@ -877,9 +894,11 @@ __global__ void __launch_bounds__(256) unpad_resize_kernel(const float* __restri
 
 // One CTA = one output row x 64 columns x a block of 64 channels: each thread interpolates 4 channels of a pixel from
 // float4 loads (whole 128/256-byte pixel rows), the transposed write stores float4 runs along W.
+template <bool POST>
 __global__ void __launch_bounds__(256) unpad_resize_vec_kernel(const float* __restrict__ y, int ld, float* __restrict__ out,
                                                                 int C, int Hd, int Wd, int top, int left, int Hc, int Wc,
-                                                                int Ho, int Wo, float sh, float sw, int cblocks, int o0) {
+                                                                int Ho, int Wo, float sh, float sw, int cblocks, int o0,
+                                                                UnpadPost post) {
   wxf_pdl_trigger();
   wxf_pdl_wait();
   __shared__ float tile[64][65];  // [channel][column]
@@ -913,6 +932,13 @@ __global__ void __launch_bounds__(256) unpad_resize_vec_kernel(const float* __re
       v.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
       v.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
       v.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+      if constexpr (POST) {
+        const int c = ch0 + 4 * q;
+        v.x = unpad_post(v.x, post, c);
+        v.y = unpad_post(v.y, post, c + 1);
+        v.z = unpad_post(v.z, post, c + 2);
+        v.w = unpad_post(v.w, post, c + 3);
+      }
     }
     tile[4 * q][colx] = v.x;
     tile[4 * q + 1][colx] = v.y;
@@ -936,29 +962,139 @@ __global__ void __launch_bounds__(256) unpad_resize_vec_kernel(const float* __re
   }
 }
 
-extern "C" int wxf_unpad_resize_to_nchw(const float* y, int ld, float* out, int B, int C, int Hd, int Wd, int top,
-                                        int left, int Hc, int Wc, int Ho, int Wo, int o0, int n_out, void* stream) {
+static int unpad_launch(const float* y, int ld, float* out, int B, int C, int Hd, int Wd, int top, int left, int Hc, int Wc,
+                        int Ho, int Wo, int o0, int n_out, const UnpadPost* post, void* stream) {
   if (B <= 0 || C <= 0 || Hc <= 0 || Wc <= 0 || Ho <= 0 || Wo <= 0 || top < 0 || left < 0 || top + Hc > Hd ||
       left + Wc > Wd || ld < C)
     WXF_FAIL(WXF_EINVAL, "unpad_resize: bad dims");
   if (o0 < 0 || n_out < 0 || o0 + n_out > Ho) WXF_FAIL(WXF_EINVAL, "unpad_resize: rows [%d, %d) outside [0, %d)", o0, o0 + n_out, Ho);
   if (n_out == 0) return 0;
   const float sh = (float)Hc / (float)Ho, sw = (float)Wc / (float)Wo;
+  const UnpadPost pp = post ? *post : UnpadPost{};
+  cudaStream_t st = (cudaStream_t)stream;
   if ((C & 3) == 0 && (ld & 3) == 0 && wxf_aligned16(y) && wxf_aligned16(out)) {
     const int cblocks = (C + 63) / 64;
     if (n_out > 65535 || (int64_t)B * cblocks > 65535) WXF_FAIL(WXF_EINVAL, "unpad_resize: grid too large");
     dim3 grid((Wo + 63) / 64, n_out, B * cblocks);
-    wxf_launch(unpad_resize_vec_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, y, ld, out, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, sh,
-                                                                    sw, cblocks, o0);
+    if (post)
+      wxf_launch(unpad_resize_vec_kernel<true>, dim3(grid), dim3(256), 0, st, y, ld, out, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, sh, sw,
+                 cblocks, o0, pp);
+    else
+      wxf_launch(unpad_resize_vec_kernel<false>, dim3(grid), dim3(256), 0, st, y, ld, out, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, sh, sw,
+                 cblocks, o0, pp);
     WXF_CHECK_LAUNCH("unpad_resize");
     return 0;
   }
   const int cgroups = (C + 31) / 32;
   if (n_out > 65535 || (int64_t)B * cgroups > 65535) WXF_FAIL(WXF_EINVAL, "unpad_resize: grid too large");
   dim3 grid((Wo + 31) / 32, n_out, B * cgroups), block(32, 8);
-  unpad_resize_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(y, ld, out, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, sh,
-                                                                 sw, cgroups, o0);
+  if (post)
+    unpad_resize_kernel<true><<<grid, block, 0, st>>>(y, ld, out, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, sh, sw, cgroups, o0, pp);
+  else
+    unpad_resize_kernel<false><<<grid, block, 0, st>>>(y, ld, out, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, sh, sw, cgroups, o0, pp);
   WXF_CHECK_LAUNCH("unpad_resize");
+  return 0;
+}
+
+extern "C" int wxf_unpad_resize_to_nchw(const float* y, int ld, float* out, int B, int C, int Hd, int Wd, int top,
+                                        int left, int Hc, int Wc, int Ho, int Wo, int o0, int n_out, void* stream) {
+  return unpad_launch(y, ld, out, B, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, o0, n_out, nullptr, stream);
+}
+
+extern "C" int wxf_unpad_resize_post_to_nchw(const float* y, int ld, float* out, int B, int C, int Hd, int Wd, int top,
+                                             int left, int Hc, int Wc, int Ho, int Wo, int o0, int n_out, const float* scale,
+                                             const float* shift, const float* clamp_lo, const float* clamp_hi, void* stream) {
+  if (!scale || !shift || !clamp_lo || !clamp_hi) WXF_FAIL(WXF_EINVAL, "unpad_resize_post: null per-channel table");
+  const UnpadPost post{scale, shift, clamp_lo, clamp_hi};
+  return unpad_launch(y, ld, out, B, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, o0, n_out, &post, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GlobalMassFixer (credit/postblock/conservation.py:118-176), hybrid-sigma grid, midpoint quantities:
+//   sums[b] = ( sum_p area[p] * sum_l da[l] (1 - q[b,l,p]),  sum_p area[p] * sp[b,p] * sum_l db[l] (1 - q[b,l,p]) )
+// One thread per pixel walks the column; block partials are combined in fp64 by the last block (deterministic order).
+__global__ void __launch_bounds__(256) dry_mass_sums_kernel(const float* __restrict__ q, int64_t q_bstride, int64_t q_lstride,
+                                                            const float* __restrict__ sp, int64_t sp_bstride,
+                                                            const float* __restrict__ area, const float* __restrict__ da,
+                                                            const float* __restrict__ db, int L, int64_t p0, int64_t np,
+                                                            double* __restrict__ partial, double* __restrict__ sums,
+                                                            unsigned int* __restrict__ counter) {
+  const int b = blockIdx.y;
+  double a = 0.0, c = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = p0 + i;
+    float pa = 0.f, pb = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const float dry = 1.0f - q[b * q_bstride + l * q_lstride + p];
+      pa = __fadd_rn(pa, __fmul_rn(__ldg(da + l), dry));   // ((da * (1 - q)).sum(1)): level order, fp32, no contraction
+      pb = __fadd_rn(pb, __fmul_rn(__ldg(db + l), dry));
+    }
+    const float ar = __ldg(area + p);
+    a += (double)__fmul_rn(pa, ar);
+    c += (double)__fmul_rn(__fmul_rn(pb, sp[b * sp_bstride + p]), ar);
+  }
+  __shared__ double sa[256], sc[256];
+  sa[threadIdx.x] = a;
+  sc[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sa[threadIdx.x] += sa[threadIdx.x + o];
+      sc[threadIdx.x] += sc[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    partial[((int64_t)b * gridDim.x + blockIdx.x) * 2] = sa[0];
+    partial[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 1] = sc[0];
+    __threadfence();
+    last = atomicAdd(counter + b, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    double ta = 0.0, tc = 0.0;
+    for (unsigned int k = 0; k < gridDim.x; ++k) {
+      ta += partial[((int64_t)b * gridDim.x + k) * 2];
+      tc += partial[((int64_t)b * gridDim.x + k) * 2 + 1];
+    }
+    sums[2 * b] = ta;
+    sums[2 * b + 1] = tc;
+    counter[b] = 0;
+  }
+}
+
+extern "C" int64_t wxf_dry_mass_scratch_bytes(int B) { return (int64_t)B * 296 * 2 * 8 + (int64_t)B * 4 + 64; }
+
+extern "C" int wxf_dry_mass_sums(const float* q, int64_t q_bstride, int64_t q_lstride, const float* sp, int64_t sp_bstride,
+                                 const float* area, const float* da, const float* db, int B, int L, int64_t p0, int64_t np,
+                                 double* sums, void* scratch, void* stream) {
+  if (!q || !sp || !area || !da || !db || !sums || !scratch || B <= 0 || L <= 0 || p0 < 0 || np <= 0)
+    WXF_FAIL(WXF_EINVAL, "dry_mass_sums: bad arguments");
+  double* partial = reinterpret_cast<double*>(scratch);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partial + (int64_t)B * 296 * 2);
+  int64_t blocks = (np + 255) / 256;
+  if (blocks > 296) blocks = 296;
+  dry_mass_sums_kernel<<<dim3((unsigned)blocks, B), 256, 0, (cudaStream_t)stream>>>(q, q_bstride, q_lstride, sp, sp_bstride, area, da, db, L,
+                                                                                    p0, np, partial, sums, counter);
+  WXF_CHECK_LAUNCH("dry_mass_sums");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) scale_planes_kernel(float* __restrict__ x, int64_t bstride, int64_t n,
+                                                           const float* __restrict__ ratio) {
+  const int b = blockIdx.y;
+  const float r = __ldg(ratio + b);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[b * bstride + i] *= r;
+}
+
+extern "C" int wxf_scale_planes(float* x, int64_t bstride, int64_t n, const float* ratio, int B, void* stream) {
+  if (!x || !ratio || B <= 0 || n <= 0) WXF_FAIL(WXF_EINVAL, "scale_planes: bad arguments");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  scale_planes_kernel<<<dim3((unsigned)blocks, B), 256, 0, (cudaStream_t)stream>>>(x, bstride, n, ratio);
+  WXF_CHECK_LAUNCH("scale_planes");
   return 0;
 }
 

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 12
+WXF_ABI_VERSION = 13
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -88,6 +88,8 @@ _SIGNATURES = {
     "wxf_last_error": (c_char_p, []),
     "wxf_pad_to_pixel_major": (c_int, [c_void_p, c_void_p] + [c_int] * 13 + [c_void_p]),
     "wxf_pad_to_pixel_major_f16x2": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 13 + [c_void_p]),
+    "wxf_preblock_pad_to_pixel_major": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 13
+                                        + [c_void_p]),
     "wxf_cross_embed_toeplitz_tc": (c_int, [POINTER(WxfToeplitzDesc), c_void_p]),
     "wxf_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
     "wxf_layernorm_f16x2": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float,
@@ -133,6 +135,11 @@ _SIGNATURES = {
     "wxf_peer_wait": (c_int, [POINTER(c_void_p), c_int, c_void_p, c_void_p]),
     "wxf_sum_rank_slots": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "wxf_history_update": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_int64, c_void_p]),
+    "wxf_unpad_resize_post_to_nchw": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 12 + [c_void_p] * 5),
+    "wxf_dry_mass_scratch_bytes": (c_int64, [c_int]),
+    "wxf_dry_mass_sums": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                  c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "wxf_scale_planes": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "wxf_copy_channels": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int64, POINTER(c_int32), POINTER(c_int32),
                                   POINTER(c_int32), c_int, c_void_p]),
 }

@@ -438,21 +438,48 @@ class _Plan:
         else:
             ops.pad_to_pixel_major(x, lat, lon, mode, self.ld0, out=self.xp)
 
-    def _unpad(self, out):
+    def _pad_fields(self, tab):
+        """The pre-blocks fused into the padding pass (pipeline.FusedPreblocks.tables): per-variable planes in, z-scored,
+        concatenated and padded operand planes out — the [B, C, T, H, W] input tensor never exists."""
+        g = self.geo
+        table, mean, std, B, C, T, H, W, _keep = tab
+        if (B, C * T, T, H, W) != (self.batch, g.input_channels, g.frames, g.image_height, g.image_width):
+            raise ValueError(f"fields [B={B}, C={C}, T={T}, {H}, {W}] do not match the model input {(self.batch, *g.in_shape)}")
+        lat, lon, mode = ((g.padding.pad_lat, g.padding.pad_lon, g.padding.mode) if g.padding.activate
+                          else ((0, 0), (0, 0), "earth"))
+        if self.toeplitz:
+            ops.preblock_pad_to_pixel_major(table, mean, std, B, C, T, H, W, lat, lon, mode, 64, out_hi=self.xp_planes[0],
+                                            out_lo=self.xp_planes[1])
+        elif self.ld0 % 8 == 0:
+            ops.preblock_pad_to_pixel_major(table, mean, std, B, C, T, H, W, lat, lon, mode, self.ld0, out=self.xp)
+        else:
+            raise NotImplementedError("the fused pre-blocks need a padded-input channel stride that is a multiple of 8")
+
+    def _unpad(self, out, post=None):
         g, B = self.geo, self.batch
         pt, pl = (g.padding.pad_lat[0], g.padding.pad_lon[0]) if g.padding.activate else (0, 0)
+        if post is not None:  # inverse scaling + tracer clamps in the epilogue (pipeline.FusedPostblocks)
+            ops.unpad_resize_post_to_nchw(self.y_dec, g.output_channels, out, B, g.output_channels, g.h_dec, g.w_dec, pt, pl,
+                                          g.h_crop, g.w_crop, g.h_out, g.w_out, post.scale, post.shift, post.lo, post.hi)
+            return
         ops.unpad_resize_to_nchw(self.y_dec, g.output_channels, out, B, g.output_channels, g.h_dec, g.w_dec, pt, pl,
                                  g.h_crop, g.w_crop, g.h_out, g.w_out)
 
-    def run(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def run(self, x: Optional[torch.Tensor], out: Optional[torch.Tensor] = None, fields=None, post=None) -> torch.Tensor:
         g, B = self.geo, self.batch
-        self._pad(x)
+        if fields is not None:
+            self._pad_fields(fields)
+        else:
+            self._pad(x)
         for fn, args, _tag, _fl, _by in self.steps:
             fn(*args)
         if out is None:
-            out = torch.empty((B, g.base_output_channels, g.output_frames, g.h_out, g.w_out), device=x.device,
-                              dtype=torch.float32)
-        self._unpad(out)
+            dev = x.device if x is not None else fields[0].device
+            out = torch.empty((B, g.base_output_channels, g.output_frames, g.h_out, g.w_out), device=dev, dtype=torch.float32)
+        if post is not None:
+            self._unpad(out, post)
+        else:
+            self._unpad(out)
         return out
 
     def run_profiled(self, x: torch.Tensor):
@@ -620,6 +647,28 @@ class CrossFormerB200(_Base):
         x, plan = self._plan_for(x)
         with torch.cuda.device(x.device):
             return plan.run(x)
+
+    @torch.no_grad()
+    def forward_fields(self, batch_input, pre, post=None) -> torch.Tensor:
+        """The forecast step on the batch dict itself: ``batch_input`` is ``batch["input"]`` of the gen2
+        pipeline (source -> var_key -> [B, n_levels, T, H, W] fp32 CUDA tensors, physical units), ``pre`` a
+        ``pipeline.FusedPreblocks`` (normalisation + channel order, fused into the padding kernel: the concatenated input
+        tensor is never built) and ``post`` an optional ``pipeline.FusedPostblocks`` (inverse scaling + tracer clamps in the
+        epilogue of the output pass: the prediction comes back in physical units)."""
+        if self._domain is not None:
+            raise NotImplementedError("forward_fields runs on the single-GPU plan")
+        tab = pre.tables(batch_input)
+        probe = tab[8][0]
+        if self.training:
+            raise NotImplementedError("eval-mode forecast forward only: call .eval()")
+        if self._prepared is None or self._prepared_sig != self._signature():
+            self.refresh_weights()
+        key = (tab[3], probe.device.index, self.exact_fp32)
+        plan = self._plans.get(key)
+        with torch.cuda.device(probe.device):
+            if plan is None:
+                plan = self._plans[key] = _Plan(self.geometry, self._prepared, tab[3], probe.device, not self.exact_fp32)
+            return plan.run(None, fields=tab, post=post)
 
 
 class WXFormerB200(CrossFormerB200):

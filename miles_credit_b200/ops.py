@@ -432,3 +432,69 @@ def history_update(x: torch.Tensor, y: torch.Tensor, forcing: Optional[torch.Ten
                                         y.shape[2], plane, _stream())
     _lib.check(st, "wxf_history_update")
     LAUNCHES += 1
+
+
+def preblock_pad_to_pixel_major(chan_table: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, B: int, C: int, T: int, H: int,
+                                W: int, pad_lat, pad_lon, mode: str, ld: int, out: Optional[torch.Tensor] = None,
+                                out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None, rows=None):
+    """Normalise + concat + pad in one pass: ``chan_table`` is an int64 device tensor [B*C] of plane addresses ([T, H, W] fp32
+    each), ``mean`` / ``std`` are [C] fp32.  Output like ``pad_to_pixel_major`` (``out``) or its f16x2 variant."""
+    global LAUNCHES
+    hp, wp = H + pad_lat[0] + pad_lat[1], W + pad_lon[0] + pad_lon[1]
+    r0, nr = rows if rows is not None else (0, hp)
+    m = _lib.PAD_EARTH if mode == "earth" else _lib.PAD_MIRROR
+    st = _lib.load().wxf_preblock_pad_to_pixel_major(chan_table.data_ptr(), mean.data_ptr(), std.data_ptr(), _ptr(out),
+                                                     _ptr(out_hi), _ptr(out_lo), B, C, T, H, W, pad_lat[0], pad_lat[1],
+                                                     pad_lon[0], pad_lon[1], m, ld, r0, nr, _stream())
+    _lib.check(st, "wxf_preblock_pad_to_pixel_major")
+    LAUNCHES += 1
+
+
+def unpad_resize_post_to_nchw(y: torch.Tensor, ld: int, out: torch.Tensor, B: int, C: int, Hd: int, Wd: int, top: int, left: int,
+                              Hc: int, Wc: int, Ho: int, Wo: int, scale: torch.Tensor, shift: torch.Tensor, lo: torch.Tensor,
+                              hi: torch.Tensor, rows=None):
+    """``unpad_resize_to_nchw`` with the inverse scaling and the tracer clamps in its epilogue (per output channel)."""
+    global LAUNCHES
+    o0, n_out = rows if rows is not None else (0, Ho)
+    st = _lib.load().wxf_unpad_resize_post_to_nchw(y.data_ptr(), ld, out.data_ptr(), B, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, o0,
+                                                   n_out, scale.data_ptr(), shift.data_ptr(), lo.data_ptr(), hi.data_ptr(),
+                                                   _stream())
+    _lib.check(st, "wxf_unpad_resize_post_to_nchw")
+    LAUNCHES += 1
+
+
+_MASS_SCRATCH = {}
+
+
+def dry_mass_sums(q: torch.Tensor, sp: torch.Tensor, area: torch.Tensor, da: torch.Tensor, db: torch.Tensor, rows=None):
+    """q [B, L, H, W] and sp [B, H, W] (views of an NCHW state: contiguous planes) -> fp64 [B, 2] (GlobalMassFixer sums)."""
+    global LAUNCHES
+    _req(q, "q")
+    _req(sp, "sp")
+    B, L, H, W = q.shape
+    if q.stride(3) != 1 or q.stride(2) != W or sp.stride(2) != 1 or sp.stride(1) != W:
+        raise ValueError("dry_mass_sums needs contiguous [H, W] planes")
+    r0, nr = rows if rows is not None else (0, H)
+    key = (q.device, B)
+    if key not in _MASS_SCRATCH:
+        n = int(_lib.load().wxf_dry_mass_scratch_bytes(B))
+        _MASS_SCRATCH[key] = torch.zeros(n, device=q.device, dtype=torch.uint8)
+    sums = torch.empty((B, 2), device=q.device, dtype=torch.float64)
+    st = _lib.load().wxf_dry_mass_sums(q.data_ptr(), q.stride(0), q.stride(1), sp.data_ptr(), sp.stride(0), area.data_ptr(),
+                                       da.data_ptr(), db.data_ptr(), B, L, r0 * W, nr * W, sums.data_ptr(),
+                                       _MASS_SCRATCH[key].data_ptr(), _stream())
+    _lib.check(st, "wxf_dry_mass_sums")
+    LAUNCHES += 1
+    return sums
+
+
+def scale_planes(x: torch.Tensor, ratio: torch.Tensor):
+    """x[b] *= ratio[b] in place for a [B, H, W] view with contiguous planes."""
+    global LAUNCHES
+    _req(x, "x")
+    B, H, W = x.shape
+    if x.stride(2) != 1 or x.stride(1) != W:
+        raise ValueError("scale_planes needs contiguous [H, W] planes")
+    st = _lib.load().wxf_scale_planes(x.data_ptr(), x.stride(0), H * W, ratio.data_ptr(), B, _stream())
+    _lib.check(st, "wxf_scale_planes")
+    LAUNCHES += 1

