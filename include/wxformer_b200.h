@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 13
+#define WXF_ABI_VERSION 14
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -411,6 +411,24 @@ int wxf_unpatchify_unpad_resize_to_nchw(const float* y, float* out, int B, int C
  */
 int wxf_history_update(float* x, const float* y, const float* forcing, int B, int C, int T, int n_prog, int n_dyn, int Cy,
                        int Ty, int64_t plane, void* stream);
+
+/*
+ * Noise injection of the ensemble variant CrossFormerWithNoise (credit/models/wxformer/crossformer_ensemble.py:110-177;
+ * StochasticDecompositionLayer.forward, credit/models/wxformer/stochastic_decomposition_layer.py:21-42):
+ *     feature + noise_factor * eps * Linear(latent)[b, c] * modulation[c],   eps ~ N(0, 1) per element, latent ~ N(0, 1)^D
+ * wxf_noise_coef   : coef[b, c] = factor[0] * (W[c, :] . latent[b, :] + bias[c]) * modulation[c]; latent == NULL draws it
+ *                    (Philox, keyed by seed / *step_counter / site / b)
+ * wxf_noise_inject : out[p, c] = x[p, c] + eps[p, c] * coef[b, c] on a pixel-major field ([B*HW, ld]), written as fp32 (out,
+ *                    optional, may alias x) and / or fp16 hi/lo planes at column h_off; eps == NULL draws it (Philox).
+ *                    eps, when given, is pixel-major [B*HW, C] (the tests feed the reference's recorded draws).
+ * wxf_noise_step_advance : *step_counter += 1 (uint64, once per forward: a replayed CUDA graph draws fresh noise).
+ */
+int wxf_noise_coef(const float* latent, const float* W, const float* bias, const float* modulation, const float* factor,
+                   float* coef, int B, int C, int D, uint64_t seed, const void* step_counter, int site, void* stream);
+int wxf_noise_inject(const float* x, int ldx, float* out, int ldo, void* out_hi, void* out_lo, int ldh, int h_off,
+                     const float* coef, const float* eps, int B, int64_t HW, int C, uint64_t seed, const void* step_counter,
+                     int site, void* stream);
+int wxf_noise_step_advance(void* step_counter, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Exchanges of the lat-lon domain decomposition over NVLink peer memory (csrc/wxf_peer.cu): what the reference does with

@@ -1,6 +1,7 @@
 """File to list under ``custom_models:`` in a CREDIT config (credit/models/__init__.py:278-298).
 
-CREDIT executes it before the registry lookup; it registers the B200 forecast step under ``type: crossformer_b200``.
+CREDIT executes it before the registry lookup; it registers the B200 forecast steps under ``type: crossformer_b200``,
+``wxformer_b200``, ``fuxi_b200`` and ``crossformer-ensemble_b200``.
 """
 import os
 import sys

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 13
+WXF_ABI_VERSION = 14
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -140,6 +140,10 @@ _SIGNATURES = {
     "wxf_dry_mass_sums": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "wxf_scale_planes": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "wxf_noise_coef": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_int, c_void_p]),
+    "wxf_noise_inject": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
+                                 c_int64, c_int, ctypes.c_uint64, c_void_p, c_int, c_void_p]),
+    "wxf_noise_step_advance": (c_int, [c_void_p, c_void_p]),
     "wxf_copy_channels": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int64, POINTER(c_int32), POINTER(c_int32),
                                   POINTER(c_int32), c_int, c_void_p]),
 }

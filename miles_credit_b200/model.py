@@ -144,8 +144,9 @@ class _Plan:
     kernel (validation path).
     """
 
-    def __init__(self, geo: Geometry, wts: PreparedWeights, batch: int, device, tensor_cores: bool = True):
+    def __init__(self, geo: Geometry, wts: PreparedWeights, batch: int, device, tensor_cores: bool = True, noise=None):
         self.geo, self.batch = geo, batch
+        self.noise = noise  # ensemble.NoiseState of CrossFormerWithNoiseB200, or None
         if tensor_cores:
             ok = all(c is not None for brs in wts.embeds_tc[1:] for c in brs) and \
                 all(u.up.n % 4 == 0 for u in wts.ups)
@@ -153,6 +154,8 @@ class _Plan:
                 logger.warning("channel counts not multiples of 4: using the exact-fp32 CUDA-core path")
                 tensor_cores = False
         self.tensor_cores = tensor_cores
+        if noise is not None and not tensor_cores:
+            raise NotImplementedError("the noise-injection variant runs on the tensor-core plan only")
         self.attention_tc = tensor_cores and os.environ.get("WXF_ATTN_TC", "1") != "0"
         self.ff_fused = tensor_cores and os.environ.get("WXF_FF_FUSED", "0") == "1"
         self.attn_simt_small = tensor_cores and os.environ.get("WXF_ATTN_SIMT_SMALL", "0") == "1"
@@ -212,6 +215,15 @@ class _Plan:
         desc = ops.make_conv_tc_desc(in_hi, in_lo, wts, **kw)
         m = kw["B"] * kw["Ho"] * kw["Wo"]
         self._add(ops.conv_f16x2_tc, (desc,), tag, 2.0 * m * wts.n * wts.t * wts.cin * wts.phases)
+
+    def _noise(self, site, x, ldx, out, ldo, planes, B, HW, C):
+        """One injection site of the ensemble variant (crossformer_ensemble.py:139-162): the per-(batch, channel)
+        coefficient, then feature + eps * coef as fp32 (``out``) and / or operand planes (``planes`` = (hi, lo, ld))."""
+        ns = self.noise
+        hi, lo, ldh = planes if planes is not None else (None, None, 0)
+        self._add(ns.coef, (site, B), "noise_coef", 0, 0)
+        self._add(ns.inject, (site, x, ldx, out, ldo, hi, lo, ldh, B, HW, C), "noise_inject", 0,
+                  (8.0 if out is not None else 4.0) * B * HW * C + (4.0 * B * HW * C if hi is not None else 0.0))
 
     def _transformer(self, layers, st, B, h, w, xv, ld, out_planes):
         """Launches of one Transformer stage (crossformer.py:358-365) on the residual stream ``xv`` ([B, h, w, d] view with
@@ -338,6 +350,9 @@ class _Plan:
                     self._conv(src, bw, xbuf, tag=f"embed{s}.k{br.kernel}", B=B, Hi=src_h, Wi=src_w, lda=src_ld,
                                Ho=st.h, Wo=st.w, ldc=ld, c_off=xoff + br.c_off)
             self._transformer(wts.blocks[s], st, B, st.h, st.w, xv, ld, (xp_hi, xp_lo, pld) if tc else None)
+            if self.noise is not None and self.noise.encoder and s < 3:
+                # encoder noise: the stage output (skip connection AND next cross-embed input) is perturbed in place
+                self._noise(s, xv, ld, xv, ld, (xp_hi, xp_lo, pld), B, st.h * st.w, d)
             src, src_ld, src_h, src_w = xv, ld, st.h, st.w
             if tc:
                 src_planes = (xp_hi, xp_lo)
@@ -383,7 +398,15 @@ class _Plan:
                                                b_hi, b_lo, c, 0, B, ho * wo, c, up.groups), "groupnorm_silu", 0, 8.0 * n)
                 self._conv_tc(b_hi, b_lo, uw.convs_tc[1], "dec_conv3x3", B=B, Hi=ho, Wi=wo, lda=c, Ho=ho, Wo=wo, out=a,
                               ldc=c)
-                if skip == 0 and not head_tc:  # fp32 head (odd channel count): keep the fp32 concat buffer
+                if self.noise is not None:
+                    # decoder noise (noise_inject1..3): UpBlock output -> fp32 temporary -> + eps * coef -> concat buffer
+                    add(ops.groupnorm_silu, (a, c, self.gn_stats, self.gn_scratch, uw.gn_w[1], uw.gn_b[1], short, c, b, c, B,
+                                             ho * wo, c, up.groups), "groupnorm_silu", 0, 16.0 * n)
+                    if skip == 0 and not head_tc:
+                        self._noise(5 - skip, b, c, dst, 2 * c, None, B, ho * wo, c)
+                    else:
+                        self._noise(5 - skip, b, c, None, 0, (self.catp[skip][0], self.catp[skip][1], 2 * c), B, ho * wo, c)
+                elif skip == 0 and not head_tc:  # fp32 head (odd channel count): keep the fp32 concat buffer
                     add(ops.groupnorm_silu, (a, c, self.gn_stats, self.gn_scratch, uw.gn_w[1], uw.gn_b[1], short, c,
                                              dst, 2 * c, B, ho * wo, c, up.groups), "groupnorm_silu", 0, 16.0 * n)
                 else:
@@ -480,6 +503,8 @@ class _Plan:
             self._unpad(out, post)
         else:
             self._unpad(out)
+        if self.noise is not None:
+            self.noise.advance()
         return out
 
     def run_profiled(self, x: torch.Tensor):
@@ -707,9 +732,16 @@ class WXFormerB200(CrossFormerB200):
 
 
 def register_with_credit(key: str = "crossformer_b200", message: Optional[str] = None):
-    """Register under CREDIT's model registry (credit/models/__init__.py:128-161) so ``type: crossformer_b200``
-    (and ``wxformer_b200`` for the PixelShuffle variant) selects these classes from YAML; needs CREDIT importable."""
+    """Register under CREDIT's model registry (credit/models/__init__.py:128-161) so ``type: crossformer_b200`` selects
+    ``CrossFormerB200`` from YAML; likewise ``wxformer_b200`` (PixelShuffle variant), ``fuxi_b200`` (FuXi) and
+    ``crossformer-ensemble_b200`` (noise-injection variant).  Needs CREDIT importable."""
     from credit.models import register_model  # type: ignore
 
+    from .ensemble import CrossFormerWithNoiseB200
+    from .fuxi import FuxiB200
+
     register_model("wxformer_b200", "Loading the B200-native WXFormer (PixelShuffle decoder) forecast step ...")(WXFormerB200)
+    register_model("fuxi_b200", "Loading the B200-native FuXi forecast step ...")(FuxiB200)
+    register_model("crossformer-ensemble_b200", "Loading the B200-native CrossFormer with noise injection ...")(
+        CrossFormerWithNoiseB200)
     return register_model(key, message or "Loading the B200-native CrossFormer forecast step ...")(CrossFormerB200)

@@ -498,3 +498,31 @@ def scale_planes(x: torch.Tensor, ratio: torch.Tensor):
     st = _lib.load().wxf_scale_planes(x.data_ptr(), x.stride(0), H * W, ratio.data_ptr(), B, _stream())
     _lib.check(st, "wxf_scale_planes")
     LAUNCHES += 1
+
+
+# ---- ensemble noise injection (crossformer_ensemble.py) ------------------------------------------------------------------------
+
+def noise_coef(latent: Optional[torch.Tensor], W: torch.Tensor, bias: torch.Tensor, mod: torch.Tensor, factor: torch.Tensor,
+               coef: torch.Tensor, B: int, C: int, D: int, seed: int, step_counter: Optional[torch.Tensor], site: int):
+    global LAUNCHES
+    st = _lib.load().wxf_noise_coef(_ptr(latent), W.data_ptr(), bias.data_ptr(), mod.data_ptr(), factor.data_ptr(), coef.data_ptr(),
+                                    B, C, D, seed, _ptr(step_counter), site, _stream())
+    _lib.check(st, "wxf_noise_coef")
+    LAUNCHES += 1
+
+
+def noise_inject(x: torch.Tensor, ldx: int, out: Optional[torch.Tensor], ldo: int, out_hi, out_lo, ldh: int, h_off: int,
+                 coef: torch.Tensor, eps: Optional[torch.Tensor], B: int, HW: int, C: int, seed: int,
+                 step_counter: Optional[torch.Tensor], site: int):
+    global LAUNCHES
+    st = _lib.load().wxf_noise_inject(x.data_ptr(), ldx, _ptr(out), ldo, _ptr(out_hi), _ptr(out_lo), ldh, h_off, coef.data_ptr(),
+                                      _ptr(eps), B, HW, C, seed, _ptr(step_counter), site, _stream())
+    _lib.check(st, "wxf_noise_inject")
+    LAUNCHES += 1
+
+
+def noise_step_advance(step_counter: torch.Tensor):
+    global LAUNCHES
+    st = _lib.load().wxf_noise_step_advance(step_counter.data_ptr(), _stream())
+    _lib.check(st, "wxf_noise_step_advance")
+    LAUNCHES += 1

@@ -42,7 +42,7 @@ class EmulatedLib:
                     raise AssertionError(f"{what}: input {rn} [{r0:#x}, {r1:#x}) overlaps output {wn} [{w0:#x}, {w1:#x})")
 
     def wxf_abi_version(self):
-        return 13
+        return 14
 
     def wxf_last_error(self):
         return b"emulator"
@@ -607,3 +607,31 @@ class EmulatedLib:
         v = out * _t(_arr(scale, C)).view(1, C, 1, 1) + _t(_arr(shift, C)).view(1, C, 1, 1)
         out.copy_(torch.minimum(torch.maximum(v, _t(_arr(lo, C)).view(1, C, 1, 1)), _t(_arr(hi, C)).view(1, C, 1, 1)))
         return rc
+
+    # ---- ensemble noise injection (recorded draws only: the emulator has no generator) ---------------------------------------
+
+    def wxf_noise_coef(self, latent, W, bias, mod, factor, coef, B, C, D, seed, step, site, stream):
+        self.calls.append("noise_coef")
+        assert latent, "the emulator needs the latent draw"
+        lat = _t(_arr(latent, B * D)).view(B, D)
+        style = lat @ _t(_arr(W, C * D)).view(C, D).t() + _t(_arr(bias, C))
+        _t(_arr(coef, B * C)).view(B, C).copy_(_t(_arr(factor, 1)) * style * _t(_arr(mod, C)))
+        return 0
+
+    def wxf_noise_inject(self, x, ldx, out, ldo, out_hi, out_lo, ldh, h_off, coef, eps, B, HW, C, seed, step, site, stream):
+        self.calls.append("noise_inject")
+        assert eps, "the emulator needs the eps draw"
+        M = B * HW
+        xs = _t(_arr(x, (M - 1) * ldx + C)).as_strided((M, C), (ldx, 1))
+        k = _t(_arr(coef, B * C)).view(B, 1, C).expand(B, HW, C).reshape(M, C)
+        v = xs + _t(_arr(eps, M * C)).view(M, C) * k
+        if out:
+            _t(_arr(out, (M - 1) * ldo + C)).as_strided((M, C), (ldo, 1)).copy_(v)
+        if out_hi:
+            hi, lo = self._split(v)
+            self._harr(out_hi, (M - 1) * ldh + h_off + C).as_strided((M, C), (ldh, 1), h_off).copy_(hi)
+            self._harr(out_lo, (M - 1) * ldh + h_off + C).as_strided((M, C), (ldh, 1), h_off).copy_(lo)
+        return 0
+
+    def wxf_noise_step_advance(self, step, stream):
+        return 0

@@ -129,3 +129,56 @@ def test_forecast_handoff_double_buffered_d2h():
         assert t.shape == (1, 6, 1, 8, 32) and t.is_pinned() is False or True
         assert torch.equal(t, (torch.full((1, 6, 1, 8, 32), float(s)) + torch.arange(4, 12).view(1, 1, 1, 8, 1).float()))
     assert h.bytes_per_step == 6 * 8 * 32 * 4
+
+
+@pytest.mark.parametrize("case", ["unit_ensemble", "unit_ensemble_correlated"])
+def test_ensemble_variant_matches_reference_with_recorded_noise(golden_dir, case):
+    """CrossFormerWithNoise: same weights, same input, the reference's recorded torch.randn draws -> same prediction."""
+    from miles_credit_b200.ensemble import CrossFormerWithNoiseB200
+
+    fx = torch.load(os.path.join(golden_dir, f"{case}.pt"), weights_only=False)
+    base_kw = {k: v for k, v in fx["kwargs"].items() if k not in ("noise_latent_dim", "encoder_noise_factor",
+                                                                   "decoder_noise_factor", "encoder_noise", "freeze", "correlated")}
+    geo = build_geometry(**base_kw)
+    model = CrossFormerWithNoiseB200(**fx["kwargs"])
+    model.load_state_dict(dict(synthetic_state_dict(geo, seed=fx["seed"]), **fx["noise_state"]), strict=True)
+    model = model.cuda().eval()
+    model.set_recorded_noise(fx["draws"])
+    y = model(fx["x"].cuda())
+    err = float((y.cpu() - fx["y"]).abs().max() / fx["y"].abs().max())
+    print(f"{case}: rel-max vs the reference module = {err:.3e}")
+    assert err < 1e-4
+    # generator mode: finite, differs from step to step and between member seeds, reproducible for a seed
+    model.set_recorded_noise(None)
+    a1, a2 = model(fx["x"].cuda()).clone(), model(fx["x"].cuda()).clone()
+    assert torch.isfinite(a1).all() and not torch.equal(a1, a2)
+    twin = CrossFormerWithNoiseB200(**fx["kwargs"], noise_seed=0)
+    twin.load_state_dict(model.state_dict(), strict=True)
+    assert torch.equal(twin.cuda().eval()(fx["x"].cuda()), a1)
+    other = CrossFormerWithNoiseB200(**fx["kwargs"], noise_seed=7)
+    other.load_state_dict(model.state_dict(), strict=True)
+    assert not torch.equal(other.cuda().eval()(fx["x"].cuda()), a1)
+    spread = float((a1 - a2).abs().mean() / a1.abs().mean())
+    print(f"{case}: member-to-member relative spread {spread:.3e}")
+    assert 1e-4 < spread < 1.0
+
+
+def test_noise_generator_statistics():
+    """Philox draws of wxf_noise_inject: x = 0, coef = 1 -> the output IS eps: mean 0, variance 1, no repeats across sites."""
+    B, HW, C = 2, 4096, 64
+    x = torch.zeros(B * HW, C, device="cuda")
+    coef = torch.ones(B, C, device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    outs = []
+    for site in (0, 1):
+        out = torch.empty_like(x)
+        ops.noise_inject(x, C, out, C, None, None, 0, 0, coef, None, B, HW, C, 1234, step, site)
+        outs.append(out)
+    e = outs[0]
+    assert abs(float(e.mean())) < 5e-3 and abs(float(e.var()) - 1.0) < 1e-2
+    assert abs(float((e ** 4).mean()) - 3.0) < 0.1                      # Gaussian kurtosis
+    assert float((outs[0] * outs[1]).mean().abs()) < 5e-3              # sites are independent streams
+    ops.noise_step_advance(step)
+    again = torch.empty_like(x)
+    ops.noise_inject(x, C, again, C, None, None, 0, 0, coef, None, B, HW, C, 1234, step, 0)
+    assert int(step.item()) == 1 and float((again * e).mean().abs()) < 5e-3

@@ -99,6 +99,15 @@ assert {{k: tuple(v.shape) for k, v in ref2.state_dict().items()}} == {{k: tuple
 ref = load_model({{"model": dict(workload("unit"), type="crossformer")}})
 assert {{k: tuple(v.shape) for k, v in ref.state_dict().items()}} == {{k: tuple(v.shape) for k, v in m.state_dict().items()}}
 m.load_state_dict(ref.state_dict(), strict=True)
+# the other classes of the path registered by the same plugin file
+from miles_credit_b200.fuxi import fuxi_workload
+fk = dict(fuxi_workload("fuxi_1deg"), dim=32, num_groups=4, num_heads=2, depth=2)
+mf = load_model({{"custom_models": conf["custom_models"], "model": dict(fk, type="fuxi_b200")}})
+assert isinstance(mf, BaseModel) and type(mf).__name__ == "FuxiB200"
+ek = dict(workload("unit"), noise_latent_dim=8)
+me = load_model({{"custom_models": conf["custom_models"], "model": dict(ek, type="crossformer-ensemble_b200")}})
+re_ = load_model({{"model": dict(ek, type="crossformer-ensemble")}})
+assert {{k: tuple(v.shape) for k, v in re_.state_dict().items()}} == {{k: tuple(v.shape) for k, v in me.state_dict().items()}}
 print("ok")
 """
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
