@@ -57,7 +57,7 @@ class Arm:
             self.input = lambda seed=1000: F.synthetic_fuxi_input(geo, batch=1, seed=seed)
             self.flops = F.fuxi_flops_per_forward(geo)["total"]
             self.label = "FuXi-6h"
-            self.can_decompose = False
+            self.can_decompose = True  # latitude bands of whole window rows (miles_credit_b200/fuxi_domain.py)
         else:
             from miles_credit_b200.geometry import build_geometry, flops_per_forward, workload
             from miles_credit_b200.model import CrossFormerB200, WXFormerB200

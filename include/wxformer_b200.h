@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 14
+#define WXF_ABI_VERSION 15
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -378,10 +378,13 @@ int wxf_layernorm_residual(const float* x, int ldx, const float* res, int ldr, f
  *   bias        : [heads, L, L] fp32 = 16 * sigmoid(cpb_mlp(log-spaced relative coordinates)), L = ws_h*ws_w <= 64
  *   logit_scale : [heads] fp32 = exp(min(logit_scale, ln 100))
  *   output: fp16 hi/lo planes [B*H*W, ldh] (input of the proj GEMM) or fp32 [B*H*W, ldh] (exactly one of the two).
+ *   mask_shift_h: row shift the -100 mask is built for; < 0 = shift_h.  A latitude band of a decomposed forecast does the
+ *            row roll itself (its buffer starts shift rows into the band: shift_h = 0) and passes the true shift here on the
+ *            one band that holds the wrapped window row, 0 elsewhere.
  */
 int wxf_swin_window_attention(const float* qkv, int ldq, const float* bias, const float* logit_scale, void* out_hi,
                               void* out_lo, float* out_f32, int ldh, int B, int H, int W, int d, int heads, int ws_h,
-                              int ws_w, int shift_h, int shift_w, void* stream);
+                              int ws_w, int shift_h, int shift_w, int mask_shift_h, void* stream);
 
 /*
  * Row gather with zero fill: dst[i, 0:d] = idx[i] >= 0 ? src[idx[i], 0:d] : 0, written as fp32 (dst, optional) and / or
@@ -395,10 +398,12 @@ int wxf_gather_rows_ex(const float* src, int ld_src, const int32_t* idx, float* 
  * Dense-head output -> prediction (fuxi.py:484-498): y is token-major [B, Lat, Lon, ph*pw*cp] where pixel (py, px) of a
  * patch owns the columns (py*pw + px)*cp + c, c < C <= cp (the head's weight rows re-ordered and padded at load);
  * un-patchify, crop rows [top, top+Hc) x cols [left, left+Wc), bilinear resize (align_corners = False) to Ho x Wo,
- * write NCHW [B, C, Ho, Wo]; only output rows [o0, o0 + n_out).
+ * write NCHW [B, C, Ho, Wo]; only output rows [o0, o0 + n_out).  The buffer holds the patch rows [lat0, lat0 + Lat) of
+ * the grid (lat0 = 0: all of it; a latitude band with its halo rows otherwise; top / Hc stay those of the whole grid).
  */
 int wxf_unpatchify_unpad_resize_to_nchw(const float* y, float* out, int B, int C, int cp, int Lat, int Lon, int ph, int pw,
-                                        int top, int left, int Hc, int Wc, int Ho, int Wo, int o0, int n_out, void* stream);
+                                        int top, int left, int Hc, int Wc, int Ho, int Wo, int o0, int n_out, int lat0,
+                                        void* stream);
 
 /*
  * Autoregressive state update with a history window of T input frames (the gen2 rollout's slide,

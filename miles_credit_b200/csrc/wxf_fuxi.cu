@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(SW_THREADS) swin_attention_kernel(const float*
                                                                     __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                                                     float* __restrict__ out_f32, int ldh, int H, int W,
                                                                     int d, int dh, int wsh, int wsw, int sh, int sw, int nwx,
-                                                                    int nwy) {
+                                                                    int nwy, int msh) {
   wxf_pdl_trigger();
   wxf_pdl_wait();
   extern __shared__ __align__(16) float smem[];
@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(SW_THREADS) swin_attention_kernel(const float*
     if (sx >= W) sx -= W;
     pix[t] = ((int64_t)b * H + sy) * W + sx;
     int r = 0;
-    if (sh > 0) r += 3 * (ry < H - wsh ? 0 : (ry < H - sh ? 1 : 2));
+    // msh: the row shift the MASK is built for.  It equals sh except on a latitude band of a decomposed forecast, where the
+    // roll over rows is done by the caller (the band buffer starts `shift` rows into the rank's rows: sh = 0) and only the
+    // band that holds the wrapped window row still needs the mask (msh = shift there, 0 elsewhere).
+    if (msh > 0) r += 3 * (ry < H - wsh ? 0 : (ry < H - msh ? 1 : 2));
     if (sw > 0) r += (rx < W - wsw ? 0 : (rx < W - sw ? 1 : 2));
     rid[t] = r;
   }
@@ -281,7 +284,7 @@ __device__ __forceinline__ void bilin_axis_f(int dst, float scale, int n_in, int
 __global__ void __launch_bounds__(256) unpatchify_resize_kernel(const float* __restrict__ y, float* __restrict__ out, int C,
                                                                 int cp, int Lat, int Lon, int ph, int pw, int top, int left,
                                                                 int Hc, int Wc, int Ho, int Wo, float sh, float sw,
-                                                                int cgroups, int o0) {
+                                                                int cgroups, int o0, int lat0) {
   wxf_pdl_trigger();
   wxf_pdl_wait();
   __shared__ float tile[32][33];  // [channel][column]
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(256) unpatchify_resize_kernel(const float* __r
   const int64_t tok = (int64_t)ph * pw * cp;
   // row part of the source address once per CTA, column part once per (thread, column); zero-weight taps are not loaded
   // (W is not resized in the forecast configs, so half of the four taps usually drop out)
-  const int Y0 = y0 + top, Y1 = y1 + top;
+  const int Y0 = y0 + top - lat0 * ph, Y1 = y1 + top - lat0 * ph;  // rows of the buffer (it starts at patch row lat0)
   const float* row0 = y + ((int64_t)b * Lat + Y0 / ph) * Lon * tok + (int64_t)(Y0 % ph) * pw * cp + ch;
   const float* row1 = y + ((int64_t)b * Lat + Y1 / ph) * Lon * tok + (int64_t)(Y1 % ph) * pw * cp + ch;
 #pragma unroll
@@ -394,7 +397,7 @@ extern "C" int wxf_layernorm_residual(const float* x, int ldx, const float* res,
 
 extern "C" int wxf_swin_window_attention(const float* qkv, int ldq, const float* bias, const float* logit_scale, void* out_hi,
                                          void* out_lo, float* out_f32, int ldh, int B, int H, int W, int d, int heads,
-                                         int ws_h, int ws_w, int shift_h, int shift_w, void* stream) {
+                                         int ws_h, int ws_w, int shift_h, int shift_w, int mask_shift_h, void* stream) {
   if (!qkv || !bias || !logit_scale || B <= 0 || H <= 0 || W <= 0 || d <= 0 || heads <= 0 || d % heads)
     WXF_FAIL(WXF_EINVAL, "swin_attention: bad arguments");
   if ((out_hi == nullptr) != (out_lo == nullptr) || (!out_hi && !out_f32) || (out_hi && out_f32))
@@ -405,6 +408,8 @@ extern "C" int wxf_swin_window_attention(const float* qkv, int ldq, const float*
   if (dh % 4 || ldq % 4 || ldh % 4 || ldq < 3 * d || ldh < d || !wxf_aligned16(qkv))
     WXF_FAIL(WXF_EALIGN, "swin_attention: head dim / strides must be multiples of 4, qkv 16-byte aligned");
   if (shift_h < 0 || shift_w < 0 || shift_h >= ws_h || shift_w >= ws_w) WXF_FAIL(WXF_EINVAL, "swin_attention: bad shift");
+  if (mask_shift_h < 0) mask_shift_h = shift_h;
+  if (mask_shift_h >= ws_h) WXF_FAIL(WXF_EINVAL, "swin_attention: bad mask shift");
   const size_t smem = (size_t)(3 * L * (dh + 4) + L * (L + 1)) * 4 + (size_t)((L + 1) & ~1) * 4 + (size_t)L * 8;
   if (smem > 227 * 1024) WXF_FAIL(WXF_EUNSUPPORTED, "swin_attention: window %d x head dim %d needs %zu bytes of shared memory", L, dh, smem);
   static WxfPerDevice<size_t> attr_pd;
@@ -419,7 +424,7 @@ extern "C" int wxf_swin_window_attention(const float* qkv, int ldq, const float*
   if (nwin > INT32_MAX || heads > 65535) WXF_FAIL(WXF_EINVAL, "swin_attention: grid too large");
   wxf_launch(swin_attention_kernel, dim3((unsigned)nwin, (unsigned)heads), dim3(SW_THREADS), smem, (cudaStream_t)stream, qkv, ldq,
              bias, logit_scale, (__half*)out_hi, (__half*)out_lo, out_f32, ldh, H, W, d, dh, ws_h, ws_w, shift_h, shift_w, nwx,
-             nwy);
+             nwy, mask_shift_h);
   WXF_CHECK_LAUNCH("swin_attention");
   return 0;
 }
@@ -443,18 +448,35 @@ extern "C" int wxf_gather_rows_ex(const float* src, int ld_src, const int32_t* i
 
 extern "C" int wxf_unpatchify_unpad_resize_to_nchw(const float* y, float* out, int B, int C, int cp, int Lat, int Lon, int ph,
                                                    int pw, int top, int left, int Hc, int Wc, int Ho, int Wo, int o0,
-                                                   int n_out, void* stream) {
+                                                   int n_out, int lat0, void* stream) {
   if (!y || !out || B <= 0 || C <= 0 || cp < C || Lat <= 0 || Lon <= 0 || ph <= 0 || pw <= 0 || Hc <= 0 || Wc <= 0 || Ho <= 0 ||
-      Wo <= 0 || top < 0 || left < 0 || top + Hc > Lat * ph || left + Wc > Lon * pw)
+      Wo <= 0 || top < 0 || left < 0 || left + Wc > Lon * pw)
     WXF_FAIL(WXF_EINVAL, "unpatchify_resize: bad dims");
   if (o0 < 0 || n_out < 0 || o0 + n_out > Ho) WXF_FAIL(WXF_EINVAL, "unpatchify_resize: rows [%d, %d) outside [0, %d)", o0, o0 + n_out, Ho);
   if (n_out == 0) return 0;
   const float sh = (float)Hc / (float)Ho, sw = (float)Wc / (float)Wo;
+  {
+    // the source rows the requested output rows touch must lie inside the buffer, which holds patch rows
+    // [lat0, lat0 + Lat) (lat0 = 0 and Lat = the whole grid, or a latitude band with its halo rows)
+    auto src_rows = [&](int dst, int& i0, int& i1) {
+      float src = fmaf(sh, (float)dst + 0.5f, -0.5f);
+      if (src < 0.f) src = 0.f;
+      i0 = (int)src;
+      if (i0 > Hc - 1) i0 = Hc - 1;
+      i1 = i0 + ((i0 < Hc - 1) ? 1 : 0);
+    };
+    int a0, a1, b0, b1;
+    src_rows(o0, a0, a1);
+    src_rows(o0 + n_out - 1, b0, b1);
+    if (a0 + top < lat0 * ph || b1 + top >= (lat0 + Lat) * ph)
+      WXF_FAIL(WXF_EINVAL, "unpatchify_resize: output rows [%d, %d) read source rows [%d, %d] outside patch rows [%d, %d)", o0,
+               o0 + n_out, a0 + top, b1 + top, lat0, lat0 + Lat);
+  }
   const int cgroups = (C + 31) / 32;
   if (n_out > 65535 || (int64_t)B * cgroups > 65535) WXF_FAIL(WXF_EINVAL, "unpatchify_resize: grid too large");
   dim3 grid((Wo + 31) / 32, n_out, B * cgroups), block(32, 8);
   wxf_launch(unpatchify_resize_kernel, grid, block, 0, (cudaStream_t)stream, y, out, C, cp, Lat, Lon, ph, pw, top, left, Hc, Wc,
-             Ho, Wo, sh, sw, cgroups, o0);
+             Ho, Wo, sh, sw, cgroups, o0, lat0);
   WXF_CHECK_LAUNCH("unpatchify_resize");
   return 0;
 }

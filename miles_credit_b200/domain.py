@@ -24,7 +24,7 @@ from __future__ import annotations
 
 import logging
 import os
-from typing import List
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist
@@ -125,10 +125,10 @@ class _Comm:
 class Exchange:
     """band <-> unit re-layout of a stage's residual stream for this rank (index lists are computed once)."""
 
-    def __init__(self, st, lay: DomainLayout, comm: _Comm, device):
+    def __init__(self, st, lay: DomainLayout, comm: Optional[_Comm], device, rank: Optional[int] = None):
         bo, bl, uo, ul = _pixel_maps(st, lay)
-        world, rank = lay.world, comm.rank
-        self.comm = comm
+        world, rank = lay.world, (comm.rank if rank is None else rank)
+        self.comm = comm  # None: the peer-memory path only (in-process ranks of the CPU tests)
         self.rank, self.world, self.d = rank, world, st.dim
         send_idx, recv_idx = [], []
         self.send_counts, self.recv_counts = [], []
@@ -220,7 +220,9 @@ def _shift_taps(w: ConvTcWeights, dy: int) -> ConvTcWeights:
 class DomainPlan(_Plan):
     """Launch plan of one rank.  Input: the full state (replicated); output: the full prediction on every rank."""
 
-    def __init__(self, geo: Geometry, wts: PreparedWeights, rank: int, world: int, device, group=None):
+    def __init__(self, geo: Geometry, wts: PreparedWeights, rank: int, world: int, device, group=None, peer=None):
+        """``peer``: an already constructed peer communicator (the in-process stand-in of the CPU tests); by default a CUDA
+        plan builds its own ``peer.PeerComm`` and a CPU plan uses the ``torch.distributed`` path."""
         self.wx = geo.variant == "wxformer"
         if wts.embed0_toep is None or wts.head_tc is None or any(c is None for brs in wts.embeds_tc[1:] for c in brs):
             raise NotImplementedError("domain decomposition needs the tensor-core path (channel counts % 4 == 0)")
@@ -228,7 +230,7 @@ class DomainPlan(_Plan):
             raise NotImplementedError("domain decomposition of the wxformer variant needs output channels % 8 == 0")
         self.geo, self.batch = geo, 1
         self.rank, self.world = rank, world
-        self.comm = _Comm(rank, world, group)
+        self.comm = _Comm(rank, world, group) if not getattr(peer, "fake", False) else None
         self.tensor_cores = True
         self.attention_tc = True
         self.ff_fused = False
@@ -286,10 +288,13 @@ class DomainPlan(_Plan):
 
         own = shapes(rank)
         numel = lambda shp: int(torch.Size(shp).numel())  # noqa: E731
-        self.peer = None
+        self.peer = peer
         self._off = {}
         mode = os.environ.get("WXF_DOMAIN_COMM", "peer")
-        if world > 1 and torch.device(device).type == "cuda" and mode == "peer":
+        if peer is not None:
+            every = self._every = [shapes(r) for r in range(world)]
+            biggest = {k: max((every[r][k][0] for r in range(world)), key=numel) for k in own}
+        elif world > 1 and torch.device(device).type == "cuda" and mode == "peer":
             from .peer import PeerComm, _ITEMSIZE
 
             every = self._every = [shapes(r) for r in range(world)]
@@ -330,7 +335,7 @@ class DomainPlan(_Plan):
         for k in own:
             if k.endswith(".hi"):
                 self._halo_names[buf[k].data_ptr()] = k[:-3]
-        self.ex = [Exchange(g.stages[s], lay, self.comm, device) for s in range(4)]
+        self.ex = [Exchange(g.stages[s], lay, self.comm, device, rank) for s in range(4)]
         self.steps: List[tuple] = []
         self.bias_tiles: List[torch.Tensor] = []
         self._keep: List[object] = []
@@ -417,14 +422,20 @@ class DomainPlan(_Plan):
             self._conv_tc(sp_hi, sp_lo, _shift_taps(uw.convs_tc[0], 1), "dec_conv3x3", B=1, Hi=ro + 2, Wi=wo, lda=c,
                           Ho=ro, Wo=wo, out=bufs["a"], ldc=c)
             count = float(4 * up.h_in * up.w_in) * (c // up.groups)  # global pixels x channels per group
+            site = self._gn_site()
+            if site is not None:
+                add(self._gn_put, (bufs["a"], c, ro * wo, c, up.groups, site), "groupnorm_silu", 0, 4.0 * n)
             add(self._groupnorm, (bufs["a"], c, uw.gn_w[0], uw.gn_b[0], None, 0, bp_hi[1:], bp_lo[1:], c, 0, ro * wo, c,
-                                  up.groups, count, self._gn_site()), "groupnorm_silu", 0, 8.0 * n)
+                                  up.groups, count, site), "groupnorm_silu", 0, 8.0 * n)
             self._add_halo((bp_hi, bp_lo), ro)
             self._conv_tc(bp_hi, bp_lo, _shift_taps(uw.convs_tc[1], 1), "dec_conv3x3", B=1, Hi=ro + 2, Wi=wo, lda=c,
                           Ho=ro, Wo=wo, out=bufs["a"], ldc=c)
             chi, clo = self.catp[skip]
+            site = self._gn_site()
+            if site is not None:
+                add(self._gn_put, (bufs["a"], c, ro * wo, c, up.groups, site), "groupnorm_silu", 0, 4.0 * n)
             add(self._groupnorm, (bufs["a"], c, uw.gn_w[1], uw.gn_b[1], bufs["short"], c, chi[1:], clo[1:], 2 * c, 0,
-                                  ro * wo, c, up.groups, count, self._gn_site()), "groupnorm_silu", 0, 12.0 * n)
+                                  ro * wo, c, up.groups, count, site), "groupnorm_silu", 0, 12.0 * n)
             dec_planes, dec_ld, dec_rows, dec_halo = self.catp[skip], 2 * c, ro, 1
         # up_block4 (ConvT k4 s2 p1) reads one halo row of the full concat buffer
         st0 = g.stages[0]
@@ -504,19 +515,24 @@ class DomainPlan(_Plan):
         self._gn_calls += 1
         return (self.peer.site(), self._buf[f"gn_slots{i}"], self._off[f"gn_slots{i}"])
 
+    def _gn_put(self, x, ldx, hw_local, C, G, site):
+        """GroupNorm, first half (peer path): the band's sums -> slot ``rank`` of every rank's arena."""
+        ops.groupnorm_sums(x, ldx, self.gn_sums, self.gn_scratch, 1, hw_local, C, G)
+        P, (sg, slots, off) = self.peer, site
+        nb = G * 2 * 8
+        segs = [(self.gn_sums.data_ptr(), P.arena.base[r] + off + self.rank * slots.shape[1] * 8, nb) for r in range(self.world)]
+        P.put(segs, [P.sig(r, sg, self.rank) for r in range(self.world)])
+
     def _groupnorm(self, x, ldx, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, hw_local, C, G, count, site=None):
         """GroupNorm + SiLU with statistics over the whole (all-rank) image: local sums, all-reduce, apply."""
-        ops.groupnorm_sums(x, ldx, self.gn_sums, self.gn_scratch, 1, hw_local, C, G)
         if site is not None:
             P, (sg, slots, off) = self.peer, site
-            nb = G * 2 * 8
-            segs = [(self.gn_sums.data_ptr(), P.arena.base[r] + off + self.rank * slots.shape[1] * 8, nb) for r in range(self.world)]
-            P.put(segs, [P.sig(r, sg, self.rank) for r in range(self.world)])
             P.wait_all(sg)
             # every rank adds the slots in rank order: bit-identical statistics everywhere
             assert slots.shape[1] == 2 * G
             P.sum_slots(slots, self.gn_sums, 2 * G)
         else:
+            ops.groupnorm_sums(x, ldx, self.gn_sums, self.gn_scratch, 1, hw_local, C, G)
             self.comm.all_reduce(self.gn_sums)
         ops.groupnorm_stats_from_sums(self.gn_sums, self.gn_stats, 1, G, count)
         ops.groupnorm_apply_f16x2(x, ldx, self.gn_stats, gamma, beta, res, ldr, y_hi, y_lo, ldh, h_off, 1, hw_local, C, G)

@@ -563,6 +563,7 @@ class FuxiB200(_Base):
         self._prepared_sig = None
         self._plans: Dict[tuple, _FuxiPlan] = {}
         self._weights_version = 0
+        self._domain = None  # set by domain.convert_to_domain_parallel
 
     @staticmethod
     def _loaded_hook(module, incompatible):
@@ -627,7 +628,16 @@ class FuxiB200(_Base):
         plan = self._plans.get(key)
         if plan is None:
             with torch.cuda.device(x.device):
-                plan = self._plans[key] = _FuxiPlan(geo, self._prepared, int(x.shape[0]), x.device)
+                if self._domain is not None:
+                    from .fuxi_domain import FuxiDomainPlan
+
+                    if x.shape[0] != 1:
+                        raise ValueError("the domain-decomposed forward takes one state at a time (batch 1)")
+                    dm = self._domain
+                    plan = FuxiDomainPlan(geo, self._prepared, dm.domain_rank, dm.domain_world_size, x.device, dm.domain_group)
+                else:
+                    plan = _FuxiPlan(geo, self._prepared, int(x.shape[0]), x.device)
+                self._plans[key] = plan
         return x.contiguous(), plan
 
     @torch.no_grad()

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 14
+WXF_ABI_VERSION = 15
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -118,10 +118,10 @@ _SIGNATURES = {
     "wxf_layernorm_residual": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                        c_void_p, c_int64, c_int, c_float, c_void_p]),
     "wxf_swin_window_attention": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]
-                                  + [c_int] * 9 + [c_void_p]),
+                                  + [c_int] * 10 + [c_void_p]),
     "wxf_gather_rows_ex": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int64,
                                    c_int, c_void_p]),
-    "wxf_unpatchify_unpad_resize_to_nchw": (c_int, [c_void_p, c_void_p] + [c_int] * 15 + [c_void_p]),
+    "wxf_unpatchify_unpad_resize_to_nchw": (c_int, [c_void_p, c_void_p] + [c_int] * 16 + [c_void_p]),
     "wxf_peer_alloc": (c_int, [POINTER(c_void_p), c_int64]),
     "wxf_peer_free": (c_int, [c_void_p]),
     "wxf_peer_export": (c_int, [c_void_p, c_void_p]),

@@ -383,12 +383,12 @@ def layernorm_residual(x: torch.Tensor, ldx: int, res: Optional[torch.Tensor], l
 
 
 def swin_window_attention(qkv: torch.Tensor, ldq: int, bias: torch.Tensor, logit_scale: torch.Tensor, out_hi, out_lo, out_f32,
-                          ldh: int, B: int, H: int, W: int, d: int, heads: int, ws, shift):
+                          ldh: int, B: int, H: int, W: int, d: int, heads: int, ws, shift, mask_shift_h: int = -1):
     """Swin-V2 scaled-cosine window attention of one block (cyclic shift, per-head bias and scale, -100 shift masks)."""
     global LAUNCHES
     st = _lib.load().wxf_swin_window_attention(qkv.data_ptr(), ldq, bias.data_ptr(), logit_scale.data_ptr(), _ptr(out_hi),
                                                _ptr(out_lo), _ptr(out_f32), ldh, B, H, W, d, heads, ws[0], ws[1], shift[0],
-                                               shift[1], _stream())
+                                               shift[1], mask_shift_h, _stream())
     _lib.check(st, "wxf_swin_window_attention")
     LAUNCHES += 1
 
@@ -406,12 +406,13 @@ def gather_rows_ex(src: torch.Tensor, ld_src: int, idx: torch.Tensor, dst: Optio
 
 
 def unpatchify_unpad_resize_to_nchw(y: torch.Tensor, out: torch.Tensor, B: int, C: int, cp: int, Lat: int, Lon: int, ph: int,
-                                    pw: int, top: int, left: int, Hc: int, Wc: int, Ho: int, Wo: int, rows=None):
-    """Token-major dense-head output -> un-patchify, crop, bilinear resize, NCHW (fuxi.py:484-498)."""
+                                    pw: int, top: int, left: int, Hc: int, Wc: int, Ho: int, Wo: int, rows=None, lat0: int = 0):
+    """Token-major dense-head output -> un-patchify, crop, bilinear resize, NCHW (fuxi.py:484-498).  ``lat0``: first patch row
+    the buffer holds (a latitude band with halo rows; 0 = the whole grid)."""
     global LAUNCHES
     o0, n_out = rows if rows is not None else (0, Ho)
     st = _lib.load().wxf_unpatchify_unpad_resize_to_nchw(y.data_ptr(), out.data_ptr(), B, C, cp, Lat, Lon, ph, pw, top, left, Hc,
-                                                         Wc, Ho, Wo, o0, n_out, _stream())
+                                                         Wc, Ho, Wo, o0, n_out, lat0, _stream())
     _lib.check(st, "wxf_unpatchify_unpad_resize_to_nchw")
     LAUNCHES += 1
 

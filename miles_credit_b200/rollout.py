@@ -116,8 +116,6 @@ class Rollout:
             with dev_ctx:
                 ops.copy_channels(x, y, [(0, 0, self.n_prog)])
         else:
-            if self.frames > 1:
-                raise NotImplementedError("the sharded rollout keeps a single-frame state (frames == 1)")
             xc, plan = self.model._plan_for(x)
             if xc.data_ptr() != x.data_ptr():
                 raise ValueError("sharded rollout updates the state in place: pass a contiguous fp32 tensor")
@@ -127,6 +125,13 @@ class Rollout:
                 y = plan.run_band(x, self._y)
                 # rows of the new state the next padding pass of each rank reads: own rows + halo rows from the neighbours
                 plan.exchange_rows(y, self.n_prog, plan.src_rows)
+            if self.frames > 1:
+                # history window: slide every frame, newest from the prediction (rows outside this rank's share carry stale
+                # values on both sides and are never read by its padding pass)
+                n_dyn = 0 if forcing is None else (forcing.shape[1] if n_dynamic is None else n_dynamic)
+                with (torch.cuda.device(x.device) if x.is_cuda else contextlib.nullcontext()):
+                    ops.history_update(x, y, forcing, self.n_prog, n_dyn)
+                return y
             a, b = plan.src_rows[plan.rank]
             x[:, : self.n_prog, :, a:b].copy_(y[:, : self.n_prog, :, a:b])
         if forcing is not None:

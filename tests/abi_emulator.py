@@ -42,7 +42,7 @@ class EmulatedLib:
                     raise AssertionError(f"{what}: input {rn} [{r0:#x}, {r1:#x}) overlaps output {wn} [{w0:#x}, {w1:#x})")
 
     def wxf_abi_version(self):
-        return 14
+        return 15
 
     def wxf_last_error(self):
         return b"emulator"
@@ -508,7 +508,9 @@ class EmulatedLib:
         return 0
 
     def wxf_swin_window_attention(self, qkv, ldq, bias, logit_scale, out_hi, out_lo, out_f32, ldh, B, H, W, d, heads, ws_h,
-                                  ws_w, shift_h, shift_w, stream):
+                                  ws_w, shift_h, shift_w, mask_shift_h, stream):
+        if mask_shift_h < 0:
+            mask_shift_h = shift_h
         self.calls.append("swin_attention")
         dh, L = d // heads, ws_h * ws_w
         q3 = _t(_arr(qkv, (B * H * W - 1) * ldq + 3 * d)).as_strided((B, H, W, 3 * d), (H * W * ldq, W * ldq, ldq, 1))
@@ -529,7 +531,7 @@ class EmulatedLib:
                 r[n - sh:] = 2
             return r
 
-        ry, rx = region(H, ws_h, shift_h), region(W, ws_w, shift_w)
+        ry, rx = region(H, ws_h, mask_shift_h), region(W, ws_w, shift_w)
         rid = (3 * ry[:, None] + rx[None, :]).view(nwy, ws_h, nwx, ws_w).permute(0, 2, 1, 3).reshape(nwy, nwx, L)
         mask = torch.where(rid[..., :, None] != rid[..., None, :], -100.0, 0.0).double()
         s = s + mask.view(1, nwy, nwx, 1, L, L)
@@ -560,10 +562,19 @@ class EmulatedLib:
         return 0
 
     def wxf_unpatchify_unpad_resize_to_nchw(self, y, outp, B, C, cp, Lat, Lon, ph, pw, top, left, Hc, Wc, Ho, Wo, o0, n_out,
-                                            stream):
+                                            lat0, stream):
         self.calls.append("unpatchify_resize")
         ys = _t(_arr(y, B * Lat * Lon * ph * pw * cp)).view(B, Lat, Lon, ph, pw, cp)[..., :C]
-        img = ys.permute(0, 1, 3, 2, 4, 5).reshape(B, Lat * ph, Lon * pw, C).contiguous()
+        band = ys.permute(0, 1, 3, 2, 4, 5).reshape(B, Lat * ph, Lon * pw, C)
+        # place the band (patch rows [lat0, lat0 + Lat)) into a whole-grid image; rows outside it must not be read
+        n_all = max(top + Hc, (lat0 + Lat) * ph)
+        img = torch.full((B, n_all, Lon * pw, C), float("nan"))
+        lo = max(lat0 * ph, 0)
+        img[:, lo: (lat0 + Lat) * ph] = band[:, lo - lat0 * ph:]
+        Lat = n_all // ph if n_all % ph == 0 else (n_all + ph - 1) // ph
+        if img.shape[1] != Lat * ph:
+            img = torch.cat([img, torch.full((B, Lat * ph - img.shape[1], Lon * pw, C), float("nan"))], dim=1)
+        img = img.contiguous()
         # the rest is wxf_unpad_resize_to_nchw on a pixel-major image with ld = C
         keep = self.calls
         self.calls = []

@@ -55,6 +55,55 @@ def rollout240(dev, rank, world, steps=240, check=(1, 10, 240)):
     return rec
 
 
+def fuxi_case(name, dev, rank, world):
+    """One FuXi forecast decomposed over latitude bands of whole window rows (miles_credit_b200/fuxi_domain.py) vs the
+    single-GPU forward, vs the CPU oracle, and a 3-step sharded rollout (history window of 2 frames) vs the full-state one."""
+    from miles_credit_b200 import fuxi as F
+    from miles_credit_b200.rollout import Rollout
+
+    kw = F.fuxi_workload(name)
+    geo = F.build_fuxi_geometry(**kw)
+    sd = F.synthetic_fuxi_state_dict(geo, seed=31, sn_iters=5)
+    model = F.FuxiB200(**kw)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    x = F.synthetic_fuxi_input(geo, batch=1, seed=31).to(dev)
+    y1 = model(x).clone()
+    err_oracle = None
+    if rank == 0 and name == "fuxi_1deg":
+        from oracle import fuxi_oracle
+
+        with torch.no_grad():
+            y_or = fuxi_oracle.forward(x.cpu(), sd, fuxi_oracle.FuxiSpec.from_kwargs(**kw))
+    single = F.FuxiB200(**kw)
+    single.load_state_dict(sd, strict=True)
+    single = single.to(dev).eval()
+    convert_to_domain_parallel(model)
+    y2 = model(x).clone()
+    y3 = model(x)
+    if rank == 0 and name == "fuxi_1deg":
+        err_oracle = float((y2.cpu() - y_or).abs().max() / y_or.abs().max())
+    lo, hi = y2.clone(), y2.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    rec = {"rel_max_vs_single_gpu": float((y2 - y1).abs().max() / y1.abs().max()), "ranks_identical": bool(torch.equal(lo, hi)),
+           "repeatable": bool(torch.equal(y2, y3)), "finite": bool(torch.isfinite(y2).all()), "rel_max_vs_oracle": err_oracle}
+    # sharded rollout, eager and graph-replayed, vs the single-GPU rollout
+    xs, xg, xf = x.clone(), x.clone(), x.clone()
+    ro, rg, rf = Rollout(model), Rollout(model, graph=True), Rollout(single)
+    for _ in range(3):
+        ys, yg, yf = ro.step(xs), rg.step(xg), rf.step(xf)
+    a, b = ro.own_rows(xs)
+    zero = torch.zeros((), device=dev)
+    e = torch.stack([((ys[..., a:b, :] - yf[..., a:b, :]).abs().max() if b > a else zero) / yf.abs().max(),
+                     (ro.gather(ys.clone()) - yf).abs().max() / yf.abs().max(),
+                     (yg[..., a:b, :] - ys[..., a:b, :]).abs().max() if b > a else zero])
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    rec["sharded_rollout_rel_max"] = float(e[:2].max())
+    rec["graph_replay_max_abs_diff"] = float(e[2])
+    return rec
+
+
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -65,6 +114,10 @@ def main():
     for name in sys.argv[1:]:
         if name == "rollout240":
             out[name] = rollout240(dev, rank, world)
+            torch.cuda.empty_cache()
+            continue
+        if name.startswith("fuxi"):
+            out[name] = fuxi_case(name, dev, rank, world)
             torch.cuda.empty_cache()
             continue
         if name == "unit":

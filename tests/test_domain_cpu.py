@@ -242,3 +242,41 @@ def test_sharded_boundary_row_ranges(name, world):
             o_lo, o_hi = plan.out_rows[r]
             s_lo, s_hi = plan.src_rows[r]
             assert o_lo - s_lo <= 17 and s_hi - o_hi <= 17
+
+
+@pytest.mark.parametrize("world,variant", [(2, "crossformer"), (3, "crossformer"), (2, "wxformer")])
+def test_peer_memory_plan_in_lockstep_matches_oracle(world, variant, monkeypatch):
+    """The NVLink peer-memory path of the decomposition (arena offsets, halo rows, per-row re-layout targets, GroupNorm slots)
+    on in-process ranks: every rank's plan executed in lock-step through the C-ABI emulator, vs the CPU oracle."""
+    from abi_emulator import EmulatedLib
+    from fake_peer import make_fake_world, run_lockstep
+    from miles_credit_b200 import lib as wlib
+    from miles_credit_b200 import model as wmodel
+    from miles_credit_b200 import ops
+    from miles_credit_b200.domain import DomainPlan
+    from miles_credit_b200.geometry import build_geometry, workload
+    from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
+    from miles_credit_b200.weights import prepare
+    from oracle import crossformer_oracle as oracle
+
+    monkeypatch.setattr(wlib, "_lib", EmulatedLib())
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(ops, "_req", lambda *a, **k: None)
+    kw = dict(workload("unit"), depth=[1, 1, 1, 1], output_only_channels=(8 if variant == "wxformer" else 4), variant=variant)
+    geo = build_geometry(**kw)
+    sd = synthetic_state_dict(geo, seed=41)
+    wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
+    peers = make_fake_world(world, 96 << 20)
+    plans = [DomainPlan(geo, wts, r, world, torch.device("cpu"), peer=peers[r]) for r in range(world)]
+    x = synthetic_input(geo, batch=1, seed=41)
+    outs = run_lockstep(plans, x)
+    y = torch.full_like(outs[0], float("nan"))
+    for r, o in enumerate(outs):
+        lo, hi = plans[r].out_rows[r]
+        y[..., lo:hi, :] = o[..., lo:hi, :]
+    with torch.no_grad():
+        ref = oracle.forward(x, sd, geo)
+    err = float((y - ref).abs().max() / ref.abs().max())
+    print(variant, "world", world, "peer path rel-max vs the oracle", err)
+    assert torch.isfinite(y).all() and err < 2e-5, err
+    assert all(p.puts > 0 for p in peers)
