@@ -117,6 +117,32 @@ __device__ __forceinline__ float2 wxf_gelu_erf2(float2 x) {
   return __ffma2_rn(h, make_float2(copysignf(1.0f - e0, x.x), copysignf(1.0f - e1, x.y)), h);
 }
 
+// The same function with three instructions fewer per pair: GELU(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2), and with
+// t = min(|x| / sqrt 2, 4): 0.5 |x| = t / sqrt 2 wherever the clamp is inactive (beyond it the term is < 5e-8 either way).
+// No copysign, no 1 - e: u = x / sqrt 2 (packed), t = min(|u|, 4), e = 2^(-q(t) t), result = max(x, 0) - (t e) / sqrt 2.
+__device__ __forceinline__ float2 wxf_gelu_erf2_relu(float2 x) {
+  const float2 u = __fmul2_rn(x, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  float2 t;
+  t.x = fminf(fabsf(u.x), 4.0f);
+  t.y = fminf(fabsf(u.y), 4.0f);
+  float2 q = make_float2(-1.160479314e-05f, -1.160479314e-05f);
+  q = __ffma2_rn(q, t, make_float2(1.529642177e-04f, 1.529642177e-04f));
+  q = __ffma2_rn(q, t, make_float2(-8.482338744e-04f, -8.482338744e-04f));
+  q = __ffma2_rn(q, t, make_float2(2.274784725e-03f, 2.274784725e-03f));
+  q = __ffma2_rn(q, t, make_float2(-8.480441466e-05f, -8.480441466e-05f));
+  q = __ffma2_rn(q, t, make_float2(-2.772447653e-02f, -2.772447653e-02f));
+  q = __ffma2_rn(q, t, make_float2(1.483079046e-01f, 1.483079046e-01f));
+  q = __ffma2_rn(q, t, make_float2(9.184429049e-01f, 9.184429049e-01f));
+  q = __ffma2_rn(q, t, make_float2(1.627907276e+00f, 1.627907276e+00f));
+  const float2 a = __fmul2_rn(q, t);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-a.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-a.y));
+  const float2 m = __fmul2_rn(t, make_float2(e0, e1));
+  return __ffma2_rn(m, make_float2(-0.70710678118654752440f, -0.70710678118654752440f),
+                    make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
+}
+
 // two values at once: packed conversions (cvt.rn.f16x2.f32)
 __device__ __forceinline__ void wxf_split2_f16x2(float a, float b, __half2& hi, __half2& lo) {
   uint32_t h;

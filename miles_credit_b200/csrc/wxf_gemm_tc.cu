@@ -66,6 +66,7 @@ struct TcParams {
   int bias_zs;        // bias index = phase * bias_zs + n
   int step, J, ch;    // Toeplitz mode: tile step along x (128 - (J-1)), taps folded into N, channels of the branch
   int concat;         // persistent kernel: issue A_hi [W_hi | W_lo] as one N=256 instruction
+  uint32_t park_ns;   // specialised epilogues: suspend-time hint of the far-away mbarrier waits (0 = plain spin)
   int16_t taps[4][MAX_TAPS][2];  // [phase][tap] = (dy, dx); only [0] used when phases == 1
 };
 
@@ -339,7 +340,16 @@ constexpr int p_smem() {
   return STAGES * P_STAGE_BYTES + EW * 4096 + 8 * (2 * STAGES + 4) + 16 + 1024;
 }
 
-template <int MODE, int EW, int STAGES>
+// Specialised GEMM epilogues (EPI != 0; EPI = 0 is the generic one with run-time switches).  The ncu source page of the
+// stage-0 fc1 launch showed 950 issued instructions per warp and tile where ~500 are needed: predicated-off residual code,
+// spilled residual registers, eight predicated bias loads with their address arithmetic, unpacked accumulator adds, a
+// two-division tile decode.  With the switches as template parameters none of that is compiled in.
+constexpr int EPI_GELU = 1;    // erf GELU
+constexpr int EPI_RED = 2;     // in-place residual (out == res): the fp32 tile leaves as a TMA REDUCE-ADD store, the L2 does x += f(x)
+constexpr int EPI_F32 = 4;     // fp32 output tile
+constexpr int EPI_PLANES = 8;  // fp16 hi / lo operand planes
+
+template <int MODE, int EW, int STAGES, int EPI = 0>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
@@ -426,7 +436,8 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         for (int ks = 0; ks < num_k; ++ks, ++g) {
           const int s = g % STAGES;
           const uint32_t ph = (g / STAGES) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
+          if constexpr (EPI != 0) mbar_wait_parked(empty_bar(s), ph ^ 1u, p.park_ns);
+          else mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t st = base + s * STAGE_BYTES;
           mbar_expect_tx(full_bar(s), stage_tx);
           int wk;
@@ -452,7 +463,8 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       int i = 0;  // local tile counter
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
         const int slot = i & 1;
-        mbar_wait(tempty_bar(slot), (((uint32_t)i >> 1) & 1u) ^ 1u);  // epilogue has drained this slot
+        if constexpr (EPI != 0) mbar_wait_parked(tempty_bar(slot), (((uint32_t)i >> 1) & 1u) ^ 1u, p.park_ns);
+        else mbar_wait(tempty_bar(slot), (((uint32_t)i >> 1) & 1u) ^ 1u);  // epilogue has drained this slot
         tc_fence_after();
         const uint32_t d_cross = tmem_base + (uint32_t)(slot * 2 * BN), d_main = d_cross + BN;
         for (int ks = 0; ks < num_k; ++ks, ++g) {
@@ -489,7 +501,112 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     // ---- epilogue warps: quarter = TMEM lane quarter, half = which CW-column slice of the 128 columns ----
     const int ew = warp - 2;
     const int quarter = warp & 3, half = ew >> 2;
-    if constexpr (!CONV) {
+    if constexpr (!CONV && EPI != 0) {
+      // ---- specialised GEMM epilogue: lane = output row, 32-column chunks, everything decided at compile time ----
+      constexpr bool E_GELU = (EPI & EPI_GELU) != 0, E_RED = (EPI & EPI_RED) != 0, E_F32 = (EPI & EPI_F32) != 0,
+                     E_PLANES = (EPI & EPI_PLANES) != 0;
+      static_assert(E_F32 || E_PLANES, "an epilogue needs an output");
+      static_assert(!E_RED || E_F32, "the reduce-add store carries the fp32 tile");
+      uint8_t* stg_b = reinterpret_cast<uint8_t*>(staging) + ew * 4096;
+      const uint32_t stg_a = base + STAGES * STAGE_BYTES + ew * 4096;
+      const bool has_bias = p.bias != nullptr;  // (the host takes this path only when N % 32 == 0: no column predicates)
+      // tile coordinates advance incrementally (n fastest): no division per tile
+      int nt = (int)(blockIdx.x % (unsigned)n_tiles), mt = (int)(blockIdx.x / (unsigned)n_tiles);
+      const int dn = (int)(gridDim.x % (unsigned)n_tiles), dm = (int)(gridDim.x / (unsigned)n_tiles);
+      const float2 sc = make_float2(p.w_scale, p.w_scale);
+      int i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        const int slot = i & 1;
+        const int nb0 = nt * BN + half * CW;
+        const int row0 = mt * BLOCK_M + quarter * 32;
+        nt += dn;
+        mt += dm;
+        if (nt >= n_tiles) {
+          nt -= n_tiles;
+          ++mt;
+        }
+        mbar_wait_parked(tfull_bar(slot), ((uint32_t)i >> 1) & 1u, p.park_ns);
+        tc_fence_after();
+        float2 acc[NCH][16];
+        {
+          const uint32_t tb_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 2 * BN + half * CW);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t ra[32], rb[32];
+            tmem_ld32_nowait(tb_addr + (uint32_t)(c * 32), ra);
+            tmem_ld32_nowait(tb_addr + (uint32_t)(BN + c * 32), rb);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              acc[c][j] = __fadd2_rn(make_float2(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1])),
+                                     make_float2(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1])));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(slot));  // TMEM slot free for the MMA of tile i+2
+
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int nb = nb0 + c * 32;
+          if (nb >= p.N) break;  // warp-uniform (columns beyond N inside a chunk are clipped by the TMA store)
+          float2* a = acc[c];
+          if (has_bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);  // the same address in every lane: one transaction
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = __ldg(bp + q);
+              a[2 * q] = __ffma2_rn(a[2 * q], sc, make_float2(b4.x, b4.y));
+              a[2 * q + 1] = __ffma2_rn(a[2 * q + 1], sc, make_float2(b4.z, b4.w));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = __fmul2_rn(a[j], sc);
+          }
+          if constexpr (E_GELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = wxf_gelu_erf2_relu(a[j]);
+          }
+          if constexpr (E_F32) {
+            if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the staging buffer
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)  // fp32 row of 128 B, SWIZZLE_128B: 16-byte chunk ^= row % 8
+              *reinterpret_cast<float4*>(stg_b + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                  make_float4(a[2 * q].x, a[2 * q].y, a[2 * q + 1].x, a[2 * q + 1].y);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (E_RED) tma_reduce_add_2d(&tmO, stg_a, nb, row0);
+              else tma_store_2d(&tmO, stg_a, nb, row0);
+              bulk_commit();
+            }
+          }
+          if constexpr (E_PLANES) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // fp16 rows of 64 B, SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
+              __align__(16) __half2 h8[4];
+              __align__(16) __half2 l8[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) wxf_split2_f16x2(a[4 * q + e].x, a[4 * q + e].y, h8[e], l8[e]);
+              const int off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
+              *reinterpret_cast<uint4*>(stg_b + off) = *reinterpret_cast<const uint4*>(h8);
+              *reinterpret_cast<uint4*>(stg_b + 2048 + off) = *reinterpret_cast<const uint4*>(l8);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmO_hi, stg_a, nb, row0);
+              tma_store_2d(&tmO_lo, stg_a + 2048, nb, row0);
+              bulk_commit();
+            }
+          }
+        }
+      }
+      if (lane == 0) bulk_wait0();  // all stores of this warp have landed before the CTA exits
+    } else if constexpr (!CONV) {
       // GEMM mode: lane = output row.  Accumulator row -> registers -> scale/bias/GELU/residual -> 32-column chunks
       // staged in swizzled shared memory -> TMA store (fp32 tile and/or fp16 hi/lo plane tiles).
       uint8_t* stg_b = reinterpret_cast<uint8_t*>(staging) + ew * 4096;
@@ -1309,6 +1426,25 @@ bool resident_w_enabled() {  // WXF_GEMM_RESIDENT_W=1: K <= 128 GEMMs keep their
   return v == 1;
 }
 
+bool fast_epilogue_enabled() {  // WXF_GEMM_EPI=0: every GEMM takes the generic run-time-switched epilogue (A/B, debugging)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXF_GEMM_EPI");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+uint32_t park_ns() {  // WXF_MBAR_PARK_NS: suspend-time hint (ns) of the far-away mbarrier waits; 0 = plain try_wait spin
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXF_MBAR_PARK_NS");
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
+  }
+  return (uint32_t)v;
+}
+
 bool persistent_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -1318,14 +1454,14 @@ bool persistent_enabled() {
   return v == 1;
 }
 
-template <int MODE, int EW, int STAGES>
+template <int MODE, int EW, int STAGES, int EPI = 0>
 int launch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tw_hi, const CUtensorMap& tw_lo,
                       const CUtensorMap& to, const CUtensorMap& to_hi, const CUtensorMap& to_lo, const TcParams& p,
                       int n_tiles, int m_tiles, int phases, cudaStream_t st) {
   static WxfPerDevice<bool> attr_set_pd;
   bool& attr_set = attr_set_pd.get();  // function attributes are per device
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_persistent_kernel<MODE, EW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tc_persistent_kernel<MODE, EW, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          p_smem<EW, STAGES>());
     if (e != cudaSuccess)
       WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", p_smem<EW, STAGES>(), cudaGetErrorString(e));
@@ -1334,7 +1470,7 @@ int launch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const 
   const int64_t total = (int64_t)n_tiles * m_tiles * phases;
   if (total > INT32_MAX) WXF_FAIL(WXF_EINVAL, "tc: too many tiles");
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  wxf_launch(tc_persistent_kernel<MODE, EW, STAGES>, dim3(grid), dim3(64 + 32 * EW), p_smem<EW, STAGES>(), st, ta_hi, ta_lo,
+  wxf_launch(tc_persistent_kernel<MODE, EW, STAGES, EPI>, dim3(grid), dim3(64 + 32 * EW), p_smem<EW, STAGES>(), st, ta_hi, ta_lo,
              tw_hi, tw_lo, to, to_hi, to_lo, p, n_tiles, m_tiles, (int)total);
   WXF_CHECK_LAUNCH("tc_persistent");
   return 0;
@@ -1455,8 +1591,37 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
       WXF_CHECK_LAUNCH("tc_cluster2");
       return 0;
     }
-    if (d->K <= 256) return launch_persistent<MODE_GEMM, 16, 2>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, nt, mt, 1, st);
-    return launch_persistent<MODE_GEMM, 8, 3>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, nt, mt, 1, st);
+    // specialised epilogues for the combinations the forecast plans use; anything else takes the generic one
+    int epi = 0;
+    p.park_ns = park_ns();
+    if (fast_epilogue_enabled()) {
+      const bool gelu = d->act == WXF_ACT_GELU_ERF, planes = d->out_hi != nullptr, f32 = d->out != nullptr;
+      const bool inplace = d->res && f32 && d->res + d->r_off == d->out + d->c_off && d->ldr == d->ldc;
+      if ((d->act == WXF_ACT_NONE || gelu) && d->N % 32 == 0) {
+        if (!d->res && planes && !f32) epi = EPI_PLANES | (gelu ? EPI_GELU : 0);
+        else if (!d->res && f32 && !planes && !gelu) epi = EPI_F32;
+        else if (inplace && !planes && !gelu) epi = EPI_F32 | EPI_RED;
+      }
+    }
+#define WXF_P_LAUNCH(EW_, ST_, EPI_) \
+  return launch_persistent<MODE_GEMM, EW_, ST_, EPI_>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, nt, mt, 1, st)
+    if (d->K <= 256) {
+      switch (epi) {
+        case EPI_PLANES: WXF_P_LAUNCH(16, 2, EPI_PLANES);
+        case EPI_PLANES | EPI_GELU: WXF_P_LAUNCH(16, 2, EPI_PLANES | EPI_GELU);
+        case EPI_F32: WXF_P_LAUNCH(16, 2, EPI_F32);
+        case EPI_F32 | EPI_RED: WXF_P_LAUNCH(16, 2, EPI_F32 | EPI_RED);
+        default: WXF_P_LAUNCH(16, 2, 0);
+      }
+    }
+    switch (epi) {
+      case EPI_PLANES: WXF_P_LAUNCH(8, 3, EPI_PLANES);
+      case EPI_PLANES | EPI_GELU: WXF_P_LAUNCH(8, 3, EPI_PLANES | EPI_GELU);
+      case EPI_F32: WXF_P_LAUNCH(8, 3, EPI_F32);
+      case EPI_F32 | EPI_RED: WXF_P_LAUNCH(8, 3, EPI_F32 | EPI_RED);
+      default: WXF_P_LAUNCH(8, 3, 0);
+    }
+#undef WXF_P_LAUNCH
   }
   dim3 grid((unsigned)((d->N + BN - 1) / BN), (unsigned)((d->M + BLOCK_M - 1) / BLOCK_M), 1);
   if (BN == 256) return launch<256, 2, MODE_GEMM>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);

@@ -35,6 +35,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Same wait for a barrier whose completion is far away (an epilogue warp waiting for the next accumulator, the producer
+// waiting for a free stage): the suspend-time hint lets the hardware park the thread instead of returning to the spin loop
+// every few hundred cycles (ncu source page: the spin loops were 10-20 % of all issued instructions of the issue-bound
+// small-K GEMM launches).  The thread still wakes as soon as the phase completes.
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, uint32_t ns) {
+  if (ns == 0) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(ns)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) {
+      printf("wxf tc kernel: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -125,6 +151,14 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, uint32_t bar,
 // TMA store: shared -> global tile, completion tracked by bulk async-groups
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+// TMA reduce-add store (fp32): global tile += shared tile, performed by the L2 reduction units.  Used for the residual
+// connections that update the stream in place (x <- x + f(x)): the SM never loads the residual.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(tm)),
                "r"(src), "r"(c0), "r"(c1)
                : "memory");

@@ -92,6 +92,45 @@ def test_gemm_tc_epilogues_match_exact_kernel():
     assert float((hid.cpu() - h).abs().max() / h.abs().max()) < 3e-6
 
 
+@pytest.mark.parametrize("m,n,k", [(1000, 384, 128), (333, 96, 256), (5000, 512, 512), (700, 160, 2048), (129, 1536, 512)])
+@pytest.mark.parametrize("bias", [False, True])
+def test_gemm_tc_specialised_epilogues(m, n, k, bias):
+    """The compile-time-specialised epilogues (planes, GELU -> planes, fp32, in-place residual as a TMA reduce-add store)
+    of both kernel shapes (K <= 256: 16 epilogue warps; K >= 512: 8) vs fp64, ragged M and N % 128 != 0 included."""
+    torch.manual_seed(m + n + k + int(bias))
+    a = torch.randn(m, k)
+    w = torch.randn(n, k) / k**0.5
+    b = torch.randn(n) * 0.1 if bias else None
+    lin = a.double() @ w.double().t() + (b.double() if bias else 0.0)
+    a_hi, a_lo = planes(a.to(DEV))
+    gw = gemm_weights(w.to(DEV), b.to(DEV) if bias else None)
+    scale = float(lin.abs().max())
+    tol = 1e-5 if k >= 2048 else 4e-6
+    # fp16 planes, without and with GELU
+    for act, ref in ((wlib.ACT_NONE, lin), (wlib.ACT_GELU, torch.nn.functional.gelu(lin))):
+        o_hi = torch.full((m, n), float("nan"), device=DEV, dtype=torch.float16)
+        o_lo = torch.full_like(o_hi, float("nan"))
+        ops.gemm_f16x2_tc(ops.make_gemm_desc(a_hi, a_lo, gw, M=m, lda=k, out_hi=o_hi, out_lo=o_lo, ldh=n, act=act))
+        got = (o_hi.float() + o_lo.float()).cpu().double()
+        assert torch.isfinite(got).all()
+        assert float((got - ref).abs().max()) < tol * scale, (act, float((got - ref).abs().max()) / scale)
+    # fp32 tile into a strided slice
+    wide = torch.full((m, n + 32), float("nan"), device=DEV)
+    ops.gemm_f16x2_tc(ops.make_gemm_desc(a_hi, a_lo, gw, M=m, lda=k, out=wide[:, 32:], ldc=n + 32))
+    assert float((wide[:, 32:].cpu().double() - lin).abs().max()) < tol * scale
+    assert torch.isnan(wide[:, :32]).all()
+    # in-place residual (x <- x + a w^T + b): the reduce-add store, twice on the same buffer
+    res = torch.randn(m, n + 32)
+    stream = res.to(DEV).clone()
+    xv = stream[:, :n]
+    for rep in (1, 2):
+        ops.gemm_f16x2_tc(ops.make_gemm_desc(a_hi, a_lo, gw, M=m, lda=k, out=xv, ldc=n + 32, res=xv, ldr=n + 32))
+        torch.cuda.synchronize()
+        ref = res[:, :n].double() + rep * lin
+        assert float((stream[:, :n].cpu().double() - ref).abs().max()) < rep * tol * scale + 1e-6
+    assert torch.equal(stream[:, n:].cpu(), res[:, n:])
+
+
 def test_gemm_tc_rejects_bad_arguments():
     a = torch.zeros(8, 12, device=DEV, dtype=torch.float16)
     gw = gemm_weights(torch.ones(8, 12, device=DEV), None)
