@@ -349,6 +349,126 @@ constexpr int EPI_RED = 2;     // in-place residual (out == res): the fp32 tile 
 constexpr int EPI_F32 = 4;     // fp32 output tile
 constexpr int EPI_PLANES = 8;  // fp16 hi / lo operand planes
 
+// ---- specialised GEMM epilogue of the persistent kernels (EPI != 0): lane = output row, 32-column chunks, every switch a
+//      template parameter.  Shared by tc_persistent_kernel and tc_resident_w_kernel (same TMEM slot / barrier protocol).
+template <int EW, int EPI>
+__device__ __forceinline__ void gemm_epilogue_fast(const TcParams& p, const CUtensorMap& tmO, const CUtensorMap& tmO_hi,
+                                                   const CUtensorMap& tmO_lo, const uint32_t tmem_base, const uint32_t tfull0,
+                                                   const uint32_t tempty0, uint8_t* staging_bytes, const uint32_t staging_addr,
+                                                   const int n_tiles, const int total_tiles, const int warp, const int lane) {
+  constexpr int BN = P_BN;
+  constexpr int CW = 128 / (EW / 4);
+  constexpr int NCH = CW / 32;
+  const int ew = warp - 2;
+  const int quarter = warp & 3, half = ew >> 2;
+  auto tfull_bar = [&](int s) { return tfull0 + 8u * s; };
+  auto tempty_bar = [&](int s) { return tempty0 + 8u * s; };
+  // ---- specialised GEMM epilogue: lane = output row, 32-column chunks, everything decided at compile time ----
+  constexpr bool E_GELU = (EPI & EPI_GELU) != 0, E_RED = (EPI & EPI_RED) != 0, E_F32 = (EPI & EPI_F32) != 0,
+                 E_PLANES = (EPI & EPI_PLANES) != 0;
+  static_assert(E_F32 || E_PLANES, "an epilogue needs an output");
+  static_assert(!E_RED || E_F32, "the reduce-add store carries the fp32 tile");
+  uint8_t* stg_b = staging_bytes + ew * 4096;
+  const uint32_t stg_a = staging_addr + ew * 4096;
+  const bool has_bias = p.bias != nullptr;  // (the host takes this path only when N % 32 == 0: no column predicates)
+  // tile coordinates advance incrementally (n fastest): no division per tile
+  int nt = (int)(blockIdx.x % (unsigned)n_tiles), mt = (int)(blockIdx.x / (unsigned)n_tiles);
+  const int dn = (int)(gridDim.x % (unsigned)n_tiles), dm = (int)(gridDim.x / (unsigned)n_tiles);
+  const float2 sc = make_float2(p.w_scale, p.w_scale);
+  int i = 0;
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+    const int slot = i & 1;
+    const int nb0 = nt * BN + half * CW;
+    const int row0 = mt * BLOCK_M + quarter * 32;
+    nt += dn;
+    mt += dm;
+    if (nt >= n_tiles) {
+      nt -= n_tiles;
+      ++mt;
+    }
+    mbar_wait_parked(tfull_bar(slot), ((uint32_t)i >> 1) & 1u, p.park_ns);
+    tc_fence_after();
+    float2 acc[NCH][16];
+    {
+      const uint32_t tb_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 2 * BN + half * CW);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t ra[32], rb[32];
+        tmem_ld32_nowait(tb_addr + (uint32_t)(c * 32), ra);
+        tmem_ld32_nowait(tb_addr + (uint32_t)(BN + c * 32), rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          acc[c][j] = __fadd2_rn(make_float2(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1])),
+                                 make_float2(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1])));
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar(slot));  // TMEM slot free for the MMA of tile i+2
+
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int nb = nb0 + c * 32;
+      if (nb >= p.N) break;  // warp-uniform (columns beyond N inside a chunk are clipped by the TMA store)
+      float2* a = acc[c];
+      if (has_bias) {
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);  // the same address in every lane: one transaction
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = __ldg(bp + q);
+          a[2 * q] = __ffma2_rn(a[2 * q], sc, make_float2(b4.x, b4.y));
+          a[2 * q + 1] = __ffma2_rn(a[2 * q + 1], sc, make_float2(b4.z, b4.w));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = __fmul2_rn(a[j], sc);
+      }
+      if constexpr (E_GELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = wxf_gelu_erf2_relu(a[j]);
+      }
+      if constexpr (E_F32) {
+        if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the staging buffer
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)  // fp32 row of 128 B, SWIZZLE_128B: 16-byte chunk ^= row % 8
+          *reinterpret_cast<float4*>(stg_b + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+              make_float4(a[2 * q].x, a[2 * q].y, a[2 * q + 1].x, a[2 * q + 1].y);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (E_RED) tma_reduce_add_2d(&tmO, stg_a, nb, row0);
+          else tma_store_2d(&tmO, stg_a, nb, row0);
+          bulk_commit();
+        }
+      }
+      if constexpr (E_PLANES) {
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // fp16 rows of 64 B, SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
+          __align__(16) __half2 h8[4];
+          __align__(16) __half2 l8[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) wxf_split2_f16x2(a[4 * q + e].x, a[4 * q + e].y, h8[e], l8[e]);
+          const int off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(stg_b + off) = *reinterpret_cast<const uint4*>(h8);
+          *reinterpret_cast<uint4*>(stg_b + 2048 + off) = *reinterpret_cast<const uint4*>(l8);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmO_hi, stg_a, nb, row0);
+          tma_store_2d(&tmO_lo, stg_a + 2048, nb, row0);
+          bulk_commit();
+        }
+      }
+    }
+  }
+  if (lane == 0) bulk_wait0();  // all stores of this warp have landed before the CTA exits
+}
+
 template <int MODE, int EW, int STAGES, int EPI = 0>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -502,110 +622,9 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     const int ew = warp - 2;
     const int quarter = warp & 3, half = ew >> 2;
     if constexpr (!CONV && EPI != 0) {
-      // ---- specialised GEMM epilogue: lane = output row, 32-column chunks, everything decided at compile time ----
-      constexpr bool E_GELU = (EPI & EPI_GELU) != 0, E_RED = (EPI & EPI_RED) != 0, E_F32 = (EPI & EPI_F32) != 0,
-                     E_PLANES = (EPI & EPI_PLANES) != 0;
-      static_assert(E_F32 || E_PLANES, "an epilogue needs an output");
-      static_assert(!E_RED || E_F32, "the reduce-add store carries the fp32 tile");
-      uint8_t* stg_b = reinterpret_cast<uint8_t*>(staging) + ew * 4096;
-      const uint32_t stg_a = base + STAGES * STAGE_BYTES + ew * 4096;
-      const bool has_bias = p.bias != nullptr;  // (the host takes this path only when N % 32 == 0: no column predicates)
-      // tile coordinates advance incrementally (n fastest): no division per tile
-      int nt = (int)(blockIdx.x % (unsigned)n_tiles), mt = (int)(blockIdx.x / (unsigned)n_tiles);
-      const int dn = (int)(gridDim.x % (unsigned)n_tiles), dm = (int)(gridDim.x / (unsigned)n_tiles);
-      const float2 sc = make_float2(p.w_scale, p.w_scale);
-      int i = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
-        const int slot = i & 1;
-        const int nb0 = nt * BN + half * CW;
-        const int row0 = mt * BLOCK_M + quarter * 32;
-        nt += dn;
-        mt += dm;
-        if (nt >= n_tiles) {
-          nt -= n_tiles;
-          ++mt;
-        }
-        mbar_wait_parked(tfull_bar(slot), ((uint32_t)i >> 1) & 1u, p.park_ns);
-        tc_fence_after();
-        float2 acc[NCH][16];
-        {
-          const uint32_t tb_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 2 * BN + half * CW);
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            uint32_t ra[32], rb[32];
-            tmem_ld32_nowait(tb_addr + (uint32_t)(c * 32), ra);
-            tmem_ld32_nowait(tb_addr + (uint32_t)(BN + c * 32), rb);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              acc[c][j] = __fadd2_rn(make_float2(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1])),
-                                     make_float2(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1])));
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(slot));  // TMEM slot free for the MMA of tile i+2
-
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int nb = nb0 + c * 32;
-          if (nb >= p.N) break;  // warp-uniform (columns beyond N inside a chunk are clipped by the TMA store)
-          float2* a = acc[c];
-          if (has_bias) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);  // the same address in every lane: one transaction
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b4 = __ldg(bp + q);
-              a[2 * q] = __ffma2_rn(a[2 * q], sc, make_float2(b4.x, b4.y));
-              a[2 * q + 1] = __ffma2_rn(a[2 * q + 1], sc, make_float2(b4.z, b4.w));
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = __fmul2_rn(a[j], sc);
-          }
-          if constexpr (E_GELU) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = wxf_gelu_erf2_relu(a[j]);
-          }
-          if constexpr (E_F32) {
-            if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the staging buffer
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 8; ++q)  // fp32 row of 128 B, SWIZZLE_128B: 16-byte chunk ^= row % 8
-              *reinterpret_cast<float4*>(stg_b + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                  make_float4(a[2 * q].x, a[2 * q].y, a[2 * q + 1].x, a[2 * q + 1].y);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              if constexpr (E_RED) tma_reduce_add_2d(&tmO, stg_a, nb, row0);
-              else tma_store_2d(&tmO, stg_a, nb, row0);
-              bulk_commit();
-            }
-          }
-          if constexpr (E_PLANES) {
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {  // fp16 rows of 64 B, SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
-              __align__(16) __half2 h8[4];
-              __align__(16) __half2 l8[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) wxf_split2_f16x2(a[4 * q + e].x, a[4 * q + e].y, h8[e], l8[e]);
-              const int off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
-              *reinterpret_cast<uint4*>(stg_b + off) = *reinterpret_cast<const uint4*>(h8);
-              *reinterpret_cast<uint4*>(stg_b + 2048 + off) = *reinterpret_cast<const uint4*>(l8);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmO_hi, stg_a, nb, row0);
-              tma_store_2d(&tmO_lo, stg_a + 2048, nb, row0);
-              bulk_commit();
-            }
-          }
-        }
-      }
-      if (lane == 0) bulk_wait0();  // all stores of this warp have landed before the CTA exits
+      gemm_epilogue_fast<EW, EPI>(p, tmO, tmO_hi, tmO_lo, tmem_base, tfull_bar(0), tempty_bar(0),
+                                  reinterpret_cast<uint8_t*>(staging), base + STAGES * STAGE_BYTES, n_tiles, total_tiles, warp,
+                                  lane);
     } else if constexpr (!CONV) {
       // GEMM mode: lane = output row.  Accumulator row -> registers -> scale/bias/GELU/residual -> 32-column chunks
       // staged in swizzled shared memory -> TMA store (fp32 tile and/or fp16 hi/lo plane tiles).
@@ -842,6 +861,7 @@ constexpr int RW_A_BYTES = 2 * TILE_BYTES;
 constexpr int RW_W_BYTES = 2 * P_BN * BLOCK_K * 2;         // W_hi | W_lo of one K-step: 32 KB
 constexpr int RW_SMEM = 2 * RW_W_BYTES + RW_STA * RW_A_BYTES + RW_EW * 4096 + 8 * (2 * RW_STA + 5) + 16 + 1024;
 
+template <int EPI>
 __global__ void __launch_bounds__(64 + 32 * RW_EW, 1)
 tc_resident_w_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
@@ -958,6 +978,9 @@ tc_resident_w_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         tc_commit(tfull_bar(slot));
       }
     }
+  } else if constexpr (EPI != 0) {
+    gemm_epilogue_fast<EW, EPI>(p, tmO, tmO_hi, tmO_lo, tmem_base, tfull_bar(0), tempty_bar(0),
+                                reinterpret_cast<uint8_t*>(staging), base + OFF_STG, n_tiles, total_tiles, warp, lane);
   } else {
     const int ew = warp - 2;
     const int quarter = warp & 3, half = ew >> 2;
@@ -1445,6 +1468,16 @@ uint32_t park_ns() {  // WXF_MBAR_PARK_NS: suspend-time hint (ns) of the far-awa
   return (uint32_t)v;
 }
 
+int ew16_max_k() {  // WXF_GEMM_EW16_MAXK: largest K that takes the <16 epilogue warps, 2 stages> shape (default 128; K = 256 measured
+                    // 4 % faster on <8, 3> once the specialised epilogues had cut the issue load)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXF_GEMM_EW16_MAXK");
+    v = e ? atoi(e) : 128;
+  }
+  return v;
+}
+
 bool persistent_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -1538,21 +1571,44 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
       if ((rc = make_map(&to_lo, d->out_lo, 2, dims, strides, box, es, 64))) return rc;
     }
     const int nt = (d->N + BN - 1) / BN, mt = (int)((d->M + BLOCK_M - 1) / BLOCK_M);
-    if (d->K <= 128 && nt <= num_sms() && resident_w_enabled()) {
-      static WxfPerDevice<bool> attr_set_pd;
-  bool& attr_set = attr_set_pd.get();  // function attributes are per device
-      if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_resident_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM);
-        if (e != cudaSuccess) WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", RW_SMEM, cudaGetErrorString(e));
-        attr_set = true;
+    // specialised epilogues for the combinations the forecast plans use; anything else takes the generic one
+    int epi = 0;
+    p.park_ns = park_ns();
+    if (fast_epilogue_enabled()) {
+      const bool gelu = d->act == WXF_ACT_GELU_ERF, planes = d->out_hi != nullptr, f32 = d->out != nullptr;
+      const bool inplace = d->res && f32 && d->res + d->r_off == d->out + d->c_off && d->ldr == d->ldc;
+      if ((d->act == WXF_ACT_NONE || gelu) && d->N % 32 == 0) {
+        if (!d->res && planes && !f32) epi = EPI_PLANES | (gelu ? EPI_GELU : 0);
+        else if (!d->res && f32 && !planes && !gelu) epi = EPI_F32;
+        else if (inplace && !planes && !gelu) epi = EPI_F32 | EPI_RED;
       }
+    }
+    if (d->K <= 128 && nt <= num_sms() && resident_w_enabled()) {
       const int64_t total = (int64_t)nt * mt;
       int64_t grid = (num_sms() / nt) * nt;   // a multiple of the N-tile count: every CTA keeps one N tile
       if (grid > total) grid = total;         // total is a multiple of nt as well
-      wxf_launch(tc_resident_w_kernel, dim3((unsigned)grid), dim3(64 + 32 * RW_EW), RW_SMEM, st, ta_hi, ta_lo, tw_hi, tw_lo, to,
-                 to_hi, to_lo, p, nt, mt, (int)total);
-      WXF_CHECK_LAUNCH("tc_resident_w");
-      return 0;
+#define WXF_RW_LAUNCH(EPI_)                                                                                              \
+  {                                                                                                                      \
+    static WxfPerDevice<bool> attr_set_pd;                                                                               \
+    bool& attr_set = attr_set_pd.get(); /* function attributes are per device */                                         \
+    if (!attr_set) {                                                                                                     \
+      cudaError_t e = cudaFuncSetAttribute(tc_resident_w_kernel<EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, RW_SMEM); \
+      if (e != cudaSuccess) WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", RW_SMEM, cudaGetErrorString(e)); \
+      attr_set = true;                                                                                                   \
+    }                                                                                                                    \
+    wxf_launch(tc_resident_w_kernel<EPI_>, dim3((unsigned)grid), dim3(64 + 32 * RW_EW), RW_SMEM, st, ta_hi, ta_lo, tw_hi, \
+               tw_lo, to, to_hi, to_lo, p, nt, mt, (int)total);                                                          \
+    WXF_CHECK_LAUNCH("tc_resident_w");                                                                                   \
+    return 0;                                                                                                            \
+  }
+      switch (epi) {
+        case EPI_PLANES: WXF_RW_LAUNCH(EPI_PLANES)
+        case EPI_PLANES | EPI_GELU: WXF_RW_LAUNCH(EPI_PLANES | EPI_GELU)
+        case EPI_F32: WXF_RW_LAUNCH(EPI_F32)
+        case EPI_F32 | EPI_RED: WXF_RW_LAUNCH(EPI_F32 | EPI_RED)
+        default: WXF_RW_LAUNCH(0)
+      }
+#undef WXF_RW_LAUNCH
     }
     if (d->K >= 512 && (nt % 2) == 0 && cluster_enabled()) {
       constexpr int SMEM = p_smem<CL_EW, CL_STAGES>();
@@ -1591,21 +1647,9 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
       WXF_CHECK_LAUNCH("tc_cluster2");
       return 0;
     }
-    // specialised epilogues for the combinations the forecast plans use; anything else takes the generic one
-    int epi = 0;
-    p.park_ns = park_ns();
-    if (fast_epilogue_enabled()) {
-      const bool gelu = d->act == WXF_ACT_GELU_ERF, planes = d->out_hi != nullptr, f32 = d->out != nullptr;
-      const bool inplace = d->res && f32 && d->res + d->r_off == d->out + d->c_off && d->ldr == d->ldc;
-      if ((d->act == WXF_ACT_NONE || gelu) && d->N % 32 == 0) {
-        if (!d->res && planes && !f32) epi = EPI_PLANES | (gelu ? EPI_GELU : 0);
-        else if (!d->res && f32 && !planes && !gelu) epi = EPI_F32;
-        else if (inplace && !planes && !gelu) epi = EPI_F32 | EPI_RED;
-      }
-    }
 #define WXF_P_LAUNCH(EW_, ST_, EPI_) \
   return launch_persistent<MODE_GEMM, EW_, ST_, EPI_>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, nt, mt, 1, st)
-    if (d->K <= 256) {
+    if (d->K <= ew16_max_k()) {
       switch (epi) {
         case EPI_PLANES: WXF_P_LAUNCH(16, 2, EPI_PLANES);
         case EPI_PLANES | EPI_GELU: WXF_P_LAUNCH(16, 2, EPI_PLANES | EPI_GELU);

@@ -321,8 +321,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
-// vectorised variant for d % 128 == 0: each lane owns float4 chunks, 16-byte loads, 8/16-byte stores
-template <int NV4, bool SPLIT>
+// vectorised variant for d % 128 == 0: each lane owns float4 chunks, 16-byte loads, 8/16-byte stores.  A warp works on RPW
+// rows at once (all their loads are issued before the first reduction: with one row per warp and d = 128 a lane has a single
+// 16-byte load in flight, 32 KB per SM, below what hides the HBM latency), and the row's 1 / sqrt(var + eps) is computed once
+// (one IEEE division per row instead of four per lane and chunk).
+template <int NV4, bool SPLIT, int RPW>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y,
                                                              int ldy, __half* __restrict__ y_hi, __half* __restrict__ y_lo,
                                                              const float* __restrict__ g, const float* __restrict__ bta,
@@ -331,45 +334,58 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
   wxf_pdl_wait();
   constexpr int d = NV4 * 128;
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
-  float4 v[NV4];
-  float s = 0.f;
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= M) return;
+  float4 v[RPW][NV4];
 #pragma unroll
-  for (int k = 0; k < NV4; ++k) {
-    v[k] = xr[lane + 32 * k];
-    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-  }
-  const float mean = wxf_warp_sum(s) / (float)d;
-  float ss = 0.f;
+  for (int r = 0; r < RPW; ++r) {
+    const int64_t row = row0 + r < M ? row0 + r : M - 1;  // a ragged last warp re-reads the last row and does not store it
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
 #pragma unroll
-  for (int k = 0; k < NV4; ++k) {
-    const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, e = v[k].w - mean;
-    ss += (a * a + b * b) + (c * c + e * e);
+    for (int k = 0; k < NV4; ++k) v[r][k] = xr[lane + 32 * k];
   }
-  const float var = wxf_warp_sum(ss) / (float)d;
-  const float den = sqrtf(var + eps);
+  float mean[RPW], inv[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) s += (v[r][k].x + v[r][k].y) + (v[r][k].z + v[r][k].w);
+    mean[r] = wxf_warp_sum(s) / (float)d;
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) {
+      const float a = v[r][k].x - mean[r], b = v[r][k].y - mean[r], c = v[r][k].z - mean[r], e = v[r][k].w - mean[r];
+      ss += (a * a + b * b) + (c * c + e * e);
+    }
+    const float var = wxf_warp_sum(ss) / (float)d;
+    inv[r] = 1.0f / sqrtf(var + eps);
+  }
 #pragma unroll
   for (int k = 0; k < NV4; ++k) {
     const int c4 = lane + 32 * k;
     const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + c4), bb = __ldg(reinterpret_cast<const float4*>(bta) + c4);
-    float4 o;
-    o.x = (v[k].x - mean) / den * gg.x + bb.x;
-    o.y = (v[k].y - mean) / den * gg.y + bb.y;
-    o.z = (v[k].z - mean) / den * gg.z + bb.z;
-    o.w = (v[k].w - mean) / den * gg.w + bb.w;
-    if constexpr (SPLIT) {
-      __align__(8) __half h4[4];
-      __align__(8) __half l4[4];
-      wxf_split_f16x2(o.x, h4[0], l4[0]);
-      wxf_split_f16x2(o.y, h4[1], l4[1]);
-      wxf_split_f16x2(o.z, h4[2], l4[2]);
-      wxf_split_f16x2(o.w, h4[3], l4[3]);
-      *reinterpret_cast<uint2*>(y_hi + row * ldy + 4 * c4) = *reinterpret_cast<const uint2*>(h4);
-      *reinterpret_cast<uint2*>(y_lo + row * ldy + 4 * c4) = *reinterpret_cast<const uint2*>(l4);
-    } else {
-      *reinterpret_cast<float4*>(y + row * ldy + 4 * c4) = o;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int64_t row = row0 + r;
+      if (row >= M) break;
+      float4 o;
+      o.x = (v[r][k].x - mean[r]) * inv[r] * gg.x + bb.x;
+      o.y = (v[r][k].y - mean[r]) * inv[r] * gg.y + bb.y;
+      o.z = (v[r][k].z - mean[r]) * inv[r] * gg.z + bb.z;
+      o.w = (v[r][k].w - mean[r]) * inv[r] * gg.w + bb.w;
+      if constexpr (SPLIT) {
+        __align__(8) __half2 h2[2];
+        __align__(8) __half2 l2[2];
+        wxf_split2_f16x2(o.x, o.y, h2[0], l2[0]);
+        wxf_split2_f16x2(o.z, o.w, h2[1], l2[1]);
+        *reinterpret_cast<uint2*>(y_hi + row * ldy + 4 * c4) = *reinterpret_cast<const uint2*>(h2);
+        *reinterpret_cast<uint2*>(y_lo + row * ldy + 4 * c4) = *reinterpret_cast<const uint2*>(l2);
+      } else {
+        *reinterpret_cast<float4*>(y + row * ldy + 4 * c4) = o;
+      }
     }
   }
 }
@@ -382,17 +398,19 @@ static int layernorm_launch(const float* x, int ldx, float* y, int ldy, void* y_
   const int nv = (d + 31) / 32;
   const unsigned blocks = (unsigned)((M + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
+  // rows per warp of the vectorised kernel: 4 for d = 128, 2 up to d = 512 (register budget: RPW * d / 32 floats per lane)
+  auto vec_blocks = [&](int rpw) { return dim3((unsigned)((M + 8 * rpw - 1) / (8 * rpw))); };
   const bool vec = (d % 128 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && wxf_aligned16(x) && wxf_aligned16(g) &&
                    wxf_aligned16(b) && (SPLIT ? ((reinterpret_cast<uintptr_t>(y_hi) | reinterpret_cast<uintptr_t>(y_lo)) % 8 == 0)
                                               : wxf_aligned16(y));
   if (vec) {
-#define LN_VEC(NV4)                                                                                                   \
+#define LN_VEC(NV4, RPW)                                                                                              \
   if (d == NV4 * 128) {                                                                                               \
-    wxf_launch(layernorm_vec_kernel<NV4, SPLIT>, dim3(blocks), dim3(256), 0, st, x, ldx, y, ldy, (__half*)y_hi, (__half*)y_lo, g, b, M, eps); \
+    wxf_launch(layernorm_vec_kernel<NV4, SPLIT, RPW>, vec_blocks(RPW), dim3(256), 0, st, x, ldx, y, ldy, (__half*)y_hi, (__half*)y_lo, g, b, M, eps); \
     WXF_CHECK_LAUNCH("layernorm");                                                                                    \
     return 0;                                                                                                         \
   }
-    LN_VEC(1) LN_VEC(2) LN_VEC(3) LN_VEC(4) LN_VEC(6) LN_VEC(8)
+    LN_VEC(1, 4) LN_VEC(2, 2) LN_VEC(3, 2) LN_VEC(4, 2) LN_VEC(6, 1) LN_VEC(8, 1)
 #undef LN_VEC
   }
 #define LN_CASE(NV)                                                                                         \
