@@ -546,75 +546,81 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t stage_tx = CONV ? (2u * p.a_bytes + 2u * W_BYTES) : (uint32_t)STAGE_BYTES;
-      uint32_t g = 0;  // K-steps issued so far (ring position)
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int n0, z, tb, oy0, ox0;
-        int64_t m0;
-        decode(t, n0, z, m0, tb, oy0, ox0);
-        for (int ks = 0; ks < num_k; ++ks, ++g) {
-          const int s = g % STAGES;
-          const uint32_t ph = (g / STAGES) & 1u;
-          if constexpr (EPI != 0) mbar_wait_parked(empty_bar(s), ph ^ 1u, p.park_ns);
-          else mbar_wait(empty_bar(s), ph ^ 1u);
-          const uint32_t st = base + s * STAGE_BYTES;
+    // ---- TMA producer: the whole warp runs the loop converged, one elected lane issues (see elect_one) ----
+    const uint32_t stage_tx = CONV ? (2u * p.a_bytes + 2u * W_BYTES) : (uint32_t)STAGE_BYTES;
+    int s = 0;
+    uint32_t ph = 0;  // ring position: stage and its phase parity
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int n0, z, tb, oy0, ox0;
+      int64_t m0;
+      decode(t, n0, z, m0, tb, oy0, ox0);
+      for (int ks = 0; ks < num_k; ++ks) {
+        mbar_wait_parked(empty_bar(s), ph ^ 1u, EPI != 0 ? p.park_ns : 0u);
+        const uint32_t st = base + s * STAGE_BYTES;
+        int wk, c0 = 0, c1 = 0, c2 = 0;
+        if constexpr (CONV) {
+          const int tp = ks / p.cblocks, cb = ks - tp * p.cblocks;
+          c2 = oy0 * p.stride + p.taps[z][tp][0];
+          c1 = ox0 * p.stride + p.taps[z][tp][1];
+          c0 = cb * BLOCK_K;
+          wk = tp * p.cin_pad + cb * BLOCK_K;
+        } else {
+          wk = ks * BLOCK_K;
+        }
+        if (elect_one()) {
           mbar_expect_tx(full_bar(s), stage_tx);
-          int wk;
           if constexpr (CONV) {
-            const int tp = ks / p.cblocks, cb = ks - tp * p.cblocks;
-            const int iy = oy0 * p.stride + p.taps[z][tp][0], ix = ox0 * p.stride + p.taps[z][tp][1];
-            tma_load_4d(&tmA_hi, full_bar(s), st, cb * BLOCK_K, ix, iy, tb);
-            tma_load_4d(&tmA_lo, full_bar(s), st + TILE_BYTES, cb * BLOCK_K, ix, iy, tb);
-            wk = tp * p.cin_pad + cb * BLOCK_K;
+            tma_load_4d(&tmA_hi, full_bar(s), st, c0, c1, c2, tb);
+            tma_load_4d(&tmA_lo, full_bar(s), st + TILE_BYTES, c0, c1, c2, tb);
           } else {
-            tma_load_2d(&tmA_hi, full_bar(s), st, ks * BLOCK_K, (int)m0);
-            tma_load_2d(&tmA_lo, full_bar(s), st + TILE_BYTES, ks * BLOCK_K, (int)m0);
-            wk = ks * BLOCK_K;
+            tma_load_2d(&tmA_hi, full_bar(s), st, wk, (int)m0);
+            tma_load_2d(&tmA_lo, full_bar(s), st + TILE_BYTES, wk, (int)m0);
           }
           tma_load_2d(&tmW_hi, full_bar(s), st + 2 * TILE_BYTES, wk, z * p.N + n0);
           tma_load_2d(&tmW_lo, full_bar(s), st + 2 * TILE_BYTES + W_BYTES, wk, z * p.N + n0);
         }
+        __syncwarp();
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t g = 0;
-      int i = 0;  // local tile counter
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
-        const int slot = i & 1;
-        if constexpr (EPI != 0) mbar_wait_parked(tempty_bar(slot), (((uint32_t)i >> 1) & 1u) ^ 1u, p.park_ns);
-        else mbar_wait(tempty_bar(slot), (((uint32_t)i >> 1) & 1u) ^ 1u);  // epilogue has drained this slot
+    // ---- MMA issuer: converged warp, descriptors advance by integer adds on their low word, one elected lane issues ----
+    int s = 0;
+    uint32_t ph = 0;
+    int i = 0;  // local tile counter
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      const int slot = i & 1;
+      mbar_wait_parked(tempty_bar(slot), (((uint32_t)i >> 1) & 1u) ^ 1u, EPI != 0 ? p.park_ns : 0u);  // epilogue drained the slot
+      tc_fence_after();
+      const uint32_t d_cross = tmem_base + (uint32_t)(slot * 2 * BN), d_main = d_cross + BN;
+      for (int ks = 0; ks < num_k; ++ks) {
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t d_cross = tmem_base + (uint32_t)(slot * 2 * BN), d_main = d_cross + BN;
-        for (int ks = 0; ks < num_k; ++ks, ++g) {
-          const int s = g % STAGES;
-          const uint32_t ph = (g / STAGES) & 1u;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t st = base + s * STAGE_BYTES;
+        const uint32_t lo = umma_desc_lo(base + s * STAGE_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t a_hi = umma_desc_sw128(st + k * 32);
-            const uint64_t a_lo = umma_desc_sw128(st + TILE_BYTES + k * 32);
-            const uint64_t w_hi = umma_desc_sw128(st + 2 * TILE_BYTES + k * 32);
-            const uint64_t w_lo = umma_desc_sw128(st + 2 * TILE_BYTES + W_BYTES + k * 32);
+            const uint64_t a_hi = umma_desc_make(lo + 2 * k, UMMA_SW128_HI);
+            const uint64_t a_lo = umma_desc_make(lo + (TILE_BYTES >> 4) + 2 * k, UMMA_SW128_HI);
+            const uint64_t w_hi = umma_desc_make(lo + (2 * TILE_BYTES >> 4) + 2 * k, UMMA_SW128_HI);
             const uint32_t acc = (ks | k) ? 1u : 0u;
-            if (p.concat) {
-              // W_hi and W_lo tiles are adjacent in the stage: ONE N=256 instruction computes A_hi [W_hi | W_lo] into the
-              // slot's two accumulators (A_hi is read from shared memory once instead of twice), then A_lo W_hi is added
-              // to the second one.  The epilogue sums both accumulators, so which one holds "main" does not matter.
-              tc_mma_f16(d_cross, a_hi, w_hi, IDESC2, acc);
-              tc_mma_f16(d_main, a_lo, w_hi, IDESC, 1u);
-            } else {
-              tc_mma_f16(d_cross, a_hi, w_lo, IDESC, acc);
-              tc_mma_f16(d_cross, a_lo, w_hi, IDESC, 1u);
-              tc_mma_f16(d_main, a_hi, w_hi, IDESC, acc);
-            }
+            // W_hi and W_lo tiles are adjacent in the stage: ONE N=256 instruction computes A_hi [W_hi | W_lo] into the
+            // slot's two accumulators (A_hi is read from shared memory once instead of twice), then A_lo W_hi is added
+            // to the second one.  The epilogue sums both accumulators, so which one holds "main" does not matter.
+            tc_mma_f16(d_cross, a_hi, w_hi, IDESC2, acc);
+            tc_mma_f16(d_main, a_lo, w_hi, IDESC, 1u);
           }
           tc_commit(empty_bar(s));
+          if (ks == num_k - 1) tc_commit(tfull_bar(slot));
         }
-        tc_commit(tfull_bar(slot));
+        __syncwarp();
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else {

@@ -75,6 +75,28 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t bar,
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// One lane of a converged warp (elect.sync).  The single-thread roles (TMA producer, MMA issuer) run their loops with all 32
+// lanes converged and only the asynchronous instruction under this predicate: inside an `if (lane == 0)` branch the compiler
+// treats every operand as divergent and wraps each UTMALDG / UTCHMMA in a register-to-uniform waterfall (ncu source page:
+// ~170 issued instructions per K-step for 8 MMAs, the issuing thread busy 80 % of the time, the tensor pipe 58 %).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// SWIZZLE_128B K-major descriptor from its two words: lo = (address >> 4) | LBO field, hi = constant (SBO 1024 B, version 1,
+// swizzle mode).  Advancing by k * 32 bytes inside the 128-byte row or by a stage is an integer add on the low word.
+constexpr uint32_t UMMA_SW128_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t umma_desc_make(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
