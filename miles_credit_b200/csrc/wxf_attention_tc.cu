@@ -527,22 +527,23 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      const int per_img = p.nh * p.nw;
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        const int st = (int)(it % A2_NST);
-        const uint32_t k = (uint32_t)(it / A2_NST);
-        int head, nv;
-        int64_t w0;
-        tile_windows(blockIdx.x + it * gridDim.x, head, w0, nv);
-        if (k > 0) mbar_wait(bar_qkv_empty(st), (k - 1u) & 1u);  // PV of the tile A2_NST back has read this stage
-        const uint32_t buf = base + (uint32_t)(st * A2_QKV);
-        const uint32_t full = bar_qkv_full(st);
-        if (p.inter) {
+    // ---- TMA producer: the warp runs converged (tile decode on the uniform datapath), an elected lane issues ----
+    const int per_img = p.nh * p.nw;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int st = (int)(it % A2_NST);
+      const uint32_t k = (uint32_t)(it / A2_NST);
+      int head, nv;
+      int64_t w0;
+      tile_windows(blockIdx.x + it * gridDim.x, head, w0, nv);
+      if (k > 0) mbar_wait(bar_qkv_empty(st), (k - 1u) & 1u);  // PV of the tile A2_NST back has read this stage
+      const uint32_t buf = base + (uint32_t)(st * A2_QKV);
+      const uint32_t full = bar_qkv_full(st);
+      if (p.inter) {
+        const int bi = (int)(w0 / per_img);
+        const int rem = (int)(w0 - (int64_t)bi * per_img);
+        const int gh = rem / p.nw, gw = rem - gh * p.nw;
+        if (elect_one()) {
           mbar_expect_tx(full, (uint32_t)(6 * p.L * p.G * 64));
-          const int bi = (int)(w0 / per_img);
-          const int rem = (int)(w0 - (int64_t)bi * per_img);
-          const int gh = rem / p.nw, gw = rem - gh * p.nw;
 #pragma unroll
           for (int which = 0; which < 3; ++which) {
             const int c0 = which * p.d + head * DH;
@@ -550,14 +551,18 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
             tma_load_5d(&tm_hi, full, dst, c0, gw, 0, gh, bi * p.wsz);
             tma_load_5d(&tm_lo, full, dst + QKV_PLANE, c0, gw, 0, gh, bi * p.wsz);
           }
-        } else {
-          mbar_expect_tx(full, (uint32_t)(nv * 6 * p.L * 64));
-          for (int g = 0; g < nv; ++g) {
-            const int64_t w = w0 + g;
-            const int bi = (int)(w / per_img);
-            const int rem = (int)(w - (int64_t)bi * per_img);
-            const int gh = rem / p.nw, gw = rem - gh * p.nw;
-            const uint32_t row_off = (uint32_t)(g * p.Lp * 64);
+        }
+        __syncwarp();
+      } else {
+        if (elect_one()) mbar_expect_tx(full, (uint32_t)(nv * 6 * p.L * 64));
+        __syncwarp();
+        // consecutive windows of a tile: (bi, gh, gw) advance incrementally, one division per tile
+        int bi = (int)(w0 / per_img);
+        const int rem = (int)(w0 - (int64_t)bi * per_img);
+        int gh = rem / p.nw, gw = rem - gh * p.nw;
+        for (int g = 0; g < nv; ++g) {
+          const uint32_t row_off = (uint32_t)(g * p.Lp * 64);
+          if (elect_one()) {
 #pragma unroll
             for (int which = 0; which < 3; ++which) {  // q, k, v
               const int c0 = which * p.d + head * DH;
@@ -571,56 +576,72 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
               }
             }
           }
+          __syncwarp();
+          if (++gw == p.nw) {
+            gw = 0;
+            if (++gh == p.nh) {
+              gh = 0;
+              ++bi;
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // S_b = Q K^T of tile `it`.  S_b / P_b is free: tcgen05.mma instructions of one thread execute in issue order, and
-      // PV(it-2), which read P_b, was issued before this.
-      auto issue_qk = [&](int64_t it) {
-        const int st = (int)(it % A2_NST);
-        const uint32_t k = (uint32_t)(it / A2_NST);
-        mbar_wait(bar_qkv_full(st), k & 1u);
-        tc_fence_after();
-        const uint32_t buf = base + (uint32_t)(st * A2_QKV);
-        const uint32_t q_hi = buf + A2_OFF_Q, q_lo = q_hi + QKV_PLANE, k_hi = buf + A2_OFF_K, k_lo = k_hi + QKV_PLANE;
-        const uint32_t d_s = tmem_base + (uint32_t)((it & 1) * 128);
+    // ---- MMA issuer: converged warp, an elected lane issues; operand descriptors = constant high word + an integer add
+    //      on the low word (the 36 tcgen05.mma of a tile are small: N = 32 for P V, so the issue cost is what counts) ----
+    constexpr uint32_t HI64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);  // SBO 512 B, version 1, SWIZZLE_64B
+    // S_b = Q K^T of tile `it`.  S_b / P_b is free: tcgen05.mma instructions of one thread execute in issue order, and
+    // PV(it-2), which read P_b, was issued before this.
+    auto issue_qk = [&](int64_t it) {
+      const int st = (int)(it % A2_NST);
+      const uint32_t k = (uint32_t)(it / A2_NST);
+      mbar_wait(bar_qkv_full(st), k & 1u);
+      tc_fence_after();
+      const uint32_t buf = base + (uint32_t)(st * A2_QKV);
+      const uint32_t q_hi = umma_desc_lo(buf + A2_OFF_Q), q_lo = q_hi + (QKV_PLANE >> 4);  // K-major: LBO field = 1
+      const uint32_t k_hi = umma_desc_lo(buf + A2_OFF_K), k_lo = k_hi + (QKV_PLANE >> 4);
+      const uint32_t d_s = tmem_base + (uint32_t)((it & 1) * 128);
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {  // dh = 32 = two K=16 steps (32 bytes each inside the 64-byte row)
-          tc_mma_f16(d_s, umma_desc_sw64_kmajor(q_hi + ks * 32), umma_desc_sw64_kmajor(k_lo + ks * 32), IDESC_S, ks ? 1u : 0u);
-          tc_mma_f16(d_s, umma_desc_sw64_kmajor(q_lo + ks * 32), umma_desc_sw64_kmajor(k_hi + ks * 32), IDESC_S, 1u);
-          tc_mma_f16(d_s, umma_desc_sw64_kmajor(q_hi + ks * 32), umma_desc_sw64_kmajor(k_hi + ks * 32), IDESC_S, 1u);
+          tc_mma_f16(d_s, umma_desc_make(q_hi + 2 * ks, HI64), umma_desc_make(k_lo + 2 * ks, HI64), IDESC_S, ks ? 1u : 0u);
+          tc_mma_f16(d_s, umma_desc_make(q_lo + 2 * ks, HI64), umma_desc_make(k_hi + 2 * ks, HI64), IDESC_S, 1u);
+          tc_mma_f16(d_s, umma_desc_make(q_hi + 2 * ks, HI64), umma_desc_make(k_hi + 2 * ks, HI64), IDESC_S, 1u);
         }
         tc_commit(bar_s_full((int)(it & 1)));
-      };
-      // O_b = P_b V: A = P from tensor memory (hi words in S_b columns [0, 64), lo words in [64, 128), 8 columns = 16 keys)
-      auto issue_pv = [&](int64_t it) {
-        const int b = (int)(it & 1), q = (int)(it & 3);
-        const uint32_t k2 = (uint32_t)(it >> 1), k4 = (uint32_t)(it >> 2);
-        const int st = (int)(it % A2_NST);
-        mbar_wait(bar_p_full(b), k2 & 1u);                        // P_b written by softmax group b
-        if (k4 > 0) mbar_wait(bar_o_empty(q), (k4 - 1u) & 1u);    // O_q of the tile four back has been read
-        tc_fence_after();
-        const uint32_t buf = base + (uint32_t)(st * A2_QKV);
-        const uint32_t v_hi = buf + A2_OFF_V, v_lo = v_hi + QKV_PLANE;
-        const uint32_t p_hi = tmem_base + (uint32_t)(b * 128), p_lo = p_hi + 64u;
-        const uint32_t d_o = tmem_base + A2_COL_O + (uint32_t)(q * 32);
+      }
+      __syncwarp();
+    };
+    // O_b = P_b V: A = P from tensor memory (hi words in S_b columns [0, 64), lo words in [64, 128), 8 columns = 16 keys)
+    auto issue_pv = [&](int64_t it) {
+      const int b = (int)(it & 1), q = (int)(it & 3);
+      const uint32_t k2 = (uint32_t)(it >> 1), k4 = (uint32_t)(it >> 2);
+      const int st = (int)(it % A2_NST);
+      mbar_wait(bar_p_full(b), k2 & 1u);                        // P_b written by softmax group b
+      if (k4 > 0) mbar_wait(bar_o_empty(q), (k4 - 1u) & 1u);    // O_q of the tile four back has been read
+      tc_fence_after();
+      const uint32_t buf = base + (uint32_t)(st * A2_QKV);
+      // MN-major V: LBO field = 512 B >> 4; one K = 16 step = 16 rows of 64 B = 1024 B = 64 descriptor units
+      const uint32_t v_hi = (((buf + A2_OFF_V) & 0x3FFFFu) >> 4) | ((uint32_t)(512 >> 4) << 16), v_lo = v_hi + (QKV_PLANE >> 4);
+      const uint32_t p_hi = tmem_base + (uint32_t)(b * 128), p_lo = p_hi + 64u;
+      const uint32_t d_o = tmem_base + A2_COL_O + (uint32_t)(q * 32);
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // 128 key rows = eight K=16 steps
-          const uint32_t va = (uint32_t)(ks * 16 * 64);
-          tc_mma_f16_ts(d_o, p_hi + ks * 8, umma_desc_sw64_mnmajor(v_lo + va), IDESC_O, ks ? 1u : 0u);
-          tc_mma_f16_ts(d_o, p_lo + ks * 8, umma_desc_sw64_mnmajor(v_hi + va), IDESC_O, 1u);
-          tc_mma_f16_ts(d_o, p_hi + ks * 8, umma_desc_sw64_mnmajor(v_hi + va), IDESC_O, 1u);
+          tc_mma_f16_ts(d_o, p_hi + ks * 8, umma_desc_make(v_lo + 64 * ks, HI64), IDESC_O, ks ? 1u : 0u);
+          tc_mma_f16_ts(d_o, p_lo + ks * 8, umma_desc_make(v_hi + 64 * ks, HI64), IDESC_O, 1u);
+          tc_mma_f16_ts(d_o, p_hi + ks * 8, umma_desc_make(v_hi + 64 * ks, HI64), IDESC_O, 1u);
         }
         tc_commit(bar_o_full(q));
         if (it + A2_NST < my_tiles) tc_commit(bar_qkv_empty(st));  // stage may be refilled (nobody waits after the last use)
-      };
-      if (my_tiles > 0) issue_qk(0);
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        if (it + 1 < my_tiles) issue_qk(it + 1);
-        issue_pv(it);
       }
+      __syncwarp();
+    };
+    if (my_tiles > 0) issue_qk(0);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      if (it + 1 < my_tiles) issue_qk(it + 1);
+      issue_pv(it);
     }
   } else {
     // ---- softmax + epilogue: thread = query row; group wg handles tiles it = wg, wg + 2, ... ----

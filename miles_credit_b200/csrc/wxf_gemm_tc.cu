@@ -344,6 +344,9 @@ constexpr int p_smem() {
 // stage-0 fc1 launch showed 950 issued instructions per warp and tile where ~500 are needed: predicated-off residual code,
 // spilled residual registers, eight predicated bias loads with their address arithmetic, unpacked accumulator adds, a
 // two-division tile decode.  With the switches as template parameters none of that is compiled in.
+#ifndef WXF_ABLATE
+#define WXF_ABLATE 0  // diagnosis builds only (tools/build_ablate.sh): 1 = no TMA stores, 2 = no GELU, 4 = drain only; results are wrong
+#endif
 constexpr int EPI_GELU = 1;    // erf GELU
 constexpr int EPI_RED = 2;     // in-place residual (out == res): the fp32 tile leaves as a TMA REDUCE-ADD store, the L2 does x += f(x)
 constexpr int EPI_F32 = 4;     // fp32 output tile
@@ -405,8 +408,11 @@ __device__ __forceinline__ void gemm_epilogue_fast(const TcParams& p, const CUte
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty_bar(slot));  // TMEM slot free for the MMA of tile i+2
+    if (elect_one()) mbar_arrive(tempty_bar(slot));  // TMEM slot free for the MMA of tile i+2
 
+#if WXF_ABLATE & 4
+    continue;  // diagnosis build: accumulator drained, nothing else
+#endif
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int nb = nb0 + c * 32;
@@ -424,12 +430,14 @@ __device__ __forceinline__ void gemm_epilogue_fast(const TcParams& p, const CUte
 #pragma unroll
         for (int j = 0; j < 16; ++j) a[j] = __fmul2_rn(a[j], sc);
       }
+#if !(WXF_ABLATE & 2)
       if constexpr (E_GELU) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) a[j] = wxf_gelu_erf2_relu(a[j]);
       }
+#endif
       if constexpr (E_F32) {
-        if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the staging buffer
+        if (elect_one()) bulk_wait_read0();  // the previous TMA store has finished reading the staging buffer
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 8; ++q)  // fp32 row of 128 B, SWIZZLE_128B: 16-byte chunk ^= row % 8
@@ -437,14 +445,16 @@ __device__ __forceinline__ void gemm_epilogue_fast(const TcParams& p, const CUte
               make_float4(a[2 * q].x, a[2 * q].y, a[2 * q + 1].x, a[2 * q + 1].y);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+#if !(WXF_ABLATE & 1)
+        if (elect_one()) {
           if constexpr (E_RED) tma_reduce_add_2d(&tmO, stg_a, nb, row0);
           else tma_store_2d(&tmO, stg_a, nb, row0);
           bulk_commit();
         }
+#endif
       }
       if constexpr (E_PLANES) {
-        if (lane == 0) bulk_wait_read0();
+        if (elect_one()) bulk_wait_read0();
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {  // fp16 rows of 64 B, SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
@@ -458,15 +468,17 @@ __device__ __forceinline__ void gemm_epilogue_fast(const TcParams& p, const CUte
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+#if !(WXF_ABLATE & 1)
+        if (elect_one()) {
           tma_store_2d(&tmO_hi, stg_a, nb, row0);
           tma_store_2d(&tmO_lo, stg_a + 2048, nb, row0);
           bulk_commit();
         }
+#endif
       }
     }
   }
-  if (lane == 0) bulk_wait0();  // all stores of this warp have landed before the CTA exits
+  if (elect_one()) bulk_wait0();  // all stores of this warp have landed before the CTA exits
 }
 
 template <int MODE, int EW, int STAGES, int EPI = 0>
