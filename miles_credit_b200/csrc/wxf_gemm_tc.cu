@@ -135,56 +135,73 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   wxf_pdl_wait();  // everything above overlaps the previous kernel's tail (programmatic dependent launch)
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t stage_tx = CONV ? (2u * p.a_bytes + 2u * W_BYTES) : (uint32_t)STAGE_BYTES;
-      for (int ks = 0; ks < num_k; ++ks) {
-        const int s = ks % STAGES;
-        const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t st = base + s * STAGE_BYTES;
+    // ---- TMA producer: converged warp, an elected lane issues (see elect_one in wxf_tc_ptx.cuh) ----
+    const uint32_t stage_tx = CONV ? (2u * p.a_bytes + 2u * W_BYTES) : (uint32_t)STAGE_BYTES;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int ks = 0; ks < num_k; ++ks) {
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      const uint32_t st = base + s * STAGE_BYTES;
+      int wk, c0 = 0, c1 = 0, c2 = 0;
+      if constexpr (CONV) {
+        const int t = ks / p.cblocks, cb = ks - t * p.cblocks;
+        c2 = oy0 * p.stride + p.taps[z][t][0];
+        c1 = ox0 * p.stride + p.taps[z][t][1];
+        c0 = cb * BLOCK_K;
+        wk = t * p.cin_pad + cb * BLOCK_K;
+      } else {
+        wk = ks * BLOCK_K;
+      }
+      if (elect_one()) {
         mbar_expect_tx(full_bar(s), stage_tx);
-        int wk;
         if constexpr (CONV) {
-          const int t = ks / p.cblocks, cb = ks - t * p.cblocks;
-          const int iy = oy0 * p.stride + p.taps[z][t][0], ix = ox0 * p.stride + p.taps[z][t][1];
-          tma_load_4d(&tmA_hi, full_bar(s), st, cb * BLOCK_K, ix, iy, tb);
-          tma_load_4d(&tmA_lo, full_bar(s), st + TILE_BYTES, cb * BLOCK_K, ix, iy, tb);
-          wk = t * p.cin_pad + cb * BLOCK_K;
+          tma_load_4d(&tmA_hi, full_bar(s), st, c0, c1, c2, tb);
+          tma_load_4d(&tmA_lo, full_bar(s), st + TILE_BYTES, c0, c1, c2, tb);
         } else {
-          tma_load_2d(&tmA_hi, full_bar(s), st, ks * BLOCK_K, (int)m0);
-          tma_load_2d(&tmA_lo, full_bar(s), st + TILE_BYTES, ks * BLOCK_K, (int)m0);
-          wk = ks * BLOCK_K;
+          tma_load_2d(&tmA_hi, full_bar(s), st, wk, (int)m0);
+          tma_load_2d(&tmA_lo, full_bar(s), st + TILE_BYTES, wk, (int)m0);
         }
         tma_load_2d(&tmW_hi, full_bar(s), st + 2 * TILE_BYTES, wk, z * p.N + n0);
         tma_load_2d(&tmW_lo, full_bar(s), st + 2 * TILE_BYTES + W_BYTES, wk, z * p.N + n0);
       }
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t started = 0;  // bit a: accumulator a already holds data
-      for (int ks = 0; ks < num_k; ++ks) {
-        const int s = ks % STAGES;
-        const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t st = base + s * STAGE_BYTES;
-        const int am = 1 + (int)(((int64_t)ks * NMAIN) / num_k);  // main accumulator of this K-step
-        const uint32_t d_cross = tmem_base, d_main = tmem_base + (uint32_t)(am * BN);
+    // ---- MMA issuer: converged warp, descriptors advance by integer adds on the low word, an elected lane issues ----
+    uint32_t started = 0;  // bit a: accumulator a already holds data
+    int s = 0;
+    uint32_t ph = 0;
+    for (int ks = 0; ks < num_k; ++ks) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint32_t lo = umma_desc_lo(base + s * STAGE_BYTES);
+      const int am = 1 + (int)(((int64_t)ks * NMAIN) / num_k);  // main accumulator of this K-step
+      const uint32_t d_cross = tmem_base, d_main = tmem_base + (uint32_t)(am * BN);
+      const uint32_t acc_cross = started & 1u, acc_main = (started >> am) & 1u;
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < BLOCK_K / 16; ++k) {
-          const uint64_t a_hi = umma_desc_sw128(st + k * 32);
-          const uint64_t a_lo = umma_desc_sw128(st + TILE_BYTES + k * 32);
-          const uint64_t w_hi = umma_desc_sw128(st + 2 * TILE_BYTES + k * 32);
-          const uint64_t w_lo = umma_desc_sw128(st + 2 * TILE_BYTES + W_BYTES + k * 32);
-          tc_mma_f16(d_cross, a_hi, w_lo, IDESC, started & 1u);
-          started |= 1u;
+          const uint64_t a_hi = umma_desc_make(lo + 2 * k, UMMA_SW128_HI);
+          const uint64_t a_lo = umma_desc_make(lo + (TILE_BYTES >> 4) + 2 * k, UMMA_SW128_HI);
+          const uint64_t w_hi = umma_desc_make(lo + (2 * TILE_BYTES >> 4) + 2 * k, UMMA_SW128_HI);
+          const uint64_t w_lo = umma_desc_make(lo + ((2 * TILE_BYTES + W_BYTES) >> 4) + 2 * k, UMMA_SW128_HI);
+          tc_mma_f16(d_cross, a_hi, w_lo, IDESC, k ? 1u : acc_cross);
           tc_mma_f16(d_cross, a_lo, w_hi, IDESC, 1u);
-          tc_mma_f16(d_main, a_hi, w_hi, IDESC, (started >> am) & 1u);
-          started |= 1u << am;
+          tc_mma_f16(d_main, a_hi, w_hi, IDESC, k ? 1u : acc_main);
         }
         tc_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+        if (ks == num_k - 1) tc_commit(tmem_full_bar);  // accumulators complete
       }
-      tc_commit(tmem_full_bar);   // accumulators complete
+      __syncwarp();
+      started |= 1u | (1u << am);
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
   } else {
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) ----
