@@ -625,22 +625,41 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       mbar_wait_parked(tempty_bar(slot), (((uint32_t)i >> 1) & 1u) ^ 1u, EPI != 0 ? p.park_ns : 0u);  // epilogue drained the slot
       tc_fence_after();
       const uint32_t d_cross = tmem_base + (uint32_t)(slot * 2 * BN), d_main = d_cross + BN;
+      // a ragged last N tile (N % 128 != 0, e.g. the 64 output channels of up_block4) issues MMAs of only the columns that
+      // exist, rounded up to 16 (the weight rows beyond N are TMA zero fill; the epilogue never stores those columns)
+      const int n_left = p.N - (t % n_tiles) * BN;
+      const int n_mma = n_left >= BN ? BN : ((n_left + 15) & ~15);
+      const uint32_t idesc_n = (1u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
       for (int ks = 0; ks < num_k; ++ks) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t lo = umma_desc_lo(base + s * STAGE_BYTES);
         if (elect_one()) {
+          if (n_mma == BN) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t a_hi = umma_desc_make(lo + 2 * k, UMMA_SW128_HI);
-            const uint64_t a_lo = umma_desc_make(lo + (TILE_BYTES >> 4) + 2 * k, UMMA_SW128_HI);
-            const uint64_t w_hi = umma_desc_make(lo + (2 * TILE_BYTES >> 4) + 2 * k, UMMA_SW128_HI);
-            const uint32_t acc = (ks | k) ? 1u : 0u;
-            // W_hi and W_lo tiles are adjacent in the stage: ONE N=256 instruction computes A_hi [W_hi | W_lo] into the
-            // slot's two accumulators (A_hi is read from shared memory once instead of twice), then A_lo W_hi is added
-            // to the second one.  The epilogue sums both accumulators, so which one holds "main" does not matter.
-            tc_mma_f16(d_cross, a_hi, w_hi, IDESC2, acc);
-            tc_mma_f16(d_main, a_lo, w_hi, IDESC, 1u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t a_hi = umma_desc_make(lo + 2 * k, UMMA_SW128_HI);
+              const uint64_t a_lo = umma_desc_make(lo + (TILE_BYTES >> 4) + 2 * k, UMMA_SW128_HI);
+              const uint64_t w_hi = umma_desc_make(lo + (2 * TILE_BYTES >> 4) + 2 * k, UMMA_SW128_HI);
+              const uint32_t acc = (ks | k) ? 1u : 0u;
+              // W_hi and W_lo tiles are adjacent in the stage: ONE N=256 instruction computes A_hi [W_hi | W_lo] into the
+              // slot's two accumulators (A_hi is read from shared memory once instead of twice), then A_lo W_hi is added
+              // to the second one.  The epilogue sums both accumulators, so which one holds "main" does not matter.
+              tc_mma_f16(d_cross, a_hi, w_hi, IDESC2, acc);
+              tc_mma_f16(d_main, a_lo, w_hi, IDESC, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t a_hi = umma_desc_make(lo + 2 * k, UMMA_SW128_HI);
+              const uint64_t a_lo = umma_desc_make(lo + (TILE_BYTES >> 4) + 2 * k, UMMA_SW128_HI);
+              const uint64_t w_hi = umma_desc_make(lo + (2 * TILE_BYTES >> 4) + 2 * k, UMMA_SW128_HI);
+              const uint64_t w_lo = umma_desc_make(lo + ((2 * TILE_BYTES + W_BYTES) >> 4) + 2 * k, UMMA_SW128_HI);
+              const uint32_t acc = (ks | k) ? 1u : 0u;
+              tc_mma_f16(d_cross, a_hi, w_hi, idesc_n, acc);
+              tc_mma_f16(d_main, a_hi, w_lo, idesc_n, acc);
+              tc_mma_f16(d_main, a_lo, w_hi, idesc_n, 1u);
+            }
           }
           tc_commit(empty_bar(s));
           if (ks == num_k - 1) tc_commit(tfull_bar(slot));
