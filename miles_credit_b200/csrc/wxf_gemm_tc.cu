@@ -66,6 +66,7 @@ struct TcParams {
   int bias_zs;        // bias index = phase * bias_zs + n
   int step, J, ch;    // Toeplitz mode: tile step along x (128 - (J-1)), taps folded into N, channels of the branch
   int concat;         // persistent kernel: issue A_hi [W_hi | W_lo] as one N=256 instruction
+  uint32_t w_bytes;   // persistent kernel: bytes of one W box (fewer than 128 rows when N < 128: up_block4 has 64 channels)
   uint32_t park_ns;   // specialised epilogues: suspend-time hint of the far-away mbarrier waits (0 = plain spin)
   int16_t taps[4][MAX_TAPS][2];  // [phase][tap] = (dy, dx); only [0] used when phases == 1
 };
@@ -576,7 +577,7 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 
   if (warp == 0) {
     // ---- TMA producer: the whole warp runs the loop converged, one elected lane issues (see elect_one) ----
-    const uint32_t stage_tx = CONV ? (2u * p.a_bytes + 2u * W_BYTES) : (uint32_t)STAGE_BYTES;
+    const uint32_t stage_tx = (CONV ? 2u * p.a_bytes : 2u * (uint32_t)TILE_BYTES) + 2u * p.w_bytes;
     int s = 0;
     uint32_t ph = 0;  // ring position: stage and its phase parity
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -1599,9 +1600,13 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
   if ((rc = make_map_2d(&ta_hi, d->a_hi, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, BLOCK_M))) return rc;
   if ((rc = make_map_2d(&ta_lo, d->a_lo, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, BLOCK_M))) return rc;
-  if ((rc = make_map_2d(&tw_hi, d->w_hi, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K, BN))) return rc;
-  if ((rc = make_map_2d(&tw_lo, d->w_lo, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K, BN))) return rc;
+  // a single ragged N tile loads only the weight rows that exist (rounded up to the MMA's N granularity of 16)
+  const bool plain_persistent = persistent && !resident_w_enabled() && !cluster_enabled();
+  const int w_rows = (plain_persistent && d->N < BN) ? ((d->N + 15) & ~15) : BN;
+  if ((rc = make_map_2d(&tw_hi, d->w_hi, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K, (uint32_t)w_rows))) return rc;
+  if ((rc = make_map_2d(&tw_lo, d->w_lo, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K, (uint32_t)w_rows))) return rc;
   TcParams p{};
+  p.w_bytes = (uint32_t)(w_rows * BLOCK_K * 2);
   p.concat = concat_enabled() ? 1 : 0;
   p.bias = d->bias;
   p.res = d->res ? d->res + d->r_off : nullptr;
@@ -1776,10 +1781,13 @@ extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
     if ((rc = make_map(&ta_hi, d->in_hi, 4, dims, strides, box, es))) return rc;
     if ((rc = make_map(&ta_lo, d->in_lo, 4, dims, strides, box, es))) return rc;
   }
-  if ((rc = make_map_2d(&tw_hi, d->w_hi, (uint64_t)d->phases * d->N, (uint64_t)K, (uint64_t)K, BN))) return rc;
-  if ((rc = make_map_2d(&tw_lo, d->w_lo, (uint64_t)d->phases * d->N, (uint64_t)K, (uint64_t)K, BN))) return rc;
+  // a single ragged N tile loads only the weight rows that exist (up_block4: 64 of 128), rounded up to the MMA's N step
+  const int w_rows = (persistent && d->N < BN) ? ((d->N + 15) & ~15) : BN;
+  if ((rc = make_map_2d(&tw_hi, d->w_hi, (uint64_t)d->phases * d->N, (uint64_t)K, (uint64_t)K, (uint32_t)w_rows))) return rc;
+  if ((rc = make_map_2d(&tw_lo, d->w_lo, (uint64_t)d->phases * d->N, (uint64_t)K, (uint64_t)K, (uint32_t)w_rows))) return rc;
 
   TcParams p{};
+  p.w_bytes = (uint32_t)(w_rows * BLOCK_K * 2);
   p.concat = concat_enabled() ? 1 : 0;
   p.bias = d->bias;
   p.res = d->res ? d->res + d->r_off : nullptr;
