@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 15
+#define WXF_ABI_VERSION 16
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -177,35 +177,6 @@ typedef struct WxfGemmDesc {
 
 int wxf_gemm_f16x2_tc(const WxfGemmDesc* desc, void* stream);
 
-/*
- * FeedForward of a d = 128 stage as one kernel (crossformer.py:195-207 + the residual of :361-363; the LayerNorm in
- * front is wxf_layernorm_f16x2): out = gelu_erf(A W1^T + b1) W2^T + b2 + res, the 4d-wide hidden activation stays on the
- * SM (fp16 hi/lo planes in tensor memory).  Same f16x2 arithmetic as two wxf_gemm_f16x2_tc calls.
- * ROUND-2 CANDIDATE: selected by WXF_FF_FUSED=1 only; not yet validated on hardware.
- *   a_hi, a_lo   : [M, lda] fp16 planes of the normalised input (d = 128 columns)
- *   w1_hi, w1_lo : [4d, d] planes of W1 * 2^w1_scale_log2;  b1 : [4d]
- *   w2_hi, w2_lo : [d, 4d] planes of W2 * 2^w2_scale_log2;  b2 : [d]
- *   res : [M, ldr] fp32 (optional);  out : [M, ldc] fp32 (optional, may alias res);  out_hi/out_lo : [M, ldh] (optional)
- */
-typedef struct WxfFfDesc {
-  const void* a_hi;
-  const void* a_lo;
-  const void* w1_hi;
-  const void* w1_lo;
-  const float* b1;
-  const void* w2_hi;
-  const void* w2_lo;
-  const float* b2;
-  const float* res;
-  float* out;
-  void* out_hi;
-  void* out_lo;
-  int64_t M;
-  int32_t d, lda, ldc, ldr, ldh;
-  int32_t w1_scale_log2, w2_scale_log2;
-} WxfFfDesc;
-
-int wxf_ff_fused_f16x2_tc(const WxfFfDesc* desc, void* stream);
 
 /*
  * Convolution as an implicit GEMM on the tcgen05 tensor cores (same f16x2 scheme and epilogue as

@@ -65,7 +65,6 @@ struct TcParams {
   uint32_t a_bytes;   // bytes of one A plane box
   int bias_zs;        // bias index = phase * bias_zs + n
   int step, J, ch;    // Toeplitz mode: tile step along x (128 - (J-1)), taps folded into N, channels of the branch
-  int concat;         // persistent kernel: issue A_hi [W_hi | W_lo] as one N=256 instruction
   uint32_t w_bytes;   // persistent kernel: bytes of one W box (fewer than 128 rows when N < 128: up_block4 has 64 channels)
   uint32_t park_ns;   // specialised epilogues: suspend-time hint of the far-away mbarrier waits (0 = plain spin)
   int16_t taps[4][MAX_TAPS][2];  // [phase][tap] = (dy, dx); only [0] used when phases == 1
@@ -1157,292 +1156,6 @@ tc_resident_w_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   }
 }
 
-// ---- K >= 512 GEMM on clusters of two CTAs that share their A tile by TMA multicast ------------------------------------
-// The 128x128-tile GEMM with three fp16 passes pulls 64 KB per K-step per CTA out of L2 (A hi/lo 32 KB + W hi/lo 32 KB): with
-// one CTA per SM that is 148 x 64 KB per ~1700 cycles = 5.5 KB/cycle, the L2 -> SM cap of the chip (~6.3 KB/cycle), while the
-// MMAs of a K-step need 768 cycles: the stage 2-3 launches are L2-bandwidth bound (profiles/README.md, headroom table).
-// Here the two CTAs of a cluster work on the SAME 128 rows and on neighbouring N tiles: CTA 0 loads A_hi, CTA 1 loads A_lo,
-// each with .multicast::cluster into both CTAs, so a CTA pulls 48 KB per K-step instead of 64 KB.  A stage is released only
-// when BOTH CTAs have consumed it (the MMA warp's tcgen05.commit arrives, multicast, on the empty barrier of both).
-// ROUND-2 CANDIDATE (WXF_GEMM_CLUSTER=1): written without GPU time left, never run on hardware.
-__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-constexpr int CL_EW = 8, CL_STAGES = 3;
-
-__global__ void __launch_bounds__(64 + 32 * CL_EW, 1)
-tc_cluster2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                   const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO_hi,
-                   const __grid_constant__ CUtensorMap tmO_lo, const __grid_constant__ TcParams p, const int n_pairs,
-                   const int total_pairs) {
-  constexpr bool CONV = false;
-  constexpr int EW = CL_EW, STAGES = CL_STAGES, BN = P_BN, STAGE_BYTES = P_STAGE_BYTES, W_BYTES = P_BN * BLOCK_K * 2;
-  constexpr int P_STG_BYTES = EW * 4096;
-  constexpr int CW = 128 / (EW / 4);
-  constexpr int NCH = CW / 32;
-  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-  constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;   // identical in both CTAs of the cluster (same kernel, same launch)
-  uint8_t* gen = smem_raw + (base - raw);
-  float* staging = reinterpret_cast<float*>(gen + STAGES * STAGE_BYTES);
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES + P_STG_BYTES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + STAGES * STAGE_BYTES + P_STG_BYTES + 8 * (2 * STAGES + 4));
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_k = p.num_ksteps;
-  uint32_t crank;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-
-  wxf_pdl_trigger();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 2);  // both CTAs of the cluster release a stage
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), EW);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // the peer's barriers exist before anything is multicast into this CTA
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  wxf_pdl_wait();
-
-  // tile pair tp -> (pair of N tiles np, M tile); this CTA takes N tile 2 np + rank
-  auto decode = [&](int tp, int& n0, int& z, int64_t& m0, int& tb, int& oy0, int& ox0) {
-    n0 = (2 * (tp % n_pairs) + (int)crank) * BN;
-    m0 = (int64_t)(tp / n_pairs) * BLOCK_M;
-    z = 0; tb = 0; oy0 = 0; ox0 = 0;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t g = 0;
-      for (int tp = cluster_id; tp < total_pairs; tp += n_clusters) {
-        int n0, z, tb, oy0, ox0;
-        int64_t m0;
-        decode(tp, n0, z, m0, tb, oy0, ox0);
-        for (int ks = 0; ks < num_k; ++ks, ++g) {
-          const int s = g % STAGES;
-          const uint32_t ph = (g / STAGES) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);   // both CTAs have consumed the previous use of this stage
-          const uint32_t st = base + s * STAGE_BYTES;
-          mbar_expect_tx(full_bar(s), (uint32_t)STAGE_BYTES);  // own W planes + own A plane + the peer's A plane
-          if (crank == 0)
-            tma_load_2d_mc(&tmA_hi, full_bar(s), st, ks * BLOCK_K, (int)m0, (uint16_t)3);
-          else
-            tma_load_2d_mc(&tmA_lo, full_bar(s), st + TILE_BYTES, ks * BLOCK_K, (int)m0, (uint16_t)3);
-          tma_load_2d(&tmW_hi, full_bar(s), st + 2 * TILE_BYTES, ks * BLOCK_K, n0);
-          tma_load_2d(&tmW_lo, full_bar(s), st + 2 * TILE_BYTES + W_BYTES, ks * BLOCK_K, n0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t g = 0;
-      int i = 0;
-      for (int tp = cluster_id; tp < total_pairs; tp += n_clusters, ++i) {
-        const int slot = i & 1;
-        mbar_wait(tempty_bar(slot), (((uint32_t)i >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(slot * 2 * BN), d1 = d0 + BN;
-        for (int ks = 0; ks < num_k; ++ks, ++g) {
-          const int s = g % STAGES;
-          const uint32_t ph = (g / STAGES) & 1u;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t st = base + s * STAGE_BYTES;
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t a_hi = umma_desc_sw128(st + k * 32);
-            const uint64_t a_lo = umma_desc_sw128(st + TILE_BYTES + k * 32);
-            const uint64_t w_hi = umma_desc_sw128(st + 2 * TILE_BYTES + k * 32);
-            const uint32_t acc = (ks | k) ? 1u : 0u;
-            tc_mma_f16(d0, a_hi, w_hi, IDESC2, acc);  // A_hi [W_hi | W_lo]
-            tc_mma_f16(d1, a_lo, w_hi, IDESC, 1u);    // + A_lo W_hi
-          }
-          tc_commit_mc(empty_bar(s), (uint16_t)3);    // arrives on the empty barrier of BOTH CTAs
-        }
-        tc_commit(tfull_bar(slot));
-      }
-    }
-  } else {
-    const int ew = warp - 2;
-    const int quarter = warp & 3, half = ew >> 2;
-    const int total_tiles = 0;
-    (void)total_tiles;
-      // GEMM mode: lane = output row.  Accumulator row -> registers -> scale/bias/GELU/residual -> 32-column chunks
-      // staged in swizzled shared memory -> TMA store (fp32 tile and/or fp16 hi/lo plane tiles).
-      uint8_t* stg_b = reinterpret_cast<uint8_t*>(staging) + ew * 4096;
-      const uint32_t stg_a = base + STAGES * STAGE_BYTES + ew * 4096;
-      const int row = quarter * 32 + lane;
-      int i = 0;
-      for (int t = cluster_id; t < total_pairs; t += n_clusters, ++i) {
-        const int slot = i & 1;
-        int n0, z, tb, oy0, ox0;
-        int64_t m0;
-        decode(t, n0, z, m0, tb, oy0, ox0);
-        const int nb0 = n0 + half * CW;
-        const int64_t m = m0 + row;
-        // Residual prefetch, issued before waiting for the accumulator.  COALESCED (this kernel only): a load instruction of
-        // the generic kernel has every lane on its own row (32 lines, 32 LSU wavefronts per instruction, 4096 per tile - the
-        // to_out launches wait on it: long_scoreboard 11.5 per issue in ncu).  Here 8 lanes read one row's 128 bytes, 4 rows
-        // per instruction: rres[cb*8 + it] = chunk cb, row it*4 + lane/8, columns 4*(lane%8)..+3; the chunk is transposed
-        // through the warp's staging slab right before it is added.
-        float4 rres[CW / 4];
-        const int rrow = lane >> 3, rc4 = lane & 7;
-        if (p.res) {
-#pragma unroll
-          for (int cb = 0; cb < NCH; ++cb) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int64_t mr = m0 + quarter * 32 + it * 4 + rrow;
-              const int nc = nb0 + cb * 32 + 4 * rc4;
-              rres[cb * 8 + it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (mr < p.M && nc < p.N) rres[cb * 8 + it] = *reinterpret_cast<const float4*>(p.res + mr * p.ldr + nc);
-            }
-          }
-        }
-        mbar_wait(tfull_bar(slot), ((uint32_t)i >> 1) & 1u);
-        tc_fence_after();
-        float v[CW];
-        {
-          const uint32_t tb_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 2 * BN + half * CW);
-          uint32_t r[32];
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            tmem_ld32(tb_addr + (uint32_t)(c * 32), r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[c * 32 + j] = __uint_as_float(r[j]);
-            tmem_ld32(tb_addr + (uint32_t)(BN + c * 32), r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[c * 32 + j] += __uint_as_float(r[j]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(slot));  // TMEM slot free for the MMA of tile i+2
-
-#pragma unroll
-        for (int cb = 0; cb < NCH; ++cb) {
-          const int nb = nb0 + cb * 32;
-          if (nb >= p.N) break;  // warp-uniform
-          if (p.res) {  // residual chunk: coalesced registers -> swizzled slab -> each lane reads its own row below
-            if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the slab
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 4 + rrow;
-              *reinterpret_cast<float4*>(stg_b + r * 128 + ((rc4 ^ (r & 7)) << 4)) = rres[cb * 8 + it];
-            }
-            __syncwarp();
-          }
-          {
-            const float2 sc = make_float2(p.w_scale, p.w_scale);
-            float2* v2 = reinterpret_cast<float2*>(v + cb * 32);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {  // packed fp32 math (FFMA2): scale + bias, GELU, residual
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias && nb + 4 * q < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 4 * q));
-              float2 a0 = __ffma2_rn(v2[2 * q], sc, make_float2(b4.x, b4.y));
-              float2 a1 = __ffma2_rn(v2[2 * q + 1], sc, make_float2(b4.z, b4.w));
-              if (p.act == WXF_ACT_GELU_ERF) {
-                a0 = wxf_gelu_erf2(a0);
-                a1 = wxf_gelu_erf2(a1);
-              }
-              if (p.res) {
-                const float4 rr = *reinterpret_cast<const float4*>(stg_b + lane * 128 + ((q ^ (lane & 7)) << 4));  // own row
-                a0 = __fadd2_rn(a0, make_float2(rr.x, rr.y));
-                a1 = __fadd2_rn(a1, make_float2(rr.z, rr.w));
-              }
-              v2[2 * q] = a0;
-              v2[2 * q + 1] = a1;
-            }
-          }
-          if (p.out) {
-            if (lane == 0) bulk_wait_read0();  // previous TMA store has finished reading the staging buffer
-            __syncwarp();                      // (also: every lane has read its residual row out of the slab)
-#pragma unroll
-            for (int q = 0; q < 8; ++q)  // fp32 row of 128 B, SWIZZLE_128B: 16-byte chunk ^= row % 8
-              *reinterpret_cast<float4*>(stg_b + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                  make_float4(v[cb * 32 + 4 * q], v[cb * 32 + 4 * q + 1], v[cb * 32 + 4 * q + 2], v[cb * 32 + 4 * q + 3]);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmO, stg_a, nb, (int)(m0 + quarter * 32));
-              bulk_commit();
-            }
-          }
-          if (p.out_hi) {
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {  // fp16 rows of 64 B, SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
-              __align__(16) __half2 h8[4];
-              __align__(16) __half2 l8[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                wxf_split2_f16x2(v[cb * 32 + 8 * q + 2 * e], v[cb * 32 + 8 * q + 2 * e + 1], h8[e], l8[e]);
-              const int off = lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
-              *reinterpret_cast<uint4*>(stg_b + off) = *reinterpret_cast<const uint4*>(h8);
-              *reinterpret_cast<uint4*>(stg_b + 2048 + off) = *reinterpret_cast<const uint4*>(l8);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmO_hi, stg_a, nb, (int)(m0 + quarter * 32));
-              tma_store_2d(&tmO_lo, stg_a + 2048, nb, (int)(m0 + quarter * 32));
-              bulk_commit();
-            }
-          }
-        }
-      }
-      if (lane == 0) bulk_wait0();  // all stores of this warp have landed before the CTA exits
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or signal its barriers
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  }
-}
-
-// ---- host side: TMA descriptors -----------------------------------------------------------------------------
-
 template <int BN, int STAGES>
 constexpr int smem_bytes() {
   return STAGES * (2 * TILE_BYTES + 2 * BN * BLOCK_K * 2) + STG_BYTES + 8 * (2 * STAGES + 1) + 16 + 1024;
@@ -1475,24 +1188,6 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
-}
-
-bool concat_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WXF_TC_CONCAT");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-bool cluster_enabled() {  // WXF_GEMM_CLUSTER=1: K >= 512 GEMMs run on 2-CTA clusters with the A tile multicast (round-2 candidate)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WXF_GEMM_CLUSTER");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
 }
 
 bool resident_w_enabled() {  // WXF_GEMM_RESIDENT_W=1: K <= 128 GEMMs keep their weight tile in shared memory (round-2 candidate)
@@ -1601,13 +1296,12 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
   if ((rc = make_map_2d(&ta_hi, d->a_hi, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, BLOCK_M))) return rc;
   if ((rc = make_map_2d(&ta_lo, d->a_lo, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, BLOCK_M))) return rc;
   // a single ragged N tile loads only the weight rows that exist (rounded up to the MMA's N granularity of 16)
-  const bool plain_persistent = persistent && !resident_w_enabled() && !cluster_enabled();
+  const bool plain_persistent = persistent && !resident_w_enabled();
   const int w_rows = (plain_persistent && d->N < BN) ? ((d->N + 15) & ~15) : BN;
   if ((rc = make_map_2d(&tw_hi, d->w_hi, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K, (uint32_t)w_rows))) return rc;
   if ((rc = make_map_2d(&tw_lo, d->w_lo, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K, (uint32_t)w_rows))) return rc;
   TcParams p{};
   p.w_bytes = (uint32_t)(w_rows * BLOCK_K * 2);
-  p.concat = concat_enabled() ? 1 : 0;
   p.bias = d->bias;
   p.res = d->res ? d->res + d->r_off : nullptr;
   p.out = d->out ? d->out + d->c_off : nullptr;
@@ -1668,43 +1362,6 @@ extern "C" int wxf_gemm_f16x2_tc(const WxfGemmDesc* d, void* stream) {
         default: WXF_RW_LAUNCH(0)
       }
 #undef WXF_RW_LAUNCH
-    }
-    if (d->K >= 512 && (nt % 2) == 0 && cluster_enabled()) {
-      constexpr int SMEM = p_smem<CL_EW, CL_STAGES>();
-      static WxfPerDevice<bool> attr_set_pd;
-  bool& attr_set = attr_set_pd.get();  // function attributes are per device
-      if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_cluster2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        if (e != cudaSuccess) WXF_FAIL((int)e, "tc: cannot opt in to %d bytes of shared memory: %s", SMEM, cudaGetErrorString(e));
-        attr_set = true;
-      }
-      const int n_pairs = nt / 2;
-      const int64_t total_pairs = (int64_t)n_pairs * mt;
-      cudaLaunchConfig_t cfg = {};
-      cfg.blockDim = dim3(64 + 32 * CL_EW);
-      cfg.dynamicSmemBytes = SMEM;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      static WxfPerDevice<int> max_clusters_pd;
-      int& max_clusters = max_clusters_pd.get();
-      if (!max_clusters) {
-        cfg.gridDim = dim3(2 * (num_sms() / 2));
-        if (cudaOccupancyMaxActiveClusters(&max_clusters, tc_cluster2_kernel, &cfg) != cudaSuccess || max_clusters <= 0)
-          max_clusters = num_sms() / 2 - 2;  // conservative: GPCs with an odd number of free SMs strand one
-      }
-      const int64_t clusters = total_pairs < max_clusters ? total_pairs : max_clusters;
-      cfg.gridDim = dim3((unsigned)(2 * clusters));
-      cudaError_t e = cudaLaunchKernelEx(&cfg, tc_cluster2_kernel, ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, n_pairs,
-                                         (int)total_pairs);
-      if (e != cudaSuccess) WXF_FAIL((int)e, "tc_cluster2: %s", cudaGetErrorString(e));
-      WXF_CHECK_LAUNCH("tc_cluster2");
-      return 0;
     }
 #define WXF_P_LAUNCH(EW_, ST_, EPI_) \
   return launch_persistent<MODE_GEMM, EW_, ST_, EPI_>(ta_hi, ta_lo, tw_hi, tw_lo, to, to_hi, to_lo, p, nt, mt, 1, st)
@@ -1788,7 +1445,6 @@ extern "C" int wxf_conv_f16x2_tc(const WxfConvTcDesc* d, void* stream) {
 
   TcParams p{};
   p.w_bytes = (uint32_t)(w_rows * BLOCK_K * 2);
-  p.concat = concat_enabled() ? 1 : 0;
   p.bias = d->bias;
   p.res = d->res ? d->res + d->r_off : nullptr;
   p.out = d->out ? d->out + d->c_off : nullptr;
@@ -1854,7 +1510,6 @@ extern "C" int wxf_cross_embed_toeplitz_tc(const WxfToeplitzDesc* d, void* strea
   if ((rc = make_map_2d(&tw_hi, d->w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN))) return rc;
   if ((rc = make_map_2d(&tw_lo, d->w_lo, (uint64_t)N, (uint64_t)K, (uint64_t)K, BN))) return rc;
   TcParams p{};
-  p.concat = concat_enabled() ? 1 : 0;
   p.bias = d->bias;
   p.out = d->out + d->c_off;
   p.N = N;

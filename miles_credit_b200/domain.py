@@ -233,7 +233,6 @@ class DomainPlan(_Plan):
         self.comm = _Comm(rank, world, group) if not getattr(peer, "fake", False) else None
         self.tensor_cores = True
         self.attention_tc = True
-        self.ff_fused = False
         self.attn_simt_small = False
         self.toeplitz = True
         self.lay = lay = DomainLayout(geo, world)

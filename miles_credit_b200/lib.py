@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 15
+WXF_ABI_VERSION = 16
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -44,17 +44,6 @@ class WxfGemmDesc(Structure):
         ("N", c_int32), ("K", c_int32), ("lda", c_int32),
         ("ldc", c_int32), ("c_off", c_int32), ("ldr", c_int32), ("r_off", c_int32), ("ldh", c_int32),
         ("act", c_int32), ("w_scale_log2", c_int32),
-    ]
-
-
-class WxfFfDesc(Structure):
-    _fields_ = [
-        ("a_hi", c_void_p), ("a_lo", c_void_p), ("w1_hi", c_void_p), ("w1_lo", c_void_p), ("b1", c_void_p),
-        ("w2_hi", c_void_p), ("w2_lo", c_void_p), ("b2", c_void_p), ("res", c_void_p), ("out", c_void_p),
-        ("out_hi", c_void_p), ("out_lo", c_void_p),
-        ("M", c_int64),
-        ("d", c_int32), ("lda", c_int32), ("ldc", c_int32), ("ldr", c_int32), ("ldh", c_int32),
-        ("w1_scale_log2", c_int32), ("w2_scale_log2", c_int32),
     ]
 
 
@@ -96,7 +85,6 @@ _SIGNATURES = {
                                     c_void_p]),
     "wxf_conv_igemm_f32": (c_int, [POINTER(WxfConvDesc), c_void_p]),
     "wxf_gemm_f16x2_tc": (c_int, [POINTER(WxfGemmDesc), c_void_p]),
-    "wxf_ff_fused_f16x2_tc": (c_int, [POINTER(WxfFfDesc), c_void_p]),
     "wxf_conv_f16x2_tc": (c_int, [POINTER(WxfConvTcDesc), c_void_p]),
     "wxf_groupnorm_silu_f16x2": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                          c_int, c_int, c_int, c_int64, c_int, c_int, c_void_p]),

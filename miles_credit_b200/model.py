@@ -157,7 +157,6 @@ class _Plan:
         if noise is not None and not tensor_cores:
             raise NotImplementedError("the noise-injection variant runs on the tensor-core plan only")
         self.attention_tc = tensor_cores and os.environ.get("WXF_ATTN_TC", "1") != "0"
-        self.ff_fused = tensor_cores and os.environ.get("WXF_FF_FUSED", "0") == "1"
         self.attn_simt_small = tensor_cores and os.environ.get("WXF_ATTN_SIMT_SMALL", "0") == "1"
         f32 = dict(device=device, dtype=torch.float32)
         f16 = dict(device=device, dtype=torch.float16)
@@ -287,14 +286,6 @@ class _Plan:
                         self._gemm(ln_hi, ln_lo, att.out_tc, f"out_proj.s{s}", M=m, lda=d, out=xv, ldc=ld, res=xv, ldr=ld)
                     add(ops.layernorm_f16x2, (xv, ld, ln_hi, ln_lo, d, ff.ln_g, ff.ln_b, m, d), f"layernorm.s{s}", 0,
                         8.0 * m * d)
-                    if self.ff_fused and d == 128:
-                        # round-2 candidate (WXF_FF_FUSED=1): fc1 -> GELU -> fc2 -> + residual in one kernel, the hidden
-                        # activation never leaves the SM (csrc/wxf_ff_fused.cu)
-                        planes = dict(out_hi=xp_hi, out_lo=xp_lo, ldh=pld) if (last and out_planes is not None) else {}
-                        desc = ops.make_ff_desc(ln_hi, ln_lo, ff.fc1_tc, ff.fc2_tc, M=m, lda=d, out=xv, ldc=ld, res=xv, ldr=ld,
-                                                **planes)
-                        add(ops.ff_fused_f16x2_tc, (desc,), f"ff_fused.s{s}", 4.0 * m * d * 4 * d)
-                        continue
                     self._gemm(ln_hi, ln_lo, ff.fc1_tc, f"ff1.s{s}", M=m, lda=d, out_hi=hid_hi, out_lo=hid_lo, ldh=4 * d,
                                act=_lib.ACT_GELU)
                     if last and out_planes is not None:  # the stage output also feeds the next cross-embed / the decoder

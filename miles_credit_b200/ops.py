@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import lib as _lib
-from .lib import WxfConvDesc, WxfConvTcDesc, WxfFfDesc, WxfGemmDesc, WxfToeplitzDesc
+from .lib import WxfConvDesc, WxfConvTcDesc, WxfGemmDesc, WxfToeplitzDesc
 from .weights import ConvWeights
 
 LAUNCHES = 0
@@ -137,27 +137,6 @@ def gemm_f16x2_tc(desc: WxfGemmDesc):
     global LAUNCHES
     st = _lib.load().wxf_gemm_f16x2_tc(ctypes.byref(desc), _stream())
     _lib.check(st, "wxf_gemm_f16x2_tc")
-    LAUNCHES += 1
-
-
-def make_ff_desc(a_hi: torch.Tensor, a_lo: torch.Tensor, fc1, fc2, *, M: int, lda: int, out: Optional[torch.Tensor] = None,
-                 ldc: int = 0, res: Optional[torch.Tensor] = None, ldr: int = 0, out_hi: Optional[torch.Tensor] = None,
-                 out_lo: Optional[torch.Tensor] = None, ldh: int = 0) -> WxfFfDesc:
-    """Descriptor of one fused FeedForward launch (d = 128 stages); ``fc1`` / ``fc2`` are weights.GemmWeights."""
-    d = WxfFfDesc()
-    d.a_hi, d.a_lo = a_hi.data_ptr(), a_lo.data_ptr()
-    d.w1_hi, d.w1_lo, d.b1 = fc1.w_hi.data_ptr(), fc1.w_lo.data_ptr(), _ptr(fc1.bias)
-    d.w2_hi, d.w2_lo, d.b2 = fc2.w_hi.data_ptr(), fc2.w_lo.data_ptr(), _ptr(fc2.bias)
-    d.res, d.out, d.out_hi, d.out_lo = _ptr(res), _ptr(out), _ptr(out_hi), _ptr(out_lo)
-    d.M, d.d, d.lda, d.ldc, d.ldr, d.ldh = M, fc2.n, lda, ldc, ldr, ldh
-    d.w1_scale_log2, d.w2_scale_log2 = fc1.scale_log2, fc2.scale_log2
-    return d
-
-
-def ff_fused_f16x2_tc(desc: WxfFfDesc):
-    global LAUNCHES
-    st = _lib.load().wxf_ff_fused_f16x2_tc(ctypes.byref(desc), _stream())
-    _lib.check(st, "wxf_ff_fused_f16x2_tc")
     LAUNCHES += 1
 
 

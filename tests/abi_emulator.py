@@ -42,7 +42,7 @@ class EmulatedLib:
                     raise AssertionError(f"{what}: input {rn} [{r0:#x}, {r1:#x}) overlaps output {wn} [{w0:#x}, {w1:#x})")
 
     def wxf_abi_version(self):
-        return 15
+        return 16
 
     def wxf_last_error(self):
         return b"emulator"
@@ -181,33 +181,6 @@ class EmulatedLib:
             hi, lo = self._split(v)
             self._harr(d.out_hi, (M - 1) * d.ldh + N).as_strided((M, N), (d.ldh, 1)).copy_(hi)
             self._harr(d.out_lo, (M - 1) * d.ldh + N).as_strided((M, N), (d.ldh, 1)).copy_(lo)
-        return 0
-
-    def wxf_ff_fused_f16x2_tc(self, dref, stream):
-        """fc1 (+bias, exact-erf GELU) -> hidden as fp16 hi/lo planes -> fc2 (+bias, +residual): the arithmetic of two
-        wxf_gemm_f16x2_tc calls with the hidden planes in between."""
-        d = dref._obj
-        self.calls.append("ff_fused")
-        M, dd = d.M, d.d
-        assert dd == 128, "the fused kernel is built for d = 128"
-        hid = 4 * dd
-        a_hi = self._harr(d.a_hi, (M - 1) * d.lda + dd).as_strided((M, dd), (d.lda, 1)).double()
-        a_lo = self._harr(d.a_lo, (M - 1) * d.lda + dd).as_strided((M, dd), (d.lda, 1)).double()
-        w1_hi, w1_lo = self._harr(d.w1_hi, hid * dd).view(hid, dd).double(), self._harr(d.w1_lo, hid * dd).view(hid, dd).double()
-        h = (a_hi @ w1_lo.t() + a_lo @ w1_hi.t() + a_hi @ w1_hi.t()).float() * (2.0 ** -d.w1_scale_log2) + _t(_arr(d.b1, hid))
-        h = 0.5 * h * (1 + torch.erf(h * 0.7071067811865476))
-        h_hi, h_lo = self._split(h)
-        h_hi, h_lo = h_hi.double(), h_lo.double()
-        w2_hi, w2_lo = self._harr(d.w2_hi, dd * hid).view(dd, hid).double(), self._harr(d.w2_lo, dd * hid).view(dd, hid).double()
-        v = (h_hi @ w2_lo.t() + h_lo @ w2_hi.t() + h_hi @ w2_hi.t()).float() * (2.0 ** -d.w2_scale_log2) + _t(_arr(d.b2, dd))
-        if d.res:
-            v = v + _t(_arr(d.res, (M - 1) * d.ldr + dd)).as_strided((M, dd), (d.ldr, 1))
-        if d.out:
-            _t(_arr(d.out, (M - 1) * d.ldc + dd)).as_strided((M, dd), (d.ldc, 1)).copy_(v)
-        if d.out_hi:
-            hi, lo = self._split(v)
-            self._harr(d.out_hi, (M - 1) * d.ldh + dd).as_strided((M, dd), (d.ldh, 1)).copy_(hi)
-            self._harr(d.out_lo, (M - 1) * d.ldh + dd).as_strided((M, dd), (d.ldh, 1)).copy_(lo)
         return 0
 
     def wxf_conv_f16x2_tc(self, dref, stream):

@@ -136,65 +136,3 @@ def test_gemm_tc_rejects_bad_arguments():
     gw = gemm_weights(torch.ones(8, 12, device=DEV), None)
     with pytest.raises(RuntimeError):  # K not a multiple of 8
         ops.gemm_f16x2_tc(ops.make_gemm_desc(a, a, gw, M=8, lda=12, out=torch.zeros(8, 8, device=DEV), ldc=8))
-
-
-@pytest.mark.skipif(__import__("os").environ.get("WXF_FF_FUSED") != "1",
-                    reason="round-2 candidate: the fused FeedForward kernel has not run on hardware yet (set WXF_FF_FUSED=1)")
-@pytest.mark.parametrize("m", [128, 300, 5000, 148 * 128 * 2 + 77])
-def test_ff_fused_matches_two_gemms(m):
-    """wxf_ff_fused_f16x2_tc == fc1 GEMM (+GELU, planes) followed by fc2 GEMM (+residual), d = 128."""
-    from miles_credit_b200.weights import gemm_weights
-
-    torch.manual_seed(m)
-    d = 128
-    x = torch.randn(m, d)
-    w1, b1 = torch.randn(4 * d, d) / d ** 0.5, torch.randn(4 * d) * 0.1
-    w2, b2 = torch.randn(d, 4 * d) / (4 * d) ** 0.5, torch.randn(d) * 0.1
-    res = torch.randn(m, d)
-    ref = torch.nn.functional.gelu(x.double() @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double() + res.double()
-    a_hi = torch.empty(m, d, device=DEV, dtype=torch.float16)
-    a_lo = torch.empty_like(a_hi)
-    ops.split_f16x2(x.to(DEV), d, a_hi, a_lo, d, m, d)
-    fc1, fc2 = gemm_weights(w1.to(DEV), b1.to(DEV)), gemm_weights(w2.to(DEV), b2.to(DEV))
-    # fused
-    out = res.to(DEV).clone()
-    o_hi = torch.zeros(m, d, device=DEV, dtype=torch.float16)
-    o_lo = torch.zeros_like(o_hi)
-    ops.ff_fused_f16x2_tc(ops.make_ff_desc(a_hi, a_lo, fc1, fc2, M=m, lda=d, out=out, ldc=d, res=out, ldr=d, out_hi=o_hi,
-                                           out_lo=o_lo, ldh=d))
-    # two GEMM launches
-    hid_hi = torch.empty(m, 4 * d, device=DEV, dtype=torch.float16)
-    hid_lo = torch.empty_like(hid_hi)
-    ops.gemm_f16x2_tc(ops.make_gemm_desc(a_hi, a_lo, fc1, M=m, lda=d, out_hi=hid_hi, out_lo=hid_lo, ldh=4 * d, act=1))
-    out2 = res.to(DEV).clone()
-    ops.gemm_f16x2_tc(ops.make_gemm_desc(hid_hi, hid_lo, fc2, M=m, lda=4 * d, out=out2, ldc=d, res=out2, ldr=d))
-    torch.cuda.synchronize()
-    e_ref = float((out.cpu().double() - ref).abs().max() / ref.abs().max())
-    e_two = float((out - out2).abs().max() / out2.abs().max())
-    e_pl = float(((o_hi.float() + o_lo.float()) - out).abs().max() / out.abs().max())
-    print(f"ff_fused M={m}: vs fp64 {e_ref:.3e}, vs two GEMMs {e_two:.3e}, planes {e_pl:.3e}")
-    assert e_ref < 5e-6 and e_two < 2e-6 and e_pl < 2e-6
-
-
-@pytest.mark.skipif(__import__("os").environ.get("WXF_GEMM_CLUSTER") != "1",
-                    reason="round-2 candidate: the 2-CTA multicast GEMM has not run on hardware yet (set WXF_GEMM_CLUSTER=1)")
-@pytest.mark.parametrize("m,n,k", [(3000, 512, 512), (20000, 2048, 512), (700, 256, 2048), (129, 1536, 512)])
-def test_gemm_cluster_multicast(m, n, k):
-    """K >= 512 with an even number of N tiles takes tc_cluster2_kernel: fp32 + residual and plane outputs vs fp64."""
-    torch.manual_seed(m + n + k)
-    a = torch.randn(m, k)
-    w, b = torch.randn(n, k) / k**0.5, torch.randn(n) * 0.1
-    res = torch.randn(m, n)
-    ref = a.double() @ w.double().t() + b.double()
-    a_hi, a_lo = planes(a.to(DEV))
-    gw = gemm_weights(w.to(DEV), b.to(DEV))
-    out = res.to(DEV).clone()
-    ops.gemm_f16x2_tc(ops.make_gemm_desc(a_hi, a_lo, gw, M=m, lda=k, out=out, ldc=n, res=out, ldr=n))
-    o_hi = torch.zeros(m, n, device=DEV, dtype=torch.float16)
-    o_lo = torch.zeros_like(o_hi)
-    ops.gemm_f16x2_tc(ops.make_gemm_desc(a_hi, a_lo, gw, M=m, lda=k, out_hi=o_hi, out_lo=o_lo, ldh=n))
-    torch.cuda.synchronize()
-    e1 = float((out.cpu().double() - (ref + res.double())).abs().max() / ref.abs().max())
-    e2 = float(((o_hi.float() + o_lo.float()).cpu().double() - ref).abs().max() / ref.abs().max())
-    print(f"gemm cluster {m}x{n}x{k}: fp32+res {e1:.3e}, planes {e2:.3e}")
-    assert e1 < 8e-6 and e2 < 8e-6

@@ -149,26 +149,6 @@ def test_plan_edge_configurations_vs_oracle(emulated, variant):
     assert err < 2e-5, err
 
 
-def test_plan_with_fused_feedforward_vs_oracle(emulated, monkeypatch):
-    """WXF_FF_FUSED=1 (round-2 candidate): the d = 128 stage runs its FeedForwards through wxf_ff_fused_f16x2_tc."""
-    from miles_credit_b200.geometry import workload
-    from oracle import crossformer_oracle as oracle
-
-    monkeypatch.setenv("WXF_FF_FUSED", "1")
-    kw = dict(workload("unit"), output_only_channels=4)  # dims 32, 64, 128, 256: stage 2 has d = 128, depth 2
-    geo = build_geometry(**kw)
-    sd = synthetic_state_dict(geo, seed=14)
-    wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
-    plan = wmodel._Plan(geo, wts, 1, torch.device("cpu"), True)
-    x = synthetic_input(geo, batch=1, seed=14)
-    y = plan.run(x)
-    with torch.no_grad():
-        ref = oracle.forward(x, sd, geo)
-    assert float((y - ref).abs().max() / ref.abs().max()) < 2e-5
-    assert emulated.calls.count("ff_fused") == 2 * geo.depth[2]
-    assert emulated.calls.count("gemm_tc") == 8 * sum(geo.depth) - 2 * emulated.calls.count("ff_fused")
-
-
 def test_plan_with_simt_small_window_attention_vs_oracle(emulated, monkeypatch):
     """WXF_ATTN_SIMT_SMALL=1 (round-2 candidate): dilated groups of <= 8 tokens go through the CUDA-core attention kernel
     (fp32 qkv in, planes out); everything else stays on the tensor-core kernel."""
