@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define WXF_ABI_VERSION 16
+#define WXF_ABI_VERSION 17
 
 #define WXF_EINVAL (-1)      /* bad argument / unsupported geometry */
 #define WXF_EALIGN (-2)      /* pointer or stride not aligned as the kernel requires */
@@ -310,6 +310,71 @@ int wxf_dry_mass_sums(const float* q, int64_t q_bstride, int64_t q_lstride, cons
                       const float* area, const float* da, const float* db, int B, int L, int64_t p0, int64_t np, double* sums,
                       void* scratch, void* stream);
 int wxf_scale_planes(float* x, int64_t bstride, int64_t n, const float* ratio, int B, void* stream);
+
+/*
+ * GlobalWaterFixer (credit/postblock/conservation.py:179-236) and GlobalEnergyFixerUpDown (:239-376) on the hybrid-sigma grid
+ * with midpoint quantities.  Fields are channel views of NCHW tensors: a 3-D field x is addressed x[b*bs + l*ls + p], a 2-D
+ * field x[b*bs + p]; "pred" fields are the prediction (t1), "in" fields the last frame of the input state (t0); pixels
+ * p in [p0, p0 + np) (a latitude band of a decomposed forecast: the caller adds the bands' sums).  coef_a / coef_b: the L + 1
+ * interface coefficients.  The per-pixel terms are formed in fp32 in the reference's order, the area-weighted sums in fp64
+ * (deterministic two-level reduction).  scratch: wxf_budget_scratch_bytes(B), zeroed once.
+ *   wxf_water_budget_sums : sums[b] = ( sum area dTWC/dt, sum area evaporation flux, sum area precipitation flux );
+ *                           the caller forms ratio = (-TWC - E) / P and rescales precipitation with wxf_scale_planes.
+ *   wxf_energy_budget_sums: sums[b] = ( sum area R_T, sum area F_S, sum area TE(t0), sum area TE(t1) );
+ *                           ratio = (N (R_T - F_S) + TE0) / TE1.
+ *   wxf_energy_fix_temperature: T_pred <- (E_level(t1) * ratio[b] - E_qgk(t1)) / CP(t1), in place.
+ */
+typedef struct {
+  const float* q_pred;  int64_t q_pred_bs, q_pred_ls;
+  const float* sp_pred; int64_t sp_pred_bs;
+  const float* q_in;    int64_t q_in_bs, q_in_ls;
+  const float* sp_in;   int64_t sp_in_bs;
+  const float* precip;  int64_t precip_bs;
+  const float* evapor;  int64_t evapor_bs;
+  const float* area;
+  const float* coef_a;
+  const float* coef_b;
+  int64_t p0, np;
+  int32_t B, L;
+  float n_seconds;
+} WxfWaterDesc;
+
+typedef struct {
+  float* t_pred;                 /* 3-D prediction fields share pred3_bs / pred3_ls (channels of one NCHW tensor) */
+  const float* q_pred;
+  const float* u_pred;
+  const float* v_pred;
+  int64_t pred3_bs, pred3_ls;
+  const float* sp_pred;          /* 2-D prediction fields share pred2_bs */
+  const float* toa_up_solar;
+  const float* toa_up_olr;
+  const float* surf_down_solar;
+  const float* surf_up_solar;
+  const float* surf_down_lw;
+  const float* surf_up_lw;
+  const float* surf_sh;
+  const float* surf_lh;
+  int64_t pred2_bs;
+  const float* t_in;             /* 3-D input fields share in3_bs / in3_ls */
+  const float* q_in;
+  const float* u_in;
+  const float* v_in;
+  int64_t in3_bs, in3_ls;
+  const float* sp_in;       int64_t sp_in_bs;
+  const float* toa_down_in; int64_t toa_down_bs;
+  const float* gph_surf;         /* [pixels] surface geopotential */
+  const float* area;
+  const float* coef_a;
+  const float* coef_b;
+  int64_t p0, np;
+  int32_t B, L;
+  float n_seconds;
+} WxfEnergyDesc;
+
+int64_t wxf_budget_scratch_bytes(int B);
+int wxf_water_budget_sums(const WxfWaterDesc* desc, double* sums, void* scratch, void* stream);
+int wxf_energy_budget_sums(const WxfEnergyDesc* desc, double* sums, void* scratch, void* stream);
+int wxf_energy_fix_temperature(const WxfEnergyDesc* desc, const float* ratio, void* stream);
 
 /*
  * Autoregressive state update (update_x, credit/datasets/gen_2/channel_utils.py:253-291):

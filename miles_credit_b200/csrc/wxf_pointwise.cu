@@ -1117,6 +1117,190 @@ extern "C" int wxf_scale_planes(float* x, int64_t bstride, int64_t n, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
+// GlobalWaterFixer / GlobalEnergyFixerUpDown (credit/postblock/conservation.py:179-236, 239-376), hybrid-sigma grid with
+// midpoint quantities.  One thread per pixel walks the column of the input state (t0) and of the prediction (t1) and forms
+// the per-pixel budget terms exactly as the reference does in fp32 (pressure = a + b * sp at the L + 1 interfaces, thickness =
+// difference, integral = sum_l x_l * thickness_l); the area-weighted global sums are accumulated in fp64 per block and combined
+// by the last block in a fixed order (deterministic; the reference sums in fp32: tolerance, not bit equality).
+
+template <int NQ>
+__device__ __forceinline__ void budget_reduce(const double (&v)[NQ], double* __restrict__ partial, double* __restrict__ sums,
+                                              unsigned int* __restrict__ counter, int b) {
+  __shared__ double red[NQ][256];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) red[q][threadIdx.x] = v[q];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) partial[((int64_t)b * gridDim.x + blockIdx.x) * NQ + q] = red[q][0];
+    __threadfence();
+    last = atomicAdd(counter + b, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    double t[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) t[q] = 0.0;
+    for (unsigned int k = 0; k < gridDim.x; ++k) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) t[q] += partial[((int64_t)b * gridDim.x + k) * NQ + q];
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) sums[NQ * b + q] = t[q];
+    counter[b] = 0;
+  }
+}
+
+// thickness of layer l at surface pressure sp: (a[l+1] + b[l+1] sp) - (a[l] + b[l] sp), each interface rounded like torch does
+__device__ __forceinline__ float layer_dp(const float* __restrict__ ca, const float* __restrict__ cb, int l, float sp) {
+  const float lo = __fadd_rn(__ldg(ca + l), __fmul_rn(__ldg(cb + l), sp));
+  const float hi = __fadd_rn(__ldg(ca + l + 1), __fmul_rn(__ldg(cb + l + 1), sp));
+  return __fsub_rn(hi, lo);
+}
+
+constexpr float WXF_GRAVITY = 9.80665f, WXF_RHO_WATER = 1000.0f, WXF_CP_DRY = 1004.64f, WXF_CP_VAPOR = 1810.0f,
+                WXF_LH_WATER = 2.501e6f;
+
+// sums[b] = ( sum area dTWC/dt, sum area evaporation flux, sum area precipitation flux )
+__global__ void __launch_bounds__(256) water_budget_sums_kernel(const WxfWaterDesc d, double* __restrict__ partial,
+                                                                double* __restrict__ sums, unsigned int* __restrict__ counter) {
+  const int b = blockIdx.y;
+  double acc[3] = {0.0, 0.0, 0.0};
+  const float nsec = d.n_seconds;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.np; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = d.p0 + i;
+    const float sp1 = d.sp_pred[b * d.sp_pred_bs + p], sp0 = d.sp_in[b * d.sp_in_bs + p];
+    float w1 = 0.f, w0 = 0.f;
+    for (int l = 0; l < d.L; ++l) {
+      w1 = __fadd_rn(w1, __fmul_rn(d.q_pred[b * d.q_pred_bs + l * d.q_pred_ls + p], layer_dp(d.coef_a, d.coef_b, l, sp1)));
+      w0 = __fadd_rn(w0, __fmul_rn(d.q_in[b * d.q_in_bs + l * d.q_in_ls + p], layer_dp(d.coef_a, d.coef_b, l, sp0)));
+    }
+    const float twc1 = __fdiv_rn(w1, WXF_GRAVITY), twc0 = __fdiv_rn(w0, WXF_GRAVITY);
+    const float dtwc = __fdiv_rn(__fsub_rn(twc1, twc0), nsec);
+    const float ef = __fdiv_rn(__fmul_rn(d.evapor[b * d.evapor_bs + p], WXF_RHO_WATER), nsec);
+    const float pf = __fdiv_rn(__fmul_rn(d.precip[b * d.precip_bs + p], WXF_RHO_WATER), nsec);
+    const float ar = __ldg(d.area + p);
+    acc[0] += (double)__fmul_rn(dtwc, ar);
+    acc[1] += (double)__fmul_rn(ef, ar);
+    acc[2] += (double)__fmul_rn(pf, ar);
+  }
+  budget_reduce<3>(acc, partial, sums, counter, b);
+}
+
+__device__ __forceinline__ void energy_terms(float T, float q, float U, float V, float gph, float& cp, float& e_qgk) {
+  cp = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, q), WXF_CP_DRY), __fmul_rn(q, WXF_CP_VAPOR));
+  const float ken = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(U, U), __fmul_rn(V, V)));
+  e_qgk = __fadd_rn(__fadd_rn(__fmul_rn(WXF_LH_WATER, q), gph), ken);
+  (void)T;
+}
+
+// sums[b] = ( sum area R_T, sum area F_S, sum area TE(t0), sum area TE(t1) )
+__global__ void __launch_bounds__(256) energy_budget_sums_kernel(const WxfEnergyDesc d, double* __restrict__ partial,
+                                                                 double* __restrict__ sums, unsigned int* __restrict__ counter) {
+  const int b = blockIdx.y;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const float nsec = d.n_seconds;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.np; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = d.p0 + i;
+    const float sp1 = d.sp_pred[b * d.pred2_bs + p], sp0 = d.sp_in[b * d.sp_in_bs + p];
+    const float gph = __ldg(d.gph_surf + p);
+    float te1 = 0.f, te0 = 0.f;
+    for (int l = 0; l < d.L; ++l) {
+      const int64_t o1 = b * d.pred3_bs + l * d.pred3_ls + p, o0 = b * d.in3_bs + l * d.in3_ls + p;
+      float cp, eq;
+      energy_terms(0.f, d.q_pred[o1], d.u_pred[o1], d.v_pred[o1], gph, cp, eq);
+      te1 = __fadd_rn(te1, __fmul_rn(__fadd_rn(__fmul_rn(cp, d.t_pred[o1]), eq), layer_dp(d.coef_a, d.coef_b, l, sp1)));
+      energy_terms(0.f, d.q_in[o0], d.u_in[o0], d.v_in[o0], gph, cp, eq);
+      te0 = __fadd_rn(te0, __fmul_rn(__fadd_rn(__fmul_rn(cp, d.t_in[o0]), eq), layer_dp(d.coef_a, d.coef_b, l, sp0)));
+    }
+    te1 = __fdiv_rn(te1, WXF_GRAVITY);
+    te0 = __fdiv_rn(te0, WXF_GRAVITY);
+    const int64_t o2 = b * d.pred2_bs + p;
+    const float down = __fmul_rn(d.toa_down_in[b * d.toa_down_bs + p], nsec);
+    const float rt = __fdiv_rn(__fsub_rn(__fsub_rn(down, __fmul_rn(d.toa_up_solar[o2], nsec)), __fmul_rn(d.toa_up_olr[o2], nsec)), nsec);
+    float fs = __fsub_rn(d.surf_down_solar[o2], d.surf_up_solar[o2]);
+    fs = __fadd_rn(fs, d.surf_down_lw[o2]);
+    fs = __fsub_rn(fs, d.surf_up_lw[o2]);
+    fs = __fadd_rn(fs, d.surf_sh[o2]);
+    fs = __fadd_rn(fs, d.surf_lh[o2]);
+    fs = __fdiv_rn(fs, nsec);
+    const float ar = __ldg(d.area + p);
+    acc[0] += (double)__fmul_rn(rt, ar);
+    acc[1] += (double)__fmul_rn(fs, ar);
+    acc[2] += (double)__fmul_rn(te0, ar);
+    acc[3] += (double)__fmul_rn(te1, ar);
+  }
+  budget_reduce<4>(acc, partial, sums, counter, b);
+}
+
+// T_pred <- (E_level(t1) * ratio - E_qgk(t1)) / CP(t1), in place (conservation.py:368-372)
+__global__ void __launch_bounds__(256) energy_fix_temperature_kernel(const WxfEnergyDesc d, const float* __restrict__ ratio) {
+  const int b = blockIdx.y;
+  const float r = __ldg(ratio + b);
+  const int64_t n = (int64_t)d.L * d.np;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int l = (int)(i / d.np);
+    const int64_t p = d.p0 + (i - (int64_t)l * d.np);
+    const int64_t o1 = b * d.pred3_bs + l * d.pred3_ls + p;
+    float cp, eq;
+    energy_terms(0.f, d.q_pred[o1], d.u_pred[o1], d.v_pred[o1], __ldg(d.gph_surf + p), cp, eq);
+    const float e = __fadd_rn(__fmul_rn(cp, d.t_pred[o1]), eq);
+    d.t_pred[o1] = __fdiv_rn(__fsub_rn(__fmul_rn(e, r), eq), cp);
+  }
+}
+
+extern "C" int64_t wxf_budget_scratch_bytes(int B) { return (int64_t)B * 296 * 4 * 8 + (int64_t)B * 4 + 64; }
+
+extern "C" int wxf_water_budget_sums(const WxfWaterDesc* d, double* sums, void* scratch, void* stream) {
+  if (!d || !sums || !scratch) WXF_FAIL(WXF_EINVAL, "water_budget_sums: null argument");
+  if (!d->q_pred || !d->sp_pred || !d->q_in || !d->sp_in || !d->precip || !d->evapor || !d->area || !d->coef_a || !d->coef_b ||
+      d->B <= 0 || d->L <= 0 || d->p0 < 0 || d->np <= 0 || !(d->n_seconds > 0.f))
+    WXF_FAIL(WXF_EINVAL, "water_budget_sums: bad arguments");
+  double* partial = reinterpret_cast<double*>(scratch);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partial + (int64_t)d->B * 296 * 4);
+  int64_t blocks = (d->np + 255) / 256;
+  if (blocks > 296) blocks = 296;
+  water_budget_sums_kernel<<<dim3((unsigned)blocks, d->B), 256, 0, (cudaStream_t)stream>>>(*d, partial, sums, counter);
+  WXF_CHECK_LAUNCH("water_budget_sums");
+  return 0;
+}
+
+static int energy_desc_ok(const WxfEnergyDesc* d) {
+  return d && d->t_pred && d->q_pred && d->u_pred && d->v_pred && d->sp_pred && d->t_in && d->q_in && d->u_in && d->v_in &&
+         d->sp_in && d->gph_surf && d->toa_down_in && d->toa_up_solar && d->toa_up_olr && d->surf_down_solar &&
+         d->surf_up_solar && d->surf_down_lw && d->surf_up_lw && d->surf_sh && d->surf_lh && d->area && d->coef_a && d->coef_b &&
+         d->B > 0 && d->L > 0 && d->p0 >= 0 && d->np > 0 && d->n_seconds > 0.f;
+}
+
+extern "C" int wxf_energy_budget_sums(const WxfEnergyDesc* d, double* sums, void* scratch, void* stream) {
+  if (!energy_desc_ok(d) || !sums || !scratch) WXF_FAIL(WXF_EINVAL, "energy_budget_sums: bad arguments");
+  double* partial = reinterpret_cast<double*>(scratch);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partial + (int64_t)d->B * 296 * 4);
+  int64_t blocks = (d->np + 255) / 256;
+  if (blocks > 296) blocks = 296;
+  energy_budget_sums_kernel<<<dim3((unsigned)blocks, d->B), 256, 0, (cudaStream_t)stream>>>(*d, partial, sums, counter);
+  WXF_CHECK_LAUNCH("energy_budget_sums");
+  return 0;
+}
+
+extern "C" int wxf_energy_fix_temperature(const WxfEnergyDesc* d, const float* ratio, void* stream) {
+  if (!energy_desc_ok(d) || !ratio) WXF_FAIL(WXF_EINVAL, "energy_fix_temperature: bad arguments");
+  int64_t blocks = ((int64_t)d->L * d->np + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  energy_fix_temperature_kernel<<<dim3((unsigned)blocks, d->B), 256, 0, (cudaStream_t)stream>>>(*d, ratio);
+  WXF_CHECK_LAUNCH("energy_fix_temperature");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // rollout channel copy (update_x, datasets/gen_2/channel_utils.py:253-291)
 
 struct CopyGroups {

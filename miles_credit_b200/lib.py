@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "csrc", "libwxformer_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "wxformer_b200.h")
 
-WXF_ABI_VERSION = 16
+WXF_ABI_VERSION = 17
 
 PAD_EARTH, PAD_MIRROR = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -44,6 +44,40 @@ class WxfGemmDesc(Structure):
         ("N", c_int32), ("K", c_int32), ("lda", c_int32),
         ("ldc", c_int32), ("c_off", c_int32), ("ldr", c_int32), ("r_off", c_int32), ("ldh", c_int32),
         ("act", c_int32), ("w_scale_log2", c_int32),
+    ]
+
+
+class WxfWaterDesc(Structure):
+    _fields_ = [
+        ("q_pred", c_void_p), ("q_pred_bs", c_int64), ("q_pred_ls", c_int64),
+        ("sp_pred", c_void_p), ("sp_pred_bs", c_int64),
+        ("q_in", c_void_p), ("q_in_bs", c_int64), ("q_in_ls", c_int64),
+        ("sp_in", c_void_p), ("sp_in_bs", c_int64),
+        ("precip", c_void_p), ("precip_bs", c_int64),
+        ("evapor", c_void_p), ("evapor_bs", c_int64),
+        ("area", c_void_p), ("coef_a", c_void_p), ("coef_b", c_void_p),
+        ("p0", c_int64), ("np", c_int64),
+        ("B", c_int32), ("L", c_int32),
+        ("n_seconds", c_float),
+    ]
+
+
+class WxfEnergyDesc(Structure):
+    _fields_ = [
+        ("t_pred", c_void_p), ("q_pred", c_void_p), ("u_pred", c_void_p), ("v_pred", c_void_p),
+        ("pred3_bs", c_int64), ("pred3_ls", c_int64),
+        ("sp_pred", c_void_p), ("toa_up_solar", c_void_p), ("toa_up_olr", c_void_p), ("surf_down_solar", c_void_p),
+        ("surf_up_solar", c_void_p), ("surf_down_lw", c_void_p), ("surf_up_lw", c_void_p), ("surf_sh", c_void_p),
+        ("surf_lh", c_void_p),
+        ("pred2_bs", c_int64),
+        ("t_in", c_void_p), ("q_in", c_void_p), ("u_in", c_void_p), ("v_in", c_void_p),
+        ("in3_bs", c_int64), ("in3_ls", c_int64),
+        ("sp_in", c_void_p), ("sp_in_bs", c_int64),
+        ("toa_down_in", c_void_p), ("toa_down_bs", c_int64),
+        ("gph_surf", c_void_p), ("area", c_void_p), ("coef_a", c_void_p), ("coef_b", c_void_p),
+        ("p0", c_int64), ("np", c_int64),
+        ("B", c_int32), ("L", c_int32),
+        ("n_seconds", c_float),
     ]
 
 
@@ -128,6 +162,10 @@ _SIGNATURES = {
     "wxf_dry_mass_sums": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "wxf_scale_planes": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "wxf_budget_scratch_bytes": (c_int64, [c_int]),
+    "wxf_water_budget_sums": (c_int, [POINTER(WxfWaterDesc), c_void_p, c_void_p, c_void_p]),
+    "wxf_energy_budget_sums": (c_int, [POINTER(WxfEnergyDesc), c_void_p, c_void_p, c_void_p]),
+    "wxf_energy_fix_temperature": (c_int, [POINTER(WxfEnergyDesc), c_void_p, c_void_p]),
     "wxf_noise_coef": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_int, c_void_p]),
     "wxf_noise_inject": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
                                  c_int64, c_int, ctypes.c_uint64, c_void_p, c_int, c_void_p]),

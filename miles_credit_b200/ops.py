@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import lib as _lib
-from .lib import WxfConvDesc, WxfConvTcDesc, WxfGemmDesc, WxfToeplitzDesc
+from .lib import WxfConvDesc, WxfConvTcDesc, WxfEnergyDesc, WxfGemmDesc, WxfToeplitzDesc, WxfWaterDesc
 from .weights import ConvWeights
 
 LAUNCHES = 0
@@ -466,6 +466,97 @@ def dry_mass_sums(q: torch.Tensor, sp: torch.Tensor, area: torch.Tensor, da: tor
     _lib.check(st, "wxf_dry_mass_sums")
     LAUNCHES += 1
     return sums
+
+
+_BUDGET_SCRATCH = {}
+
+
+def _budget_scratch(device, B: int) -> torch.Tensor:
+    key = (device, B)
+    if key not in _BUDGET_SCRATCH:
+        _BUDGET_SCRATCH[key] = torch.zeros(int(_lib.load().wxf_budget_scratch_bytes(B)), device=device, dtype=torch.uint8)
+    return _BUDGET_SCRATCH[key]
+
+
+def _plane3(t: torch.Tensor, name: str):
+    """[B, L, H, W] view with contiguous planes -> (pointer, batch stride, level stride)."""
+    _req(t, name)
+    if t.dim() != 4 or t.stride(3) != 1 or t.stride(2) != t.shape[3]:
+        raise ValueError(f"{name}: needs a [B, L, H, W] view with contiguous [H, W] planes")
+    return t.data_ptr(), t.stride(0), t.stride(1)
+
+
+def _plane2(t: torch.Tensor, name: str):
+    """[B, H, W] view with contiguous planes -> (pointer, batch stride)."""
+    _req(t, name)
+    if t.dim() != 3 or t.stride(2) != 1 or t.stride(1) != t.shape[2]:
+        raise ValueError(f"{name}: needs a [B, H, W] view with contiguous [H, W] planes")
+    return t.data_ptr(), t.stride(0)
+
+
+def water_budget_sums(q_pred, sp_pred, q_in, sp_in, precip, evapor, area, coef_a, coef_b, n_seconds: float, rows=None):
+    """GlobalWaterFixer sums (conservation.py:208-231): fp64 [B, 3] = (sum area dTWC/dt, sum area E flux, sum area P flux)."""
+    global LAUNCHES
+    B, L, H, W = q_pred.shape
+    r0, nr = rows if rows is not None else (0, H)
+    d = WxfWaterDesc()
+    d.q_pred, d.q_pred_bs, d.q_pred_ls = _plane3(q_pred, "q_pred")
+    d.q_in, d.q_in_bs, d.q_in_ls = _plane3(q_in, "q_in")
+    d.sp_pred, d.sp_pred_bs = _plane2(sp_pred, "sp_pred")
+    d.sp_in, d.sp_in_bs = _plane2(sp_in, "sp_in")
+    d.precip, d.precip_bs = _plane2(precip, "precip")
+    d.evapor, d.evapor_bs = _plane2(evapor, "evapor")
+    d.area, d.coef_a, d.coef_b = area.data_ptr(), coef_a.data_ptr(), coef_b.data_ptr()
+    d.p0, d.np, d.B, d.L, d.n_seconds = r0 * W, nr * W, B, L, float(n_seconds)
+    sums = torch.empty((B, 3), device=q_pred.device, dtype=torch.float64)
+    st = _lib.load().wxf_water_budget_sums(ctypes.byref(d), sums.data_ptr(), _budget_scratch(q_pred.device, B).data_ptr(), _stream())
+    _lib.check(st, "wxf_water_budget_sums")
+    LAUNCHES += 1
+    return sums
+
+
+def make_energy_desc(pred3, pred2, in3, sp_in, toa_down_in, gph_surf, area, coef_a, coef_b, n_seconds: float, rows=None):
+    """pred3 = (T, q, U, V) prediction views [B, L, H, W] of ONE tensor (same strides), pred2 = (sp, toa_up_solar, toa_up_olr,
+    surf_down_solar, surf_up_solar, surf_down_lw, surf_up_lw, surf_sh, surf_lh) [B, H, W] views of one tensor, in3 = (T, q, U,
+    V) input views (same strides)."""
+    B, L, H, W = pred3[0].shape
+    r0, nr = rows if rows is not None else (0, H)
+    d = WxfEnergyDesc()
+    p3 = [_plane3(t, "pred3") for t in pred3]
+    i3 = [_plane3(t, "in3") for t in in3]
+    p2 = [_plane2(t, "pred2") for t in pred2]
+    if len({(a[1], a[2]) for a in p3}) != 1 or len({(a[1], a[2]) for a in i3}) != 1 or len({a[1] for a in p2}) != 1:
+        raise ValueError("energy fixer: the fields of a group must be channel views of one tensor (equal strides)")
+    d.t_pred, d.q_pred, d.u_pred, d.v_pred = (a[0] for a in p3)
+    d.pred3_bs, d.pred3_ls = p3[0][1], p3[0][2]
+    (d.sp_pred, d.toa_up_solar, d.toa_up_olr, d.surf_down_solar, d.surf_up_solar, d.surf_down_lw, d.surf_up_lw, d.surf_sh,
+     d.surf_lh) = (a[0] for a in p2)
+    d.pred2_bs = p2[0][1]
+    d.t_in, d.q_in, d.u_in, d.v_in = (a[0] for a in i3)
+    d.in3_bs, d.in3_ls = i3[0][1], i3[0][2]
+    d.sp_in, d.sp_in_bs = _plane2(sp_in, "sp_in")
+    d.toa_down_in, d.toa_down_bs = _plane2(toa_down_in, "toa_down_in")
+    d.gph_surf, d.area, d.coef_a, d.coef_b = gph_surf.data_ptr(), area.data_ptr(), coef_a.data_ptr(), coef_b.data_ptr()
+    d.p0, d.np, d.B, d.L, d.n_seconds = r0 * W, nr * W, B, L, float(n_seconds)
+    return d
+
+
+def energy_budget_sums(desc: WxfEnergyDesc, device) -> torch.Tensor:
+    """GlobalEnergyFixerUpDown sums (conservation.py:314-366): fp64 [B, 4] = (sum area R_T, sum area F_S, TE(t0), TE(t1))."""
+    global LAUNCHES
+    sums = torch.empty((desc.B, 4), device=device, dtype=torch.float64)
+    st = _lib.load().wxf_energy_budget_sums(ctypes.byref(desc), sums.data_ptr(), _budget_scratch(device, desc.B).data_ptr(), _stream())
+    _lib.check(st, "wxf_energy_budget_sums")
+    LAUNCHES += 1
+    return sums
+
+
+def energy_fix_temperature(desc: WxfEnergyDesc, ratio: torch.Tensor):
+    """T_pred <- (E_level(t1) * ratio - E_qgk(t1)) / CP(t1), in place (conservation.py:368-372)."""
+    global LAUNCHES
+    st = _lib.load().wxf_energy_fix_temperature(ctypes.byref(desc), ratio.data_ptr(), _stream())
+    _lib.check(st, "wxf_energy_fix_temperature")
+    LAUNCHES += 1
 
 
 def scale_planes(x: torch.Tensor, ratio: torch.Tensor):

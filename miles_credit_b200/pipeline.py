@@ -187,6 +187,57 @@ class GlobalMassFixerB200:
         return ratio
 
 
+class GlobalWaterFixerB200:
+    """``GlobalWaterFixer`` (credit/postblock/conservation.py:179-236), hybrid-sigma grid with midpoint quantities: the
+    column-water tendency plus evaporation must balance precipitation; precipitation is rescaled by
+    ratio = (-sum dTWC/dt - sum E) / sum P (area-weighted global sums, one kernel)."""
+
+    def __init__(self, area: torch.Tensor, coef_a: torch.Tensor, coef_b: torch.Tensor, lead_time_periods: int, device="cuda"):
+        f32 = dict(device=device, dtype=torch.float32)
+        self.area, self.coef_a, self.coef_b = (t.to(**f32).contiguous() for t in (area, coef_a, coef_b))
+        self.n_seconds = int(lead_time_periods) * 3600
+
+    def sums(self, q_pred, sp_pred, q_input, sp_input, precip, evapor, rows=None) -> torch.Tensor:
+        """fp64 [B, 3]; ``rows`` = (first, count) restricts the sums to a latitude band (a decomposed caller adds the bands)."""
+        return ops.water_budget_sums(q_pred, sp_pred, q_input, sp_input, precip, evapor, self.area, self.coef_a, self.coef_b,
+                                     self.n_seconds, rows)
+
+    def apply(self, q_pred, sp_pred, q_input, sp_input, precip, evapor):
+        """Rescales ``precip`` ([B, H, W] view of the prediction) in place; returns the ratio [B] (fp32 like the reference)."""
+        s = self.sums(q_pred, sp_pred, q_input, sp_input, precip, evapor).float()
+        twc, e, p = s[:, 0], s[:, 1], s[:, 2]
+        residual = -twc - e - p
+        ratio = ((p + residual) / p).contiguous()
+        ops.scale_planes(precip, ratio)
+        return ratio
+
+
+class GlobalEnergyFixerB200:
+    """``GlobalEnergyFixerUpDown`` (credit/postblock/conservation.py:239-376), hybrid-sigma grid with midpoint quantities: the
+    column total-energy tendency is forced to match the net TOA + surface fluxes, temperature carries the correction.  One
+    kernel forms the four global sums (R_T, F_S, TE(t0), TE(t1)), a second one rewrites T in place."""
+
+    def __init__(self, area, coef_a, coef_b, gph_surf, lead_time_periods: int, device="cuda"):
+        f32 = dict(device=device, dtype=torch.float32)
+        self.area, self.coef_a, self.coef_b, self.gph_surf = (t.to(**f32).contiguous() for t in (area, coef_a, coef_b, gph_surf))
+        self.n_seconds = int(lead_time_periods) * 3600
+
+    def describe(self, pred3, pred2, in3, sp_input, toa_down_input, rows=None):
+        return ops.make_energy_desc(pred3, pred2, in3, sp_input, toa_down_input, self.gph_surf, self.area, self.coef_a,
+                                    self.coef_b, self.n_seconds, rows)
+
+    def apply(self, pred3, pred2, in3, sp_input, toa_down_input):
+        """pred3 = (T, q, U, V), pred2 = (sp, toa_up_solar, toa_up_olr, surf_down_solar, surf_up_solar, surf_down_lw, surf_up_lw,
+        surf_sh, surf_lh) views of the prediction, in3 = (T, q, U, V) of the last input frame.  T is corrected in place;
+        returns the ratio [B]."""
+        desc = self.describe(pred3, pred2, in3, sp_input, toa_down_input)
+        s = ops.energy_budget_sums(desc, pred3[0].device).float()
+        r_t, f_s, te0, te1 = s[:, 0], s[:, 1], s[:, 2], s[:, 3]
+        ratio = ((self.n_seconds * (r_t - f_s) + te0) / te1).contiguous()
+        ops.energy_fix_temperature(desc, ratio)
+        return ratio
+
+
 class ForecastHandoff:
     """Device -> pinned-host hand-off of every step's prediction, double buffered on a copy stream so the D2H of step k
     overlaps the forward of step k + 1.  ``push(y)`` returns at once; ``pop()`` yields (step, host tensor) in order once that

@@ -42,7 +42,7 @@ class EmulatedLib:
                     raise AssertionError(f"{what}: input {rn} [{r0:#x}, {r1:#x}) overlaps output {wn} [{w0:#x}, {w1:#x})")
 
     def wxf_abi_version(self):
-        return 16
+        return 17
 
     def wxf_last_error(self):
         return b"emulator"
@@ -459,6 +459,94 @@ class EmulatedLib:
         ss = _t(_arr(src, B * src_C * plane)).view(B, src_C, plane)
         for g in range(n):
             dd[:, d0[g]: d0[g] + ln[g]] = ss[:, s0[g]: s0[g] + ln[g]]
+        return 0
+
+    # ---- global conservation fixers (documented semantics: fp32 per-pixel terms, fp64 area-weighted sums) --------------
+
+    @staticmethod
+    def _f3(ptr, bs, ls, B, L, p0, n):
+        a = _t(_arr(ptr, (B - 1) * bs + (L - 1) * ls + p0 + n))
+        return a.as_strided((B, L, n), (bs, ls, 1), p0)
+
+    @staticmethod
+    def _f2(ptr, bs, B, p0, n):
+        a = _t(_arr(ptr, (B - 1) * bs + p0 + n))
+        return a.as_strided((B, n), (bs, 1), p0)
+
+    @staticmethod
+    def _dp(ca, cb, sp):
+        pres = ca.view(1, -1, 1) + cb.view(1, -1, 1) * sp.unsqueeze(1)      # [B, L + 1, n]
+        return pres.diff(dim=1)
+
+    def wxf_budget_scratch_bytes(self, B):
+        return 64
+
+    def wxf_scale_planes(self, x, bstride, n, ratio, B, stream):
+        self.calls.append("scale_planes")
+        xs = self._f2(x, bstride, B, 0, n)
+        xs *= _t(_arr(ratio, B)).view(B, 1)
+        return 0
+
+    def wxf_water_budget_sums(self, dref, sums, scratch, stream):
+        self.calls.append("water_budget_sums")
+        d = dref._obj
+        B, L, p0, n = d.B, d.L, d.p0, d.np
+        ca, cb, area = _t(_arr(d.coef_a, L + 1)), _t(_arr(d.coef_b, L + 1)), _t(_arr(d.area, p0 + n))[p0:]
+        nsec = torch.tensor(d.n_seconds, dtype=torch.float32)
+
+        def twc(q, sp):
+            return (q * self._dp(ca, cb, sp)).sum(1) / 9.80665
+
+        sp1, sp0 = self._f2(d.sp_pred, d.sp_pred_bs, B, p0, n), self._f2(d.sp_in, d.sp_in_bs, B, p0, n)
+        dtwc = (twc(self._f3(d.q_pred, d.q_pred_bs, d.q_pred_ls, B, L, p0, n), sp1)
+                - twc(self._f3(d.q_in, d.q_in_bs, d.q_in_ls, B, L, p0, n), sp0)) / nsec
+        ef = self._f2(d.evapor, d.evapor_bs, B, p0, n) * 1000.0 / nsec
+        pf = self._f2(d.precip, d.precip_bs, B, p0, n) * 1000.0 / nsec
+        out = np.ctypeslib.as_array(ctypes.cast(sums, ctypes.POINTER(ctypes.c_double)), shape=(B, 3))
+        for k, t in enumerate((dtwc, ef, pf)):
+            out[:, k] = (t * area).double().sum(1).numpy()
+        return 0
+
+    def _energy_fields(self, d):
+        B, L, p0, n = d.B, d.L, d.p0, d.np
+        f3p = lambda ptr: self._f3(ptr, d.pred3_bs, d.pred3_ls, B, L, p0, n)  # noqa: E731
+        f3i = lambda ptr: self._f3(ptr, d.in3_bs, d.in3_ls, B, L, p0, n)  # noqa: E731
+        gph = _t(_arr(d.gph_surf, p0 + n))[p0:].view(1, 1, n)
+
+        def level_energy(T, q, U, V):
+            cp = (1 - q) * 1004.64 + q * 1810.0
+            e_qgk = 2.501e6 * q + gph + 0.5 * (U**2 + V**2)
+            return cp, e_qgk, cp * T + e_qgk
+
+        return f3p, f3i, level_energy
+
+    def wxf_energy_budget_sums(self, dref, sums, scratch, stream):
+        self.calls.append("energy_budget_sums")
+        d = dref._obj
+        B, L, p0, n = d.B, d.L, d.p0, d.np
+        f3p, f3i, level_energy = self._energy_fields(d)
+        f2p = lambda ptr: self._f2(ptr, d.pred2_bs, B, p0, n)  # noqa: E731
+        ca, cb, area = _t(_arr(d.coef_a, L + 1)), _t(_arr(d.coef_b, L + 1)), _t(_arr(d.area, p0 + n))[p0:]
+        nsec = torch.tensor(d.n_seconds, dtype=torch.float32)
+        e1 = level_energy(f3p(d.t_pred), f3p(d.q_pred), f3p(d.u_pred), f3p(d.v_pred))[2]
+        e0 = level_energy(f3i(d.t_in), f3i(d.q_in), f3i(d.u_in), f3i(d.v_in))[2]
+        te1 = (e1 * self._dp(ca, cb, f2p(d.sp_pred))).sum(1) / 9.80665
+        te0 = (e0 * self._dp(ca, cb, self._f2(d.sp_in, d.sp_in_bs, B, p0, n))).sum(1) / 9.80665
+        r_t = (self._f2(d.toa_down_in, d.toa_down_bs, B, p0, n) * nsec - f2p(d.toa_up_solar) * nsec - f2p(d.toa_up_olr) * nsec) / nsec
+        f_s = (f2p(d.surf_down_solar) - f2p(d.surf_up_solar) + f2p(d.surf_down_lw) - f2p(d.surf_up_lw) + f2p(d.surf_sh)
+               + f2p(d.surf_lh)) / nsec
+        out = np.ctypeslib.as_array(ctypes.cast(sums, ctypes.POINTER(ctypes.c_double)), shape=(B, 4))
+        for k, t in enumerate((r_t, f_s, te0, te1)):
+            out[:, k] = (t * area).double().sum(1).numpy()
+        return 0
+
+    def wxf_energy_fix_temperature(self, dref, ratio, stream):
+        self.calls.append("energy_fix_temperature")
+        d = dref._obj
+        f3p, _f3i, level_energy = self._energy_fields(d)
+        T = f3p(d.t_pred)
+        cp, e_qgk, e = level_energy(T, f3p(d.q_pred), f3p(d.u_pred), f3p(d.v_pred))
+        T.copy_((e * _t(_arr(ratio, d.B)).view(-1, 1, 1) - e_qgk) / cp)
         return 0
 
     # ---- FuXi entry points (documented semantics of include/wxformer_b200.h) ------------------------------------------

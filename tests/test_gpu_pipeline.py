@@ -182,3 +182,32 @@ def test_noise_generator_statistics():
     again = torch.empty_like(x)
     ops.noise_inject(x, C, again, C, None, None, 0, 0, coef, None, B, HW, C, 1234, step, 0)
     assert int(step.item()) == 1 and float((again * e).mean().abs()) < 5e-3
+
+
+def test_water_and_energy_fixers_vs_reference_classes(golden_dir):
+    """GlobalWaterFixer / GlobalEnergyFixerUpDown (credit/postblock/conservation.py:179-376) as two / three kernels on channel
+    views of the prediction, against the outputs of the UNMODIFIED reference classes (tests/golden/make_golden_fixers.py)."""
+    import os
+
+    from test_pipeline_cpu import _fixer_views
+
+    fx = torch.load(os.path.join(golden_dir, "fixers.pt"), weights_only=False)
+    _packed, pred3, pred2, in3, sp_in, solin = _fixer_views(fx, "cuda")
+    hours = fx["n_seconds"] // 3600
+    wf = pipeline.GlobalWaterFixerB200(fx["area"], fx["coef_a"], fx["coef_b"], hours)
+    ratio = wf.apply(pred3["Q"], pred2["SP"], in3["Q"], sp_in, pred2["tp"], pred2["evap"])
+    ref = fx["water_fixed_tp"][:, 0, 0]
+    err = float((pred2["tp"].cpu() - ref).abs().max() / ref.abs().max())
+    print("water fixer ratio", ratio.tolist(), "rel err vs the reference", err)
+    assert err < 5e-6
+    H = ref.shape[-2]
+    args = (pred3["Q"], pred2["SP"], in3["Q"], sp_in, pred2["tp"], pred2["evap"])
+    assert torch.allclose(wf.sums(*args), wf.sums(*args, rows=(0, 3)) + wf.sums(*args, rows=(3, H - 3)), rtol=1e-12)
+
+    ef = pipeline.GlobalEnergyFixerB200(fx["area"], fx["coef_a"], fx["coef_b"], fx["gph_surf"], hours)
+    p2 = [pred2[k] for k in ("SP", "toa_up_sw", "toa_up_lw", "sfc_dn_sw", "sfc_up_sw", "sfc_dn_lw", "sfc_up_lw", "sfc_sh", "sfc_lh")]
+    ratio = ef.apply([pred3[k] for k in ("T", "Q", "U", "V")], p2, [in3[k] for k in ("T", "Q", "U", "V")], sp_in, solin)
+    ref = fx["energy_fixed_T"][:, :, 0]
+    err = float((pred3["T"].cpu() - ref).abs().max() / ref.abs().max())
+    print("energy fixer ratio", ratio.tolist(), "rel err vs the reference", err)
+    assert err < 5e-6

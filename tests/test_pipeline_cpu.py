@@ -60,3 +60,49 @@ def test_fused_postblocks_tables_and_emulated_epilogue(fx, emulated):
     for k, ref in fx["scaled"].items():
         assert got[k].shape == ref.shape
         assert torch.equal(got[k], ref), k                                              # Reconstruct + y*std+mean + TracerFixer
+
+
+def _fixer_views(fx, dev):
+    """The prediction packed into ONE [B, C, 1, H, W] tensor (the model's output layout) and channel views of it; the input
+    state as one tensor per variable (the batch dict's layout), last frame."""
+    nm, y, xin = fx["names"], fx["y"], fx["x_physical"]
+    order3, order2 = ["T", "Q", "U", "V"], ["SP", "toa_up_sw", "toa_up_lw", "sfc_dn_sw", "sfc_up_sw", "sfc_dn_lw", "sfc_up_lw",
+                                             "sfc_sh", "sfc_lh", "tp", "evap"]
+    packed = torch.cat([y[nm[k]] for k in order3 + order2], dim=1).to(dev).contiguous()
+    L = y[nm["T"]].shape[1]
+    pred3 = {k: packed[:, i * L: (i + 1) * L, 0] for i, k in enumerate(order3)}
+    pred2 = {k: packed[:, 4 * L + i, 0] for i, k in enumerate(order2)}
+    in_all = torch.cat([xin[nm[k]] for k in order3], dim=1).to(dev).contiguous()      # [B, 4L, T, H, W]
+    in3 = {k: in_all[:, i * L: (i + 1) * L, -1] for i, k in enumerate(order3)}
+    sp_in = xin[nm["SP"]].to(dev)[:, 0, -1]
+    solin = xin[nm["SOLIN"]].to(dev)[:, 0, -1]
+    return packed, pred3, pred2, in3, sp_in, solin
+
+
+def test_water_and_energy_fixers_through_the_emulator(golden_dir, emulated, monkeypatch):
+    """GlobalWaterFixerB200 / GlobalEnergyFixerB200 (host logic + documented kernel semantics) vs the UNMODIFIED reference
+    classes GlobalWaterFixer / GlobalEnergyFixerUpDown (tests/golden/make_golden_fixers.py)."""
+    fx = torch.load(os.path.join(golden_dir, "fixers.pt"), weights_only=False)
+    _packed, pred3, pred2, in3, sp_in, solin = _fixer_views(fx, "cpu")
+    hours = fx["n_seconds"] // 3600
+    wf = pipeline.GlobalWaterFixerB200(fx["area"], fx["coef_a"], fx["coef_b"], hours, device="cpu")
+    ratio = wf.apply(pred3["Q"], pred2["SP"], in3["Q"], sp_in, pred2["tp"], pred2["evap"])
+    ref = fx["water_fixed_tp"][:, 0, 0]
+    err = float((pred2["tp"] - ref).abs().max() / ref.abs().max())
+    print("water fixer ratio", ratio.tolist(), "rel err", err)
+    assert err < 5e-6
+    # a latitude-band split of the sums adds up to the global sums (what a decomposed forecast all-reduces)
+    H = ref.shape[-2]
+    full = wf.sums(pred3["Q"], pred2["SP"], in3["Q"], sp_in, pred2["tp"], pred2["evap"])
+    parts = (wf.sums(pred3["Q"], pred2["SP"], in3["Q"], sp_in, pred2["tp"], pred2["evap"], rows=(0, 4))
+             + wf.sums(pred3["Q"], pred2["SP"], in3["Q"], sp_in, pred2["tp"], pred2["evap"], rows=(4, H - 4)))
+    assert torch.allclose(full, parts, rtol=1e-12)
+
+    ef = pipeline.GlobalEnergyFixerB200(fx["area"], fx["coef_a"], fx["coef_b"], fx["gph_surf"], hours, device="cpu")
+    p2 = [pred2[k] for k in ("SP", "toa_up_sw", "toa_up_lw", "sfc_dn_sw", "sfc_up_sw", "sfc_dn_lw", "sfc_up_lw", "sfc_sh", "sfc_lh")]
+    ratio = ef.apply([pred3[k] for k in ("T", "Q", "U", "V")], p2, [in3[k] for k in ("T", "Q", "U", "V")], sp_in, solin)
+    ref = fx["energy_fixed_T"][:, :, 0]
+    err = float((pred3["T"] - ref).abs().max() / ref.abs().max())
+    print("energy fixer ratio", ratio.tolist(), "rel err", err)
+    assert err < 5e-6
+    assert emulated.calls.count("energy_budget_sums") == 1 and emulated.calls.count("energy_fix_temperature") == 1
