@@ -505,7 +505,8 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO_hi,
                      const __grid_constant__ CUtensorMap tmO_lo, const __grid_constant__ TcParams p, const int n_tiles,
                      const int m_tiles, const int total_tiles) {
-  constexpr bool CONV = MODE == MODE_CONV;
+  constexpr bool TOEP = MODE == MODE_TOEP;                  // Toeplitz-lifted stage-0 cross-embed: conv staging, diagonal-sum epilogue
+  constexpr bool CONV = MODE == MODE_CONV || TOEP;
   constexpr int BN = P_BN, STAGE_BYTES = P_STAGE_BYTES, W_BYTES = P_BN * BLOCK_K * 2;
   constexpr int P_STG_BYTES = EW * 4096;   // one 4 KB (1024-byte aligned) staging buffer per epilogue warp
   constexpr int CW = 128 / (EW / 4);       // columns per epilogue warp: 64 (8 warps) or 32 (16 warps)
@@ -568,7 +569,7 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       tb = mt / per_img;
       const int rem = mt - tb * per_img;
       oy0 = (rem / p.tiles_x) * p.bh;
-      ox0 = (rem % p.tiles_x) * p.bw;
+      ox0 = (rem % p.tiles_x) * (TOEP ? p.step : p.bw);
     } else {
       m0 = (int64_t)mt * BLOCK_M;
     }
@@ -679,6 +680,70 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       gemm_epilogue_fast<EW, EPI>(p, tmO, tmO_hi, tmO_lo, tmem_base, tfull_bar(0), tempty_bar(0),
                                   reinterpret_cast<uint8_t*>(staging), base + STAGES * STAGE_BYTES, n_tiles, total_tiles, warp,
                                   lane);
+    } else if constexpr (TOEP) {
+      // ---- Toeplitz epilogue: out[ox0 + i, c] = bias[c] + sum_j P[i + j, j*ch + c] (P = the 128 x 128 accumulator tile).
+      // The diagonal sum crosses rows, i.e. TMEM lanes and warps: P goes through shared memory in four passes of ch/4
+      // channels (32 of the 128 columns each, [128][33] floats in the staging area), 256 threads sum and store.
+      static_assert(EW == 8, "written for 8 epilogue warps");
+      float* st = staging;
+      constexpr int SLD = 33;
+      const int row = quarter * 32 + lane;
+      const int tid = ew * 32 + lane;        // 0..255
+      const int di = tid & 127, dh = tid >> 7;
+      const int ch = p.ch, ch4 = p.ch >> 2, ch8 = p.ch >> 3, lg_ch = 31 - __clz(p.ch);
+      int i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        const int slot = i & 1;
+        int n0, z, tb, oy0, ox0;
+        int64_t m0;
+        decode(t, n0, z, m0, tb, oy0, ox0);
+        mbar_wait(tfull_bar(slot), ((uint32_t)i >> 1) & 1u);
+        tc_fence_after();
+        float v[64];
+        {
+          const uint32_t tb_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 2 * BN + half * 64);
+          uint32_t ra[32], rb[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld32_nowait(tb_addr + (uint32_t)(c * 32), ra);
+            tmem_ld32_nowait(tb_addr + (uint32_t)(BN + c * 32), rb);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[c * 32 + j] = (__uint_as_float(ra[j]) + __uint_as_float(rb[j])) * p.w_scale;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (elect_one()) mbar_arrive(tempty_bar(slot));  // TMEM slot free for the MMA of tile i+2
+        const int64_t pix = ((int64_t)tb * p.Ho + oy0) * p.Wo + ox0 + di;
+        const bool live = di < p.step && ox0 + di < p.Wo;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          // my 64 columns col = half*64 + e: tap j = col / ch, channel c = col % ch; pass q takes c in [q ch/4, (q+1) ch/4)
+#pragma unroll
+          for (int e = 0; e < 64; ++e) {
+            const int col = half * 64 + e;
+            const int j = col >> lg_ch, c = col & (ch - 1);  // ch is a power of two (N = J ch = 128)
+            const int cq = c - q * ch4;
+            if (cq >= 0 && cq < ch4) st[row * SLD + j * ch4 + cq] = v[e];
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (live) {
+            const int c0 = dh * ch8;  // this thread's channels of the pass: [c0, c0 + ch/8)
+            for (int cc = 0; cc < ch8; cc += 2) {
+              const int c = q * ch4 + c0 + cc;
+              float2 acc = p.bias ? __ldg(reinterpret_cast<const float2*>(p.bias + c)) : make_float2(0.f, 0.f);
+              for (int j = 0; j < p.J; ++j) {
+                const float* sp = st + (di + j) * SLD + j * ch4 + c0 + cc;
+                acc.x += sp[0];
+                acc.y += sp[1];
+              }
+              *reinterpret_cast<float2*>(p.out + pix * p.ldc + c) = acc;
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
     } else if constexpr (!CONV) {
       // GEMM mode: lane = output row.  Accumulator row -> registers -> scale/bias/GELU/residual -> 32-column chunks
       // staged in swizzled shared memory -> TMA store (fp32 tile and/or fp16 hi/lo plane tiles).
@@ -1228,6 +1293,15 @@ int ew16_max_k() {  // WXF_GEMM_EW16_MAXK: largest K that takes the <16 epilogue
   return v;
 }
 
+int toep_persistent_max_k() {  // WXF_TOEP_PERSISTENT_MAXK: largest K of a Toeplitz branch on the persistent kernel (0 = never)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXF_TOEP_PERSISTENT_MAXK");
+    v = e ? atoi(e) : 1024;
+  }
+  return v;
+}
+
 bool persistent_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -1534,5 +1608,12 @@ extern "C" int wxf_cross_embed_toeplitz_tc(const WxfToeplitzDesc* d, void* strea
   if (ntiles > 65535) WXF_FAIL(WXF_EINVAL, "toeplitz: too many tiles for one launch");
   dim3 grid(1, (unsigned)ntiles, 1);
   if (BN == 256) return launch<256, 2, MODE_TOEP>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
+  // the short-K branches (k = 4, 8: 8 / 16 K-steps per tile) spend most of a one-tile CTA's life outside the main loop
+  // (launch, TMEM allocation, pipeline fill, the diagonal-sum epilogue): they take the persistent kernel (tile loop, TMEM
+  // double buffering, epilogue of tile i under the MMAs of tile i+1).  One main accumulator there, so K <= 1024 only.
+  if (N == 128 && K <= toep_persistent_max_k() && persistent_enabled() && (d->ch & 15) == 0 && (d->ch & (d->ch - 1)) == 0) {
+    p.w_bytes = (uint32_t)(BN * BLOCK_K * 2);
+    return launch_persistent<MODE_TOEP, 8, 3>(ta_hi, ta_lo, tw_hi, tw_lo, ta_hi, ta_hi, ta_hi, p, 1, (int)ntiles, 1, st);
+  }
   return launch<128, 3, MODE_TOEP>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
 }

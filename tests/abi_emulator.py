@@ -31,6 +31,9 @@ class EmulatedLib:
 
     def __init__(self):
         self.calls = []
+        # precision study only (tools/precision_table.py): "alo" drops the A_lo W_hi pass (activations rounded to fp16),
+        # "wlo" drops the A_hi W_lo pass (weights rounded to fp16) of the GEMM entry point
+        self.drop = set()
 
     @staticmethod
     def _no_overlap(what, reads, writes):
@@ -167,7 +170,12 @@ class EmulatedLib:
         a_lo = self._harr(d.a_lo, (M - 1) * d.lda + K).as_strided((M, K), (d.lda, 1)).double()
         w_hi = self._harr(d.w_hi, N * K).view(N, K).double()
         w_lo = self._harr(d.w_lo, N * K).view(N, K).double()
-        acc = (a_hi @ w_lo.t() + a_lo @ w_hi.t() + a_hi @ w_hi.t()).float()
+        acc = a_hi @ w_hi.t()
+        if "wlo" not in self.drop:
+            acc = acc + a_hi @ w_lo.t()
+        if "alo" not in self.drop:
+            acc = acc + a_lo @ w_hi.t()
+        acc = acc.float()
         v = acc * (2.0 ** -d.w_scale_log2)
         if d.bias:
             v = v + _t(_arr(d.bias, N))
