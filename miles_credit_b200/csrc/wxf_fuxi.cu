@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(256) ln_residual_kernel(const float* __restric
 //   S[i][j] = <q_i/|q_i|, k_j/|k_j|> * scale[h] + bias[h][i][j] + (region(i) != region(j) ? -100 : 0)
 // Shared memory: q, k, v rows padded to dh + 4 floats (float4 loads of 32 different rows hit 32 different bank groups),
 // S padded to L + 1.
-constexpr int SW_THREADS = 256;
+constexpr int SW_THREADS = 512;  // 16 warps x 2 CTAs per SM (87 KB of shared memory each): the phases are latency-bound, more warps hide it
 constexpr int SW_R = 4;  // query rows per warp pass
 
-__global__ void __launch_bounds__(SW_THREADS) swin_attention_kernel(const float* __restrict__ qkv, int ldq,
+__global__ void __launch_bounds__(SW_THREADS, 2) swin_attention_kernel(const float* __restrict__ qkv, int ldq,
                                                                     const float* __restrict__ bias,
                                                                     const float* __restrict__ scale,
                                                                     __half* __restrict__ out_hi, __half* __restrict__ out_lo,
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(SW_THREADS) swin_attention_kernel(const float*
   float* S = vs + L * DS;
   int* rid = reinterpret_cast<int*>(S + L * LS);
   int64_t* pix = reinterpret_cast<int64_t*>(rid + ((L + 1) & ~1));
+  float* inv_n = reinterpret_cast<float*>(pix + L);  // 1 / max(|q_i|, eps) for i < L, then 1 / max(|k_j|, eps)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SW_THREADS >> 5;
   const int head = blockIdx.y;
@@ -149,13 +150,17 @@ __global__ void __launch_bounds__(SW_THREADS) swin_attention_kernel(const float*
     *reinterpret_cast<float4*>(vs + t * DS + 4 * c4) = *reinterpret_cast<const float4*>(src + 2 * d);
   }
   __syncthreads();
-  // F.normalize(q, dim=-1), F.normalize(k, dim=-1): x / max(|x|_2, 1e-12)
+  // F.normalize(q, dim=-1), F.normalize(k, dim=-1): x / max(|x|_2, 1e-12).  The rows stay as loaded; the two reciprocal norms
+  // scale the dot product instead (one multiply per score instead of a read-modify-write of both operand tiles).
   for (int r = warp; r < 2 * L; r += nwarps) {
-    float* row = (r < L ? qs + r * DS : ks + (r - L) * DS);
+    const float* row = (r < L ? qs + r * DS : ks + (r - L) * DS);
     float ss = 0.f;
-    for (int c = lane; c < dh; c += 32) ss += row[c] * row[c];
-    const float inv = 1.0f / fmaxf(sqrtf(wxf_warp_sum(ss)), 1e-12f);
-    for (int c = lane; c < dh; c += 32) row[c] *= inv;
+    for (int c4 = lane; c4 < dh4; c4 += 32) {
+      const float4 t = *reinterpret_cast<const float4*>(row + 4 * c4);
+      ss += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+    }
+    ss = wxf_warp_sum(ss);
+    if (lane == 0) inv_n[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
   }
   __syncthreads();
   const float sc = __ldg(scale + head);
@@ -183,8 +188,9 @@ __global__ void __launch_bounds__(SW_THREADS) swin_attention_kernel(const float*
     for (int r = 0; r < SW_R; ++r) {
       const int i = i0 + r;
       if (i >= L) break;
-      if (j0 < L) S[i * LS + j0] = acc[r][0] * sc + __ldg(bh + i * L + j0) + (rid[i] != rid[j0] ? -100.f : 0.f);
-      if (j1 < L) S[i * LS + j1] = acc[r][1] * sc + __ldg(bh + i * L + j1) + (rid[i] != rid[j1] ? -100.f : 0.f);
+      const float qi = inv_n[i] * sc;
+      if (j0 < L) S[i * LS + j0] = acc[r][0] * (qi * inv_n[L + j0]) + __ldg(bh + i * L + j0) + (rid[i] != rid[j0] ? -100.f : 0.f);
+      if (j1 < L) S[i * LS + j1] = acc[r][1] * (qi * inv_n[L + j1]) + __ldg(bh + i * L + j1) + (rid[i] != rid[j1] ? -100.f : 0.f);
     }
   }
   __syncthreads();
@@ -410,7 +416,7 @@ extern "C" int wxf_swin_window_attention(const float* qkv, int ldq, const float*
   if (shift_h < 0 || shift_w < 0 || shift_h >= ws_h || shift_w >= ws_w) WXF_FAIL(WXF_EINVAL, "swin_attention: bad shift");
   if (mask_shift_h < 0) mask_shift_h = shift_h;
   if (mask_shift_h >= ws_h) WXF_FAIL(WXF_EINVAL, "swin_attention: bad mask shift");
-  const size_t smem = (size_t)(3 * L * (dh + 4) + L * (L + 1)) * 4 + (size_t)((L + 1) & ~1) * 4 + (size_t)L * 8;
+  const size_t smem = (size_t)(3 * L * (dh + 4) + L * (L + 1)) * 4 + (size_t)((L + 1) & ~1) * 4 + (size_t)L * 8 + (size_t)2 * L * 4;
   if (smem > 227 * 1024) WXF_FAIL(WXF_EUNSUPPORTED, "swin_attention: window %d x head dim %d needs %zu bytes of shared memory", L, dh, smem);
   static WxfPerDevice<size_t> attr_pd;
   size_t& have = attr_pd.get();  // function attributes are per device
