@@ -532,8 +532,13 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "grid": f"{geo.image_height}x{geo.image_width}", "batch": 1,
                        "parallelism": "single GPU" if world == 1 else
-                       (f"one forecast decomposed over {world} GPUs (lat bands + attention units, NCCL all-to-all + halo "
-                        "rows; the state stays sharded between steps)" if domain
+                       (f"one forecast decomposed over {world} GPUs ("
+                        + ("latitude bands of whole Swin window rows, 3-row q/k/v exchanges for shifted blocks"
+                           if arm.variant == "fuxi" else "lat bands + attention units, band <-> unit re-layouts")
+                        + ", halo rows and GroupNorm sums as "
+                        + ("NVLink peer-memory puts with arrival counters" if os.environ.get("WXF_DOMAIN_COMM", "peer") == "peer"
+                           else "NCCL point-to-point / all-to-all / all-reduce")
+                        + "; the state stays sharded between steps)" if domain
                         else f"{world} independent forecasts (replicas)"),
                        "l2": "no flush needed: one step streams >3 GB of activations through a 126 MB L2",
                        "flops_per_step": fl["total"], "finite": finite, "launch": graph_note},
