@@ -95,9 +95,48 @@ class GlooPeer:
             self._pending.append((dist.isend(hdr, r), hdr))
             self._pending.append((dist.isend(payload, r), payload))
 
+    def scatter_rows(self, src, ld_src, src_idx, dst_rank, dst_idx, dst_off, ld_dst, n, d, site):
+        """Row i: src[src_idx[i]] -> rank dst_rank[i]'s buffer at dst_off, row dst_idx[i]; then counter site[me] of every rank += 1."""
+        self.puts += 1
+        rows = src.reshape(-1).as_strided((int(src_idx.max()) + 1 if n else 0, d), (ld_src, 1))
+        soff = site + 4 * self.rank
+        for r in range(self.world):
+            m = dst_rank == r
+            di = dst_idx[m].long()
+            vals = rows[src_idx[m].long()].contiguous()
+            if r == self.rank:
+                if di.numel():
+                    n_dst = int(di.max()) + 1
+                    dst = torch.from_numpy(self.arena.buf[dst_off: dst_off + ((n_dst - 1) * ld_dst + d) * 4].view(np.float32))
+                    dst.as_strided((n_dst, d), (ld_dst, 1))[di] = vals
+                self._arrived[soff] = self._arrived.get(soff, 0) + 1
+                continue
+            hdr = torch.zeros(20, dtype=torch.int64)
+            hdr[0], hdr[1], hdr[2] = self.rank, soff, -1                   # kind -1: indexed rows
+            hdr[3], hdr[4], hdr[5], hdr[6] = di.numel(), dst_off, ld_dst, d
+            idx = di.clone() if di.numel() else torch.zeros(1, dtype=torch.int64)
+            payload = vals.reshape(-1).clone() if di.numel() else torch.zeros(1)
+            for t in (hdr, idx, payload):
+                self._pending.append((dist.isend(t, r), t))
+
+    def _receive_rows(self, hdr, sender):
+        cnt, dst_off, ld_dst, d = (int(v) for v in hdr[3:7])
+        idx = torch.zeros(max(cnt, 1), dtype=torch.int64)
+        dist.recv(idx, src=sender)
+        payload = torch.zeros(max(cnt * d, 1))
+        dist.recv(payload, src=sender)
+        if cnt:
+            n_dst = int(idx.max()) + 1
+            dst = torch.from_numpy(self.arena.buf[dst_off: dst_off + ((n_dst - 1) * ld_dst + d) * 4].view(np.float32))
+            dst.as_strided((n_dst, d), (ld_dst, 1))[idx] = payload.view(cnt, d)
+        soff = int(hdr[1])
+        self._arrived[soff] = self._arrived.get(soff, 0) + 1
+
     def _receive_one(self):
         hdr = torch.zeros(20, dtype=torch.int64)
         sender = dist.recv(hdr)                      # from any source
+        if int(hdr[2]) < 0:
+            return self._receive_rows(hdr, sender)
         n_parts = int(hdr[2])
         total = sum(int(hdr[4 + 2 * k]) for k in range(n_parts))
         payload = torch.zeros(max(total, 1), dtype=torch.uint8)

@@ -280,3 +280,69 @@ def test_peer_memory_plan_in_lockstep_matches_oracle(world, variant, monkeypatch
     print(variant, "world", world, "peer path rel-max vs the oracle", err)
     assert torch.isfinite(y).all() and err < 2e-5, err
     assert all(p.puts > 0 for p in peers)
+
+
+def _peer_gloo_worker(rank, world, port, out_dir, variant):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from abi_emulator import EmulatedLib
+    from gloo_peer import GlooPeer
+    from miles_credit_b200 import lib as wlib
+    from miles_credit_b200 import model as wmodel
+    from miles_credit_b200 import ops
+    from miles_credit_b200.domain import DomainPlan
+    from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
+    from miles_credit_b200.weights import prepare
+
+    torch.set_num_threads(2)
+    wlib._lib = EmulatedLib()
+    ops._stream = lambda: 0
+    ops._req = lambda *a, **k: None
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        kw = dict(workload("unit"), depth=[1, 1, 1, 1], output_only_channels=(8 if variant == "wxformer" else 4), variant=variant)
+        geo = build_geometry(**kw)
+        sd = synthetic_state_dict(geo, seed=41)
+        wts = prepare(sd, geo, wmodel._round_up(geo.input_channels, 4))
+        peer = GlooPeer(rank, world, 96 << 20)
+        plan = DomainPlan(geo, wts, rank, world, torch.device("cpu"), peer=peer)
+        x = synthetic_input(geo, batch=1, seed=41)
+        outs = []
+        for _ in range(2):                            # the second forward reuses buffers, sites and counters
+            plan._pad(x)
+            for step in plan.steps:
+                step[0](*step[1])
+            out = torch.full((1, *geo.out_shape), float("nan"))
+            plan._unpad(out)
+            outs.append(out)
+        peer.finish()
+        torch.save({"out": outs, "rows": plan.out_rows[rank], "puts": peer.puts}, os.path.join(out_dir, f"p{rank}.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,variant", [(2, "crossformer"), (3, "wxformer")])
+def test_peer_memory_plan_over_gloo_processes(tmp_path, world, variant):
+    """The peer-memory path of the WXFormer decomposition with one process per rank over gloo (tests/gloo_peer.py: puts and
+    indexed row scatters as messages, arrival counters, ranks running concurrently) vs the CPU oracle."""
+    from miles_credit_b200.synth import synthetic_input, synthetic_state_dict
+    from oracle import crossformer_oracle as oracle
+
+    mp.spawn(_peer_gloo_worker, args=(world, _free_port(), str(tmp_path), variant), nprocs=world, join=True)
+    kw = dict(workload("unit"), depth=[1, 1, 1, 1], output_only_channels=(8 if variant == "wxformer" else 4), variant=variant)
+    geo = build_geometry(**kw)
+    sd = synthetic_state_dict(geo, seed=41)
+    x = synthetic_input(geo, batch=1, seed=41)
+    with torch.no_grad():
+        ref = oracle.forward(x, sd, geo)
+    parts = [torch.load(os.path.join(tmp_path, f"p{r}.pt"), weights_only=False) for r in range(world)]
+    for k in range(2):
+        y = torch.full_like(ref, float("nan"))
+        for p in parts:
+            lo, hi = p["rows"]
+            y[..., lo:hi, :] = p["out"][k][..., lo:hi, :]
+        err = float((y - ref).abs().max() / ref.abs().max())
+        print(variant, "world", world, "forward", k, "rel-max vs the oracle", err)
+        assert torch.isfinite(y).all() and err < 2e-5, err
+    assert all(p["puts"] > 0 for p in parts)
