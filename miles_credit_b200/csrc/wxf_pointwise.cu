@@ -487,8 +487,10 @@ __global__ void __launch_bounds__(256) gn_partial_vec_kernel(const float* __rest
   int64_t p1 = p0 + ppb;
   if (p1 > HW) p1 = HW;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-  for (int64_t p = p0 + pl; p < p1; p += lanes) {
-    const float4 v = *reinterpret_cast<const float4*>(x + ((int64_t)b * HW + p) * ldx + 4 * tc);
+  const float* xb = x + (int64_t)b * HW * ldx + 4 * tc;
+#pragma unroll 4
+  for (int64_t p = p0 + pl; p < p1; p += lanes) {  // unrolled: four independent 16-byte loads in flight per thread
+    const float4 v = *reinterpret_cast<const float4*>(xb + p * ldx);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
   }
@@ -638,35 +640,45 @@ __global__ void __launch_bounds__(256) gn_silu_vec_kernel(const float* __restric
   __shared__ float smean[1024];
   for (int c = threadIdx.x; c < C; c += 256) smean[c] = stats[2 * (b * G + c / cpg)];
   __syncthreads();
+  // a thread keeps its float4 channel column and walks pixels (C <= 1024: C/4 <= 256 columns, 256 / (C/4) pixels per CTA
+  // pass), so there is no integer division per element; sigmoid = 1 / (1 + 2^(-x log2 e)) with the approximate ex2 / rcp
+  // units (2-3 ulp, far inside the decoder's error budget) instead of expf + an IEEE division
   const int C4 = C >> 2;
-  const int64_t total = HW * C4;
-  for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
-    const int64_t pl = idx / C4;
-    const int c = (int)(idx - pl * C4) * 4;
-    const int64_t pix = (int64_t)b * HW + pl;
-    const float4 v = *reinterpret_cast<const float4*>(x + pix * ldx + c);
+  const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4;
+  const int ppc = 256 / C4;                        // pixels per CTA pass; threads beyond ppc * C4 idle (C/4 not dividing 256)
+  auto act = [](float t) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * t));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return t * r;
+  };
+  if (prow < ppc) {
+    const int c = 4 * c4;
     const float4 a = *reinterpret_cast<const float4*>(sa + c), bb = *reinterpret_cast<const float4*>(sb + c);
     const float4 mm = *reinterpret_cast<const float4*>(smean + c);
-    float4 o;
-    o.x = wxf_silu((v.x - mm.x) * a.x + bb.x);
-    o.y = wxf_silu((v.y - mm.y) * a.y + bb.y);
-    o.z = wxf_silu((v.z - mm.z) * a.z + bb.z);
-    o.w = wxf_silu((v.w - mm.w) * a.w + bb.w);
-    if (res) {
-      const float4 r = *reinterpret_cast<const float4*>(res + pix * ldr + c);
-      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-    }
-    if constexpr (SPLIT) {
-      __align__(8) __half h4[4];
-      __align__(8) __half l4[4];
-      wxf_split_f16x2(o.x, h4[0], l4[0]);
-      wxf_split_f16x2(o.y, h4[1], l4[1]);
-      wxf_split_f16x2(o.z, h4[2], l4[2]);
-      wxf_split_f16x2(o.w, h4[3], l4[3]);
-      *reinterpret_cast<uint2*>(y_hi + pix * ldy + c) = *reinterpret_cast<const uint2*>(h4);
-      *reinterpret_cast<uint2*>(y_lo + pix * ldy + c) = *reinterpret_cast<const uint2*>(l4);
-    } else {
-      *reinterpret_cast<float4*>(y + pix * ldy + c) = o;
+#pragma unroll 2
+    for (int64_t pl = (int64_t)blockIdx.x * ppc + prow; pl < HW; pl += (int64_t)gridDim.x * ppc) {
+      const int64_t pix = (int64_t)b * HW + pl;
+      const float4 v = *reinterpret_cast<const float4*>(x + pix * ldx + c);
+      float4 o;
+      o.x = act((v.x - mm.x) * a.x + bb.x);
+      o.y = act((v.y - mm.y) * a.y + bb.y);
+      o.z = act((v.z - mm.z) * a.z + bb.z);
+      o.w = act((v.w - mm.w) * a.w + bb.w);
+      if (res) {
+        const float4 r = *reinterpret_cast<const float4*>(res + pix * ldr + c);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      if constexpr (SPLIT) {
+        __align__(8) __half2 h2[2];
+        __align__(8) __half2 l2[2];
+        wxf_split2_f16x2(o.x, o.y, h2[0], l2[0]);
+        wxf_split2_f16x2(o.z, o.w, h2[1], l2[1]);
+        *reinterpret_cast<uint2*>(y_hi + pix * ldy + c) = *reinterpret_cast<const uint2*>(h2);
+        *reinterpret_cast<uint2*>(y_lo + pix * ldy + c) = *reinterpret_cast<const uint2*>(l2);
+      } else {
+        *reinterpret_cast<float4*>(y + pix * ldy + c) = o;
+      }
     }
   }
 }
