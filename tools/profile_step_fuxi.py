@@ -18,6 +18,27 @@ x = F.synthetic_fuxi_input(geo, batch=1, seed=1000).cuda()
 for _ in range(2):
     model(x)
 torch.cuda.synchronize()
+# launch tags of one forward, in order, with the kernels each entry point enqueues (for tools/ncu_traffic.py)
+import json  # noqa: E402
+
+from miles_credit_b200 import ops  # noqa: E402
+
+plan = next(iter(model._plans.values()))
+tags = []
+n0 = ops.LAUNCHES
+plan._pad(x)
+tags.append(["pad", ops.LAUNCHES - n0])
+for fn, args, tag, _fl, _by in plan.steps:
+    n0 = ops.LAUNCHES
+    fn(*args)
+    tags.append([tag, ops.LAUNCHES - n0])
+out = torch.empty((1, *geo.out_shape), device="cuda")
+n0 = ops.LAUNCHES
+plan._unpad(out)
+tags.append(["unpad_resize", ops.LAUNCHES - n0])
+torch.cuda.synchronize()
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(tags, open(os.path.join(ROOT, "gpurun_out", "step_tags_fuxi.json"), "w"))
 torch.cuda.profiler.start()
 y = model(x)
 torch.cuda.synchronize()
