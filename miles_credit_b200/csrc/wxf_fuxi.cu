@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) swin_attention_kernel(const flo
   wxf_pdl_trigger();
   wxf_pdl_wait();
   extern __shared__ __align__(16) float smem[];
-  const int L = wsh * wsw, DS = dh + 4, LS = L + 1, dh4 = dh >> 2;
+  const int L = wsh * wsw, DS = dh + 4, LS = (L + 4) & ~3, dh4 = dh >> 2;  // LS % 4 == 0: float4 loads of P rows
   float* qs = smem;
   float* ks = qs + L * DS;
   float* vs = ks + L * DS;
@@ -167,22 +167,36 @@ __global__ void __launch_bounds__(SW_THREADS, 2) swin_attention_kernel(const flo
   const float* bh = bias + (size_t)head * L * L;
   // S = cos(q, k) * scale + bias + mask
   for (int i0 = warp * SW_R; i0 < L; i0 += nwarps * SW_R) {
-    float acc[SW_R][2];
+    // packed fp32 pipe (FFMA2): every accumulator is a pair (sum over even, sum over odd channel pairs), so the halves of the
+    // float4 loads are the operands as they sit in registers: 2 instructions per 4 multiply-adds
+    float2 acc2[SW_R][2];
 #pragma unroll
-    for (int r = 0; r < SW_R; ++r) acc[r][0] = acc[r][1] = 0.f;
+    for (int r = 0; r < SW_R; ++r) acc2[r][0] = acc2[r][1] = make_float2(0.f, 0.f);
     const int j0 = lane, j1 = lane + 32;
     const float* k0 = ks + (j0 < L ? j0 : 0) * DS;
     const float* k1 = ks + (j1 < L ? j1 : 0) * DS;
+    const float* qrow[SW_R];
+#pragma unroll
+    for (int r = 0; r < SW_R; ++r) qrow[r] = qs + ((i0 + r < L) ? i0 + r : L - 1) * DS;
+#pragma unroll 2
     for (int c4 = 0; c4 < dh4; ++c4) {
       const float4 a0 = *reinterpret_cast<const float4*>(k0 + 4 * c4);
       const float4 a1 = *reinterpret_cast<const float4*>(k1 + 4 * c4);
 #pragma unroll
       for (int r = 0; r < SW_R; ++r) {
-        const int i = (i0 + r < L) ? i0 + r : L - 1;
-        const float4 q4 = *reinterpret_cast<const float4*>(qs + i * DS + 4 * c4);
-        acc[r][0] = fmaf(q4.x, a0.x, fmaf(q4.y, a0.y, fmaf(q4.z, a0.z, fmaf(q4.w, a0.w, acc[r][0]))));
-        acc[r][1] = fmaf(q4.x, a1.x, fmaf(q4.y, a1.y, fmaf(q4.z, a1.z, fmaf(q4.w, a1.w, acc[r][1]))));
+        const float4 q4 = *reinterpret_cast<const float4*>(qrow[r] + 4 * c4);
+        const float2 qa = make_float2(q4.x, q4.y), qb = make_float2(q4.z, q4.w);
+        acc2[r][0] = __ffma2_rn(qa, make_float2(a0.x, a0.y), acc2[r][0]);
+        acc2[r][0] = __ffma2_rn(qb, make_float2(a0.z, a0.w), acc2[r][0]);
+        acc2[r][1] = __ffma2_rn(qa, make_float2(a1.x, a1.y), acc2[r][1]);
+        acc2[r][1] = __ffma2_rn(qb, make_float2(a1.z, a1.w), acc2[r][1]);
       }
+    }
+    float acc[SW_R][2];
+#pragma unroll
+    for (int r = 0; r < SW_R; ++r) {
+      acc[r][0] = acc2[r][0].x + acc2[r][0].y;
+      acc[r][1] = acc2[r][1].x + acc2[r][1].y;
     }
 #pragma unroll
     for (int r = 0; r < SW_R; ++r) {
@@ -210,20 +224,43 @@ __global__ void __launch_bounds__(SW_THREADS, 2) swin_attention_kernel(const flo
   // O = P V, written to the token's source pixel as fp16 hi/lo planes (A operand of the proj GEMM) or fp32
   for (int i0 = warp * SW_R; i0 < L; i0 += nwarps * SW_R) {
     for (int e4 = lane; e4 < dh4; e4 += 32) {
-      float4 o[SW_R];
+      // four keys per step: the probabilities of a row come as one float4 (broadcast load), the products run on the packed
+      // fp32 pipe with the probability as the scalar operand: 2 instructions per 4 multiply-adds
+      float2 oa[SW_R], ob[SW_R];
 #pragma unroll
-      for (int r = 0; r < SW_R; ++r) o[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int j = 0; j < L; ++j) {
-        const float4 v4 = *reinterpret_cast<const float4*>(vs + j * DS + 4 * e4);
+      for (int r = 0; r < SW_R; ++r) oa[r] = ob[r] = make_float2(0.f, 0.f);
+      const float* prow[SW_R];
+#pragma unroll
+      for (int r = 0; r < SW_R; ++r) prow[r] = S + ((i0 + r < L) ? i0 + r : L - 1) * LS;
+      const float* vcol = vs + 4 * e4;
+      int j = 0;
+      for (; j + 4 <= L; j += 4) {
+        float4 v4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v4[u] = *reinterpret_cast<const float4*>(vcol + (j + u) * DS);
 #pragma unroll
         for (int r = 0; r < SW_R; ++r) {
-          const float p = S[((i0 + r < L) ? i0 + r : L - 1) * LS + j];
-          o[r].x = fmaf(p, v4.x, o[r].x);
-          o[r].y = fmaf(p, v4.y, o[r].y);
-          o[r].z = fmaf(p, v4.z, o[r].z);
-          o[r].w = fmaf(p, v4.w, o[r].w);
+          const float4 p4 = *reinterpret_cast<const float4*>(prow[r] + j);
+          const float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            oa[r] = __ffma2_rn(make_float2(v4[u].x, v4[u].y), make_float2(pp[u], pp[u]), oa[r]);
+            ob[r] = __ffma2_rn(make_float2(v4[u].z, v4[u].w), make_float2(pp[u], pp[u]), ob[r]);
+          }
         }
       }
+      for (; j < L; ++j) {
+        const float4 v4 = *reinterpret_cast<const float4*>(vcol + j * DS);
+#pragma unroll
+        for (int r = 0; r < SW_R; ++r) {
+          const float p = prow[r][j];
+          oa[r] = __ffma2_rn(make_float2(v4.x, v4.y), make_float2(p, p), oa[r]);
+          ob[r] = __ffma2_rn(make_float2(v4.z, v4.w), make_float2(p, p), ob[r]);
+        }
+      }
+      float4 o[SW_R];
+#pragma unroll
+      for (int r = 0; r < SW_R; ++r) o[r] = make_float4(oa[r].x, oa[r].y, ob[r].x, ob[r].y);
 #pragma unroll
       for (int r = 0; r < SW_R; ++r) {
         const int i = i0 + r;
@@ -416,7 +453,7 @@ extern "C" int wxf_swin_window_attention(const float* qkv, int ldq, const float*
   if (shift_h < 0 || shift_w < 0 || shift_h >= ws_h || shift_w >= ws_w) WXF_FAIL(WXF_EINVAL, "swin_attention: bad shift");
   if (mask_shift_h < 0) mask_shift_h = shift_h;
   if (mask_shift_h >= ws_h) WXF_FAIL(WXF_EINVAL, "swin_attention: bad mask shift");
-  const size_t smem = (size_t)(3 * L * (dh + 4) + L * (L + 1)) * 4 + (size_t)((L + 1) & ~1) * 4 + (size_t)L * 8 + (size_t)2 * L * 4;
+  const size_t smem = (size_t)(3 * L * (dh + 4) + L * ((L + 4) & ~3)) * 4 + (size_t)((L + 1) & ~1) * 4 + (size_t)L * 8 + (size_t)2 * L * 4;
   if (smem > 227 * 1024) WXF_FAIL(WXF_EUNSUPPORTED, "swin_attention: window %d x head dim %d needs %zu bytes of shared memory", L, dh, smem);
   static WxfPerDevice<size_t> attr_pd;
   size_t& have = attr_pd.get();  // function attributes are per device
