@@ -183,7 +183,9 @@ def build_geometry(
         raise NotImplementedError("cube embedding (patch_height/patch_width > 1) is outside the hot path")
     if variant not in ("crossformer", "wxformer"):
         raise ValueError(f"unknown variant {variant!r}")
-    if upsample_v_conv:
+    if upsample_v_conv and variant == "crossformer":
+        # (the `wxformer` registry class has no such option: the key falls into its **kwargs and is ignored,
+        # wxformer/crossformer.py:636-653 - e.g. config/gen_2/smoke/smoke_gen2_multistep_casper.yml sets it)
         raise NotImplementedError("upsample_v_conv=True decoder is not built (no BASELINE config uses it)")
     if attention_type is not None:
         raise NotImplementedError("UpBlock attention_type is not built (None in every BASELINE config)")
