@@ -52,7 +52,8 @@ struct AttnParams {
   int H, W, d, heads, wsz, kind;
   float scale;
   int L, Lp, G, nh, nw;
-  int inter;          // 1: long windows packed interleaved (row = token*G + window), one TMA box per plane
+  int inter;          // long windows, one TMA box per plane: 1 = interleaved rows (row = token*G + window, odd L),
+                      // 2 = window-major rows (row = window*L + token, even L: a warp's 32 rows see 32 + L columns, not L*G)
   int gpr;            // interleaved: tiles (groups of G consecutive gw) per window row
   float scale2;       // scale * log2(e): softmax runs in base 2
   int64_t nwin, ntiles;
@@ -60,7 +61,7 @@ struct AttnParams {
 
 // Row r of a tile -> (window slot g, token i).  Window-major packing: rows [g*Lp, g*Lp + L); interleaved: r = i*G + g.
 __device__ __forceinline__ void row_slot(const AttnParams& p, int r, int& g, int& i) {
-  if (p.inter) {
+  if (p.inter == 1) {
     i = r / p.G;
     g = r - i * p.G;
   } else {
@@ -133,7 +134,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
     row_ok = g < p.G && i < p.L;
     ty = i / p.wsz;
     tx = i - ty * p.wsz;
-    const int col0 = p.inter ? 0 : g * p.Lp, col1 = p.inter ? p.L * p.G : col0 + p.L;
+    const int col0 = p.inter == 1 ? 0 : g * p.Lp, col1 = p.inter == 1 ? p.L * p.G : col0 + p.L;
     g_lo = __reduce_min_sync(0xffffffffu, row_ok ? (col0 >> 3) : 16);
     g_hi = __reduce_max_sync(0xffffffffu, row_ok ? ((col1 + 7) >> 3) : 0);
     if (g_hi <= g_lo) g_lo = g_hi = 0;
@@ -175,8 +176,13 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __gr
         for (int which = 0; which < 3; ++which) {
           const int c0 = which * p.d + head * DH;
           const uint32_t dst = base + (uint32_t)(which == 0 ? OFF_Q : (which == 1 ? OFF_K : OFF_V));
-          tma_load_5d(&tm_hi, bar_load, dst, c0, gw, 0, gh, b * p.wsz);
-          tma_load_5d(&tm_lo, bar_load, dst + QKV_PLANE, c0, gw, 0, gh, b * p.wsz);
+          if (p.inter == 2) {  // window-major map: dims (c, l2, (b, l1), gw, gh)
+            tma_load_5d(&tm_hi, bar_load, dst, c0, 0, b * p.wsz, gw, gh);
+            tma_load_5d(&tm_lo, bar_load, dst + QKV_PLANE, c0, 0, b * p.wsz, gw, gh);
+          } else {
+            tma_load_5d(&tm_hi, bar_load, dst, c0, gw, 0, gh, b * p.wsz);
+            tma_load_5d(&tm_lo, bar_load, dst + QKV_PLANE, c0, gw, 0, gh, b * p.wsz);
+          }
         }
       } else {
       mbar_expect_tx(bar_load, (uint32_t)(nv * 6 * p.L * 64));
@@ -548,8 +554,13 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
           for (int which = 0; which < 3; ++which) {
             const int c0 = which * p.d + head * DH;
             const uint32_t dst = buf + (uint32_t)(which == 0 ? A2_OFF_Q : (which == 1 ? A2_OFF_K : A2_OFF_V));
-            tma_load_5d(&tm_hi, full, dst, c0, gw, 0, gh, bi * p.wsz);
-            tma_load_5d(&tm_lo, full, dst + QKV_PLANE, c0, gw, 0, gh, bi * p.wsz);
+            if (p.inter == 2) {  // window-major map: dims (c, l2, (b, l1), gw, gh)
+              tma_load_5d(&tm_hi, full, dst, c0, 0, bi * p.wsz, gw, gh);
+              tma_load_5d(&tm_lo, full, dst + QKV_PLANE, c0, 0, bi * p.wsz, gw, gh);
+            } else {
+              tma_load_5d(&tm_hi, full, dst, c0, gw, 0, gh, bi * p.wsz);
+              tma_load_5d(&tm_lo, full, dst + QKV_PLANE, c0, gw, 0, gh, bi * p.wsz);
+            }
           }
         }
         __syncwarp();
@@ -656,7 +667,7 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
     // warp-uniform range of 8-column groups that hold a window column of any of the warp's rows
     int g_lo, g_hi;
     {
-      const int col0 = p.inter ? 0 : g * p.Lp, col1 = p.inter ? p.L * p.G : col0 + p.L;
+      const int col0 = p.inter == 1 ? 0 : g * p.Lp, col1 = p.inter == 1 ? p.L * p.G : col0 + p.L;
       g_lo = __reduce_min_sync(0xffffffffu, row_ok ? (col0 >> 3) : 16);
       g_hi = __reduce_max_sync(0xffffffffu, row_ok ? ((col1 + 7) >> 3) : 0);
       if (g_hi <= g_lo) g_lo = g_hi = 0;
@@ -837,7 +848,7 @@ void attn_packing(AttnParams& p, int wsz, int kind, int nw) {
   const int L = wsz * wsz;
   p.wsz = wsz; p.kind = kind; p.nw = nw;
   p.L = L; p.Lp = (L + 1) & ~1; p.G = ROWS / p.Lp;
-  p.inter = (kind == WXF_ATTN_LONG && ROWS / L >= 2) ? 1 : 0;
+  p.inter = (kind == WXF_ATTN_LONG && ROWS / L >= 2) ? ((L & 1) ? 1 : 2) : 0;
   p.gpr = 1;
   if (p.inter) {
     p.G = ROWS / L < nw ? ROWS / L : nw;
@@ -874,6 +885,8 @@ extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, i
     WXF_FAIL(WXF_EALIGN, "attention_tc: strides must be multiples of 8 and planes 16-byte aligned");
   const int nh = H / wsz, nw = W / wsz;
   const uint64_t ldb = (uint64_t)ldq * 2;
+  AttnParams p{};
+  attn_packing(p, wsz, kind, nw);
   CUtensorMap tm_hi, tm_lo;
   int rc;
   if (kind == WXF_ATTN_SHORT) {
@@ -882,17 +895,22 @@ extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, i
     const uint32_t box[4] = {(uint32_t)DH, (uint32_t)wsz, (uint32_t)wsz, 1}, es[4] = {1, 1, 1, 1};
     if ((rc = make_map(&tm_hi, qkv_hi, 4, dims, strides, box, es, 64))) return rc;
     if ((rc = make_map(&tm_lo, qkv_lo, 4, dims, strides, box, es, 64))) return rc;
+  } else if (p.inter == 2) {
+    // window-major rows (even L): pixel (y, x) = (l1*nh + gh, l2*nw + gw) viewed as dims (c, l2, (b, l1), gw, gh); the box
+    // {32 ch, wsz, wsz, G windows, 1} lands as row = window*L + l1*wsz + l2
+    const uint64_t dims[5] = {(uint64_t)3 * d, (uint64_t)wsz, (uint64_t)B * wsz, (uint64_t)nw, (uint64_t)nh};
+    const uint64_t strides[4] = {(uint64_t)nw * ldb, (uint64_t)nh * W * ldb, ldb, (uint64_t)W * ldb};
+    const uint32_t box[5] = {(uint32_t)DH, (uint32_t)wsz, (uint32_t)wsz, (uint32_t)p.G, 1}, es[5] = {1, 1, 1, 1, 1};
+    if ((rc = make_map(&tm_hi, qkv_hi, 5, dims, strides, box, es, 64))) return rc;
+    if ((rc = make_map(&tm_lo, qkv_lo, 5, dims, strides, box, es, 64))) return rc;
   } else {
     // pixel (y, x) = (l1*nh + gh, l2*nw + gw): dims (c, gw, l2, gh, (b, l1)); a group's tokens are one box
     const uint64_t dims[5] = {(uint64_t)3 * d, (uint64_t)nw, (uint64_t)wsz, (uint64_t)nh, (uint64_t)B * wsz};
     const uint64_t strides[4] = {ldb, (uint64_t)nw * ldb, (uint64_t)W * ldb, (uint64_t)nh * W * ldb};
-    const int Gw = (ROWS / L >= 2) ? (ROWS / L < nw ? ROWS / L : nw) : 1;
-    const uint32_t box[5] = {(uint32_t)DH, (uint32_t)Gw, (uint32_t)wsz, 1, (uint32_t)wsz}, es[5] = {1, 1, 1, 1, 1};
+    const uint32_t box[5] = {(uint32_t)DH, (uint32_t)(p.inter ? p.G : 1), (uint32_t)wsz, 1, (uint32_t)wsz}, es[5] = {1, 1, 1, 1, 1};
     if ((rc = make_map(&tm_hi, qkv_hi, 5, dims, strides, box, es, 64))) return rc;
     if ((rc = make_map(&tm_lo, qkv_lo, 5, dims, strides, box, es, 64))) return rc;
   }
-  AttnParams p{};
-  attn_packing(p, wsz, kind, nw);
   p.bias_tile = bias_tile;
   p.out_hi = reinterpret_cast<__half*>(out_hi);
   p.out_lo = reinterpret_cast<__half*>(out_lo);

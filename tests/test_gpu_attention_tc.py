@@ -39,7 +39,8 @@ def attention_core_reference(qkv_pm, bias, wsz, kind, heads, dh, scale):
 
 @pytest.mark.parametrize("wsz,kind,h,w,d,b", [(10, 0, 20, 30, 64, 1), (10, 1, 20, 30, 64, 2), (5, 1, 20, 30, 128, 1),
                                               (3, 0, 12, 18, 32, 2), (8, 1, 16, 24, 32, 1), (2, 1, 10, 14, 64, 1),
-                                              (1, 1, 6, 7, 96, 1), (4, 0, 12, 20, 64, 1)])
+                                              (1, 1, 6, 7, 96, 1), (4, 0, 12, 20, 64, 1), (2, 1, 12, 80, 64, 2), (4, 1, 16, 40, 32, 2),
+                                              (9, 0, 18, 27, 64, 1), (3, 1, 12, 48, 32, 1), (5, 1, 10, 15, 32, 1)])
 def test_window_attention_tc(wsz, kind, h, w, d, b):
     torch.manual_seed(wsz * 100 + kind)
     L = wsz * wsz

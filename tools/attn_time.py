@@ -2,6 +2,9 @@
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if len(sys.argv) > 1:  # python tools/attn_time.py [path of an alternative libwxformer_b200.so]
+    from miles_credit_b200 import lib as wlib
+    wlib.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), sys.argv[1]))
 from miles_credit_b200 import ops
 
 torch.manual_seed(0)
