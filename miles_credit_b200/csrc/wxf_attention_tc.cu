@@ -44,6 +44,26 @@ constexpr int AT_SMEM = OFF_BAR + 64 + 1024;
 constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 constexpr uint32_t IDESC_O = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
+// n / d for a launch-constant divisor without the 25-instruction division sequence (Granlund-Montgomery round-up form, exact
+// for every 32-bit n): the tile and window decodes run once per tile on the softmax warps' critical path
+struct FastDiv {
+  uint32_t m, sh1, sh2, d;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;  // ceil(log2 d)
+  f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.sh1 = l < 1 ? l : 1;
+  f.sh2 = l > 0 ? l - 1 : 0;
+  f.d = d;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(n, f.m);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+
 struct AttnParams {
   const float* bias_tile;  // [128 columns][128 rows] fp32: bias*log2(e) inside the row's window, -1e30 elsewhere
   __half* out_hi;
@@ -57,6 +77,7 @@ struct AttnParams {
   int gpr;            // interleaved: tiles (groups of G consecutive gw) per window row
   float scale2;       // scale * log2(e): softmax runs in base 2
   int64_t nwin, ntiles;
+  FastDiv fd_heads, fd_gpr, fd_img, fd_nw;   // divisors heads, gpr, nh*nw, nw (v2 kernel; nwin, ntiles < 2^31)
 };
 
 // Row r of a tile -> (window slot g, token i).  Window-major packing: rows [g*Lp, g*Lp + L); interleaved: r = i*G + g.
@@ -516,38 +537,45 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
   tc_fence_after();
 
   // tiles of this CTA: tile(it) = blockIdx.x + it * gridDim.x; ring stage it % A2_NST; S/P/O buffer it & 1
-  const int64_t my_tiles = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int my_tiles = p.ntiles > (int64_t)blockIdx.x ? (int)((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
-  auto tile_windows = [&](int64_t tile, int& head, int64_t& w0, int& nv) {
-    head = (int)(tile % p.heads);
-    const int64_t group = tile / p.heads;
+  // tile -> (head, first window, windows present); 32-bit, divisions by multiply-high (the host checks ntiles, nwin < 2^31)
+  auto tile_windows = [&](uint32_t tile, int& head, uint32_t& w0, int& nv) {
+    const uint32_t group = fdiv(tile, p.fd_heads);
+    head = (int)(tile - group * (uint32_t)p.heads);
     if (p.inter) {  // G consecutive gw of one (b, gh) row of groups
-      const int64_t rowi = group / p.gpr;
-      const int gw0 = (int)(group - rowi * p.gpr) * p.G;
-      w0 = rowi * p.nw + gw0;
+      const uint32_t rowi = fdiv(group, p.fd_gpr);
+      const int gw0 = (int)(group - rowi * (uint32_t)p.gpr) * p.G;
+      w0 = rowi * (uint32_t)p.nw + (uint32_t)gw0;
       nv = (p.nw - gw0) < p.G ? (p.nw - gw0) : p.G;
     } else {
-      w0 = group * p.G;
-      nv = (int)((p.nwin - w0) < p.G ? (p.nwin - w0) : p.G);
+      w0 = group * (uint32_t)p.G;
+      const uint32_t left = (uint32_t)p.nwin - w0;
+      nv = left < (uint32_t)p.G ? (int)left : p.G;
     }
+  };
+  // window -> (image, group row, group column)
+  auto window_pos = [&](uint32_t w, int& bi, int& gh, int& gw) {
+    const uint32_t b = fdiv(w, p.fd_img);
+    const uint32_t rem = w - b * p.fd_img.d;
+    const uint32_t h = fdiv(rem, p.fd_nw);
+    bi = (int)b; gh = (int)h; gw = (int)(rem - h * p.fd_nw.d);
   };
 
   if (warp == 0) {
     // ---- TMA producer: the warp runs converged (tile decode on the uniform datapath), an elected lane issues ----
-    const int per_img = p.nh * p.nw;
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      const int st = (int)(it % A2_NST);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int st = it % A2_NST;
       const uint32_t k = (uint32_t)(it / A2_NST);
       int head, nv;
-      int64_t w0;
-      tile_windows(blockIdx.x + it * gridDim.x, head, w0, nv);
+      uint32_t w0;
+      tile_windows(blockIdx.x + (uint32_t)it * gridDim.x, head, w0, nv);
       if (k > 0) mbar_wait(bar_qkv_empty(st), (k - 1u) & 1u);  // PV of the tile A2_NST back has read this stage
       const uint32_t buf = base + (uint32_t)(st * A2_QKV);
       const uint32_t full = bar_qkv_full(st);
       if (p.inter) {
-        const int bi = (int)(w0 / per_img);
-        const int rem = (int)(w0 - (int64_t)bi * per_img);
-        const int gh = rem / p.nw, gw = rem - gh * p.nw;
+        int bi, gh, gw;
+        window_pos(w0, bi, gh, gw);
         if (elect_one()) {
           mbar_expect_tx(full, (uint32_t)(6 * p.L * p.G * 64));
 #pragma unroll
@@ -568,9 +596,8 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
         if (elect_one()) mbar_expect_tx(full, (uint32_t)(nv * 6 * p.L * 64));
         __syncwarp();
         // consecutive windows of a tile: (bi, gh, gw) advance incrementally, one division per tile
-        int bi = (int)(w0 / per_img);
-        const int rem = (int)(w0 - (int64_t)bi * per_img);
-        int gh = rem / p.nw, gw = rem - gh * p.nw;
+        int bi, gh, gw;
+        window_pos(w0, bi, gh, gw);
         for (int g = 0; g < nv; ++g) {
           const uint32_t row_off = (uint32_t)(g * p.Lp * 64);
           if (elect_one()) {
@@ -604,8 +631,8 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
     constexpr uint32_t HI64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);  // SBO 512 B, version 1, SWIZZLE_64B
     // S_b = Q K^T of tile `it`.  S_b / P_b is free: tcgen05.mma instructions of one thread execute in issue order, and
     // PV(it-2), which read P_b, was issued before this.
-    auto issue_qk = [&](int64_t it) {
-      const int st = (int)(it % A2_NST);
+    auto issue_qk = [&](int it) {
+      const int st = it % A2_NST;
       const uint32_t k = (uint32_t)(it / A2_NST);
       mbar_wait(bar_qkv_full(st), k & 1u);
       tc_fence_after();
@@ -625,10 +652,10 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
       __syncwarp();
     };
     // O_b = P_b V: A = P from tensor memory (hi words in S_b columns [0, 64), lo words in [64, 128), 8 columns = 16 keys)
-    auto issue_pv = [&](int64_t it) {
-      const int b = (int)(it & 1), q = (int)(it & 3);
+    auto issue_pv = [&](int it) {
+      const int b = it & 1, q = it & 3;
       const uint32_t k2 = (uint32_t)(it >> 1), k4 = (uint32_t)(it >> 2);
-      const int st = (int)(it % A2_NST);
+      const int st = it % A2_NST;
       mbar_wait(bar_p_full(b), k2 & 1u);                        // P_b written by softmax group b
       if (k4 > 0) mbar_wait(bar_o_empty(q), (k4 - 1u) & 1u);    // O_q of the tile four back has been read
       tc_fence_after();
@@ -650,7 +677,7 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
       __syncwarp();
     };
     if (my_tiles > 0) issue_qk(0);
-    for (int64_t it = 0; it < my_tiles; ++it) {
+    for (int it = 0; it < my_tiles; ++it) {
       if (it + 1 < my_tiles) issue_qk(it + 1);
       issue_pv(it);
     }
@@ -677,13 +704,12 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
     const uint32_t s_addr = tmem_base + lane_off + (uint32_t)(wg * 128);
     const uint32_t b_addr = tmem_base + lane_off + A2_COL_BIAS;
     uint8_t* stg = gen + A2_OFF_STG + (warp - 2) * 4096;  // this warp's 32 rows x (64 B hi | 64 B lo)
-    const int per_img = p.nh * p.nw;
     const int swz = ((lane >> 1) & 3) ^ ((lane & 1) << 2);
 
     // Output of tile `it` (O buffer it & 3): O / rowsum -> fp16 hi/lo -> swizzled staging slab -> 64-byte runs.  It runs one
     // iteration late (after the softmax of this group's NEXT tile), so the PV round trip is never waited for.
-    auto epilogue = [&](int64_t it, int64_t pix, float inv, int head) {
-      const int q = (int)(it & 3);
+    auto epilogue = [&](int it, int64_t pix, float inv, int head) {
+      const int q = it & 3;
       mbar_wait(bar_o_full(q), (uint32_t)(it >> 2) & 1u);
       tc_fence_after();
       uint32_t oo[32];
@@ -721,14 +747,15 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
     // measured: the late epilogue pays for the many-window tiles of the dilated groups (L = 25: 109 -> 94 us, L = 4: 72 -> 64 us
     // at 0.25 deg) and costs 6 % on one-window tiles (L = 100), which keep the immediate epilogue
     const bool defer = p.L < 64;
-    int64_t pend_it = -1, pend_pix = -1;
+    int pend_it = -1;
+    int64_t pend_pix = -1;
     float pend_inv = 0.f;
     int pend_head = 0;
-    for (int64_t it = wg; it < my_tiles; it += 2) {
+    for (int it = wg; it < my_tiles; it += 2) {
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
       int head, nv;
-      int64_t w0;
-      tile_windows(blockIdx.x + it * gridDim.x, head, w0, nv);
+      uint32_t w0;
+      tile_windows(blockIdx.x + (uint32_t)it * gridDim.x, head, w0, nv);
 
       mbar_wait(bar_s_full(wg), par);
       tc_fence_after();
@@ -801,10 +828,8 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
       // this row's output pixel
       int64_t pix = -1;
       if (row_ok && g < nv) {
-        const int64_t w = w0 + g;
-        const int bi = (int)(w / per_img);
-        const int rem = (int)(w - (int64_t)bi * per_img);
-        const int gh = rem / p.nw, gw = rem - gh * p.nw;
+        int bi, gh, gw;
+        window_pos(w0 + (uint32_t)g, bi, gh, gw);
         int y, x;
         if (p.kind == WXF_ATTN_SHORT) {
           y = gh * p.wsz + ty;
@@ -815,10 +840,11 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
         }
         pix = ((int64_t)bi * p.H + y) * p.W + x;
       }
+      const float inv = __fdividef(1.0f, lsum);  // lsum >= 1 (the row maximum contributes 2^0): no division slow path needed
       if (defer) {
-        pend_it = it; pend_pix = pix; pend_inv = 1.0f / lsum; pend_head = head;
+        pend_it = it; pend_pix = pix; pend_inv = inv; pend_head = head;
       } else {
-        epilogue(it, pix, 1.0f / lsum, head);
+        epilogue(it, pix, inv, head);
       }
     }
     if (pend_it >= 0) epilogue(pend_it, pend_pix, pend_inv, pend_head);
@@ -921,6 +947,11 @@ extern "C" int wxf_window_attention_tc(const void* qkv_hi, const void* qkv_lo, i
   p.nwin = (int64_t)B * nh * nw;
   const int64_t groups = p.inter ? (int64_t)B * nh * p.gpr : (p.nwin + p.G - 1) / p.G;
   p.ntiles = groups * p.heads;
+  if (p.ntiles >= (int64_t)1 << 31 || p.nwin >= (int64_t)1 << 31) WXF_FAIL(WXF_EUNSUPPORTED, "attention_tc: more than 2^31 windows");
+  p.fd_heads = make_fastdiv((uint32_t)p.heads);
+  p.fd_gpr = make_fastdiv((uint32_t)p.gpr);
+  p.fd_img = make_fastdiv((uint32_t)(nh * nw));
+  p.fd_nw = make_fastdiv((uint32_t)nw);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
