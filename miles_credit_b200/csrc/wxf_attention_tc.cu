@@ -427,19 +427,11 @@ __device__ __forceinline__ void tmem_st8_nowait(uint32_t taddr, const uint32_t (
                : "memory");
 }
 
-// 16 score columns [16h, 16h+16) of the row -> 8 packed fp16x2 words of P_hi and of P_lo (zeros outside [g_lo, g_hi))
-__device__ __forceinline__ void softmax_half(uint32_t s_addr, uint32_t b_addr, int h, int g_lo, int g_hi, float2 sc2,
-                                             float2 nmx2, float2& sum_a, float2& sum_b, uint32_t (&hi)[8],
-                                             uint32_t (&lo)[8]) {
-  if (h * 2 >= g_hi || h * 2 + 2 <= g_lo) {  // warp-uniform: no column of a window of this warp
-#pragma unroll
-    for (int e = 0; e < 8; ++e) hi[e] = lo[e] = 0u;
-    return;
-  }
-  uint32_t rr[16], bb[16];
-  tmem_ld16_nowait(s_addr + (uint32_t)(h * 16), rr);
-  tmem_ld16_nowait(b_addr + (uint32_t)(h * 16), bb);
-  tmem_ld_wait();
+// 16 loaded score / bias columns [16h, 16h+16) of the row -> 8 packed fp16x2 words of P_hi and of P_lo (zeros for the
+// 8-column groups outside [g_lo, g_hi))
+__device__ __forceinline__ void softmax_half_math(const uint32_t (&rr)[16], const uint32_t (&bb)[16], int h, int g_lo, int g_hi,
+                                                  float2 sc2, float2 nmx2, float2& sum_a, float2& sum_b, uint32_t (&hi)[8],
+                                                  uint32_t (&lo)[8]) {
 #pragma unroll
   for (int q8 = 0; q8 < 2; ++q8) {
     const int gq = h * 2 + q8;
@@ -467,6 +459,25 @@ __device__ __forceinline__ void softmax_half(uint32_t s_addr, uint32_t b_addr, i
       for (int e = 0; e < 4; ++e) hi[q8 * 4 + e] = lo[q8 * 4 + e] = 0u;
     }
   }
+}
+
+// a half is active when one of its two 8-column groups holds a window column of one of the warp's rows (warp-uniform)
+__device__ __forceinline__ bool half_active(int h, int g_lo, int g_hi) { return h * 2 < g_hi && h * 2 + 2 > g_lo; }
+
+// load + arithmetic of one half; inactive halves come out as zeros without touching tensor memory
+__device__ __forceinline__ void softmax_half(uint32_t s_addr, uint32_t b_addr, int h, int g_lo, int g_hi, float2 sc2,
+                                             float2 nmx2, float2& sum_a, float2& sum_b, uint32_t (&hi)[8],
+                                             uint32_t (&lo)[8]) {
+  if (!half_active(h, g_lo, g_hi)) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) hi[e] = lo[e] = 0u;
+    return;
+  }
+  uint32_t rr[16], bb[16];
+  tmem_ld16_nowait(s_addr + (uint32_t)(h * 16), rr);
+  tmem_ld16_nowait(b_addr + (uint32_t)(h * 16), bb);
+  tmem_ld_wait();
+  softmax_half_math(rr, bb, h, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, lo);
 }
 
 __global__ void __launch_bounds__(A2_THREADS, 1)
@@ -651,7 +662,7 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
       }
       __syncwarp();
     };
-    // O_b = P_b V: A = P from tensor memory (hi words in S_b columns [0, 64), lo words in [64, 128), 8 columns = 16 keys)
+    // O_b = P_b V: A = P from tensor memory (K-step ks = 16 keys: hi words in S_b columns [16 ks, 16 ks + 8), lo words in the next 8)
     auto issue_pv = [&](int it) {
       const int b = it & 1, q = it & 3;
       const uint32_t k2 = (uint32_t)(it >> 1), k4 = (uint32_t)(it >> 2);
@@ -662,14 +673,14 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
       const uint32_t buf = base + (uint32_t)(st * A2_QKV);
       // MN-major V: LBO field = 512 B >> 4; one K = 16 step = 16 rows of 64 B = 1024 B = 64 descriptor units
       const uint32_t v_hi = (((buf + A2_OFF_V) & 0x3FFFFu) >> 4) | ((uint32_t)(512 >> 4) << 16), v_lo = v_hi + (QKV_PLANE >> 4);
-      const uint32_t p_hi = tmem_base + (uint32_t)(b * 128), p_lo = p_hi + 64u;
+      const uint32_t p_hi = tmem_base + (uint32_t)(b * 128), p_lo = p_hi + 8u;
       const uint32_t d_o = tmem_base + A2_COL_O + (uint32_t)(q * 32);
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // 128 key rows = eight K=16 steps
-          tc_mma_f16_ts(d_o, p_hi + ks * 8, umma_desc_make(v_lo + 64 * ks, HI64), IDESC_O, ks ? 1u : 0u);
-          tc_mma_f16_ts(d_o, p_lo + ks * 8, umma_desc_make(v_hi + 64 * ks, HI64), IDESC_O, 1u);
-          tc_mma_f16_ts(d_o, p_hi + ks * 8, umma_desc_make(v_hi + 64 * ks, HI64), IDESC_O, 1u);
+          tc_mma_f16_ts(d_o, p_hi + ks * 16, umma_desc_make(v_lo + 64 * ks, HI64), IDESC_O, ks ? 1u : 0u);
+          tc_mma_f16_ts(d_o, p_lo + ks * 16, umma_desc_make(v_hi + 64 * ks, HI64), IDESC_O, 1u);
+          tc_mma_f16_ts(d_o, p_hi + ks * 16, umma_desc_make(v_hi + 64 * ks, HI64), IDESC_O, 1u);
         }
         tc_commit(bar_o_full(q));
         if (it + A2_NST < my_tiles) tc_commit(bar_qkv_empty(st));  // stage may be refilled (nobody waits after the last use)
@@ -744,9 +755,8 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
       __syncwarp();  // the slab is rewritten by the next epilogue of this warp
     };
 
-    // measured: the late epilogue pays for the many-window tiles of the dilated groups (L = 25: 109 -> 94 us, L = 4: 72 -> 64 us
-    // at 0.25 deg) and costs 6 % on one-window tiles (L = 100), which keep the immediate epilogue
-    const bool defer = p.L < 64;
+    // the epilogue of a tile runs one iteration late for every tile shape (measured at 0.25 deg: L = 25: 109 -> 94 us, L = 4:
+    // 72 -> 64 us; since the decodes left the critical path also L = 100: 162 -> 154 us)
     int pend_it = -1;
     int64_t pend_pix = -1;
     float pend_inv = 0.f;
@@ -769,61 +779,36 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
           tmem_ld32_nowait(s_addr + (uint32_t)(c * 32), rr);
           tmem_ld32_nowait(b_addr + (uint32_t)(c * 32), bb);
           tmem_ld_wait();
+          // every loaded column counts: a column of another window carries bias -1e30 and cannot win (measured: the
+          // per-group range tests cost more in branches than the few columns they skip)
 #pragma unroll
-          for (int q8 = 0; q8 < 4; ++q8) {
-            const int gq = c * 4 + q8;
-            if (gq >= g_lo && gq < g_hi) {  // warp-uniform
-#pragma unroll
-              for (int e = 0; e < 8; e += 4) {
-                const int j = q8 * 8 + e;
-                const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), sc2,
-                                             make_float2(__uint_as_float(bb[j]), __uint_as_float(bb[j + 1])));
-                const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(rr[j + 2]), __uint_as_float(rr[j + 3])), sc2,
-                                             make_float2(__uint_as_float(bb[j + 2]), __uint_as_float(bb[j + 3])));
-                m0 = fmaxf(m0, t0.x); m1 = fmaxf(m1, t0.y); m2 = fmaxf(m2, t1.x); m3 = fmaxf(m3, t1.y);
-              }
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), sc2,
+                                         make_float2(__uint_as_float(bb[j]), __uint_as_float(bb[j + 1])));
+            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(rr[j + 2]), __uint_as_float(rr[j + 3])), sc2,
+                                         make_float2(__uint_as_float(bb[j + 2]), __uint_as_float(bb[j + 3])));
+            m0 = fmaxf(m0, t0.x); m1 = fmaxf(m1, t0.y); m2 = fmaxf(m2, t1.x); m3 = fmaxf(m3, t1.y);
           }
         }
         mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
-      // P over S, in place.  16-column halves h = 0..7: hi words -> columns [8h, 8h+8) (already consumed), lo words ->
-      // [64+8h, 64+8h+8) = S half 4 + h/2: the lo words of halves 0-3 wait in registers until halves 4 and 5 were read
+      // P over S, in place: the 16 score columns of half h become its 8 hi words (columns [16h, 16h+8)) and 8 lo words
+      // ([16h+8, 16h+16)) - a half only overwrites what it has just read, so no word waits in registers for another half
       const float2 nmx2 = make_float2(-mx, -mx);
       float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
-      {
-        uint32_t hi[8], lo[8], d0[8], d1[8], d2[8], d3[8];
-        softmax_half(s_addr, b_addr, 0, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, d0);
-        tmem_st8_nowait(s_addr + 0u, hi);
-        softmax_half(s_addr, b_addr, 1, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, d1);
-        tmem_st8_nowait(s_addr + 8u, hi);
-        softmax_half(s_addr, b_addr, 2, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, d2);
-        tmem_st8_nowait(s_addr + 16u, hi);
-        softmax_half(s_addr, b_addr, 3, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, d3);
-        tmem_st8_nowait(s_addr + 24u, hi);
-        softmax_half(s_addr, b_addr, 7, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, lo);   // halves 7, 6, 5, 4: every lo
-        tmem_st8_nowait(s_addr + 56u, hi);                                             // target is already consumed
-        tmem_st8_nowait(s_addr + 120u, lo);
-        softmax_half(s_addr, b_addr, 6, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, lo);
-        tmem_st8_nowait(s_addr + 48u, hi);
-        tmem_st8_nowait(s_addr + 112u, lo);
-        softmax_half(s_addr, b_addr, 5, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, lo);
-        tmem_st8_nowait(s_addr + 40u, hi);
-        tmem_st8_nowait(s_addr + 104u, lo);
-        softmax_half(s_addr, b_addr, 4, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, lo);
-        tmem_st8_nowait(s_addr + 32u, hi);
-        tmem_st8_nowait(s_addr + 96u, lo);
-        tmem_st8_nowait(s_addr + 64u, d0);   // halves 4 and 5 (columns 64..95) have been read
-        tmem_st8_nowait(s_addr + 72u, d1);
-        tmem_st8_nowait(s_addr + 80u, d2);
-        tmem_st8_nowait(s_addr + 88u, d3);
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        uint32_t hi[8], lo[8];
+        softmax_half(s_addr, b_addr, h, g_lo, g_hi, sc2, nmx2, sum_a, sum_b, hi, lo);
+        tmem_st8_nowait(s_addr + (uint32_t)(16 * h), hi);
+        tmem_st8_nowait(s_addr + (uint32_t)(16 * h + 8), lo);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       const float lsum = (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
       tc_fence_before();
       mbar_arrive(bar_p_full(wg));
 
-      if (defer && pend_it >= 0) epilogue(pend_it, pend_pix, pend_inv, pend_head);  // the previous tile of this group
+      if (pend_it >= 0) epilogue(pend_it, pend_pix, pend_inv, pend_head);  // the previous tile of this group
 
       // this row's output pixel
       int64_t pix = -1;
@@ -841,11 +826,7 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __g
         pix = ((int64_t)bi * p.H + y) * p.W + x;
       }
       const float inv = __fdividef(1.0f, lsum);  // lsum >= 1 (the row maximum contributes 2^0): no division slow path needed
-      if (defer) {
-        pend_it = it; pend_pix = pix; pend_inv = inv; pend_head = head;
-      } else {
-        epilogue(it, pix, inv, head);
-      }
+      pend_it = it; pend_pix = pix; pend_inv = inv; pend_head = head;
     }
     if (pend_it >= 0) epilogue(pend_it, pend_pix, pend_inv, pend_head);
   }
