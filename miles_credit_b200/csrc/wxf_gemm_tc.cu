@@ -139,12 +139,12 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const uint32_t stage_tx = CONV ? (2u * p.a_bytes + 2u * W_BYTES) : (uint32_t)STAGE_BYTES;
     int s = 0;
     uint32_t ph = 0;
+    int t = 0, cb = 0;  // K-step = (tap, channel block), advanced without a division per step
     for (int ks = 0; ks < num_k; ++ks) {
       mbar_wait(empty_bar(s), ph ^ 1u);
       const uint32_t st = base + s * STAGE_BYTES;
       int wk, c0 = 0, c1 = 0, c2 = 0;
       if constexpr (CONV) {
-        const int t = ks / p.cblocks, cb = ks - t * p.cblocks;
         c2 = oy0 * p.stride + p.taps[z][t][0];
         c1 = ox0 * p.stride + p.taps[z][t][1];
         c0 = cb * BLOCK_K;
@@ -165,6 +165,12 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         tma_load_2d(&tmW_lo, full_bar(s), st + 2 * TILE_BYTES + W_BYTES, wk, z * p.N + n0);
       }
       __syncwarp();
+      if constexpr (CONV) {
+        if (++cb == p.cblocks) {
+          cb = 0;
+          ++t;
+        }
+      }
       if (++s == STAGES) {
         s = 0;
         ph ^= 1u;
@@ -175,11 +181,11 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     uint32_t started = 0;  // bit a: accumulator a already holds data
     int s = 0;
     uint32_t ph = 0;
+    int am = 1, am_rem = 0;  // main accumulator of this K-step = 1 + ks * NMAIN / num_k, advanced without a division
     for (int ks = 0; ks < num_k; ++ks) {
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
       const uint32_t lo = umma_desc_lo(base + s * STAGE_BYTES);
-      const int am = 1 + (int)(((int64_t)ks * NMAIN) / num_k);  // main accumulator of this K-step
       const uint32_t d_cross = tmem_base, d_main = tmem_base + (uint32_t)(am * BN);
       const uint32_t acc_cross = started & 1u, acc_main = (started >> am) & 1u;
       if (elect_one()) {
@@ -198,6 +204,11 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       }
       __syncwarp();
       started |= 1u | (1u << am);
+      am_rem += NMAIN;
+      while (am_rem >= num_k) {
+        am_rem -= num_k;
+        ++am;
+      }
       if (++s == STAGES) {
         s = 0;
         ph ^= 1u;
@@ -607,12 +618,12 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       int n0, z, tb, oy0, ox0;
       int64_t m0;
       decode(t, n0, z, m0, tb, oy0, ox0);
+      int tp = 0, cb = 0;  // K-step = (tap, channel block), advanced without a division per step
       for (int ks = 0; ks < num_k; ++ks) {
         mbar_wait_parked(empty_bar(s), ph ^ 1u, EPI != 0 ? p.park_ns : 0u);
         const uint32_t st = base + s * STAGE_BYTES;
         int wk, c0 = 0, c1 = 0, c2 = 0;
         if constexpr (CONV) {
-          const int tp = ks / p.cblocks, cb = ks - tp * p.cblocks;
           c2 = oy0 * p.stride + p.taps[z][tp][0];
           c1 = ox0 * p.stride + p.taps[z][tp][1];
           c0 = cb * BLOCK_K;
@@ -633,6 +644,12 @@ tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           tma_load_2d(&tmW_lo, full_bar(s), st + 2 * TILE_BYTES + W_BYTES, wk, z * p.N + n0);
         }
         __syncwarp();
+        if constexpr (CONV) {
+          if (++cb == p.cblocks) {
+            cb = 0;
+            ++tp;
+          }
+        }
         if (++s == STAGES) {
           s = 0;
           ph ^= 1u;
