@@ -8,7 +8,7 @@ OBJS=""
 PIDS=""
 for f in wxf_*.cu; do
   o="${f%.cu}.o"
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ wxf_common.cuh -nt "$o" ] || [ wxf_tc_ptx.cuh -nt "$o" ] || [ wxf_tc_host.cuh -nt "$o" ] || [ ../../include/wxformer_b200.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ wxf_common.cuh -nt "$o" ] || [ wxf_tc_ptx.cuh -nt "$o" ] || [ wxf_tc_host.cuh -nt "$o" ] || [ wxf_fastdiv.h -nt "$o" ] || [ ../../include/wxformer_b200.h -nt "$o" ]; then
     echo "nvcc $f" >&2
     ( $NVCC $FLAGS -c "$f" -o "$o" || { rm -f "$o"; exit 1; } ) &
     PIDS="$PIDS $!"

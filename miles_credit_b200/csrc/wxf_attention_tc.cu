@@ -22,6 +22,7 @@
 //   epi   : O / rowsum -> fp16 hi/lo planes of the attention output at the token's pixel (the inverse gather)
 #include <stdlib.h>
 
+#include "wxf_fastdiv.h"
 #include "wxf_tc_host.cuh"
 #include "wxf_tc_ptx.cuh"
 
@@ -43,26 +44,6 @@ constexpr int OFF_BAR = OFF_P + 4 * P_ATOM;
 constexpr int AT_SMEM = OFF_BAR + 64 + 1024;
 constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 constexpr uint32_t IDESC_O = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
-// n / d for a launch-constant divisor without the 25-instruction division sequence (Granlund-Montgomery round-up form, exact
-// for every 32-bit n): the tile and window decodes run once per tile on the softmax warps' critical path
-struct FastDiv {
-  uint32_t m, sh1, sh2, d;
-};
-inline FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f;
-  uint32_t l = 0;
-  while ((1ull << l) < d) ++l;  // ceil(log2 d)
-  f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
-  f.sh1 = l < 1 ? l : 1;
-  f.sh2 = l > 0 ? l - 1 : 0;
-  f.d = d;
-  return f;
-}
-__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
-  const uint32_t t = __umulhi(n, f.m);
-  return (t + ((n - t) >> f.sh1)) >> f.sh2;
-}
 
 struct AttnParams {
   const float* bias_tile;  // [128 columns][128 rows] fp32: bias*log2(e) inside the row's window, -1e30 elsewhere
