@@ -65,6 +65,16 @@ def test_bilinear_matches_torch():
     assert torch.allclose(oracle.bilinear_resize(x, 7, 17), ref, atol=1e-6)
 
 
+def test_wxformer_variant_ignores_crossformer_only_keys():
+    """`type: wxformer` configs of the reference carry keys its class swallows in **kwargs (wxformer/crossformer.py:624-653;
+    config/example-v2026.1.0.yml:194-196, config/gen_2/smoke/smoke_gen2_multistep_casper.yml:68-69): same geometry with them."""
+    kw = dict(workload("unit"), variant="wxformer")
+    geo = build_geometry(**kw)
+    assert build_geometry(**dict(kw, upsample_v_conv=True, decoder_attention_type="scse", frame_patch_size=2)) == geo
+    with pytest.raises(NotImplementedError):  # the `crossformer` class does build a different decoder for it
+        build_geometry(**dict(workload("unit"), upsample_v_conv=True))
+
+
 def test_scope_errors():
     with pytest.raises(NotImplementedError):
         build_geometry(**dict(workload("unit"), patch_height=2, patch_width=2))
