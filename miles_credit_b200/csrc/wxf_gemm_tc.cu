@@ -1026,7 +1026,6 @@ tc_resident_w_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO_hi,
                      const __grid_constant__ CUtensorMap tmO_lo, const __grid_constant__ TcParams p, const int n_tiles,
                      const int m_tiles, const int total_tiles) {
-  constexpr bool CONV = false;
   constexpr int EW = RW_EW, STAGES = RW_STA, BN = P_BN, W_BYTES = P_BN * BLOCK_K * 2;
   constexpr int CW = 128 / (EW / 4);
   constexpr int NCH = CW / 32;
