@@ -13,8 +13,9 @@ sm_100a kernels of the C ABI (include/wxformer_b200.h):
   ->  dense head GEMM (:420, 484)  ->  un-patchify + un-pad + bilinear + NCHW (:485-498).
 
 Eval-mode forward only; no CPU path, no PyTorch fallback.  The Swin-V2 stage is third-party ``timm`` code that is absent
-from the reference tree and this image: its arithmetic here follows ``oracle/swin_v2.py`` (parity of that stage against
-timm itself: unpinned); everything FuXi owns in the reference tree is pinned by ``tests/golden/unit_fuxi*.pt``.
+from the reference tree and this image: its arithmetic here follows ``oracle/swin_v2.py`` (pinned bit-exactly against
+HuggingFace's independent ``Swinv2Stage`` port, tests/test_swin_v2_vs_hf.py; against timm itself: unpinned, SURVEY.md section
+8c); everything FuXi owns in the reference tree is pinned by ``tests/golden/unit_fuxi*.pt``.
 One reference quirk is kept: under FuXi's old-style spectral-norm hooks timm's qkv projection runs on the UN-normalised
 ``weight_orig`` (timm calls ``F.linear(x, self.qkv.weight, ...)``, so the hook never fires).
 """

@@ -1,5 +1,5 @@
-"""ORACLE — test infrastructure only.  Parity status: PINNED for everything in the reference tree, UNPINNED for the
-Swin-V2 stage (see ``oracle/swin_v2.py``).
+"""ORACLE — test infrastructure only.  Parity status: PINNED for everything in the reference tree; the Swin-V2 stage is
+pinned against HuggingFace's independent ``Swinv2Stage`` port, not against timm itself (see ``oracle/swin_v2.py``).
 
 A CPU restatement, in plain fp32 PyTorch tensor ops and as pure functions of a *state dict*, of the reference's FuXi
 forecast forward step ``y = Fuxi(x)`` (``/root/reference/credit/models/fuxi.py:454-506``): boundary padding, cube
@@ -8,7 +8,7 @@ embedding (Conv3d patchify + LayerNorm, ``:82-143``), U-Transformer (DownBlock `
 un-patchify (``:484-489``), un-pad and bilinear resize (``:491-498``).  ``use_noise`` / ``post_conf`` are off (the noise
 branch cannot even be constructed in the reference: SURVEY.md §8c).
 
-No CUDA path exists for FuXi yet: this file is the oracle the next round builds against.
+The CUDA path (``miles_credit_b200/fuxi.py``) is checked against this file.
 Pinning of the in-tree parts: ``tests/golden/make_golden_fuxi.py`` imports the UNMODIFIED ``credit/models/fuxi.py``
 through ``credit.models.load_model`` with the Swin-V2 stand-in of ``oracle/swin_v2.py`` registered as ``timm`` and stores
 input, state dict and output in ``tests/golden/unit_fuxi.pt``; ``tests/test_fuxi_oracle.py`` checks this file against it.

@@ -53,7 +53,7 @@ def reference_model(kwargs: dict, state_dict: dict, variant: str = "crossformer"
 
     if variant == "fuxi":
         # credit/models/fuxi.py:4-5 imports timm's SwinTransformerV2Stage; timm is in neither the reference tree nor this
-        # image: the restatement of oracle/swin_v2.py stands in (parity of that stage: unpinned)
+        # image: the restatement of oracle/swin_v2.py stands in (pinned against HuggingFace's Swinv2Stage, tests/test_swin_v2_vs_hf.py)
         from oracle import swin_v2
 
         swin_v2.install_timm_stub()

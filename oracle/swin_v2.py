@@ -1,11 +1,16 @@
-"""ORACLE — test infrastructure only.  Parity status of THIS file: UNPINNED.
+"""ORACLE — test infrastructure only.  Parity status of THIS file: PINNED AGAINST AN INDEPENDENT IMPLEMENTATION of the same
+algorithm (HuggingFace ``transformers`` ``Swinv2Stage``: ``tests/golden/make_golden_swin_hf.py`` -> ``swin_v2_hf.pt``,
+``tests/test_swin_v2_vs_hf.py``, bit-identical outputs on randomised parameters incl. shifted blocks and clamped logit
+scales); NOT pinned against timm itself, which neither the reference tree nor any image here contains.  What still rests on
+reading timm alone: the per-dimension window clamp of ``_calc_window_shift`` (HF clamps with one scalar; FuXi never hits
+it: its token grid is padded to window multiples) and the qkv-on-``weight_orig`` call pattern under FuXi's spectral norm.
 
 Restatement of ``timm.models.swin_transformer_v2.SwinTransformerV2Stage`` — the third-party block FuXi's
 ``UTransformer`` instantiates (``/root/reference/credit/models/fuxi.py:4-5, 250-260``; forward call ``:285-287``).
 ``timm`` (huggingface/pytorch-image-models) is NOT in the reference tree, is not pinned by the reference
 (``pyproject.toml:12-48`` does not list it; it arrives transitively) and is not installed in the build image, so this
 file restates the published Swin-V2 algorithm (Liu et al., "Swin Transformer V2", and timm's ``swin_transformer_v2.py``
-as of the 0.9 / 1.0 series) from its specification and cannot be checked against the real module here:
+as of the 0.9 / 1.0 series) from its specification; the real timm module cannot be imported here, HuggingFace's port can:
 
 * windows of ``ws x ws`` tokens, blocks alternate shift 0 / ``ws // 2`` (cyclic roll, ``attn_mask`` = -100 between the
   regions the roll glues together); a window larger than the grid is clamped to the grid and its shift set to 0;

@@ -1,8 +1,8 @@
 """CPU: the FuXi oracle (oracle/fuxi_oracle.py) against the golden vectors produced by the UNMODIFIED reference module
 ``credit/models/fuxi.py`` (tests/golden/make_golden_fuxi.py).  The in-tree parts of FuXi are pinned by these vectors; the
 Swin-V2 stage is third-party ``timm`` code that is absent here, so BOTH sides use the restatement of oracle/swin_v2.py
-(parity of the stage: unpinned) and the checks below on it are self-consistency and invariants only.
-No CUDA path exists for FuXi yet: this is the oracle the next round builds against."""
+(pinned against HuggingFace's independent Swinv2Stage in tests/test_swin_v2_vs_hf.py; timm itself is in no image here) and the
+checks below on it are self-consistency and invariants."""
 import os
 
 import pytest
